@@ -1,0 +1,132 @@
+/* include/mdapy_b200.h -- C ABI of libmdapy_b200.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for mdapy's neighbour + structural-descriptor
+ * hot path.  Every entry point in section A replaces one nanobind function of
+ * the reference (file:line given; signatures per SURVEY.md section 8b): same
+ * argument order and meaning, NumPy buffers become plain pointers + extents,
+ * `num_t` (the OpenMP team size) is accepted and ignored.  Arrays are
+ * C-contiguous, double = f64, int = int32, positions are three separate
+ * vectors, box rows are lattice vectors, boundary[d] = 1 means periodic.
+ * Section A takes HOST pointers and round-trips over PCIe per call; section B
+ * is the device-resident handle the Python `System` uses so that chained
+ * cal_* calls keep the lists in HBM.
+ *
+ * Every function returns 0 on success or an MDB_ERR_* code; the message is
+ * available from mdb_last_error().  MDB_ERR_VALUE maps to Python ValueError,
+ * everything else to RuntimeError (the reference surfaces std::runtime_error
+ * from src/box.h:85,186 the same way).
+ */
+#ifndef MDAPY_B200_H
+#define MDAPY_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define MDB_OK 0
+#define MDB_ERR_CUDA 1
+#define MDB_ERR_VALUE 2
+#define MDB_ERR_BOX 3
+#define MDB_ERR_STATE 4
+
+const char *mdb_last_error(void);
+const char *mdb_version(void);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+long long mdb_launch_count(void);
+int mdb_device_count(int *count);
+
+/* ------------------------------------------------------------------------
+ * Section A: host-pointer drop-ins, one per reference nanobind function
+ * ---------------------------------------------------------------------- */
+
+/* _neighbor.build_neighbor, src/neighbor.cpp:351.  verlet/dist/nn are caller
+ * allocated; rows are fully (re)written: -1 / rc+1.0 padding as
+ * src/mdapy/neighbor.py:125-129 prefills them.  nn always holds the true
+ * count, even beyond M (caller raises ValueError, neighbor.py:135-142). */
+int mdb_build_neighbor(const double *x, const double *y, const double *z, int N, const double *box9,
+                       const double *origin3, const int *boundary3, double rc, int *verlet, double *dist,
+                       int *nn, int M, int num_t);
+
+/* _neighbor.build_neighbor_without_max_neigh, src/neighbor.cpp:189.  Two-step
+ * form of the capsule-owning return: the first call computes the lists on the
+ * device and reports M = max(count, 1); the caller allocates (N, M) arrays and
+ * fetches them with mdb_neighbor_auto_fetch, which also releases the handle. */
+int mdb_build_neighbor_without_max_neigh(const double *x, const double *y, const double *z, int N,
+                                         const double *box9, const double *origin3, const int *boundary3,
+                                         double rc, int num_t, void **handle, int *M);
+int mdb_neighbor_auto_fetch(void *handle, int *verlet, double *dist, int *nn);
+
+/* _neighbor.sort_verlet_by_distance, src/neighbor.cpp:745 (in place). */
+int mdb_sort_verlet_by_distance(int *verlet, double *dist, int N, int M, int k, int num_t);
+
+/* _cna.fcna, src/cna.cpp:429.  pattern is fully written (0 = other). */
+int mdb_fcna(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+             const int *boundary3, const int *verlet, int M, const int *nn, int *pattern, double rc, int num_t);
+/* _cna.acna, src/cna.cpp:289.  verlet rows: >= 14 neighbours, ascending distance. */
+int mdb_acna(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+             const int *boundary3, const int *verlet, int M, int *pattern, int num_t);
+
+/* _csp.get_csp, src/centro_symmetry_parameter.cpp:12. */
+int mdb_get_csp(const double *x, const double *y, const double *z, int N, const double *box9,
+                const double *origin3, const int *boundary3, const int *verlet, int M, int nnei, double *csp,
+                int num_t);
+
+/* _aja.compute_aja, src/ackland_jones_analysis.cpp:9. */
+int mdb_compute_aja(const double *x, const double *y, const double *z, int N, const double *box9,
+                    const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                    int Md, int *aja, int num_t);
+
+/* ------------------------------------------------------------------------
+ * Section B: device-resident system handle
+ * ---------------------------------------------------------------------- */
+typedef struct MdbSystem mdb_system;
+
+int mdb_system_create(int device, mdb_system **out);
+void mdb_system_destroy(mdb_system *s);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*, e.g. torch's current stream) */
+int mdb_system_set_stream(mdb_system *s, void *cuda_stream);
+int mdb_system_synchronize(mdb_system *s);
+
+/* upload host coordinates (H2D) / borrow device coordinates (no copy; must outlive use) */
+int mdb_system_set_atoms(mdb_system *s, const double *x, const double *y, const double *z, int N,
+                         const double *box9, const double *origin3, const int *boundary3);
+int mdb_system_set_atoms_device(mdb_system *s, const double *dx, const double *dy, const double *dz, int N,
+                                const double *box9, const double *origin3, const int *boundary3);
+
+/* cut-off list kept on the device.  max_neigh <= 0: size automatically
+ * (neighbor.cpp:189 semantics, M = max(count,1)).  Returns row width and the
+ * largest count; with max_neigh > 0 and max_count > max_neigh the list is
+ * truncated exactly like the reference and the caller should raise. */
+int mdb_system_build_neighbor(mdb_system *s, double rc, int max_neigh, int *M, int *max_count);
+int mdb_system_sort_neighbor(mdb_system *s, int k);
+int mdb_system_neighbor_min_count(mdb_system *s, int *min_count);
+/* D2H of the cached list; any pointer may be NULL */
+int mdb_system_fetch_neighbor(mdb_system *s, int *verlet, double *dist, int *nn);
+/* replace the cached list by host arrays (H2D), e.g. a user-provided list */
+int mdb_system_put_neighbor(mdb_system *s, const int *verlet, const double *dist, const int *nn, int M, double rc,
+                            int kind);
+/* raw device pointers of the cached list (for zero-copy consumers); M via mdb_system_build_neighbor */
+int mdb_system_neighbor_device(mdb_system *s, int **verlet, double **dist, int **nn, int *M);
+
+/* descriptors on the cached list; results stay on the device when out == NULL */
+int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host);
+int mdb_system_acna(mdb_system *s, int *pattern_host);
+int mdb_system_csp(mdb_system *s, int nnei, double *csp_host);
+int mdb_system_aja(mdb_system *s, int *aja_host);
+/* device pointers to the most recent int32 / f64 per-atom result */
+int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
+
+/* per-kernel device times (ms) of the most recent build_neighbor / fcna, measured with CUDA events */
+int mdb_system_set_profiling(mdb_system *s, int on);
+int mdb_system_last_times(mdb_system *s, float *t_binning_ms, float *t_neighbor_ms, float *t_cna_ms);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDAPY_B200_H */

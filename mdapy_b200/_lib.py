@@ -1,0 +1,115 @@
+"""ctypes binding of libmdapy_b200.so (the C ABI in include/mdapy_b200.h).
+
+The library is the product: there is no CPU fallback.  Loading fails loudly
+when the shared object is missing, and every call fails loudly when no CUDA
+device is present (``mdb_system_create`` returns MDB_ERR_CUDA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmdapy_b200.so"
+
+MDB_OK, MDB_ERR_CUDA, MDB_ERR_VALUE, MDB_ERR_BOX, MDB_ERR_STATE = 0, 1, 2, 3, 4
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_fp = C.POINTER(C.c_float)
+c_vp = C.c_void_p
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/mdapy_b200.h one to one
+_BOX = [c_dp, c_dp, c_ip]
+_XYZN = [c_dp, c_dp, c_dp, C.c_int]
+PROTOTYPES = {
+    "mdb_last_error": (C.c_char_p, []),
+    "mdb_version": (C.c_char_p, []),
+    "mdb_launch_count": (C.c_longlong, []),
+    "mdb_device_count": (C.c_int, [c_ip]),
+    "mdb_build_neighbor": (C.c_int, _XYZN + _BOX + [C.c_double, c_ip, c_dp, c_ip, C.c_int, C.c_int]),
+    "mdb_build_neighbor_without_max_neigh": (
+        C.c_int, _XYZN + _BOX + [C.c_double, C.c_int, C.POINTER(c_vp), c_ip]),
+    "mdb_neighbor_auto_fetch": (C.c_int, [c_vp, c_ip, c_dp, c_ip]),
+    "mdb_sort_verlet_by_distance": (C.c_int, [c_ip, c_dp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mdb_fcna": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_ip, c_ip, C.c_double, C.c_int]),
+    "mdb_acna": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_ip, C.c_int]),
+    "mdb_get_csp": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, C.c_int, c_dp, C.c_int]),
+    "mdb_compute_aja": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, C.c_int, c_ip, C.c_int]),
+    "mdb_system_create": (C.c_int, [C.c_int, C.POINTER(c_vp)]),
+    "mdb_system_destroy": (None, [c_vp]),
+    "mdb_system_set_stream": (C.c_int, [c_vp, c_vp]),
+    "mdb_system_synchronize": (C.c_int, [c_vp]),
+    "mdb_system_set_atoms": (C.c_int, [c_vp] + _XYZN + _BOX),
+    "mdb_system_set_atoms_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int] + _BOX),
+    "mdb_system_build_neighbor": (C.c_int, [c_vp, C.c_double, C.c_int, c_ip, c_ip]),
+    "mdb_system_sort_neighbor": (C.c_int, [c_vp, C.c_int]),
+    "mdb_system_neighbor_min_count": (C.c_int, [c_vp, c_ip]),
+    "mdb_system_fetch_neighbor": (C.c_int, [c_vp, c_ip, c_dp, c_ip]),
+    "mdb_system_put_neighbor": (C.c_int, [c_vp, c_ip, c_dp, c_ip, C.c_int, C.c_double, C.c_int]),
+    "mdb_system_neighbor_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), c_ip]),
+    "mdb_system_fcna": (C.c_int, [c_vp, C.c_double, c_ip]),
+    "mdb_system_acna": (C.c_int, [c_vp, c_ip]),
+    "mdb_system_csp": (C.c_int, [c_vp, C.c_int, c_dp]),
+    "mdb_system_aja": (C.c_int, [c_vp, c_ip]),
+    "mdb_system_result_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
+    "mdb_system_set_profiling": (C.c_int, [c_vp, C.c_int]),
+    "mdb_system_last_times": (C.c_int, [c_vp, c_fp, c_fp, c_fp]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libmdapy_b200.so (built by ``make -C mdapy_b200/csrc`` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} not found: the CUDA extension is the only backend of mdapy_b200 "
+                "(no CPU fallback). Build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+            )
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code: int) -> None:
+    """Map MDB_ERR_* to the exception types the reference raises at this boundary."""
+    if code == MDB_OK:
+        return
+    msg = lib().mdb_last_error().decode(errors="replace")
+    if code == MDB_ERR_VALUE:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def dptr(a: np.ndarray):
+    return a.ctypes.data_as(c_dp)
+
+
+def iptr(a: np.ndarray):
+    return a.ctypes.data_as(c_ip)
+
+
+def f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def box_args(box, origin, boundary):
+    """(3,3) f64 box, (3,) f64 origin, (3,) int32 boundary -- int64 flags are converted
+    like nanobind's implicit cast does for the reference (box.py:247-259)."""
+    b = f64(box).reshape(3, 3)
+    o = f64(origin).reshape(3)
+    p = i32(boundary).reshape(3)
+    return b, o, p

@@ -1,0 +1,510 @@
+// mdapy_b200/csrc/capi.cu -- the C ABI declared in include/mdapy_b200.h.
+#include "internal.cuh"
+#include "../../include/mdapy_b200.h"
+#include <cstdarg>
+#include <new>
+
+long long g_mdb_launches = 0;
+static thread_local char g_err[1024] = "";
+
+void mdb_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define API_BEGIN try {
+#define API_END                                            \
+    }                                                      \
+    catch (const MdbError &e) { return e.code; }           \
+    catch (const std::bad_alloc &)                         \
+    {                                                      \
+        mdb_set_error("host allocation failed");           \
+        return MDB_ERR_CUDA;                               \
+    }                                                      \
+    return MDB_OK;
+
+static void set_box(MdbSystem &s, const double *box9, const double *origin3, const int *boundary3)
+{
+    MDB_REQUIRE(box9 && origin3 && boundary3, MDB_ERR_VALUE, "box, origin and boundary are required");
+    const int rc = dbox_make(s.box, box9, origin3, boundary3);
+    MDB_REQUIRE(rc == 0, MDB_ERR_BOX, "The volume of the box is zero.");
+    s.has_box = true;
+}
+
+static void invalidate(MdbSystem &s)
+{
+    s.bin_rc = -1.0;
+    s.list_kind = LIST_NONE;
+    s.list_rc = -1.0;
+    s.M = 0;
+    s.max_count = 0;
+}
+
+static void upload_atoms(MdbSystem &s, const double *x, const double *y, const double *z, int N)
+{
+    MDB_REQUIRE(N > 0, MDB_ERR_VALUE, "data must contain at least one atom.");
+    MDB_REQUIRE(x && y && z, MDB_ERR_VALUE, "x, y, z are required");
+    double *dx = s.bx.ensure<double>(N), *dy = s.by.ensure<double>(N), *dz = s.bz.ensure<double>(N);
+    CUDA_TRY(cudaMemcpyAsync(dx, x, sizeof(double) * N, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(dy, y, sizeof(double) * N, cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(dz, z, sizeof(double) * N, cudaMemcpyHostToDevice, s.stream));
+    s.x = dx;
+    s.y = dy;
+    s.z = dz;
+    s.N = N;
+    invalidate(s);
+}
+
+static void prof_mark(MdbSystem &s, int k)
+{
+    if (s.profile) CUDA_TRY(cudaEventRecord(s.ev[k], s.stream));
+}
+
+// cut-off list into s.verlet/s.dist/s.nn.  max_neigh <= 0 -> automatic width.
+static void build_neighbor(MdbSystem &s, double rc, int max_neigh)
+{
+    MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "rc must be positive, got %g.", rc);
+    prof_mark(s, 0);
+    if (s.bin_rc != rc) launch_binning(s, rc);
+    prof_mark(s, 1);
+    if (max_neigh > 0) {
+        launch_neighbor(s, rc, max_neigh, false);
+        s.M = max_neigh;
+        prof_mark(s, 2);
+        s.max_count = device_max_int(s, s.nn.as<int>(), s.N);
+    } else {
+        // Guess the width from the mean density (x1.5 + 8), fill once, then
+        // shrink (or redo if the guess was short).  Equivalent to the
+        // reference's count-then-copy (neighbor.cpp:290-343) without a
+        // second search in the common case.
+        const double vol = fabs(dbox_volume(s.box));
+        const double mean = vol > 0 ? (double)s.N / vol * 4.18879020478639 * rc * rc * rc : 16.0;
+        int guess = (int)(mean * 1.5) + 8;
+        if (guess > 256) guess = 256;
+        if ((double)guess * s.N * 12.0 > 24e9) guess = (int)(24e9 / 12.0 / s.N) > 1 ? (int)(24e9 / 12.0 / s.N) : 1;
+        launch_neighbor(s, rc, guess, false);
+        prof_mark(s, 2);
+        int mx = device_max_int(s, s.nn.as<int>(), s.N);
+        const int want = mx > 1 ? mx : 1;
+        if (mx > guess) {
+            launch_neighbor(s, rc, want, false);
+            prof_mark(s, 2);
+        } else if (want < guess) {
+            launch_compact_rows(s, guess, want);
+        }
+        s.M = want;
+        s.max_count = mx;
+    }
+    s.list_kind = LIST_CUTOFF;
+    s.list_rc = rc;
+    if (s.profile) {
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+        CUDA_TRY(cudaEventElapsedTime(&s.t_bin, s.ev[0], s.ev[1]));
+        CUDA_TRY(cudaEventElapsedTime(&s.t_neigh, s.ev[1], s.ev[2]));
+    }
+}
+
+template <class T> static void d2h(MdbSystem &s, T *host, const T *dev, size_t n)
+{
+    if (host && n) CUDA_TRY(cudaMemcpyAsync(host, dev, sizeof(T) * n, cudaMemcpyDeviceToHost, s.stream));
+}
+
+template <class T> static T *h2d(MdbSystem &s, DevBuf &buf, const T *host, size_t n)
+{
+    T *d = buf.ensure<T>(n ? n : 1);
+    if (n) CUDA_TRY(cudaMemcpyAsync(d, host, sizeof(T) * n, cudaMemcpyHostToDevice, s.stream));
+    return d;
+}
+
+static void require_list(MdbSystem &s)
+{
+    MDB_REQUIRE(s.list_kind != LIST_NONE, MDB_ERR_STATE, "no neighbour list on the device; build one first");
+}
+
+extern "C" {
+
+const char *mdb_last_error(void) { return g_err; }
+const char *mdb_version(void) { return "mdapy_b200 0.1 (sm_100a)"; }
+long long mdb_launch_count(void) { return g_mdb_launches; }
+
+int mdb_device_count(int *count)
+{
+    API_BEGIN
+    CUDA_TRY(cudaGetDeviceCount(count));
+    API_END
+}
+
+int mdb_system_create(int device, mdb_system **out)
+{
+    API_BEGIN
+    MDB_REQUIRE(out, MDB_ERR_VALUE, "out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        mdb_set_error("no CUDA device available (%s); mdapy_b200 has no CPU fallback",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return MDB_ERR_CUDA;
+    }
+    MDB_REQUIRE(device >= 0 && device < ndev, MDB_ERR_VALUE, "device %d out of range [0,%d)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    MdbSystem *s = new MdbSystem();
+    s->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->own_stream = true;
+    for (int k = 0; k < 4; ++k) CUDA_TRY(cudaEventCreate(&s->ev[k]));
+    *out = s;
+    API_END
+}
+
+void mdb_system_destroy(mdb_system *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    DevBuf *bufs[] = {&s->bx, &s->by, &s->bz, &s->cell_count, &s->cell_start, &s->perm, &s->perm_tmp, &s->sorted,
+                      &s->scan_tmp, &s->big_cells, &s->counters, &s->verlet, &s->dist, &s->nn, &s->verlet_tmp,
+                      &s->dist_tmp, &s->out_i32, &s->out_f64, &s->out_f64b, &s->out_f64c, &s->scratch, &s->scratch2};
+    for (DevBuf *b : bufs) b->release();
+    for (int k = 0; k < 4; ++k)
+        if (s->ev[k]) cudaEventDestroy(s->ev[k]);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int mdb_system_set_stream(mdb_system *s, void *cuda_stream)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->own_stream && s->stream) CUDA_TRY(cudaStreamDestroy(s->stream));
+    s->stream = static_cast<cudaStream_t>(cuda_stream);
+    s->own_stream = false;
+    API_END
+}
+
+int mdb_system_synchronize(mdb_system *s)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_system_set_atoms(mdb_system *s, const double *x, const double *y, const double *z, int N,
+                         const double *box9, const double *origin3, const int *boundary3)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    API_END
+}
+
+int mdb_system_set_atoms_device(mdb_system *s, const double *dx, const double *dy, const double *dz, int N,
+                                const double *box9, const double *origin3, const int *boundary3)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(N > 0 && dx && dy && dz, MDB_ERR_VALUE, "data must contain at least one atom.");
+    set_box(*s, box9, origin3, boundary3);
+    s->x = dx;
+    s->y = dy;
+    s->z = dz;
+    s->N = N;
+    invalidate(*s);
+    API_END
+}
+
+int mdb_system_build_neighbor(mdb_system *s, double rc, int max_neigh, int *M, int *max_count)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->N > 0 && s->has_box, MDB_ERR_STATE, "no atoms uploaded");
+    build_neighbor(*s, rc, max_neigh);
+    if (M) *M = s->M;
+    if (max_count) *max_count = s->max_count;
+    API_END
+}
+
+int mdb_system_sort_neighbor(mdb_system *s, int k)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    launch_sort_rows(*s, s->verlet.as<int>(), s->dist.as<double>(), s->N, s->M, k);
+    API_END
+}
+
+int mdb_system_neighbor_min_count(mdb_system *s, int *min_count)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    *min_count = device_min_int(*s, s->nn.as<int>(), s->N);
+    API_END
+}
+
+int mdb_system_fetch_neighbor(mdb_system *s, int *verlet, double *dist, int *nn)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    d2h(*s, verlet, s->verlet.as<int>(), (size_t)s->N * s->M);
+    d2h(*s, dist, s->dist.as<double>(), (size_t)s->N * s->M);
+    d2h(*s, nn, s->nn.as<int>(), (size_t)s->N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_system_put_neighbor(mdb_system *s, const int *verlet, const double *dist, const int *nn, int M, double rc,
+                            int kind)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->N > 0, MDB_ERR_STATE, "no atoms uploaded");
+    MDB_REQUIRE(M > 0 && verlet, MDB_ERR_VALUE, "verlet list with M > 0 required");
+    const size_t n = (size_t)s->N * M;
+    h2d(*s, s->verlet, verlet, n);
+    if (dist) h2d(*s, s->dist, dist, n);
+    else s->dist.ensure<double>(n);
+    if (nn) h2d(*s, s->nn, nn, (size_t)s->N);
+    else s->nn.ensure<int>(s->N);
+    s->M = M;
+    s->list_rc = rc;
+    s->list_kind = kind ? kind : LIST_CUTOFF;
+    API_END
+}
+
+int mdb_system_neighbor_device(mdb_system *s, int **verlet, double **dist, int **nn, int *M)
+{
+    API_BEGIN
+    require_list(*s);
+    if (verlet) *verlet = s->verlet.as<int>();
+    if (dist) *dist = s->dist.as<double>();
+    if (nn) *nn = s->nn.as<int>();
+    if (M) *M = s->M;
+    API_END
+}
+
+int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "rc must be positive, got %g.", rc);
+    int *pat = s->out_i32.ensure<int>(s->N);
+    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->N, s->stream));
+    prof_mark(*s, 2);
+    launch_fcna(*s, s->verlet.as<int>(), s->nn.as<int>(), s->M, rc, pat);
+    prof_mark(*s, 3);
+    d2h(*s, pattern_host, pat, (size_t)s->N);
+    if (pattern_host || s->profile) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->profile) CUDA_TRY(cudaEventElapsedTime(&s->t_cna, s->ev[2], s->ev[3]));
+    API_END
+}
+
+int mdb_system_acna(mdb_system *s, int *pattern_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    int *pat = s->out_i32.ensure<int>(s->N);
+    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->N, s->stream));
+    launch_acna(*s, s->verlet.as<int>(), s->M, pat);
+    d2h(*s, pattern_host, pat, (size_t)s->N);
+    if (pattern_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_system_csp(mdb_system *s, int nnei, double *csp_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    double *out = s->out_f64.ensure<double>(s->N);
+    launch_csp(*s, s->verlet.as<int>(), s->M, nnei, out);
+    d2h(*s, csp_host, out, (size_t)s->N);
+    if (csp_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_system_aja(mdb_system *s, int *aja_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    int *out = s->out_i32.ensure<int>(s->N);
+    launch_aja(*s, s->verlet.as<int>(), s->M, s->dist.as<double>(), s->M, out);
+    d2h(*s, aja_host, out, (size_t)s->N);
+    if (aja_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_system_result_device(mdb_system *s, int **i32, double **f64)
+{
+    API_BEGIN
+    if (i32) *i32 = s->out_i32.as<int>();
+    if (f64) *f64 = s->out_f64.as<double>();
+    API_END
+}
+
+int mdb_system_set_profiling(mdb_system *s, int on)
+{
+    API_BEGIN
+    s->profile = on != 0;
+    API_END
+}
+
+int mdb_system_last_times(mdb_system *s, float *t_binning_ms, float *t_neighbor_ms, float *t_cna_ms)
+{
+    API_BEGIN
+    if (t_binning_ms) *t_binning_ms = s->t_bin;
+    if (t_neighbor_ms) *t_neighbor_ms = s->t_neigh;
+    if (t_cna_ms) *t_cna_ms = s->t_cna;
+    API_END
+}
+
+// ---------------------------------------------------------------------------
+// Section A: host-pointer drop-ins.  One transient system per call.
+// ---------------------------------------------------------------------------
+struct ScopedSystem {
+    mdb_system *s{nullptr};
+    ScopedSystem()
+    {
+        const int rc = mdb_system_create(0, &s);
+        if (rc != MDB_OK) throw MdbError{rc};
+    }
+    ~ScopedSystem() { mdb_system_destroy(s); }
+    MdbSystem &operator*() { return *s; }
+    MdbSystem *operator->() { return s; }
+};
+
+int mdb_build_neighbor(const double *x, const double *y, const double *z, int N, const double *box9,
+                       const double *origin3, const int *boundary3, double rc, int *verlet, double *dist,
+                       int *nn, int M, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(M > 0, MDB_ERR_VALUE, "max_neigh must be positive, got %d.", M);
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    build_neighbor(*s, rc, M);
+    d2h(*s, verlet, s->verlet.as<int>(), (size_t)N * M);
+    d2h(*s, dist, s->dist.as<double>(), (size_t)N * M);
+    d2h(*s, nn, s->nn.as<int>(), (size_t)N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_build_neighbor_without_max_neigh(const double *x, const double *y, const double *z, int N,
+                                         const double *box9, const double *origin3, const int *boundary3,
+                                         double rc, int /*num_t*/, void **handle, int *M)
+{
+    API_BEGIN
+    MDB_REQUIRE(handle && M, MDB_ERR_VALUE, "handle and M are required");
+    mdb_system *s = nullptr;
+    int rcode = mdb_system_create(0, &s);
+    if (rcode != MDB_OK) return rcode;
+    try {
+        set_box(*s, box9, origin3, boundary3);
+        upload_atoms(*s, x, y, z, N);
+        build_neighbor(*s, rc, 0);
+    } catch (...) {
+        mdb_system_destroy(s);
+        throw;
+    }
+    *handle = s;
+    *M = s->M;
+    API_END
+}
+
+int mdb_neighbor_auto_fetch(void *handle, int *verlet, double *dist, int *nn)
+{
+    mdb_system *s = static_cast<mdb_system *>(handle);
+    if (!s) {
+        mdb_set_error("NULL handle");
+        return MDB_ERR_VALUE;
+    }
+    const int rc = mdb_system_fetch_neighbor(s, verlet, dist, nn);
+    mdb_system_destroy(s);
+    return rc;
+}
+
+int mdb_sort_verlet_by_distance(int *verlet, double *dist, int N, int M, int k, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(N > 0 && M > 0 && verlet && dist, MDB_ERR_VALUE, "verlet/dist arrays required");
+    ScopedSystem s;
+    const size_t n = (size_t)N * M;
+    int *dv = h2d(*s, s->verlet, verlet, n);
+    double *dd = h2d(*s, s->dist, dist, n);
+    launch_sort_rows(*s, dv, dd, N, M, k);
+    d2h(*s, verlet, dv, n);
+    d2h(*s, dist, dd, n);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_fcna(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+             const int *boundary3, const int *verlet, int M, const int *nn, int *pattern, double rc, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, nullptr, nn, M, rc, LIST_CUTOFF);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_fcna(s.s, rc, pattern);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_acna(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+             const int *boundary3, const int *verlet, int M, int *pattern, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, nullptr, nullptr, M, -1.0, LIST_KNN);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_acna(s.s, pattern);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_get_csp(const double *x, const double *y, const double *z, int N, const double *box9,
+                const double *origin3, const int *boundary3, const int *verlet, int M, int nnei, double *csp,
+                int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, nullptr, nullptr, M, -1.0, LIST_KNN);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_csp(s.s, nnei, csp);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_compute_aja(const double *x, const double *y, const double *z, int N, const double *box9,
+                    const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                    int Md, int *aja, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(M == Md, MDB_ERR_VALUE, "verlet_list and distance_list must have the same row width (%d vs %d)", M, Md);
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nullptr, M, -1.0, LIST_KNN);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_aja(s.s, aja);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+}  // extern "C"

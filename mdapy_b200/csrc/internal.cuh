@@ -1,0 +1,135 @@
+// mdapy_b200/csrc/internal.cuh -- device-side state behind the C ABI (include/mdapy_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <climits>
+#include <utility>
+#include <stdexcept>
+#include <string>
+#include "box.cuh"
+#include "../../include/mdapy_b200.h"
+
+enum MdbStatusInternal {
+    MDB_OK_ = 0,
+    MDB_ERR_CUDA_ = 1,     // a CUDA runtime call failed          -> RuntimeError
+    MDB_ERR_VALUE_ = 2,    // invalid argument / max_neigh small  -> ValueError
+    MDB_ERR_BOX_ = 3,      // zero-volume cell (box.h:185)        -> RuntimeError
+    MDB_ERR_STATE_ = 4,    // call order (no list built, ...)     -> RuntimeError
+};
+
+void mdb_set_error(const char *fmt, ...);
+
+// every kernel launch goes through here so the library can report how many of
+// its own kernels ran (bench.py "gpu_launches")
+extern long long g_mdb_launches;
+#define MDB_LAUNCH(kern, grid, block, smem, st, ...)              \
+    do {                                                          \
+        kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);     \
+        ++g_mdb_launches;                                         \
+    } while (0)
+
+struct MdbError {
+    int code;
+};
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            mdb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,    \
+                          cudaGetErrorString(_e));                                                  \
+            throw MdbError{MDB_ERR_CUDA};                                                           \
+        }                                                                                           \
+    } while (0)
+
+#define MDB_REQUIRE(cond, code, ...)                                                                \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            mdb_set_error(__VA_ARGS__);                                                             \
+            throw MdbError{code};                                                                   \
+        }                                                                                           \
+    } while (0)
+
+// grow-only device buffer; allocation cost is paid once per high-water mark
+struct DevBuf {
+    void *p{nullptr};
+    size_t cap{0};
+    template <class T> T *ensure(size_t count)
+    {
+        const size_t bytes = count * sizeof(T);
+        if (bytes > cap) {
+            if (p) CUDA_TRY(cudaFree(p));
+            p = nullptr;
+            cap = 0;
+            size_t want = bytes + bytes / 16 + 256;
+            CUDA_TRY(cudaMalloc(&p, want));
+            cap = want;
+        }
+        return static_cast<T *>(p);
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// 32-byte sorted record: one atom of the cell-ordered copy (raw coordinates,
+// original index).  32-byte alignment makes any run of records a legal source
+// for cp.async.bulk (TMA 1-D) and two 16-byte vector loads otherwise.
+struct __align__(32) SortedAtom {
+    double x, y, z;
+    int idx;
+    int cell;
+};
+
+enum ListKind { LIST_NONE = 0, LIST_CUTOFF = 1, LIST_KNN = 2 };
+
+struct MdbSystem {
+    int device{0};
+    cudaStream_t stream{nullptr};
+    bool own_stream{false};
+
+    // atoms (raw coordinates, SoA as mdapy's polars columns: neighbor.py:104-106)
+    int N{0};
+    DBox box{};
+    bool has_box{false};
+    DevBuf bx, by, bz;             // owned copies (host upload path)
+    const double *x{nullptr}, *y{nullptr}, *z{nullptr};  // device pointers in use (owned or borrowed)
+
+    // cell binning for a given rc
+    double bin_rc{-1.0};
+    CellGrid grid{};
+    DevBuf cell_count, cell_start, perm, perm_tmp, sorted, scan_tmp, big_cells, counters;
+
+    // neighbour list (device resident)
+    int list_kind{LIST_NONE};
+    double list_rc{-1.0};
+    int M{0};
+    int max_count{0};
+    DevBuf verlet, dist, nn, verlet_tmp, dist_tmp;
+
+    // per-atom outputs kept on device until fetched
+    DevBuf out_i32, out_f64, out_f64b, out_f64c, scratch, scratch2;
+
+    // timing of the last call, per kernel (ms), filled when profiling is on
+    bool profile{false};
+    float t_bin{0}, t_neigh{0}, t_cna{0};
+    cudaEvent_t ev[4]{};
+};
+
+// ---- kernels launchers (one per .cu) ---------------------------------------
+void launch_binning(MdbSystem &s, double rc);
+void launch_neighbor(MdbSystem &s, double rc, int M, bool count_only);
+void launch_compact_rows(MdbSystem &s, int M_from, int M_to);
+void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k);
+void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern);
+void launch_acna(MdbSystem &s, const int *verlet, int M, int *pattern);
+void launch_csp(MdbSystem &s, const int *verlet, int M, int nnei, double *csp);
+void launch_aja(MdbSystem &s, const int *verlet, int M, const double *dist, int Md, int *aja);
+int device_max_int(MdbSystem &s, const int *v, size_t n);
+int device_min_int(MdbSystem &s, const int *v, size_t n);

@@ -1,0 +1,129 @@
+"""Device-resident system handle (section B of include/mdapy_b200.h).
+
+`DeviceSystem` owns one ``mdb_system``: coordinates, the cell-sorted copy and
+the neighbour list live in HBM between calls, so chained ``cal_*`` calls do
+not round-trip over PCIe.  NumPy views are materialised only when asked for.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+LIST_NONE, LIST_CUTOFF, LIST_KNN = 0, 1, 2
+
+
+class DeviceSystem:
+    def __init__(self, device: int = 0):
+        self._lib = L.lib()
+        h = L.c_vp()
+        L.check(self._lib.mdb_system_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.N = 0
+        self.M = 0
+        self.max_count = 0
+        self._keep = None  # keeps borrowed device tensors / host arrays alive
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mdb_system_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- atoms ---------------------------------------------------------------
+    def set_atoms(self, x, y, z, box, origin, boundary):
+        x, y, z = L.f64(x), L.f64(y), L.f64(z)
+        b, o, p = L.box_args(box, origin, boundary)
+        L.check(self._lib.mdb_system_set_atoms(self._h, L.dptr(x), L.dptr(y), L.dptr(z), x.shape[0],
+                                               L.dptr(b), L.dptr(o), L.iptr(p)))
+        self.N = x.shape[0]
+        self._keep = (x, y, z)
+        self.M = 0
+
+    def set_atoms_device(self, dx, dy, dz, box, origin, boundary, stream=None):
+        """Borrow torch CUDA tensors (f64, contiguous) without copying."""
+        b, o, p = L.box_args(box, origin, boundary)
+        if stream is not None:
+            L.check(self._lib.mdb_system_set_stream(self._h, C.c_void_p(int(stream))))
+        n = int(dx.shape[0])
+        L.check(self._lib.mdb_system_set_atoms_device(
+            self._h, C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr()), C.c_void_p(dz.data_ptr()), n,
+            L.dptr(b), L.dptr(o), L.iptr(p)))
+        self.N = n
+        self._keep = (dx, dy, dz)
+        self.M = 0
+
+    def synchronize(self):
+        L.check(self._lib.mdb_system_synchronize(self._h))
+
+    # -- neighbour list ------------------------------------------------------
+    def build_neighbor(self, rc: float, max_neigh=None):
+        M, mx = C.c_int(0), C.c_int(0)
+        L.check(self._lib.mdb_system_build_neighbor(self._h, float(rc), int(max_neigh or 0), C.byref(M), C.byref(mx)))
+        self.M, self.max_count = M.value, mx.value
+        return self.M, self.max_count
+
+    def sort_neighbor(self, k: int):
+        L.check(self._lib.mdb_system_sort_neighbor(self._h, int(k)))
+
+    def min_count(self) -> int:
+        v = C.c_int(0)
+        L.check(self._lib.mdb_system_neighbor_min_count(self._h, C.byref(v)))
+        return v.value
+
+    def fetch_neighbor(self, want_verlet=True, want_dist=True, want_nn=True):
+        verlet = np.empty((self.N, self.M), np.int32) if want_verlet else None
+        dist = np.empty((self.N, self.M), np.float64) if want_dist else None
+        nn = np.empty(self.N, np.int32) if want_nn else None
+        L.check(self._lib.mdb_system_fetch_neighbor(
+            self._h, L.iptr(verlet) if want_verlet else None, L.dptr(dist) if want_dist else None,
+            L.iptr(nn) if want_nn else None))
+        return verlet, dist, nn
+
+    def put_neighbor(self, verlet, dist=None, nn=None, rc=-1.0, kind=LIST_CUTOFF):
+        verlet = L.i32(verlet)
+        assert verlet.ndim == 2 and verlet.shape[0] == self.N
+        d = L.f64(dist) if dist is not None else None
+        n = L.i32(nn) if nn is not None else None
+        L.check(self._lib.mdb_system_put_neighbor(
+            self._h, L.iptr(verlet), L.dptr(d) if d is not None else None, L.iptr(n) if n is not None else None,
+            verlet.shape[1], float(rc), int(kind)))
+        self.M = verlet.shape[1]
+
+    # -- descriptors ---------------------------------------------------------
+    def fcna(self, rc: float, fetch=True):
+        out = np.empty(self.N, np.int32) if fetch else None
+        L.check(self._lib.mdb_system_fcna(self._h, float(rc), L.iptr(out) if fetch else None))
+        return out
+
+    def acna(self, fetch=True):
+        out = np.empty(self.N, np.int32) if fetch else None
+        L.check(self._lib.mdb_system_acna(self._h, L.iptr(out) if fetch else None))
+        return out
+
+    def csp(self, nnei: int, fetch=True):
+        out = np.empty(self.N, np.float64) if fetch else None
+        L.check(self._lib.mdb_system_csp(self._h, int(nnei), L.dptr(out) if fetch else None))
+        return out
+
+    def aja(self, fetch=True):
+        out = np.empty(self.N, np.int32) if fetch else None
+        L.check(self._lib.mdb_system_aja(self._h, L.iptr(out) if fetch else None))
+        return out
+
+    # -- timing --------------------------------------------------------------
+    def set_profiling(self, on=True):
+        L.check(self._lib.mdb_system_set_profiling(self._h, int(bool(on))))
+
+    def last_times(self):
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        L.check(self._lib.mdb_system_last_times(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"binning_ms": a.value, "neighbor_ms": b.value, "cna_ms": c.value}
