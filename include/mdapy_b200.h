@@ -62,6 +62,11 @@ int mdb_neighbor_auto_fetch(void *handle, int *verlet, double *dist, int *nn);
 /* _neighbor.sort_verlet_by_distance, src/neighbor.cpp:745 (in place). */
 int mdb_sort_verlet_by_distance(int *verlet, double *dist, int N, int M, int k, int num_t);
 
+/* _fast_knn.knn, src/fast_knn.cpp:846.  k <= 24; periodic images are distinct
+ * neighbours; rows ascending in distance, short rows padded -1 / -1.0. */
+int mdb_knn(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+            const int *boundary3, int k, int *indices, double *distances, int num_t);
+
 /* _cna.fcna, src/cna.cpp:429.  pattern is fully written (0 = other). */
 int mdb_fcna(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
              const int *boundary3, const int *verlet, int M, const int *nn, int *pattern, double rc, int num_t);
@@ -101,6 +106,9 @@ int mdb_system_set_atoms_device(mdb_system *s, const double *dx, const double *d
  * largest count; with max_neigh > 0 and max_count > max_neigh the list is
  * truncated exactly like the reference and the caller should raise. */
 int mdb_system_build_neighbor(mdb_system *s, double rc, int max_neigh, int *M, int *max_count);
+/* k-nearest list (sorted, width k) kept on the device; replaces the cached list like
+ * System.build_nearest_neighbor does (src/mdapy/system.py:1226-1263) */
+int mdb_system_build_knn(mdb_system *s, int k);
 int mdb_system_sort_neighbor(mdb_system *s, int k);
 int mdb_system_neighbor_min_count(mdb_system *s, int *min_count);
 /* D2H of the cached list; any pointer may be NULL */

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "mdb_build_neighbor_without_max_neigh": (
         C.c_int, _XYZN + _BOX + [C.c_double, C.c_int, C.POINTER(c_vp), c_ip]),
     "mdb_neighbor_auto_fetch": (C.c_int, [c_vp, c_ip, c_dp, c_ip]),
+    "mdb_knn": (C.c_int, _XYZN + _BOX + [C.c_int, c_ip, c_dp, C.c_int]),
     "mdb_sort_verlet_by_distance": (C.c_int, [c_ip, c_dp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mdb_fcna": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_ip, c_ip, C.c_double, C.c_int]),
     "mdb_acna": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_ip, C.c_int]),
@@ -47,6 +48,7 @@ PROTOTYPES = {
     "mdb_system_set_atoms": (C.c_int, [c_vp] + _XYZN + _BOX),
     "mdb_system_set_atoms_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int] + _BOX),
     "mdb_system_build_neighbor": (C.c_int, [c_vp, C.c_double, C.c_int, c_ip, c_ip]),
+    "mdb_system_build_knn": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_sort_neighbor": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_neighbor_min_count": (C.c_int, [c_vp, c_ip]),
     "mdb_system_fetch_neighbor": (C.c_int, [c_vp, c_ip, c_dp, c_ip]),

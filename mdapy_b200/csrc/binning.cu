@@ -199,6 +199,35 @@ __global__ void __launch_bounds__(256) k_gather(const double *__restrict__ x, co
 
 }  // namespace
 
+// Common tail of every binning: per-cell counts are in s.cell_count, cell ids in
+// s.perm_tmp; produces s.cell_start, s.perm and the SortedAtom records gathered from X/Y/Z.
+void finish_binning(MdbSystem &s, int nc, const double *X, const double *Y, const double *Z)
+{
+    const int N = s.N;
+    cudaStream_t st = s.stream;
+    int *count = s.cell_count.as<int>();
+    int *cell_of_atom = s.perm_tmp.as<int>();
+    int *start = s.cell_start.ensure<int>((size_t)nc + 1);
+    int *perm = s.perm.ensure<int>(N);
+    int *scan_tmp = s.scan_tmp.ensure<int>(scan_tmp_ints(nc + 1));
+    int *counters = s.counters.ensure<int>(8);
+    SortedAtom *sorted = s.sorted.ensure<SortedAtom>(N);
+    const int nb = (N + 255) / 256;
+    CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * 8, st));
+    exclusive_scan(count, start, nc + 1, scan_tmp, st);
+    CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)nc, st));
+    MDB_LAUNCH(k_scatter, nb, 256, 0, st, cell_of_atom, N, start, count, perm);
+    // worst case every cell is "big": N / SMALL_CELL entries
+    int *big = s.big_cells.ensure<int>((size_t)N / SMALL_CELL + 2);
+    MDB_LAUNCH(k_order_cells, (nc + 255) / 256, 256, 0, st, start, nc, perm, big, counters);
+    // over-full cells (rare: > SMALL_CELL atoms in one cell) are rank-sorted by whole blocks
+    int *tmp = s.scratch.ensure<int>(N);
+    MDB_LAUNCH(k_order_big, 296, 256, 0, st, start, big, counters, perm, tmp);
+    MDB_LAUNCH(k_copy_big, 296, 256, 0, st, start, big, counters, perm, tmp);
+    MDB_LAUNCH(k_gather, nb, 256, 0, st, X, Y, Z, perm, cell_of_atom, N, sorted);
+    CUDA_TRY(cudaGetLastError());
+}
+
 void launch_binning(MdbSystem &s, double rc)
 {
     MDB_REQUIRE(s.N > 0 && s.x, MDB_ERR_STATE, "no atoms uploaded");
@@ -210,28 +239,9 @@ void launch_binning(MdbSystem &s, double rc)
     const int N = s.N, nc = g.total;
     cudaStream_t st = s.stream;
     int *count = s.cell_count.ensure<int>((size_t)nc + 1);
-    int *start = s.cell_start.ensure<int>((size_t)nc + 1);
-    int *perm = s.perm.ensure<int>(N);
     int *cell_of_atom = s.perm_tmp.ensure<int>(N);
-    int *scan_tmp = s.scan_tmp.ensure<int>(scan_tmp_ints(nc + 1));
-    int *counters = s.counters.ensure<int>(8);
-    SortedAtom *sorted = s.sorted.ensure<SortedAtom>(N);
-
     CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int) * ((size_t)nc + 1), st));
-    CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * 8, st));
-    const int nb = (N + 255) / 256;
-    MDB_LAUNCH(k_cell_count, nb, 256, 0, st, s.x, s.y, s.z, N, s.box, g, cell_of_atom, count);
-    exclusive_scan(count, start, nc + 1, scan_tmp, st);
-    CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)nc, st));
-    MDB_LAUNCH(k_scatter, nb, 256, 0, st, cell_of_atom, N, start, count, perm);
-    // worst case every cell is "big": N / SMALL_CELL entries
-    int *big = s.big_cells.ensure<int>((size_t)N / SMALL_CELL + 2);
-    MDB_LAUNCH(k_order_cells, (nc + 255) / 256, 256, 0, st, start, nc, perm, big, counters);
-    // over-full cells (rare: > SMALL_CELL atoms within one rc-cube) are rank-sorted by whole blocks
-    int *tmp = s.scratch.ensure<int>(N);
-    MDB_LAUNCH(k_order_big, 296, 256, 0, st, start, big, counters, perm, tmp);
-    MDB_LAUNCH(k_copy_big, 296, 256, 0, st, start, big, counters, perm, tmp);
-    MDB_LAUNCH(k_gather, nb, 256, 0, st, s.x, s.y, s.z, perm, cell_of_atom, N, sorted);
-    CUDA_TRY(cudaGetLastError());
+    MDB_LAUNCH(k_cell_count, (N + 255) / 256, 256, 0, st, s.x, s.y, s.z, N, s.box, g, cell_of_atom, count);
+    finish_binning(s, nc, s.x, s.y, s.z);
     s.bin_rc = rc;
 }

@@ -229,6 +229,15 @@ int mdb_system_build_neighbor(mdb_system *s, double rc, int max_neigh, int *M, i
     API_END
 }
 
+int mdb_system_build_knn(mdb_system *s, int k)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->N > 0 && s->has_box, MDB_ERR_STATE, "no atoms uploaded");
+    launch_knn(*s, k);
+    API_END
+}
+
 int mdb_system_sort_neighbor(mdb_system *s, int k)
 {
     API_BEGIN
@@ -431,6 +440,20 @@ int mdb_neighbor_auto_fetch(void *handle, int *verlet, double *dist, int *nn)
     const int rc = mdb_system_fetch_neighbor(s, verlet, dist, nn);
     mdb_system_destroy(s);
     return rc;
+}
+
+int mdb_knn(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+            const int *boundary3, int k, int *indices, double *distances, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    launch_knn(*s, k);
+    d2h(*s, indices, s->verlet.as<int>(), (size_t)N * k);
+    d2h(*s, distances, s->dist.as<double>(), (size_t)N * k);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
 }
 
 int mdb_sort_verlet_by_distance(int *verlet, double *dist, int N, int M, int k, int /*num_t*/)

@@ -115,6 +115,7 @@ struct MdbSystem {
 
     // per-atom outputs kept on device until fetched
     DevBuf out_i32, out_f64, out_f64b, out_f64c, scratch, scratch2;
+    DevBuf wx, wy, wz;  // kNN: wrapped coordinates (fast_knn.cpp wrap arithmetic)
 
     // timing of the last call, per kernel (ms), filled when profiling is on
     bool profile{false};
@@ -124,6 +125,8 @@ struct MdbSystem {
 
 // ---- kernels launchers (one per .cu) ---------------------------------------
 void launch_binning(MdbSystem &s, double rc);
+void finish_binning(MdbSystem &s, int nc, const double *X, const double *Y, const double *Z);
+void launch_knn(MdbSystem &s, int k);
 void launch_neighbor(MdbSystem &s, double rc, int M, bool count_only);
 void launch_compact_rows(MdbSystem &s, int M_from, int M_to);
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k);

@@ -71,6 +71,10 @@ class DeviceSystem:
         self.M, self.max_count = M.value, mx.value
         return self.M, self.max_count
 
+    def build_knn(self, k: int):
+        L.check(self._lib.mdb_system_build_knn(self._h, int(k)))
+        self.M = self.max_count = int(k)
+
     def sort_neighbor(self, k: int):
         L.check(self._lib.mdb_system_sort_neighbor(self._h, int(k)))
 

@@ -1,0 +1,93 @@
+"""GPU parity: k-nearest-neighbour lists (mdb_knn / build_knn) against the oracle's fast_knn.
+
+Distances must be bit-identical row by row.  Indices must match wherever the
+distance is unique within the row AND is not tied with the (k+1)-th candidate;
+inside a tie group the index sets must agree unless the group straddles slot k
+(the reference's own tie order comes from libstdc++ nth_element).
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import checker as K
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    from mdapy_b200.device import DeviceSystem
+
+    return DeviceSystem(0)
+
+
+def compare_knn(idx, dst, ridx, rdst):
+    assert np.array_equal(dst.view(np.int64), rdst.view(np.int64)), "kNN distances are not bit-identical"
+    N, k = idx.shape
+    same = idx == ridx
+    if same.all():
+        return
+    for i in np.nonzero(~same.all(axis=1))[0]:
+        d = dst[i]
+        for v in np.unique(d[~same[i]]):
+            grp = np.nonzero(d == v)[0]
+            if grp[-1] == k - 1:
+                continue  # tie group touches the k-th slot: membership may legitimately differ
+            assert sorted(idx[i, grp].tolist()) == sorted(ridx[i, grp].tolist()), (i, v)
+
+
+def _cases():
+    out = []
+    p, b = H.fcc(3.615, 6)
+    out.append(("fcc6_rattled", H.rattle(p, 0.05, 0), b, [1, 1, 1]))
+    out.append(("fcc6_perfect", p, b, [1, 1, 1]))
+    out.append(("fcc6_hot_unwrapped", H.rattle(p, 0.5, 1), b, [1, 1, 1]))
+    out.append(("fcc6_slab", H.rattle(p, 0.05, 2), b, [1, 1, 0]))
+    out.append(("fcc6_wire", H.rattle(p, 0.05, 3), b, [1, 0, 0]))
+    out.append(("fcc6_open", H.rattle(p, 0.05, 4), b, [0, 0, 0]))
+    ps, bs = H.shear(H.rattle(p, 0.05, 5), b, xy=0.2, xz=0.1, yz=-0.15)
+    out.append(("fcc6_triclinic", ps, bs, [1, 1, 1]))
+    ps, bs = H.shear(H.rattle(p, 0.05, 6), b, xy=0.6, xz=0.0, yz=0.45)
+    out.append(("fcc6_tilted_mixed", ps, bs, [1, 0, 1]))
+    p3, b3 = H.fcc(3.615, 3)
+    out.append(("fcc3_small108", H.rattle(p3, 0.05, 7), b3, [1, 1, 1]))  # N < 200 -> nimages = 1 (200/108)
+    p2, b2 = H.fcc(3.615, 2)
+    out.append(("fcc2_small32", H.rattle(p2, 0.05, 8), b2, [1, 1, 1]))  # nimages = 4
+    ps, bs = H.shear(H.rattle(p2, 0.05, 9), b2, xy=0.3, xz=0.0, yz=0.2)
+    out.append(("fcc2_small32_tri", ps, bs, [1, 1, 0]))
+    g, bg = H.random_gas(3000, 30.0, 10)
+    out.append(("gas", g, bg, [1, 1, 1]))
+    gz = g.copy()
+    gz[:, 2] *= 0.02
+    out.append(("gas_flat_open_z", gz, bg, [1, 1, 0]))
+    out.append(("fcc6_far_images", H.rattle(p, 0.05, 11) + np.array([3, -2, 5]) * np.diag(b), b, [1, 1, 1]))
+    return out
+
+
+CASES = _cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("k", [1, 4, 12, 14, 18, 24])
+def test_knn_matches_reference(case, k):
+    name, pos, box, boundary = case
+    x, y, z = (np.ascontiguousarray(pos[:, d]) for d in range(3))
+    ridx, rdst = K.knn(x, y, z, box, np.zeros(3), boundary, k)
+    ds = _dev()
+    ds.set_atoms(x, y, z, box, np.zeros(3), boundary)
+    ds.build_knn(k)
+    idx, dst, nn = ds.fetch_neighbor()
+    assert np.all(nn == k)
+    compare_knn(idx, dst, ridx, rdst)
+
+
+def test_knn_with_origin_shift():
+    p, b = H.fcc(3.615, 5)
+    pr = H.rattle(p, 0.08, 12) + np.array([10.0, -7.5, 3.25])
+    x, y, z = (np.ascontiguousarray(pr[:, d]) for d in range(3))
+    origin = np.array([10.0, -7.5, 3.25])
+    ridx, rdst = K.knn(x, y, z, b, origin, [1, 1, 1], 12)
+    ds = _dev()
+    ds.set_atoms(x, y, z, b, origin, [1, 1, 1])
+    ds.build_knn(12)
+    idx, dst, _ = ds.fetch_neighbor()
+    compare_knn(idx, dst, ridx, rdst)
