@@ -4,3 +4,23 @@ Host side mirrors the reference's Python surface (System.cal_*, Neighbor, Neares
 all computation runs in hand-written CUDA behind the C ABI of include/mdapy_b200.h.
 """
 __version__ = "0.1.0"
+
+from .box import Box  # noqa: E402,F401
+from .frame import Frame  # noqa: E402,F401
+
+
+def __getattr__(name):
+    # heavier modules (they dlopen the CUDA library) are imported on first use
+    import importlib
+
+    table = {
+        "System": ("system", "System"),
+        "Neighbor": ("neighbor", "Neighbor"),
+        "NearestNeighbor": ("knn", "NearestNeighbor"),
+        "DeviceSystem": ("device", "DeviceSystem"),
+        "build_crystal": ("lattice", "build_crystal"),
+    }
+    if name in table:
+        mod, attr = table[name]
+        return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)
+    raise AttributeError(name)

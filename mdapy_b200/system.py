@@ -1,0 +1,261 @@
+"""``System`` façade for the hot path, mirroring the reference's ``mdapy.System``
+(src/mdapy/system.py): ``build_neighbor`` 1108-1166, ``build_nearest_neighbor`` 1226-1263,
+``cal_ackland_jones_analysis`` 1605-1636, ``cal_steinhardt_bond_orientation`` 1716-1861,
+``cal_polyhedral_template_matching`` 1863-1970, ``cal_centro_symmetry_parameter`` 1972-2003,
+``cal_common_neighbor_analysis`` 2005-2064, ``cal_radial_distribution_function`` 2235-2361,
+``_get_compute_view`` 765-784 and the cache invalidation of 232-245 / 748-763.
+
+Same neighbour-list reuse policy and result columns; the difference is where
+the data lives: coordinates and the neighbour list stay in HBM (one
+``DeviceSystem`` per compute view) and ``verlet_list`` / ``distance_list`` /
+``neighbor_number`` are materialised as NumPy arrays only when read.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import tool_function as tool
+from .ackland_jones_analysis import AcklandJonesAnalysis
+from .box import Box
+from .centro_symmetry_parameter import CentroSymmetryParameter
+from .common_neighbor_analysis import CommonNeighborAnalysis
+from .device import LIST_CUTOFF, LIST_KNN, DeviceSystem
+from .frame import Frame
+from .knn import NearestNeighbor
+from .neighbor import Neighbor
+
+_LIST_ATTRS = ("verlet_list", "distance_list", "neighbor_number")
+
+
+class System:
+    def __init__(self, filename=None, data=None, pos=None, box=None, device: int = 0, **_unused):
+        if filename is not None:
+            raise NotImplementedError("file readers are outside the hot path (SURVEY.md 2.2); pass pos/data + box")
+        if data is not None and box is not None:
+            self._data = Frame.from_any(data)
+        elif pos is not None and box is not None:
+            pos = np.asarray(pos, np.float64)
+            assert pos.ndim == 2 and pos.shape[1] == 3, "pos must be (N, 3)"
+            self._data = Frame({"x": pos[:, 0].copy(), "y": pos[:, 1].copy(), "z": pos[:, 2].copy()})
+        else:
+            raise RuntimeError(
+                "One must at least provide filename or [data, box] or [pos, box] or ase_atom or ovito_atom."
+            )
+        self._box = box if isinstance(box, Box) else Box(box)
+        self._device = int(device)
+        self._dev: Optional[DeviceSystem] = None     # device copy of the compute view
+        self._dev_enlarged = False
+        self._host_list = {}                         # lazily fetched / user supplied NumPy arrays
+        self._host_dirty = False                     # user assigned a list on the host side
+        self._has_list = False
+
+    # ------------------------------------------------------------------ data / box
+    @property
+    def data(self) -> Frame:
+        return self._data
+
+    @property
+    def N(self) -> int:
+        return self._data.shape[0]
+
+    @property
+    def box(self) -> Box:
+        return self._box
+
+    @box.setter
+    def box(self, value):
+        self._box = value if isinstance(value, Box) else Box(value)
+        self._reset_neighbor()
+
+    def update_data(self, data, reset_neighbor: bool = False, **_kw) -> None:
+        """system.py:700-763: replace the frame; positions changed => caller passes reset_neighbor."""
+        self._data = Frame.from_any(data)
+        if reset_neighbor:
+            self._reset_neighbor()
+
+    def _reset_neighbor(self):
+        self._has_list = False
+        self._host_list = {}
+        self._host_dirty = False
+        self._dev = None
+        self._dev_enlarged = False
+        for a in ("rc", "_enlarge_box", "_enlarge_data"):
+            if a in self.__dict__:
+                del self.__dict__[a]
+
+    def _get_compute_view(self):
+        if "_enlarge_data" in self.__dict__:
+            return self._enlarge_box, self._enlarge_data
+        return self.box, self.data
+
+    # ------------------------------------------------------------------ lazy neighbour-list attributes
+    def __getattr__(self, name):
+        # only reached when normal lookup fails
+        if name in _LIST_ATTRS:
+            d = self.__dict__
+            if not d.get("_has_list", False):
+                raise AttributeError(name)
+            host = d["_host_list"]
+            if name not in host:
+                k = _LIST_ATTRS.index(name)
+                want = [False, False, False]
+                want[k] = True
+                host[name] = d["_dev"].fetch_neighbor(*want)[k]
+            return host[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in _LIST_ATTRS:
+            self._host_list[name] = value
+            self._host_dirty = True
+            self._has_list = True
+            return
+        object.__setattr__(self, name, value)
+
+    def __delattr__(self, name):
+        if name in _LIST_ATTRS:
+            self._host_list.pop(name, None)
+            if not self._host_list:
+                self._has_list = False
+            return
+        object.__delattr__(self, name)
+
+    def _device_view(self) -> DeviceSystem:
+        """Device copy of the current compute view (uploads once per view)."""
+        enlarged = "_enlarge_data" in self.__dict__
+        if self._dev is None or self._dev_enlarged != enlarged:
+            box, data = self._get_compute_view()
+            dev = DeviceSystem(self._device)
+            dev.set_atoms(data["x"], data["y"], data["z"], box.box, box.origin, box.boundary)
+            self._dev, self._dev_enlarged = dev, enlarged
+        return self._dev
+
+    def _device_list(self) -> DeviceSystem:
+        """Device view with the cached list in place (pushes a host-assigned list first)."""
+        dev = self._device_view()
+        if self._host_dirty:
+            h = self._host_list
+            dev.put_neighbor(h["verlet_list"], h.get("distance_list"), h.get("neighbor_number"),
+                             rc=float(self.__dict__.get("rc", -1.0)),
+                             kind=LIST_CUTOFF if "rc" in self.__dict__ else LIST_KNN)
+            self._host_dirty = False
+        return dev
+
+    def _min_neighbor_number(self) -> int:
+        if self._host_dirty and "neighbor_number" in self._host_list:
+            return int(np.min(self._host_list["neighbor_number"]))
+        return self._device_list().min_count()
+
+    def _sort_neighbor(self, k: int):
+        """tool.sort_neighbor on the cached list (mutates it, as the reference does: Appendix D.3)."""
+        dev = self._device_list()
+        min_number = self._min_neighbor_number()
+        assert min_number >= k, f"The min neighbor number {min_number} is lower than k {k}."
+        dev.sort_neighbor(k)
+        self._host_list.pop("verlet_list", None)
+        self._host_list.pop("distance_list", None)
+
+    # ------------------------------------------------------------------ list builders
+    def build_neighbor(self, rc: float, max_neigh: Optional[int] = None) -> None:
+        neigh = Neighbor(rc, self.box, self.data, max_neigh, device=self._device)
+        dev = None
+        if "_enlarge_data" not in self.__dict__ and sum(self.box.check_small_box(float(rc))) == 3:
+            dev = self._device_view()
+        neigh.compute(dev=dev, fetch=False)
+        self.rc = rc
+        if hasattr(neigh, "_enlarge_box"):
+            self._enlarge_box = neigh._enlarge_box
+            self._enlarge_data = neigh._enlarge_data
+            self._dev_enlarged = True
+        elif "_enlarge_data" in self.__dict__ and dev is None:
+            # previous enlarged view is stale for this rc: the list now indexes the original atoms
+            del self.__dict__["_enlarge_box"], self.__dict__["_enlarge_data"]
+            self._dev_enlarged = False
+        self._dev = neigh.dev
+        self._host_list = {}
+        self._host_dirty = False
+        self._has_list = True
+
+    def build_nearest_neighbor(self, k: int) -> None:
+        kdt = NearestNeighbor(self.data, self.box, k, device=self._device)
+        dev = None
+        if "_enlarge_data" not in self.__dict__ and sum(kdt._check_repeat_nearest()) == 3:
+            dev = self._device_view()
+        kdt.compute(dev=dev, fetch=False)
+        if hasattr(kdt, "_enlarge_box"):
+            self._enlarge_box = kdt._enlarge_box
+            self._enlarge_data = kdt._enlarge_data
+            self._dev_enlarged = True
+        elif "_enlarge_data" in self.__dict__ and dev is None:
+            del self.__dict__["_enlarge_box"], self.__dict__["_enlarge_data"]
+            self._dev_enlarged = False
+        self._dev = kdt.dev
+        self._host_list = {}
+        self._host_dirty = False
+        self._has_list = True
+        # like the reference (system.py:1262-1263), self.rc is left untouched
+
+    def _safe_repeat(self, safe_L=15):
+        repeat = np.ceil(safe_L / self.box.get_thickness()).astype(int)
+        for i in range(3):
+            if self.box.boundary[i] == 0:
+                repeat[i] = 1
+        return repeat
+
+    # ------------------------------------------------------------------ descriptors
+    def cal_common_neighbor_analysis(self, rc: Optional[float] = None, max_neigh: Optional[int] = None):
+        use_cached = False
+        repeat = self._safe_repeat()
+        if sum(repeat) == 3:
+            if "rc" in self.__dict__:
+                if rc is None:
+                    if self._min_neighbor_number() >= 14:
+                        self._sort_neighbor(14)
+                        use_cached = True
+                else:
+                    if self.rc < rc:
+                        self.build_neighbor(rc, max_neigh)
+                        use_cached = True
+            else:
+                if rc is not None:
+                    self.build_neighbor(rc, max_neigh)
+                    use_cached = True
+        box, data = self._get_compute_view()
+        cna = CommonNeighborAnalysis(data, box, rc=rc, dev=self._device_list() if use_cached else None,
+                                     device=self._device)
+        cna.compute()
+        self.update_data(self._data.with_columns(cna=cna.pattern[: self.N]))
+
+    def cal_centro_symmetry_parameter(self, N: int):
+        assert N % 2 == 0 and N > 0, f"N must be a positive even number: {N}."
+        if self.N <= N and sum(self.box.boundary) == 0:
+            res = np.full(self.N, 10000, float)
+        else:
+            has_verlet = False
+            if self._has_list:
+                if self._min_neighbor_number() >= N and "rc" in self.__dict__:
+                    self._sort_neighbor(N)
+                    has_verlet = True
+            if not has_verlet:
+                self.build_nearest_neighbor(N)
+            box, data = self._get_compute_view()
+            csp = CentroSymmetryParameter(data, box, N, dev=self._device_list())
+            csp.compute()
+            res = csp.csp[: self.N]
+        self.update_data(self.data.with_columns(csp=res))
+
+    def cal_ackland_jones_analysis(self) -> None:
+        N_neigh = 14
+        if self.data.shape[0] < N_neigh and sum(self.box.boundary) == 0:
+            self.update_data(self._data.with_columns(aja=np.zeros(self.N, np.int32)))
+            return
+        if self._has_list and self._min_neighbor_number() >= N_neigh:
+            self._sort_neighbor(N_neigh)
+        else:
+            self.build_nearest_neighbor(N_neigh)
+        box, data = self._get_compute_view()
+        aja = AcklandJonesAnalysis(data, box, dev=self._device_list())
+        aja.compute()
+        self.update_data(self._data.with_columns(aja=aja.aja[: self.N]))

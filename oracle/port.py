@@ -1,0 +1,275 @@
+"""oracle/port.py -- TEST INFRASTRUCTURE ONLY (never imported by mdapy_b200).
+
+ctypes bindings to ``oracle/_port/libmdapy_port.so``, the plain-C restatement of the
+reference algorithms in oracle/port/mdapy_port.c.  Same Python function names and
+signatures as ``oracle.ref`` so either can back ``oracle.checker`` / ``oracle.pipeline``.
+PTM is not restated (see mdapy_port.c header): ``ptm`` raises here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_PORT = _HERE / "_port" / "libmdapy_port.so"
+_libs: dict = {}
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+def available() -> bool:
+    return _PORT.exists()
+
+
+def num_threads() -> int:
+    return int(os.environ.get("MDAPY_NUM_THREADS", os.cpu_count() or 1))
+
+
+def _lib(name: str = "") -> C.CDLL:
+    if "port" not in _libs:
+        if not _PORT.exists():
+            raise FileNotFoundError(f"{_PORT} missing: run `make -C oracle port`")
+        _libs["port"] = C.CDLL(str(_PORT))
+    return _libs["port"]
+
+
+def _d(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _boxargs(box, origin, boundary):
+    b = _f64(box).reshape(3, 3)
+    o = _f64(origin).reshape(3)
+    p = _i32(boundary).reshape(3)
+    return b, o, p
+
+
+# --------------------------------------------------------------------------
+# src/neighbor.cpp
+# --------------------------------------------------------------------------
+def build_neighbor(x, y, z, box, origin, boundary, rc, max_neigh, nt=None):
+    """neighbor.cpp:351 build_neighbor with the neighbor.py:125-129 prefill."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    N = x.shape[0]
+    verlet = np.full((N, max_neigh), -1, np.int32)
+    dist = np.full((N, max_neigh), rc + 1.0, np.float64)
+    nn = np.zeros(N, np.int32)
+    _lib("neighbor").port_build_neighbor(
+        _d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), C.c_double(rc),
+        _i(verlet), _d(dist), _i(nn), C.c_int(max_neigh), C.c_int(nt or num_threads()))
+    return verlet, dist, nn
+
+
+def build_neighbor_auto(x, y, z, box, origin, boundary, rc, nt=None):
+    """neighbor.cpp:189 build_neighbor_without_max_neigh: count, size to max(count, 1), fill."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    N = x.shape[0]
+    nn = np.zeros(N, np.int32)
+    _lib().port_build_neighbor(
+        _d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), C.c_double(rc),
+        None, None, _i(nn), C.c_int(0), C.c_int(nt or num_threads()))
+    M = max(int(nn.max(initial=0)), 1)
+    return build_neighbor(x, y, z, box, origin, boundary, rc, M, nt)
+
+
+def sort_verlet_by_distance(verlet, dist, k, nt=None):
+    """neighbor.cpp:745 (in place)."""
+    assert verlet.flags.c_contiguous and dist.flags.c_contiguous
+    N, M = verlet.shape
+    _lib("neighbor").port_sort_verlet_by_distance(
+        _i(verlet), _d(dist), C.c_int(N), C.c_int(M), C.c_int(k), C.c_int(nt or num_threads()))
+
+
+# --------------------------------------------------------------------------
+# src/fast_knn.cpp
+# --------------------------------------------------------------------------
+def knn(x, y, z, box, origin, boundary, k, nt=None):
+    """fast_knn.cpp:846."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    N = x.shape[0]
+    idx = np.zeros((N, k), np.int32)
+    dst = np.zeros((N, k), np.float64)
+    _lib("knn").port_knn(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), C.c_int(k),
+                        _i(idx), _d(dst), C.c_int(nt or num_threads()))
+    return idx, dst
+
+
+# --------------------------------------------------------------------------
+# src/cna.cpp
+# --------------------------------------------------------------------------
+def fcna(x, y, z, box, origin, boundary, verlet, nn, rc, nt=None):
+    """cna.cpp:429 FixedCNA."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet, nn = _i32(verlet), _i32(nn)
+    N, M = verlet.shape
+    pattern = np.zeros(N, np.int32)
+    _lib("cna").port_fcna(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _i(verlet), C.c_int(M),
+                         _i(nn), _i(pattern), C.c_double(rc), C.c_int(nt or num_threads()))
+    return pattern
+
+
+def acna(x, y, z, box, origin, boundary, verlet, nt=None):
+    """cna.cpp:289 AdaptiveCNA."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet = _i32(verlet)
+    N, M = verlet.shape
+    pattern = np.zeros(N, np.int32)
+    _lib("cna").port_acna(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _i(verlet), C.c_int(M),
+                         _i(pattern), C.c_int(nt or num_threads()))
+    return pattern
+
+
+# --------------------------------------------------------------------------
+# src/centro_symmetry_parameter.cpp, src/ackland_jones_analysis.cpp
+# --------------------------------------------------------------------------
+def csp(x, y, z, box, origin, boundary, verlet, nnei, nt=None):
+    """centro_symmetry_parameter.cpp:12 get_csp."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet = _i32(verlet)
+    N, M = verlet.shape
+    out = np.zeros(N, np.float64)
+    _lib("csp").port_csp(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _i(verlet), C.c_int(M),
+                        C.c_int(nnei), _d(out), C.c_int(nt or num_threads()))
+    return out
+
+
+def aja(x, y, z, box, origin, boundary, verlet, dist, nt=None):
+    """ackland_jones_analysis.cpp:9 compute_aja."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet, dist = _i32(verlet), _f64(dist)
+    N, M = verlet.shape
+    out = np.zeros(N, np.int32)
+    _lib("aja").port_aja(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _i(verlet), C.c_int(M),
+                        _d(dist), C.c_int(dist.shape[1]), _i(out), C.c_int(nt or num_threads()))
+    return out
+
+
+# --------------------------------------------------------------------------
+# src/polyhedral_template_matching.cpp (+ extern/ptm)
+# --------------------------------------------------------------------------
+def ptm(*_a, **_k):
+    raise NotImplementedError("PTM is not restated in the C port; use oracle.ref or tests/golden fixtures")
+
+
+# --------------------------------------------------------------------------
+# src/steinhardt_bond_orientation.cpp
+# --------------------------------------------------------------------------
+def get_sq(x, y, z, box, origin, boundary, verlet, dist, nn, llist, nnn=0, rc=-1.0, average=False,
+           wl=False, wlhat=False, use_voronoi=False, weight=None, nt=None):
+    """steinhardt_bond_orientation.cpp:677 get_sq -> (qnarray, qlm_r, qlm_i).
+
+    ``rc`` follows steinhardt_bond_orientation.py:238-245 (huge rc for nnn / voronoi)."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet, dist, nn = _i32(verlet), _f64(dist), _i32(nn)
+    ll = _i32(llist)
+    N, M = verlet.shape
+    lmax = int(ll.max())
+    ndeg = ll.shape[0]
+    qr = np.zeros((N, ndeg, 2 * lmax + 1))
+    qi = np.zeros_like(qr)
+    ncol = ndeg * (1 + int(bool(wl)) + int(bool(wlhat)))
+    qn = np.zeros((N, ncol))
+    if use_voronoi:
+        rc = 10000000000.0
+    elif nnn > 0:
+        rc = 1000000000.0
+    use_weight = weight is not None
+    w = _f64(weight) if use_weight else np.zeros((2, 2))
+    _lib("sbo").port_get_sq(
+        _d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _i(verlet), C.c_int(M), _d(dist), _i(nn),
+        _d(w), _i(ll), C.c_int(ndeg), C.c_int(nnn),
+        C.c_int(lmax), C.c_int(wl), C.c_int(wlhat), C.c_int(average), C.c_int(use_voronoi),
+        C.c_double(rc), C.c_int(use_weight), _d(qr), _d(qi), _d(qn), C.c_int(ncol),
+        C.c_int(nt or num_threads()))
+    return qn, qr, qi
+
+
+def solid_liquid(q6index, q6, verlet, dist, nn, qlm_r, qlm_i, threshold, n_bond, nnn=0, rc=-1.0,
+                 use_voronoi=False, nt=None):
+    """steinhardt_bond_orientation.cpp:578 identifySolidLiquid -> (solidliquid, nbond)."""
+    verlet, dist, nn = _i32(verlet), _f64(dist), _i32(nn)
+    q6, qlm_r, qlm_i = _f64(q6), _f64(qlm_r), _f64(qlm_i)
+    N, M = verlet.shape
+    if use_voronoi:
+        rc = 10000000000.0
+    elif nnn > 0:
+        rc = 1000000000.0
+    sl = np.zeros(N, np.int32)
+    nb = np.zeros(N, np.int32)
+    _lib("sbo").port_solid_liquid(
+        C.c_int(q6index), _d(q6), _i(verlet), C.c_int(N), C.c_int(M), _d(dist), _i(nn), _d(qlm_r), _d(qlm_i),
+        C.c_int(qlm_r.shape[1]), C.c_int(qlm_r.shape[2]), C.c_double(threshold), C.c_int(n_bond),
+        _i(sl), _i(nb), C.c_int(use_voronoi), C.c_int(nnn), C.c_double(rc), C.c_int(nt or num_threads()))
+    return sl, nb
+
+
+# --------------------------------------------------------------------------
+# src/radial_distribution_function.cpp
+# --------------------------------------------------------------------------
+def rdf_list(verlet, dist, nn, type_list, ntype, rc, nbin):
+    """radial_distribution_function.cpp:22 _rdf -> counts[T,T,nbin]."""
+    verlet, dist, nn, t = _i32(verlet), _f64(dist), _i32(nn), _i32(type_list)
+    N, M = verlet.shape
+    g = np.zeros((ntype, ntype, nbin))
+    _lib("rdf").port_rdf(_i(verlet), C.c_int(N), C.c_int(M), _d(dist), _i(nn), _i(t), _d(g), C.c_int(ntype),
+                        C.c_double(rc), C.c_int(nbin))
+    return g
+
+
+def rdf_single(verlet, dist, nn, rc, nbin):
+    """radial_distribution_function.cpp:56 _rdf_single_species -> counts[nbin]."""
+    verlet, dist, nn = _i32(verlet), _f64(dist), _i32(nn)
+    N, M = verlet.shape
+    g = np.zeros(nbin)
+    _lib("rdf").port_rdf_single(_i(verlet), C.c_int(N), C.c_int(M), _d(dist), _i(nn), _d(g), C.c_double(rc),
+                               C.c_int(nbin))
+    return g
+
+
+def rdf_streaming(x, y, z, type_list, ntype, box, origin, boundary, rc, nbin, nt=None):
+    """radial_distribution_function.cpp:143 _rdf_streaming -> counts[T,T,nbin]."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    t = _i32(type_list)
+    g = np.zeros((ntype, ntype, nbin))
+    _lib("rdf").port_rdf_streaming(_d(x), _d(y), _d(z), C.c_int(x.shape[0]), _i(t), _d(b), _d(o), _i(p), _d(g),
+                                  C.c_int(ntype), C.c_double(rc), C.c_int(nbin), C.c_int(nt or num_threads()))
+    return g
+
+
+# --------------------------------------------------------------------------
+# src/repeat_cell.cpp
+# --------------------------------------------------------------------------
+def repeat_cell(box, pos, nx, ny, nz, nt=None):
+    """repeat_cell.cpp:19 -> new_pos[n*nx*ny*nz, 3]."""
+    b = _f64(box).reshape(3, 3)
+    pos = _f64(pos)
+    n = pos.shape[0]
+    out = np.zeros(n * nx * ny * nz * 3)
+    _lib("repeat").port_repeat_cell(_d(out), _d(b), _d(pos), C.c_int(n), C.c_int(nx), C.c_int(ny), C.c_int(nz),
+                                   C.c_int(nt or num_threads()))
+    return out.reshape(-1, 3)

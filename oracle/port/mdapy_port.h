@@ -1,0 +1,43 @@
+/* oracle/port/mdapy_port.h -- TEST INFRASTRUCTURE ONLY (see mdapy_port.c). */
+#ifndef MDAPY_PORT_H
+#define MDAPY_PORT_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+void port_build_neighbor(const double *x, const double *y, const double *z, int N, const double *box9,
+                         const double *origin3, const int *boundary3, double rc, int *verlet, double *dist, int *nn,
+                         int M, int num_t);
+void port_sort_verlet_by_distance(int *verlet, double *dist, int N, int M, int k, int num_t);
+void port_knn(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+              const int *boundary3, int k, int *indices, double *distances, int num_t);
+void port_fcna(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+               const int *boundary3, const int *verlet, int M, const int *nn, int *pattern, double rc, int num_t);
+void port_acna(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+               const int *boundary3, const int *verlet, int M, int *pattern, int num_t);
+void port_csp(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+              const int *boundary3, const int *verlet, int M, int nnei, double *csp, int num_t);
+void port_aja(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+              const int *boundary3, const int *verlet, int M, const double *dist, int Md, int *aja, int num_t);
+void port_get_sq(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+                 const int *boundary3, const int *verlet, int M, const double *dist, const int *nn,
+                 const double *weight, const int *llist, int ndeg, int nnn, int lmax, int wl, int wlhat, int average,
+                 int use_voronoi, double rc, int use_weight, double *qlm_r, double *qlm_i, double *qnarray, int ncol,
+                 int num_t);
+void port_solid_liquid(int q6index, const double *Q6, const int *verlet, int N, int M, const double *dist,
+                       const int *nn, const double *qlm_r, const double *qlm_i, int ndeg, int nz, double threshold,
+                       int n_bond, int *solidliquid, int *nbond, int use_voronoi, int nnn, double rc, int num_t);
+void port_rdf(const int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list, double *g,
+              int ntype, double rc, int nbin);
+void port_rdf_single(const int *verlet, int N, int M, const double *dist, const int *nn, double *g, double rc,
+                     int nbin);
+void port_rdf_streaming(const double *x, const double *y, const double *z, int N, const int *type_list,
+                        const double *box9, const double *origin3, const int *boundary3, double *g, int ntype,
+                        double rc, int nbin, int num_t);
+void port_repeat_cell(double *new_pos, const double *old_box, const double *old_pos, int n_old, int nx, int ny,
+                      int nz, int num_t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

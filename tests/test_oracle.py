@@ -1,0 +1,162 @@
+"""CPU tests: pin the oracle.
+
+1. oracle/_ref (reference C++ compiled unmodified) and oracle/port (our C restatement) each
+   reproduce the reference's golden fixtures through the orchestration restatement
+   (oracle/pipeline.py) -- the same assertions and tolerances the reference's own tests use
+   (tests/test_common_neighbor_analysis.py:19-29, test_centro_symmetry_parameter.py:18-27,
+   test_ackland_jones_analysis.py:15-25, test_polyhedral_template_matching.py:21-31,
+   test_steinhardt_bond_orientation.py:25-47, test_radial_distribution_function.py:11-24).
+2. port == _ref bit for bit on seeded inputs (skipped where _ref is not prebuilt).
+"""
+import glob
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import pipeline as P
+from oracle import port, ref
+
+GOLD = Path(__file__).resolve().parent / "golden"
+SA = sorted(glob.glob(str(GOLD / "sa_*.npz")))
+BACKENDS = [pytest.param(port, id="port", marks=pytest.mark.skipif(not port.available(), reason="port not built")),
+            pytest.param(ref, id="ref", marks=pytest.mark.skipif(not ref.available(), reason="_ref not prebuilt"))]
+
+
+def _load(path):
+    d = np.load(path)
+    return d, P.Frame(d["pos"], d["box"], d["boundary"])
+
+
+@pytest.mark.parametrize("K", BACKENDS)
+@pytest.mark.parametrize("path", SA, ids=[Path(p).stem[3:] for p in SA])
+def test_golden_labels_and_csp(K, path):
+    d, fr = _load(path)
+    if "cna" in d.files:
+        assert np.array_equal(P.cal_cna(K, fr, float(d["cna_cutoff"])), d["cna"])
+    assert np.array_equal(P.cal_aja(K, fr), d["aja"])
+    assert np.array_equal(P.cal_cna(K, fr, None), d["ref_acna"])
+    if "csp" in d.files:
+        got = P.cal_csp(K, fr, int(d["csp_num_neighbors"]))
+        assert np.allclose(got, d["csp"], atol=1e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("K", BACKENDS)
+@pytest.mark.parametrize("path", [p for p in SA if "q6" in np.load(p).files],
+                         ids=[Path(p).stem[3:] for p in SA if "q6" in np.load(p).files])
+def test_golden_steinhardt(K, path):
+    d, fr = _load(path)
+    rc = float(d["ql_cutoff"])
+    r = P.cal_steinhardt(K, fr, [4, 6], rc=rc)
+    assert np.allclose(r["qnarray"][:, 0], d["q4"], atol=1e-6, rtol=1e-6)
+    assert np.allclose(r["qnarray"][:, 1], d["q6"], atol=1e-6, rtol=1e-6)
+    ra = P.cal_steinhardt(K, fr, [4, 6], rc=rc, average=True)
+    assert np.allclose(ra["qnarray"][:, 0], d["q4_avg"], atol=1e-6, rtol=1e-6)
+    assert np.allclose(ra["qnarray"][:, 1], d["q6_avg"], atol=1e-6, rtol=1e-6)
+    # w_l / w_l-hat pinned on vectors produced by the compiled reference
+    rw = P.cal_steinhardt(K, fr, [4, 6, 8], rc=rc, wl=True, wlhat=True)
+    assert np.allclose(rw["qnarray"], d["ref_q468_wl_wlhat"], atol=1e-12, rtol=1e-9)
+
+
+@pytest.mark.skipif(not ref.available(), reason="_ref not prebuilt")
+@pytest.mark.parametrize("path", SA, ids=[Path(p).stem[3:] for p in SA])
+def test_golden_ptm_reference(path):
+    d, fr = _load(path)
+    out, ind = P.cal_ptm(ref, fr, "fcc-hcp-bcc", 0.1)
+    assert np.array_equal(out[:, 0].astype(np.int32), d["ptm"])
+    assert np.array_equal(out.view(np.int64), d["ref_ptm_output"].view(np.int64))
+    assert np.array_equal(ind, d["ref_ptm_indices"])
+
+
+@pytest.mark.parametrize("K", BACKENDS)
+def test_golden_rdf(K):
+    d = np.load(GOLD / "rdf_alcrni.npz")
+    fr = P.Frame(d["pos"], d["box"], d["boundary"])
+    res = P.cal_rdf(K, fr, float(d["cutoff"]), int(d["nbins"]), type_list=d["element"])
+    el = [str(e) for e in d["elements"]]
+    assert res["elements"] == sorted(el)
+    for i in range(len(el)):
+        for j in range(i, len(el)):
+            a, b = sorted((res["elements"].index(el[i]), res["elements"].index(el[j])))
+            assert np.allclose(res["g_partial"][(a, b)], d["g"][i, j], atol=1e-6)
+    # streaming == list path (tests/test_rdf_streaming.py)
+    res2 = P.cal_rdf(K, fr, float(d["cutoff"]), int(d["nbins"]), type_list=d["element"], streaming=True)
+    assert np.allclose(res2["g_total"], res["g_total"], atol=1e-9)
+
+
+@pytest.mark.parametrize("K", BACKENDS)
+def test_known_answers(K):
+    """Perfect-crystal invariants the reference tests assert (test_common_neighbor_analysis.py:32-45,
+    test_centro_symmetry_parameter.py:30-34, test_steinhardt_bond_orientation.py:50-59)."""
+    p, b = H.fcc(3.615, 5)
+    fr = P.Frame(p, b)
+    assert np.all(P.cal_cna(K, fr, 3.615 * 0.8536) == 1)
+    assert np.all(P.cal_cna(K, fr, None) == 1)
+    assert np.all(P.cal_aja(K, fr) == 1)
+    assert np.allclose(P.cal_csp(K, fr, 12), 0.0, atol=1e-10)
+    q = P.cal_steinhardt(K, fr, [4, 6], nnn=12)["qnarray"]
+    assert np.allclose(q[:, 0], 0.190941, atol=1e-5) and np.allclose(q[:, 1], 0.574524, atol=1e-5)
+    p2, b2 = H.bcc(2.8665, 6)
+    fr2 = P.Frame(p2, b2)
+    assert np.all(P.cal_cna(K, fr2, None) == 3)
+    assert np.all(P.cal_aja(K, fr2) == 3)
+
+
+# ------------------------------------------------------------------ port == reference, bit for bit
+def _seeded():
+    out = []
+    p, b = H.fcc(3.615, 5)
+    out.append(("fcc_rattled", H.rattle(p, 0.06, 0), b, [1, 1, 1], 3.3))
+    out.append(("fcc_hot_slab", H.rattle(p, 0.3, 1), b, [1, 1, 0], 4.1))
+    ps, bs = H.shear(H.rattle(p, 0.05, 2), b, xy=0.25, xz=-0.1, yz=0.3)
+    out.append(("triclinic", ps, bs, [1, 1, 1], 3.4))
+    g, bg = H.random_gas(1500, 24.0, 3)
+    out.append(("gas_open", g, bg, [0, 1, 0], 3.5))
+    return out
+
+
+@pytest.mark.skipif(not (ref.available() and port.available()), reason="needs both checkers")
+@pytest.mark.parametrize("case", _seeded(), ids=[c[0] for c in _seeded()])
+def test_port_equals_reference(case):
+    _, pos, box, bnd, rc = case
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    o = np.zeros(3)
+    rv, rd, rn = ref.build_neighbor_auto(x, y, z, box, o, bnd, rc)
+    pv, pd, pn = port.build_neighbor_auto(x, y, z, box, o, bnd, rc)
+    assert np.array_equal(rv, pv) and np.array_equal(rn, pn) and np.array_equal(rd.view(np.int64), pd.view(np.int64))
+    assert np.array_equal(ref.fcna(x, y, z, box, o, bnd, rv, rn, rc), port.fcna(x, y, z, box, o, bnd, pv, pn, rc))
+    # kNN: distances bit-identical (index ties may differ)
+    for k in (12, 14):
+        ri, rdd = ref.knn(x, y, z, box, o, bnd, k)
+        pi, pdd = port.knn(x, y, z, box, o, bnd, k)
+        assert np.array_equal(rdd.view(np.int64), pdd.view(np.int64))
+        uniq = np.all(np.diff(rdd, axis=1) > 0, axis=1)
+        assert np.array_equal(ri[uniq], pi[uniq])
+    ri, rdd = ref.knn(x, y, z, box, o, bnd, 14)
+    assert np.array_equal(ref.acna(x, y, z, box, o, bnd, ri), port.acna(x, y, z, box, o, bnd, ri))
+    assert np.array_equal(ref.aja(x, y, z, box, o, bnd, ri, rdd), port.aja(x, y, z, box, o, bnd, ri, rdd))
+    a, b = ref.csp(x, y, z, box, o, bnd, ri, 12), port.csp(x, y, z, box, o, bnd, ri, 12)
+    assert np.array_equal(a.view(np.int64), b.view(np.int64))
+    rs = ref.sort_verlet_by_distance
+    if rn.min() >= 6:
+        v1, d1, v2, d2 = rv.copy(), rd.copy(), pv.copy(), pd.copy()
+        ref.sort_verlet_by_distance(v1, d1, 6)
+        port.sort_verlet_by_distance(v2, d2, 6)
+        assert np.array_equal(v1, v2) and np.array_equal(d1, d2)
+    for kw in (dict(), dict(average=True), dict(wl=True, wlhat=True)):
+        q1 = ref.get_sq(x, y, z, box, o, bnd, rv, rd, rn, [4, 6], rc=rc, **kw)
+        q2 = port.get_sq(x, y, z, box, o, bnd, pv, pd, pn, [4, 6], rc=rc, **kw)
+        for u, w in zip(q1, q2):
+            assert np.array_equal(np.nan_to_num(u).view(np.int64), np.nan_to_num(w).view(np.int64))
+    q1 = ref.get_sq(x, y, z, box, o, bnd, rv, rd, rn, [4, 6], rc=rc)
+    s1 = ref.solid_liquid(1, np.ascontiguousarray(q1[0][:, 1]), rv, rd, rn, q1[1], q1[2], 0.7, 7, rc=rc)
+    s2 = port.solid_liquid(1, np.ascontiguousarray(q1[0][:, 1]), rv, rd, rn, q1[1], q1[2], 0.7, 7, rc=rc)
+    assert np.array_equal(s1[0], s2[0]) and np.array_equal(s1[1], s2[1])
+    t = (np.arange(x.shape[0]) % 2).astype(np.int32)
+    assert np.array_equal(ref.rdf_list(rv, rd, rn, t, 2, rc, 40), port.rdf_list(pv, pd, pn, t, 2, rc, 40))
+    assert np.array_equal(ref.rdf_single(rv, rd, rn, rc, 40), port.rdf_single(pv, pd, pn, rc, 40))
+    assert np.array_equal(ref.rdf_streaming(x, y, z, t, 2, box, o, bnd, rc, 40),
+                          port.rdf_streaming(x, y, z, t, 2, box, o, bnd, rc, 40))
+    assert np.array_equal(ref.repeat_cell(box, pos[:50], 2, 3, 2), port.repeat_cell(box, pos[:50], 2, 3, 2))
