@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: atoms/s of neighbour build + CNA on a ~100 M-atom FCC box.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...            # reference C++/OpenMP on the host cores
+
+One "step" = one pass of the hot path over one frame: cell binning + fixed-radius neighbour
+build (lists materialised, automatic width) + fixed-cutoff CNA.  Workload: BASELINE.json
+configs[4], FCC Al a=4.05, n^3*4 atoms (n=292 -> 99,588,352), rc = 0.8536*a, generated
+exactly like the reference's build_crystal.  `value` is device-resident
+throughput (inputs already in HBM), `e2e` goes through the public API (`System(...)` +
+`cal_common_neighbor_analysis`) from pinned HOST arrays with the label read-back inside
+the timed region.  N > 1: the frame is split into x-slabs of the global cell grid, one rank
+per GPU, ghost cell planes exchanged over NCCL (mdapy_b200/distributed.py), strong scaling.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+A_AL = 4.05
+RC_RATIO = 0.8536
+METRIC = "atoms/sec (neighbor+CNA) on 100M-atom FCC; HBM GB/s vs roofline"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- workload
+def fcc_slab_torch(n, a, ix0, ix1, device):
+    """FCC positions for lattice planes ix in [ix0, ix1) of an n^3 supercell, generated on the device
+    with the reference's arithmetic: pos = basis*a + (ix*a, iy*a, iz*a), cell-major, iz fastest."""
+    import torch
+
+    basis = torch.tensor([[0.0, 0.0, 0.0], [0.5, 0.5, 0.0], [0.0, 0.5, 0.5], [0.5, 0.0, 0.5]], dtype=torch.float64,
+                         device=device)
+    old = basis * a                      # (4,3): basis @ (a*I), adding exact zeros
+    ix = torch.arange(ix0, ix1, dtype=torch.float64, device=device) * a
+    iy = torch.arange(n, dtype=torch.float64, device=device) * a
+    iz = torch.arange(n, dtype=torch.float64, device=device) * a
+    nxl = ix1 - ix0
+    x = (ix.view(nxl, 1, 1, 1) + old[:, 0].view(1, 1, 1, 4)).expand(nxl, n, n, 4).reshape(-1).contiguous()
+    y = (iy.view(1, n, 1, 1) + old[:, 1].view(1, 1, 1, 4)).expand(nxl, n, n, 4).reshape(-1).contiguous()
+    z = (iz.view(1, 1, n, 1) + old[:, 2].view(1, 1, 1, 4)).expand(nxl, n, n, 4).reshape(-1).contiguous()
+    return x, y, z
+
+
+def fcc_numpy(n, a):
+    sys.path.insert(0, str(ROOT / "tests"))
+    import helpers as H
+
+    return H.fcc(a, n)
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """Reference C++/OpenMP (oracle/_ref, compiled unmodified) on the host cores: neighbour build
+    (automatic width) + FixedCNA on a bounded sample of the same workload (same lattice, rc)."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import checker as K
+
+    n = args.ref_n
+    pos, box = fcc_numpy(n, A_AL)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    N = x.shape[0]
+    rc = RC_RATIO * A_AL
+    o, bnd = np.zeros(3), np.array([1, 1, 1], np.int32)
+    cores = os.cpu_count() or 1
+
+    def step():
+        v, d, nn = K.build_neighbor_auto(x, y, z, box, o, bnd, rc, nt=cores)
+        pat = K.fcna(x, y, z, box, o, bnd, v, nn, rc, nt=cores)
+        return pat
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pat = step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    assert np.all(pat == 1)
+    val = N / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "atoms/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"FCC Al a={A_AL} neighbor(rc={RC_RATIO}a, auto width)+CNA, reference CPU path",
+                   "sample_atoms": N, "lattice_n": n},
+        "cpu_baseline": {"value": val, "unit": "atoms/s", "cores": cores, "kind": K.KIND,
+                         "sample": f"{N}-atom FCC Al ({n}^3x4), same rc, {args.steps} timed passes"},
+        "e2e": {"value": val, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(n=100):
+    from oracle import checker as K
+
+    pos, box = fcc_numpy(n, A_AL)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    rc = RC_RATIO * A_AL
+    o, bnd = np.zeros(3), np.array([1, 1, 1], np.int32)
+    cores = os.cpu_count() or 1
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        v, d, nn = K.build_neighbor_auto(x, y, z, box, o, bnd, rc, nt=cores)
+        K.fcna(x, y, z, box, o, bnd, v, nn, rc, nt=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    N = x.shape[0]
+    return {"value": N / best, "unit": "atoms/s", "cores": cores, "kind": K.KIND,
+            "sample": f"{N}-atom FCC Al ({n}^3x4), neighbour(auto)+CNA, best of 2, all host threads"}
+
+
+# --------------------------------------------------------------------------- this repo
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from mdapy_b200 import _lib
+    from mdapy_b200.device import DeviceSystem
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    n = args.n
+    a = A_AL
+    rc = RC_RATIO * a
+    L = n * a
+    box = np.diag([L, L, L]).astype(np.float64)
+    origin = np.zeros(3)
+    boundary = np.array([1, 1, 1], np.int32)
+    N_total = 4 * n ** 3
+    lib = _lib.lib()
+
+    if world > 1:
+        from mdapy_b200.distributed import SlabDecomposition
+
+        dec = SlabDecomposition(box, origin, boundary, rc, rank, world, device)
+        lo, hi = dec.lattice_planes(n, a)
+        x, y, z = fcc_slab_torch(n, a, lo, hi, device)
+        gid0 = lo * n * n * 4
+        ids = torch.arange(gid0, gid0 + x.numel(), dtype=torch.int32, device=device)
+        step = dec.make_step(x, y, z, ids)
+        n_local = None
+    else:
+        x, y, z = fcc_slab_torch(n, a, 0, n, device)
+        ds = DeviceSystem(local)
+        stream = torch.cuda.current_stream().cuda_stream
+        ds.set_atoms_device(x, y, z, box, origin, boundary, stream=stream)
+        ds.set_profiling(True)
+        t_neigh, t_bin, t_cna = [], [], []
+
+        def step(record=False):
+            ds.set_atoms_device(x, y, z, box, origin, boundary)   # invalidates the binning: a new frame
+            M, mx = ds.build_neighbor(rc, None)
+            ds.fcna(rc, fetch=False)
+            if record:
+                t = ds.last_times()
+                t_neigh.append(t["neighbor_ms"])
+                t_bin.append(t["binning_ms"])
+                t_cna.append(t["cna_ms"])
+            return M
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.mdb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        M = step(True) if world == 1 else step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / max(args.steps, 1)
+    launches = lib.mdb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- e2e through the public API from pinned host arrays (rank-local slab for N > 1)
+    e2e = None
+    if world == 1:
+        import mdapy_b200 as mp
+
+        hx = torch.empty(N_total, dtype=torch.float64, pin_memory=True)
+        hy = torch.empty_like(hx, pin_memory=True)
+        hz = torch.empty_like(hx, pin_memory=True)
+        hx.copy_(x)
+        hy.copy_(y)
+        hz.copy_(z)
+        torch.cuda.synchronize()
+        del ds
+        hxn, hyn, hzn = hx.numpy(), hy.numpy(), hz.numpy()
+
+        def e2e_step():
+            system = mp.System(data={"x": hxn, "y": hyn, "z": hzn}, box=mp.Box(box), device=local)
+            system.cal_common_neighbor_analysis(rc)
+            return system.data["cna"]
+
+        e2e_step()
+        torch.cuda.synchronize()
+        reps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cna = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        assert int(np.asarray(cna).min()) == 1 and int(np.asarray(cna).max()) == 1
+        e2e = {"value": N_total / dt, "unit": "atoms/s", "h2d_bytes_per_step": 24 * N_total,
+               "d2h_bytes_per_step": 4 * N_total, "ms_per_step": dt * 1e3,
+               "api": "System(data, box).cal_common_neighbor_analysis(rc) -> data['cna'] (host)"}
+    else:
+        e2e = dec.e2e(step, args)
+
+    if rank != 0:
+        return
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    line = {
+        "metric": METRIC, "value": N_total / (ms * 1e-3), "unit": "atoms/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[4]: FCC Al a={a}, {n}^3x4 = {N_total} atoms, "
+                               f"neighbor(rc={RC_RATIO}a, auto width M)+CNA, one frame per step",
+                   "atoms": N_total, "rc": rc, "l2_policy": "inputs (2.4 GB) and lists (14 GB) exceed the 126 MB L2",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} x-slabs of the cell grid, NCCL ghost planes"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+    }
+    if world == 1:
+        tn = float(np.mean(t_neigh))
+        alg = (28 + 12 * M) * N_total
+        line["roofline"] = {
+            "kernel": "k_neighbor (cut-off neighbour build)", "bound": "hbm", "achieved": alg / (tn * 1e-3) / 1e9,
+            "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if pk.exists() else "fallback",
+            "unit": "GB/s", "frac": alg / (tn * 1e-3) / 1e9 / peak, "traffic": None,
+            "algorithmic_bytes_per_atom": 28 + 12 * M, "kernel_ms": tn,
+            "step_breakdown_ms": {"binning": float(np.mean(t_bin)), "neighbor": tn, "cna": float(np.mean(t_cna))},
+        }
+        try:
+            line["cpu_baseline"] = cpu_baseline_sample(args.cpu_n)
+        except Exception as e:  # the checker is test infrastructure; never fail the bench on it
+            line["cpu_baseline"] = {"unavailable": repr(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=292, help="FCC supercell edge in unit cells (292 -> 99.6 M atoms)")
+    ap.add_argument("--ref-n", type=int, default=136, help="reference arm sample: 136 -> 10.06 M atoms")
+    ap.add_argument("--cpu-n", type=int, default=100, help="cpu_baseline sample: 100 -> 4 M atoms")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
