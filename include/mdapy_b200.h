@@ -101,6 +101,21 @@ int mdb_system_set_atoms(mdb_system *s, const double *x, const double *y, const 
 int mdb_system_set_atoms_device(mdb_system *s, const double *dx, const double *dy, const double *dz, int N,
                                 const double *box9, const double *origin3, const int *boundary3);
 
+/* Decomposed frame (one rank per GPU, mdapy_b200/distributed.py): the first n_owned atoms are
+ * owned, the rest are ghosts; dgid holds GLOBAL atom ids (device int32).  Only the window of
+ * nplanes global x cell planes starting at plane0 (ghost, owned..., ghost; periodic wrap) is
+ * stored.  Lists and per-atom outputs then have n_owned rows; rows are ordered exactly like the
+ * single-GPU build (cells are the GLOBAL grid, ties inside a cell by global id) and
+ * mdb_system_fetch_neighbor exports global ids. */
+int mdb_system_set_slab_device(mdb_system *s, const double *dx, const double *dy, const double *dz,
+                               const int *dgid, int n_local, int n_owned, int plane0, int nplanes,
+                               const double *box9, const double *origin3, const int *boundary3);
+/* cell grid of the cut-off search for (box, rc): src/neighbor.cpp:367-370 */
+int mdb_cell_grid(const double *box9, const double *origin3, const int *boundary3, double rc, int *n3);
+/* global x cell plane of each atom (device arrays), same arithmetic as src/neighbor.cpp:30-62 */
+int mdb_cell_planes_device(const double *dx, const double *dy, const double *dz, int N, const double *box9,
+                           const double *origin3, const int *boundary3, double rc, int *dplane, void *cuda_stream);
+
 /* cut-off list kept on the device.  max_neigh <= 0: size automatically
  * (neighbor.cpp:189 semantics, M = max(count,1)).  Returns row width and the
  * largest count; with max_neigh > 0 and max_count > max_neigh the list is

@@ -22,7 +22,8 @@ constexpr int SMALL_CELL = 48;  // insertion-sorted by one thread; larger cells 
 
 __global__ void __launch_bounds__(256) k_cell_count(const double *__restrict__ x, const double *__restrict__ y,
                                                     const double *__restrict__ z, int N, DBox box, CellGrid g,
-                                                    int *__restrict__ cell_of_atom, int *__restrict__ count)
+                                                    int *__restrict__ cell_of_atom, int *__restrict__ count,
+                                                    int *__restrict__ bad)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -30,7 +31,11 @@ __global__ void __launch_bounds__(256) k_cell_count(const double *__restrict__ x
     if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
     int ic, jc, kc;
     cell_of(box, g, xi, yi, zi, ic, jc, kc);
-    const int c = (ic * g.n[1] + jc) * g.n[2] + kc;
+    int c = cell_linear(g, ic, jc, kc);
+    if (c < 0) {  // atom outside the stored slab window: caller error, flagged and parked in cell 0
+        atomicAdd(bad, 1);
+        c = 0;
+    }
     cell_of_atom[i] = c;
     atomicAdd(&count[c], 1);
 }
@@ -122,8 +127,12 @@ __global__ void __launch_bounds__(256) k_scatter(const int *__restrict__ cell_of
 }
 
 // ascending original index within each cell; big cells are deferred
+// order key: the atom's own index, or its global id when the frame is decomposed
+__device__ __forceinline__ int okey(const int *__restrict__ gid, int i) { return gid ? gid[i] : i; }
+
 __global__ void __launch_bounds__(256) k_order_cells(const int *__restrict__ cell_start, int ncell, int *__restrict__ perm,
-                                                     int *__restrict__ big_cells, int *__restrict__ n_big)
+                                                     int *__restrict__ big_cells, int *__restrict__ n_big,
+                                                     const int *__restrict__ gid)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
@@ -136,8 +145,9 @@ __global__ void __launch_bounds__(256) k_order_cells(const int *__restrict__ cel
     }
     for (int a = b + 1; a < e; ++a) {
         const int v = perm[a];
+        const int kv = okey(gid, v);
         int q = a - 1;
-        while (q >= b && perm[q] > v) {
+        while (q >= b && okey(gid, perm[q]) > kv) {
             perm[q + 1] = perm[q];
             --q;
         }
@@ -149,15 +159,16 @@ __global__ void __launch_bounds__(256) k_order_cells(const int *__restrict__ cel
 // (grid-stride over the deferred list; the list length stays on the device)
 __global__ void __launch_bounds__(256) k_order_big(const int *__restrict__ cell_start, const int *__restrict__ big_cells,
                                                    const int *__restrict__ n_big, const int *__restrict__ perm,
-                                                   int *__restrict__ perm_out)
+                                                   int *__restrict__ perm_out, const int *__restrict__ gid)
 {
     for (int w = blockIdx.x; w < *n_big; w += gridDim.x) {
         const int c = big_cells[w];
         const int b = cell_start[c], e = cell_start[c + 1];
         for (int a = b + threadIdx.x; a < e; a += blockDim.x) {
             const int v = perm[a];
+            const int kv = okey(gid, v);
             int rank = 0;
-            for (int q = b; q < e; ++q) rank += (perm[q] < v);
+            for (int q = b; q < e; ++q) rank += (okey(gid, perm[q]) < kv);
             perm_out[b + rank] = v;
         }
     }
@@ -197,7 +208,47 @@ __global__ void __launch_bounds__(256) k_gather(const double *__restrict__ x, co
     dst[1] = hi;
 }
 
+// global x cell plane of every atom (ownership / ghost selection of a decomposed frame)
+__global__ void __launch_bounds__(256) k_cell_planes(const double *__restrict__ x, const double *__restrict__ y,
+                                                     const double *__restrict__ z, int N, DBox box, CellGrid g,
+                                                     int *__restrict__ plane)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double xi = x[i], yi = y[i], zi = z[i];
+    if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
+    int ic, jc, kc;
+    cell_of(box, g, xi, yi, zi, ic, jc, kc);
+    plane[i] = ic;
+}
+
+__global__ void __launch_bounds__(256) k_translate_ids(const int *__restrict__ in, int *__restrict__ out, size_t n,
+                                                       const int *__restrict__ gid)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; t < n; t += stride) {
+        const int j = in[t];
+        out[t] = j >= 0 ? gid[j] : j;
+    }
+}
+
 }  // namespace
+
+void launch_cell_planes(const double *x, const double *y, const double *z, int N, const DBox &b, const CellGrid &g,
+                        int *plane, cudaStream_t st)
+{
+    if (N <= 0) return;
+    MDB_LAUNCH(k_cell_planes, (N + 255) / 256, 256, 0, st, x, y, z, N, b, g, plane);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_translate_ids(MdbSystem &s, const int *local_ids, int *global_ids, size_t n)
+{
+    if (!n) return;
+    MDB_LAUNCH(k_translate_ids, 1184, 256, 0, s.stream, local_ids, global_ids, n, s.gid);
+    CUDA_TRY(cudaGetLastError());
+}
 
 // Common tail of every binning: per-cell counts are in s.cell_count, cell ids in
 // s.perm_tmp; produces s.cell_start, s.perm and the SortedAtom records gathered from X/Y/Z.
@@ -213,16 +264,16 @@ void finish_binning(MdbSystem &s, int nc, const double *X, const double *Y, cons
     int *counters = s.counters.ensure<int>(8);
     SortedAtom *sorted = s.sorted.ensure<SortedAtom>(N);
     const int nb = (N + 255) / 256;
-    CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * 8, st));
+    CUDA_TRY(cudaMemsetAsync(counters, 0, sizeof(int) * 4, st));
     exclusive_scan(count, start, nc + 1, scan_tmp, st);
     CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)nc, st));
     MDB_LAUNCH(k_scatter, nb, 256, 0, st, cell_of_atom, N, start, count, perm);
     // worst case every cell is "big": N / SMALL_CELL entries
     int *big = s.big_cells.ensure<int>((size_t)N / SMALL_CELL + 2);
-    MDB_LAUNCH(k_order_cells, (nc + 255) / 256, 256, 0, st, start, nc, perm, big, counters);
+    MDB_LAUNCH(k_order_cells, (nc + 255) / 256, 256, 0, st, start, nc, perm, big, counters, s.gid);
     // over-full cells (rare: > SMALL_CELL atoms in one cell) are rank-sorted by whole blocks
     int *tmp = s.scratch.ensure<int>(N);
-    MDB_LAUNCH(k_order_big, 296, 256, 0, st, start, big, counters, perm, tmp);
+    MDB_LAUNCH(k_order_big, 296, 256, 0, st, start, big, counters, perm, tmp, s.gid);
     MDB_LAUNCH(k_copy_big, 296, 256, 0, st, start, big, counters, perm, tmp);
     MDB_LAUNCH(k_gather, nb, 256, 0, st, X, Y, Z, perm, cell_of_atom, N, sorted);
     CUDA_TRY(cudaGetLastError());
@@ -232,8 +283,16 @@ void launch_binning(MdbSystem &s, double rc)
 {
     MDB_REQUIRE(s.N > 0 && s.x, MDB_ERR_STATE, "no atoms uploaded");
     MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "rc must be positive, got %g", rc);
-    const CellGrid g = cellgrid_make(s.box, rc);
-    MDB_REQUIRE((double)g.n[0] * g.n[1] * g.n[2] < 2.0e9, MDB_ERR_VALUE, "cell grid %dx%dx%d too large", g.n[0],
+    CellGrid g = cellgrid_make(s.box, rc);
+    if (s.slab_nx > 0) {
+        MDB_REQUIRE(s.slab_nx <= g.n[0] && s.slab_x0 >= 0 && s.slab_x0 < g.n[0], MDB_ERR_VALUE,
+                    "slab window [%d,+%d) does not fit the %d x-planes of the cell grid", s.slab_x0, s.slab_nx,
+                    g.n[0]);
+        g.x0 = s.slab_x0;
+        g.nxl = s.slab_nx;
+    }
+    g.total = g.nxl * g.n[1] * g.n[2];
+    MDB_REQUIRE((double)g.nxl * g.n[1] * g.n[2] < 2.0e9, MDB_ERR_VALUE, "cell grid %dx%dx%d too large", g.nxl,
                 g.n[1], g.n[2]);
     s.grid = g;
     const int N = s.N, nc = g.total;
@@ -241,7 +300,16 @@ void launch_binning(MdbSystem &s, double rc)
     int *count = s.cell_count.ensure<int>((size_t)nc + 1);
     int *cell_of_atom = s.perm_tmp.ensure<int>(N);
     CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int) * ((size_t)nc + 1), st));
-    MDB_LAUNCH(k_cell_count, (N + 255) / 256, 256, 0, st, s.x, s.y, s.z, N, s.box, g, cell_of_atom, count);
+    int *counters = s.counters.ensure<int>(8);
+    CUDA_TRY(cudaMemsetAsync(counters + 7, 0, sizeof(int), st));
+    MDB_LAUNCH(k_cell_count, (N + 255) / 256, 256, 0, st, s.x, s.y, s.z, N, s.box, g, cell_of_atom, count,
+               counters + 7);
+    if (s.slab_nx > 0) {
+        int bad = 0;
+        CUDA_TRY(cudaMemcpyAsync(&bad, counters + 7, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        MDB_REQUIRE(bad == 0, MDB_ERR_VALUE, "%d atoms lie outside the slab window (owned + ghost planes)", bad);
+    }
     finish_binning(s, nc, s.x, s.y, s.z);
     s.bin_rc = rc;
 }

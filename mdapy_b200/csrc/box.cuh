@@ -161,10 +161,15 @@ MDB_HD double pbc_dist_sq(const DBox &b, double xi, double yi, double zi, double
 }
 
 // Cell grid of the cut-off search, src/neighbor.cpp:30-62 and 367-370.
+// x0/nxl describe the window of x-planes that is actually stored: the whole grid on one
+// GPU (x0 = 0, nxl = n[0]); an owned slab plus one ghost plane on each side when the frame
+// is decomposed across GPUs (mdapy_b200/distributed.py).  Cell geometry is always GLOBAL.
 struct CellGrid {
     int n[3];
-    int total;
+    int total;   // stored cells = nxl * n[1] * n[2]
     double rc_inv;
+    int x0;
+    int nxl;
 };
 
 static inline CellGrid cellgrid_make(const DBox &b, double rc)
@@ -176,6 +181,8 @@ static inline CellGrid cellgrid_make(const DBox &b, double rc)
     }
     g.total = g.n[0] * g.n[1] * g.n[2];
     g.rc_inv = 1.0 / rc;
+    g.x0 = 0;
+    g.nxl = g.n[0];
     return g;
 }
 
@@ -208,4 +215,13 @@ MDB_HD int wrap_cell(int a, int n)
 {
     int r = a % n;
     return r < 0 ? r + n : r;
+}
+
+// stored linear id of global cell (ci, cj, ck), ci already wrapped into [0, n0); -1 outside the window
+MDB_HD int cell_linear(const CellGrid &g, int ci, int cj, int ck)
+{
+    int p = ci - g.x0;
+    if (p < 0) p += g.n[0];
+    if (p >= g.nxl) return -1;
+    return (p * g.n[1] + cj) * g.n[2] + ck;
 }

@@ -55,6 +55,9 @@ static void upload_atoms(MdbSystem &s, const double *x, const double *y, const d
     s.y = dy;
     s.z = dz;
     s.N = N;
+    s.n_rows = N;
+    s.gid = nullptr;
+    s.slab_x0 = s.slab_nx = 0;
     invalidate(s);
 }
 
@@ -74,7 +77,7 @@ static void build_neighbor(MdbSystem &s, double rc, int max_neigh)
         launch_neighbor(s, rc, max_neigh, false);
         s.M = max_neigh;
         prof_mark(s, 2);
-        s.max_count = device_max_int(s, s.nn.as<int>(), s.N);
+        s.max_count = device_max_int(s, s.nn.as<int>(), s.n_rows);
     } else {
         // Guess the width from the mean density (x1.5 + 8), fill once, then
         // shrink (or redo if the guess was short).  Equivalent to the
@@ -87,7 +90,7 @@ static void build_neighbor(MdbSystem &s, double rc, int max_neigh)
         if ((double)guess * s.N * 12.0 > 24e9) guess = (int)(24e9 / 12.0 / s.N) > 1 ? (int)(24e9 / 12.0 / s.N) : 1;
         launch_neighbor(s, rc, guess, false);
         prof_mark(s, 2);
-        int mx = device_max_int(s, s.nn.as<int>(), s.N);
+        int mx = device_max_int(s, s.nn.as<int>(), s.n_rows);
         const int want = mx > 1 ? mx : 1;
         if (mx > guess) {
             launch_neighbor(s, rc, want, false);
@@ -214,7 +217,57 @@ int mdb_system_set_atoms_device(mdb_system *s, const double *dx, const double *d
     s->y = dy;
     s->z = dz;
     s->N = N;
+    s->n_rows = N;
+    s->gid = nullptr;
+    s->slab_x0 = s->slab_nx = 0;
     invalidate(*s);
+    API_END
+}
+
+int mdb_system_set_slab_device(mdb_system *s, const double *dx, const double *dy, const double *dz,
+                               const int *dgid, int n_local, int n_owned, int plane0, int nplanes,
+                               const double *box9, const double *origin3, const int *boundary3)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(n_local > 0 && dx && dy && dz && dgid, MDB_ERR_VALUE, "slab needs coordinates and global ids");
+    MDB_REQUIRE(n_owned > 0 && n_owned <= n_local, MDB_ERR_VALUE, "n_owned=%d must be in (0, n_local=%d]", n_owned,
+                n_local);
+    MDB_REQUIRE(nplanes >= 3, MDB_ERR_VALUE, "a slab window needs >= 3 planes (ghost, owned, ghost), got %d", nplanes);
+    set_box(*s, box9, origin3, boundary3);
+    s->x = dx;
+    s->y = dy;
+    s->z = dz;
+    s->gid = dgid;
+    s->N = n_local;
+    s->n_rows = n_owned;
+    s->slab_x0 = plane0;
+    s->slab_nx = nplanes;
+    invalidate(*s);
+    API_END
+}
+
+int mdb_cell_grid(const double *box9, const double *origin3, const int *boundary3, double rc, int *n3)
+{
+    API_BEGIN
+    MDB_REQUIRE(rc > 0 && n3, MDB_ERR_VALUE, "rc must be positive");
+    DBox b;
+    MDB_REQUIRE(dbox_make(b, box9, origin3, boundary3) == 0, MDB_ERR_BOX, "The volume of the box is zero.");
+    const CellGrid g = cellgrid_make(b, rc);
+    n3[0] = g.n[0];
+    n3[1] = g.n[1];
+    n3[2] = g.n[2];
+    API_END
+}
+
+int mdb_cell_planes_device(const double *dx, const double *dy, const double *dz, int N, const double *box9,
+                           const double *origin3, const int *boundary3, double rc, int *dplane, void *cuda_stream)
+{
+    API_BEGIN
+    MDB_REQUIRE(rc > 0 && dplane, MDB_ERR_VALUE, "rc must be positive");
+    DBox b;
+    MDB_REQUIRE(dbox_make(b, box9, origin3, boundary3) == 0, MDB_ERR_BOX, "The volume of the box is zero.");
+    launch_cell_planes(dx, dy, dz, N, b, cellgrid_make(b, rc), dplane, static_cast<cudaStream_t>(cuda_stream));
     API_END
 }
 
@@ -243,7 +296,7 @@ int mdb_system_sort_neighbor(mdb_system *s, int k)
     API_BEGIN
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
-    launch_sort_rows(*s, s->verlet.as<int>(), s->dist.as<double>(), s->N, s->M, k);
+    launch_sort_rows(*s, s->verlet.as<int>(), s->dist.as<double>(), s->n_rows, s->M, k);
     API_END
 }
 
@@ -252,7 +305,7 @@ int mdb_system_neighbor_min_count(mdb_system *s, int *min_count)
     API_BEGIN
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
-    *min_count = device_min_int(*s, s->nn.as<int>(), s->N);
+    *min_count = device_min_int(*s, s->nn.as<int>(), s->n_rows);
     API_END
 }
 
@@ -261,9 +314,16 @@ int mdb_system_fetch_neighbor(mdb_system *s, int *verlet, double *dist, int *nn)
     API_BEGIN
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
-    d2h(*s, verlet, s->verlet.as<int>(), (size_t)s->N * s->M);
-    d2h(*s, dist, s->dist.as<double>(), (size_t)s->N * s->M);
-    d2h(*s, nn, s->nn.as<int>(), (size_t)s->N);
+    const size_t n = (size_t)s->n_rows * s->M;
+    if (verlet && s->gid) {  // decomposed frame: rows hold local indices, export global ids
+        int *tmp = s->verlet_tmp.ensure<int>(n);
+        launch_translate_ids(*s, s->verlet.as<int>(), tmp, n);
+        d2h(*s, verlet, tmp, n);
+    } else {
+        d2h(*s, verlet, s->verlet.as<int>(), n);
+    }
+    d2h(*s, dist, s->dist.as<double>(), n);
+    d2h(*s, nn, s->nn.as<int>(), (size_t)s->n_rows);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
 }
@@ -275,12 +335,12 @@ int mdb_system_put_neighbor(mdb_system *s, const int *verlet, const double *dist
     CUDA_TRY(cudaSetDevice(s->device));
     MDB_REQUIRE(s->N > 0, MDB_ERR_STATE, "no atoms uploaded");
     MDB_REQUIRE(M > 0 && verlet, MDB_ERR_VALUE, "verlet list with M > 0 required");
-    const size_t n = (size_t)s->N * M;
+    const size_t n = (size_t)s->n_rows * M;
     h2d(*s, s->verlet, verlet, n);
     if (dist) h2d(*s, s->dist, dist, n);
     else s->dist.ensure<double>(n);
-    if (nn) h2d(*s, s->nn, nn, (size_t)s->N);
-    else s->nn.ensure<int>(s->N);
+    if (nn) h2d(*s, s->nn, nn, (size_t)s->n_rows);
+    else s->nn.ensure<int>(s->n_rows);
     s->M = M;
     s->list_rc = rc;
     s->list_kind = kind ? kind : LIST_CUTOFF;
@@ -304,12 +364,12 @@ int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host)
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
     MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "rc must be positive, got %g.", rc);
-    int *pat = s->out_i32.ensure<int>(s->N);
-    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->N, s->stream));
+    int *pat = s->out_i32.ensure<int>(s->n_rows);
+    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->n_rows, s->stream));
     prof_mark(*s, 2);
     launch_fcna(*s, s->verlet.as<int>(), s->nn.as<int>(), s->M, rc, pat);
     prof_mark(*s, 3);
-    d2h(*s, pattern_host, pat, (size_t)s->N);
+    d2h(*s, pattern_host, pat, (size_t)s->n_rows);
     if (pattern_host || s->profile) CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->profile) CUDA_TRY(cudaEventElapsedTime(&s->t_cna, s->ev[2], s->ev[3]));
     API_END
@@ -320,10 +380,10 @@ int mdb_system_acna(mdb_system *s, int *pattern_host)
     API_BEGIN
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
-    int *pat = s->out_i32.ensure<int>(s->N);
-    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->N, s->stream));
+    int *pat = s->out_i32.ensure<int>(s->n_rows);
+    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->n_rows, s->stream));
     launch_acna(*s, s->verlet.as<int>(), s->M, pat);
-    d2h(*s, pattern_host, pat, (size_t)s->N);
+    d2h(*s, pattern_host, pat, (size_t)s->n_rows);
     if (pattern_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
 }
@@ -333,9 +393,9 @@ int mdb_system_csp(mdb_system *s, int nnei, double *csp_host)
     API_BEGIN
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
-    double *out = s->out_f64.ensure<double>(s->N);
+    double *out = s->out_f64.ensure<double>(s->n_rows);
     launch_csp(*s, s->verlet.as<int>(), s->M, nnei, out);
-    d2h(*s, csp_host, out, (size_t)s->N);
+    d2h(*s, csp_host, out, (size_t)s->n_rows);
     if (csp_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
 }
@@ -345,9 +405,9 @@ int mdb_system_aja(mdb_system *s, int *aja_host)
     API_BEGIN
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
-    int *out = s->out_i32.ensure<int>(s->N);
+    int *out = s->out_i32.ensure<int>(s->n_rows);
     launch_aja(*s, s->verlet.as<int>(), s->M, s->dist.as<double>(), s->M, out);
-    d2h(*s, aja_host, out, (size_t)s->N);
+    d2h(*s, aja_host, out, (size_t)s->n_rows);
     if (aja_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
 }

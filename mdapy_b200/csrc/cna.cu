@@ -160,14 +160,14 @@ __global__ void __launch_bounds__(128) k_acna(const double *__restrict__ x, cons
 
 void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern)
 {
-    const int N = s.N;
+    const int N = s.n_rows;
     MDB_LAUNCH(k_fcna, (N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, nn, M, rc * rc, pattern);
     CUDA_TRY(cudaGetLastError());
 }
 
 void launch_acna(MdbSystem &s, const int *verlet, int M, int *pattern)
 {
-    const int N = s.N;
+    const int N = s.n_rows;
     MDB_REQUIRE(M >= 14, MDB_ERR_VALUE, "adaptive CNA needs >= 14 sorted neighbours per atom, row width is %d", M);
     const double f = 1.0 + std::sqrt(2.0);
     MDB_LAUNCH(k_acna, (N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, M, f, pattern);

@@ -166,13 +166,13 @@ void launch_csp(MdbSystem &s, const int *verlet, int M, int nnei, double *csp)
     MDB_REQUIRE(nnei > 0 && nnei % 2 == 0, MDB_ERR_VALUE, "N must be a positive even number: %d.", nnei);
     MDB_REQUIRE(nnei <= CSP_MAX_N, MDB_ERR_VALUE, "N=%d exceeds the device limit %d", nnei, CSP_MAX_N);
     MDB_REQUIRE(nnei <= M, MDB_ERR_VALUE, "N=%d exceeds neighbour row width %d", nnei, M);
-    MDB_LAUNCH(k_csp, (s.N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, s.N, s.box, verlet, M, nnei, csp);
+    MDB_LAUNCH(k_csp, (s.n_rows + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, s.n_rows, s.box, verlet, M, nnei, csp);
     CUDA_TRY(cudaGetLastError());
 }
 
 void launch_aja(MdbSystem &s, const int *verlet, int M, const double *dist, int Md, int *aja)
 {
     MDB_REQUIRE(M >= 14 && Md >= 14, MDB_ERR_VALUE, "Ackland-Jones needs >= 14 sorted neighbours, row width is %d", M);
-    MDB_LAUNCH(k_aja, (s.N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, s.N, s.box, verlet, M, dist, Md, aja);
+    MDB_LAUNCH(k_aja, (s.n_rows + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, s.n_rows, s.box, verlet, M, dist, Md, aja);
     CUDA_TRY(cudaGetLastError());
 }

@@ -100,6 +100,11 @@ struct MdbSystem {
     bool has_box{false};
     DevBuf bx, by, bz;             // owned copies (host upload path)
     const double *x{nullptr}, *y{nullptr}, *z{nullptr};  // device pointers in use (owned or borrowed)
+    // rows of every list / per-atom output.  n_rows == N on one GPU; in a decomposed frame the
+    // first n_rows atoms are owned, the rest are ghosts that only serve as neighbours.
+    int n_rows{0};
+    const int *gid{nullptr};  // optional global ids (order inside a cell, exported lists)
+    int slab_x0{0}, slab_nx{0};  // stored window of global x cell planes (0,0 = whole grid)
 
     // cell binning for a given rc
     double bin_rc{-1.0};
@@ -127,6 +132,9 @@ struct MdbSystem {
 void launch_binning(MdbSystem &s, double rc);
 void finish_binning(MdbSystem &s, int nc, const double *X, const double *Y, const double *Z);
 void launch_knn(MdbSystem &s, int k);
+void launch_cell_planes(const double *x, const double *y, const double *z, int N, const DBox &b, const CellGrid &g,
+                        int *plane, cudaStream_t st);
+void launch_translate_ids(MdbSystem &s, const int *local_ids, int *global_ids, size_t n);
 void launch_neighbor(MdbSystem &s, double rc, int M, bool count_only);
 void launch_compact_rows(MdbSystem &s, int M_from, int M_to);
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k);

@@ -275,6 +275,7 @@ void launch_knn(MdbSystem &s, int k)
 {
     MDB_REQUIRE(k >= 1 && k <= KNN_MAX_K, MDB_ERR_VALUE, "k must be in [1, %d], got %d.", KNN_MAX_K, k);
     MDB_REQUIRE(s.N > 0 && s.x, MDB_ERR_STATE, "no atoms uploaded");
+    MDB_REQUIRE(s.n_rows == s.N && !s.gid, MDB_ERR_STATE, "kNN on a decomposed frame is not supported yet");
     const int N = s.N;
     cudaStream_t st = s.stream;
     const DBox &b = s.box;

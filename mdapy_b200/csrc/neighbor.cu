@@ -34,17 +34,19 @@ __device__ __forceinline__ SortedAtom load_sorted(const SortedAtom *__restrict__
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(128) k_neighbor_direct(const SortedAtom *__restrict__ sorted,
                                                          const int *__restrict__ cell_start, int N, DBox box,
-                                                         CellGrid g, double rcsq, int M, int *__restrict__ verlet,
-                                                         double *__restrict__ dist, int *__restrict__ nn)
+                                                         CellGrid g, double rcsq, int M, int n_rows,
+                                                         int *__restrict__ verlet, double *__restrict__ dist,
+                                                         int *__restrict__ nn)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     const SortedAtom me = load_sorted(sorted + s);
+    if (me.idx >= n_rows) return;  // ghost atom of a decomposed frame: neighbour only
     double xi = me.x, yi = me.y, zi = me.z;
     if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
     const int kc = me.cell % g.n[2];
     const int jc = (me.cell / g.n[2]) % g.n[1];
-    const int ic = me.cell / (g.n[2] * g.n[1]);
+    const int ic = wrap_cell(me.cell / (g.n[2] * g.n[1]) + g.x0, g.n[0]);  // global x plane
     int *vrow = verlet + (size_t)me.idx * M;
     double *drow = dist + (size_t)me.idx * M;
     int cnt = 0;
@@ -54,7 +56,8 @@ __global__ void __launch_bounds__(128) k_neighbor_direct(const SortedAtom *__res
             const int cj = wrap_cell(jc + dj, g.n[1]);
             for (int dk = -1; dk <= 1; ++dk) {
                 const int ck = wrap_cell(kc + dk, g.n[2]);
-                const int c = (ci * g.n[1] + cj) * g.n[2] + ck;
+                const int c = cell_linear(g, ci, cj, ck);
+                if (c < 0) continue;  // cannot happen for an owned atom with both ghost planes present
                 const int b = __ldg(cell_start + c), e = __ldg(cell_start + c + 1);
                 for (int q = e - 1; q >= b; --q) {  // descending original index
                     if (q == s) continue;
@@ -158,28 +161,28 @@ int device_min_int(MdbSystem &s, const int *v, size_t n)
 void launch_neighbor(MdbSystem &s, double rc, int M, bool count_only)
 {
     MDB_REQUIRE(s.bin_rc == rc, MDB_ERR_STATE, "binning for rc=%g missing", rc);
-    const int N = s.N;
+    const int N = s.N, R = s.n_rows;
     cudaStream_t st = s.stream;
-    int *nn = s.nn.ensure<int>(N);
+    int *nn = s.nn.ensure<int>(R);
     const double rcsq = rc * rc;
     const int nb = (N + 127) / 128;
     if (count_only) {
         MDB_LAUNCH(k_neighbor_direct<true>, nb, 128, 0, st, s.sorted.as<SortedAtom>(), s.cell_start.as<int>(), N, s.box, s.grid,
-                                                    rcsq, 0, nullptr, nullptr, nn);
+                                                    rcsq, 0, s.n_rows, nullptr, nullptr, nn);
     } else {
         MDB_REQUIRE(M > 0, MDB_ERR_VALUE, "max_neigh must be positive, got %d", M);
-        int *verlet = s.verlet.ensure<int>((size_t)N * M);
-        double *dist = s.dist.ensure<double>((size_t)N * M);
-        MDB_LAUNCH(k_fill_rows, 1184, 256, 0, st, verlet, dist, (size_t)N * M, rc + 1.0);
+        int *verlet = s.verlet.ensure<int>((size_t)R * M);
+        double *dist = s.dist.ensure<double>((size_t)R * M);
+        MDB_LAUNCH(k_fill_rows, 1184, 256, 0, st, verlet, dist, (size_t)R * M, rc + 1.0);
         MDB_LAUNCH(k_neighbor_direct<false>, nb, 128, 0, st, s.sorted.as<SortedAtom>(), s.cell_start.as<int>(), N, s.box,
-                                                     s.grid, rcsq, M, verlet, dist, nn);
+                                                     s.grid, rcsq, M, s.n_rows, verlet, dist, nn);
     }
     CUDA_TRY(cudaGetLastError());
 }
 
 void launch_compact_rows(MdbSystem &s, int M_from, int M_to)
 {
-    const int N = s.N;
+    const int N = s.n_rows;
     int *vout = s.verlet_tmp.ensure<int>((size_t)N * M_to);
     double *dout = s.dist_tmp.ensure<double>((size_t)N * M_to);
     MDB_LAUNCH(k_compact_rows, 1184, 256, 0, s.stream, s.verlet.as<int>(), s.dist.as<double>(), vout, dout, N, M_from, M_to);

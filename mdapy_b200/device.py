@@ -22,7 +22,8 @@ class DeviceSystem:
         L.check(self._lib.mdb_system_create(int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
-        self.N = 0
+        self.N = 0        # atoms on the device (owned + ghosts)
+        self.n_rows = 0   # rows of lists / per-atom outputs (owned atoms)
         self.M = 0
         self.max_count = 0
         self._keep = None  # keeps borrowed device tensors / host arrays alive
@@ -44,7 +45,7 @@ class DeviceSystem:
         b, o, p = L.box_args(box, origin, boundary)
         L.check(self._lib.mdb_system_set_atoms(self._h, L.dptr(x), L.dptr(y), L.dptr(z), x.shape[0],
                                                L.dptr(b), L.dptr(o), L.iptr(p)))
-        self.N = x.shape[0]
+        self.N = self.n_rows = x.shape[0]
         self._keep = (x, y, z)
         self.M = 0
 
@@ -57,8 +58,22 @@ class DeviceSystem:
         L.check(self._lib.mdb_system_set_atoms_device(
             self._h, C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr()), C.c_void_p(dz.data_ptr()), n,
             L.dptr(b), L.dptr(o), L.iptr(p)))
-        self.N = n
+        self.N = self.n_rows = n
         self._keep = (dx, dy, dz)
+        self.M = 0
+
+    def set_slab_device(self, dx, dy, dz, dgid, n_owned, plane0, nplanes, box, origin, boundary, stream=None):
+        """Decomposed frame: torch CUDA tensors of owned atoms followed by ghosts, int32 global ids,
+        and the stored window of global x cell planes (see mdb_system_set_slab_device)."""
+        b, o, p = L.box_args(box, origin, boundary)
+        if stream is not None:
+            L.check(self._lib.mdb_system_set_stream(self._h, C.c_void_p(int(stream))))
+        n = int(dx.shape[0])
+        L.check(self._lib.mdb_system_set_slab_device(
+            self._h, C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr()), C.c_void_p(dz.data_ptr()),
+            C.c_void_p(dgid.data_ptr()), n, int(n_owned), int(plane0), int(nplanes), L.dptr(b), L.dptr(o), L.iptr(p)))
+        self.N, self.n_rows = n, int(n_owned)
+        self._keep = (dx, dy, dz, dgid)
         self.M = 0
 
     def synchronize(self):
@@ -84,9 +99,9 @@ class DeviceSystem:
         return v.value
 
     def fetch_neighbor(self, want_verlet=True, want_dist=True, want_nn=True):
-        verlet = np.empty((self.N, self.M), np.int32) if want_verlet else None
-        dist = np.empty((self.N, self.M), np.float64) if want_dist else None
-        nn = np.empty(self.N, np.int32) if want_nn else None
+        verlet = np.empty((self.n_rows, self.M), np.int32) if want_verlet else None
+        dist = np.empty((self.n_rows, self.M), np.float64) if want_dist else None
+        nn = np.empty(self.n_rows, np.int32) if want_nn else None
         L.check(self._lib.mdb_system_fetch_neighbor(
             self._h, L.iptr(verlet) if want_verlet else None, L.dptr(dist) if want_dist else None,
             L.iptr(nn) if want_nn else None))
@@ -94,7 +109,7 @@ class DeviceSystem:
 
     def put_neighbor(self, verlet, dist=None, nn=None, rc=-1.0, kind=LIST_CUTOFF):
         verlet = L.i32(verlet)
-        assert verlet.ndim == 2 and verlet.shape[0] == self.N
+        assert verlet.ndim == 2 and verlet.shape[0] == self.n_rows
         d = L.f64(dist) if dist is not None else None
         n = L.i32(nn) if nn is not None else None
         L.check(self._lib.mdb_system_put_neighbor(
@@ -104,24 +119,30 @@ class DeviceSystem:
 
     # -- descriptors ---------------------------------------------------------
     def fcna(self, rc: float, fetch=True):
-        out = np.empty(self.N, np.int32) if fetch else None
+        out = np.empty(self.n_rows, np.int32) if fetch else None
         L.check(self._lib.mdb_system_fcna(self._h, float(rc), L.iptr(out) if fetch else None))
         return out
 
     def acna(self, fetch=True):
-        out = np.empty(self.N, np.int32) if fetch else None
+        out = np.empty(self.n_rows, np.int32) if fetch else None
         L.check(self._lib.mdb_system_acna(self._h, L.iptr(out) if fetch else None))
         return out
 
     def csp(self, nnei: int, fetch=True):
-        out = np.empty(self.N, np.float64) if fetch else None
+        out = np.empty(self.n_rows, np.float64) if fetch else None
         L.check(self._lib.mdb_system_csp(self._h, int(nnei), L.dptr(out) if fetch else None))
         return out
 
     def aja(self, fetch=True):
-        out = np.empty(self.N, np.int32) if fetch else None
+        out = np.empty(self.n_rows, np.int32) if fetch else None
         L.check(self._lib.mdb_system_aja(self._h, L.iptr(out) if fetch else None))
         return out
+
+    def result_device(self):
+        """Raw device pointers (int) of the latest int32 / f64 per-atom result."""
+        a, b = C.c_void_p(), C.c_void_p()
+        L.check(self._lib.mdb_system_result_device(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # -- timing --------------------------------------------------------------
     def set_profiling(self, on=True):
