@@ -84,6 +84,31 @@ int mdb_compute_aja(const double *x, const double *y, const double *z, int N, co
                     const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
                     int Md, int *aja, int num_t);
 
+/* _sbo.get_sq, src/steinhardt_bond_orientation.cpp:677.  qlm_r/qlm_i (N, ndeg, 2*lmax+1) are inout
+ * (zeroed by the caller, steinhardt_bond_orientation.py:228-229), qnarray (N, ncol) is out; rc is the
+ * value the Python wrapper passes (1e9 / 1e10 for the nnn / voronoi neighbour sources).  llist is
+ * int32 (the reference wrapper hands int64 and relies on nanobind's cast: convert before calling). */
+int mdb_get_sq(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+               const int *boundary3, const int *verlet, int M, const double *dist, const int *nn,
+               const double *weight, const int *llist, int ndeg, int nnn, int lmax, int wl, int wlhat, int average,
+               int use_voronoi, double rc, int use_weight, double *qlm_r, double *qlm_i, double *qnarray, int ncol,
+               int num_t);
+/* _sbo.identifySolidLiquid, src/steinhardt_bond_orientation.cpp:578.  solidliquid must be pre-zeroed. */
+int mdb_identify_solid_liquid(int Q6index, const double *Q6, const int *verlet, int N, int M, const double *dist,
+                              const int *nn, const double *qlm_r, const double *qlm_i, int ndeg, int nz,
+                              double threshold, int n_bond, int *solidliquid, int *nbond, int use_voronoi, int nnn,
+                              double rc, int num_t);
+
+/* _rdf._rdf / _rdf._rdf_single_species / _rdf._rdf_streaming,
+ * src/radial_distribution_function.cpp:22, 56, 143.  g is ACCUMULATED into (caller zeroes it). */
+int mdb_rdf(const int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list, double *g,
+            int ntype, double rc, int nbin);
+int mdb_rdf_single_species(const int *verlet, int N, int M, const double *dist, const int *nn, double *g, double rc,
+                           int nbin);
+int mdb_rdf_streaming(const double *x, const double *y, const double *z, int N, const int *type_list,
+                      const double *box9, const double *origin3, const int *boundary3, double *g, int ntype,
+                      double rc, int nbin, int num_t);
+
 /* ------------------------------------------------------------------------
  * Section B: device-resident system handle
  * ---------------------------------------------------------------------- */
@@ -139,6 +164,17 @@ int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host);
 int mdb_system_acna(mdb_system *s, int *pattern_host);
 int mdb_system_csp(mdb_system *s, int nnei, double *csp_host);
 int mdb_system_aja(mdb_system *s, int *aja_host);
+/* Steinhardt q_l (+ w_l, w_l-hat) on the cached list; q_lm stay on the device for solid_liquid.
+ * Host outputs may be NULL.  rc rule as in steinhardt_bond_orientation.py:238-245. */
+int mdb_system_steinhardt(mdb_system *s, const int *llist, int ndeg, int nnn, double rc, int average, int wl,
+                          int wlhat, int use_voronoi, const double *weight_host, double *qnarray_host,
+                          double *qlm_r_host, double *qlm_i_host);
+int mdb_system_solid_liquid(mdb_system *s, int q6index, double threshold, int n_bond, int use_voronoi, int nnn,
+                            double rc, int *solidliquid_host, int *nbond_host);
+/* RDF counts accumulated into g_host: list kernels (streaming = 0; types_host NULL -> single species)
+ * or straight from positions (streaming = 1) */
+int mdb_system_rdf(mdb_system *s, const int *types_host, int ntype, double rc, int nbin, int streaming,
+                   double *g_host);
 /* device pointers to the most recent int32 / f64 per-atom result */
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 

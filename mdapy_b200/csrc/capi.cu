@@ -167,6 +167,8 @@ void mdb_system_destroy(mdb_system *s)
     if (!s) return;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
+    DevBuf *more[] = {&s->wx, &s->wy, &s->wz, &s->qlm_r, &s->qlm_i, &s->qn, &s->types, &s->weight};
+    for (DevBuf *b : more) b->release();
     DevBuf *bufs[] = {&s->bx, &s->by, &s->bz, &s->cell_count, &s->cell_start, &s->perm, &s->perm_tmp, &s->sorted,
                       &s->scan_tmp, &s->big_cells, &s->counters, &s->verlet, &s->dist, &s->nn, &s->verlet_tmp,
                       &s->dist_tmp, &s->out_i32, &s->out_f64, &s->out_f64b, &s->out_f64c, &s->scratch, &s->scratch2};
@@ -412,6 +414,97 @@ int mdb_system_aja(mdb_system *s, int *aja_host)
     API_END
 }
 
+// qlm_r/qlm_i/qnarray hosts may be NULL (results stay on the device).  weight_host: (n_rows, M) or NULL.
+int mdb_system_steinhardt(mdb_system *s, const int *llist, int ndeg, int nnn, double rc, int average, int wl,
+                          int wlhat, int use_voronoi, const double *weight_host, double *qnarray_host,
+                          double *qlm_r_host, double *qlm_i_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(llist && ndeg > 0, MDB_ERR_VALUE, "llist is required");
+    int lmax = 0;
+    for (int i = 0; i < ndeg; ++i) lmax = llist[i] > lmax ? llist[i] : lmax;
+    const int nz = 2 * lmax + 1, R = s->n_rows;
+    const int ncol = ndeg * (1 + (wl ? 1 : 0) + (wlhat ? 1 : 0));
+    const size_t nq = (size_t)R * ndeg * nz;
+    double *qr = s->qlm_r.ensure<double>(nq), *qi = s->qlm_i.ensure<double>(nq);
+    double *qn = s->qn.ensure<double>((size_t)R * ncol);
+    CUDA_TRY(cudaMemsetAsync(qr, 0, sizeof(double) * nq, s->stream));
+    CUDA_TRY(cudaMemsetAsync(qi, 0, sizeof(double) * nq, s->stream));
+    CUDA_TRY(cudaMemsetAsync(qn, 0, sizeof(double) * (size_t)R * ncol, s->stream));
+    const double *w = nullptr;
+    if (weight_host) w = h2d(*s, s->weight, weight_host, (size_t)R * s->M);
+    // steinhardt_bond_orientation.py:238-245: a huge rc for the voronoi / nnn neighbour sources
+    double rc_eff = rc;
+    if (use_voronoi) rc_eff = 10000000000.0;
+    else if (nnn > 0) rc_eff = 1000000000.0;
+    else MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "At least use voronoi, or set positive nnn, or positive rc.");
+    launch_steinhardt(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, w, llist, ndeg, nnn, lmax,
+                      wl != 0, wlhat != 0, average != 0, use_voronoi != 0, rc_eff, weight_host != nullptr, qr, qi, qn);
+    s->sbo_ndeg = ndeg;
+    s->sbo_nz = nz;
+    s->sbo_ncol = ncol;
+    d2h(*s, qnarray_host, qn, (size_t)R * ncol);
+    d2h(*s, qlm_r_host, qr, nq);
+    d2h(*s, qlm_i_host, qi, nq);
+    if (qnarray_host || qlm_r_host || qlm_i_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+// uses q_lm / q_l of the latest mdb_system_steinhardt call
+int mdb_system_solid_liquid(mdb_system *s, int q6index, double threshold, int n_bond, int use_voronoi, int nnn,
+                            double rc, int *solidliquid_host, int *nbond_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(s->sbo_ndeg > 0, MDB_ERR_STATE, "run mdb_system_steinhardt first");
+    MDB_REQUIRE(q6index >= 0 && q6index < s->sbo_ndeg, MDB_ERR_VALUE, "Q6index %d out of range", q6index);
+    const int R = s->n_rows;
+    double rc_eff = rc;
+    if (use_voronoi) rc_eff = 10000000000.0;
+    else if (nnn > 0) rc_eff = 1000000000.0;
+    // contiguous copy of the q6 column (np.ascontiguousarray(qnarray[:, Q6index]) in the reference wrapper)
+    double *q6 = s->out_f64.ensure<double>(R);
+    CUDA_TRY(cudaMemcpy2DAsync(q6, sizeof(double), s->qn.as<double>() + q6index, sizeof(double) * s->sbo_ncol,
+                               sizeof(double), R, cudaMemcpyDeviceToDevice, s->stream));
+    int *solid = s->out_i32.ensure<int>((size_t)2 * R);
+    int *nbond = solid + R;
+    CUDA_TRY(cudaMemsetAsync(solid, 0, sizeof(int) * 2 * (size_t)R, s->stream));
+    launch_solid_liquid(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, q6index, q6,
+                        s->qlm_r.as<double>(), s->qlm_i.as<double>(), s->sbo_ndeg, s->sbo_nz, threshold, n_bond,
+                        use_voronoi != 0, nnn, rc_eff, solid, nbond);
+    d2h(*s, solidliquid_host, solid, (size_t)R);
+    d2h(*s, nbond_host, nbond, (size_t)R);
+    if (solidliquid_host || nbond_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+// g_host (ntype*ntype*nbin doubles, or nbin when types_host == NULL) is ACCUMULATED into, like the reference
+int mdb_system_rdf(mdb_system *s, const int *types_host, int ntype, double rc, int nbin, int streaming,
+                   double *g_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(g_host && nbin > 0, MDB_ERR_VALUE, "g and nbin are required");
+    const int *types = nullptr;
+    if (types_host) types = h2d(*s, s->types, types_host, (size_t)s->N);
+    const int nslot = (types ? ntype * ntype : 1) * nbin;
+    double *g = h2d(*s, s->out_f64b, g_host, (size_t)nslot);
+    if (streaming) {
+        MDB_REQUIRE(types, MDB_ERR_VALUE, "streaming RDF needs a type list");
+        launch_rdf_streaming(*s, types, ntype, rc, nbin, g);
+    } else {
+        require_list(*s);
+        launch_rdf_list(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->n_rows, s->M, types, ntype,
+                        rc, nbin, g);
+    }
+    d2h(*s, g_host, g, (size_t)nslot);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64)
 {
     API_BEGIN
@@ -586,6 +679,107 @@ int mdb_compute_aja(const double *x, const double *y, const double *z, int N, co
     int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nullptr, M, -1.0, LIST_KNN);
     if (rcode != MDB_OK) return rcode;
     rcode = mdb_system_aja(s.s, aja);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_get_sq(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+               const int *boundary3, const int *verlet, int M, const double *dist, const int *nn,
+               const double *weight, const int *llist, int ndeg, int nnn, int lmax, int wl, int wlhat, int average,
+               int use_voronoi, double rc, int use_weight, double *qlm_r, double *qlm_i, double *qnarray, int ncol,
+               int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(qlm_r && qlm_i && qnarray, MDB_ERR_VALUE, "output arrays are required");
+    MDB_REQUIRE(ncol == ndeg * (1 + (wl ? 1 : 0) + (wlhat ? 1 : 0)), MDB_ERR_VALUE, "qnarray has %d columns", ncol);
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nn, M, rc, LIST_CUTOFF);
+    if (rcode != MDB_OK) return rcode;
+    const int nz = 2 * lmax + 1;
+    const size_t nq = (size_t)N * ndeg * nz;
+    // inout semantics of the reference: start from the caller's arrays (zeros in the wrapper)
+    double *qr = h2d(*s, s->qlm_r, qlm_r, nq), *qi = h2d(*s, s->qlm_i, qlm_i, nq);
+    double *qn = h2d(*s, s->qn, qnarray, (size_t)N * ncol);
+    const double *w = use_weight ? h2d(*s, s->weight, weight, (size_t)N * M) : nullptr;
+    launch_steinhardt(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), M, w, llist, ndeg, nnn, lmax,
+                      wl != 0, wlhat != 0, average != 0, use_voronoi != 0, rc, use_weight != 0, qr, qi, qn);
+    d2h(*s, qlm_r, qr, nq);
+    d2h(*s, qlm_i, qi, nq);
+    d2h(*s, qnarray, qn, (size_t)N * ncol);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_identify_solid_liquid(int Q6index, const double *Q6, const int *verlet, int N, int M, const double *dist,
+                              const int *nn, const double *qlm_r, const double *qlm_i, int ndeg, int nz,
+                              double threshold, int n_bond, int *solidliquid, int *nbond, int use_voronoi, int nnn,
+                              double rc, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    s->N = s->n_rows = N;
+    const size_t nq = (size_t)N * ndeg * nz;
+    int *dv = h2d(*s, s->verlet, verlet, (size_t)N * M);
+    double *dd = h2d(*s, s->dist, dist, (size_t)N * M);
+    int *dn = h2d(*s, s->nn, nn, (size_t)N);
+    double *qr = h2d(*s, s->qlm_r, qlm_r, nq), *qi = h2d(*s, s->qlm_i, qlm_i, nq);
+    double *q6 = h2d(*s, s->out_f64, Q6, (size_t)N);
+    int *solid = h2d(*s, s->out_i32, solidliquid, (size_t)N);  // only 1s are written: keep the caller's zeros
+    int *nb = s->scratch2.ensure<int>(N);
+    launch_solid_liquid(*s, dv, dd, dn, M, Q6index, q6, qr, qi, ndeg, nz, threshold, n_bond, use_voronoi != 0, nnn, rc,
+                        solid, nb);
+    d2h(*s, solidliquid, solid, (size_t)N);
+    d2h(*s, nbond, nb, (size_t)N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+static int rdf_list_host(const int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list,
+                         double *g, int ntype, double rc, int nbin)
+{
+    API_BEGIN
+    MDB_REQUIRE(N > 0 && M > 0 && verlet && dist && nn && g, MDB_ERR_VALUE, "lists and g are required");
+    ScopedSystem s;
+    s->N = s->n_rows = N;
+    int *dv = h2d(*s, s->verlet, verlet, (size_t)N * M);
+    double *dd = h2d(*s, s->dist, dist, (size_t)N * M);
+    int *dn = h2d(*s, s->nn, nn, (size_t)N);
+    const int *dt = type_list ? h2d(*s, s->types, type_list, (size_t)N) : nullptr;
+    const int nslot = (type_list ? ntype * ntype : 1) * nbin;
+    double *dg = h2d(*s, s->out_f64b, g, (size_t)nslot);
+    launch_rdf_list(*s, dv, dd, dn, N, M, dt, ntype, rc, nbin, dg);
+    d2h(*s, g, dg, (size_t)nslot);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_rdf(const int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list, double *g,
+            int ntype, double rc, int nbin)
+{
+    if (!type_list) {
+        mdb_set_error("type_list is required");
+        return MDB_ERR_VALUE;
+    }
+    return rdf_list_host(verlet, N, M, dist, nn, type_list, g, ntype, rc, nbin);
+}
+
+int mdb_rdf_single_species(const int *verlet, int N, int M, const double *dist, const int *nn, double *g, double rc,
+                           int nbin)
+{
+    return rdf_list_host(verlet, N, M, dist, nn, nullptr, g, 1, rc, nbin);
+}
+
+int mdb_rdf_streaming(const double *x, const double *y, const double *z, int N, const int *type_list,
+                      const double *box9, const double *origin3, const int *boundary3, double *g, int ntype,
+                      double rc, int nbin, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    const int rcode = mdb_system_rdf(s.s, type_list, ntype, rc, nbin, 1, g);
     if (rcode != MDB_OK) return rcode;
     API_END
 }

@@ -121,6 +121,9 @@ struct MdbSystem {
     // per-atom outputs kept on device until fetched
     DevBuf out_i32, out_f64, out_f64b, out_f64c, scratch, scratch2;
     DevBuf wx, wy, wz;  // kNN: wrapped coordinates (fast_knn.cpp wrap arithmetic)
+    // Steinhardt state kept for identifySolidLiquid / repeated reads
+    DevBuf qlm_r, qlm_i, qn, types, weight;
+    int sbo_ndeg{0}, sbo_nz{0}, sbo_ncol{0};
 
     // timing of the last call, per kernel (ms), filled when profiling is on
     bool profile{false};
@@ -142,5 +145,14 @@ void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double r
 void launch_acna(MdbSystem &s, const int *verlet, int M, int *pattern);
 void launch_csp(MdbSystem &s, const int *verlet, int M, int nnei, double *csp);
 void launch_aja(MdbSystem &s, const int *verlet, int M, const double *dist, int Md, int *aja);
+void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M,
+                       const double *weight, const int *llist, int ndeg, int nnn, int lmax, bool wl, bool wlhat,
+                       bool average, bool use_voronoi, double rc, bool use_weight, double *qr, double *qi, double *qn);
+void launch_solid_liquid(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, int q6index,
+                         const double *Q6, const double *qr, const double *qi, int ndeg, int nz, double threshold,
+                         int n_bond, bool use_voronoi, int nnn, double rc, int *solid, int *nbond);
+void launch_rdf_list(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int N, int M,
+                     const int *types, int ntype, double rc, int nbin, double *g);
+void launch_rdf_streaming(MdbSystem &s, const int *types, int ntype, double rc, int nbin, double *g);
 int device_max_int(MdbSystem &s, const int *v, size_t n);
 int device_min_int(MdbSystem &s, const int *v, size_t n);

@@ -1,0 +1,168 @@
+// mdapy_b200/csrc/rdf.cu
+//
+// Pair-distance histograms.  Replaces src/radial_distribution_function.cpp:22-54 (_rdf),
+// 56-85 (_rdf_single_species) and 143-317 (_rdf_streaming).  Counts are integers, so the result
+// does not depend on summation order; they are accumulated as 64-bit integers (per-block shared
+// histograms, then global atomics) and ADDED to the caller's f64 histogram at the end, like the
+// reference's `+=`.
+//
+// List kernels use the stored distances: `dis < rc` strict, bin (int)(dis/dr), dr = rc/nbin.
+// The reference has no `k < nbin` guard there (Appendix D.5, an out-of-bounds write when dis/dr
+// rounds up to nbin); such a pair is dropped here.
+// The streaming kernel walks the cut-off cell grid straight from positions: xi wrapped, x[j] raw,
+// min-image, r2 < rc^2 strict, k = (int)(sqrt(r2)/dr), k < nbin (cpp:214-256).  Pair membership
+// does not depend on the cell decomposition, so the reference's "cell list vs all pairs" switch
+// (cpp:167-176) needs no counterpart.
+#include "internal.cuh"
+
+namespace {
+
+constexpr int RDF_SMEM_BINS = 8192;  // 64 KB of 64-bit... kept as 32-bit counters in shared memory (32 KB)
+
+__device__ __forceinline__ void hist_add(unsigned *sh, unsigned long long *gl, bool use_sh, int slot, unsigned v)
+{
+    if (use_sh)
+        atomicAdd(&sh[slot], v);
+    else
+        atomicAdd(&gl[slot], (unsigned long long)v);
+}
+
+__device__ __forceinline__ void hist_flush(unsigned *sh, unsigned long long *gl, int nslot)
+{
+    __syncthreads();
+    for (int t = threadIdx.x; t < nslot; t += blockDim.x) {
+        const unsigned v = sh[t];
+        if (v) atomicAdd(&gl[t], (unsigned long long)v);
+    }
+}
+
+// _rdf (typed) and _rdf_single_species (types == nullptr)
+__global__ void __launch_bounds__(256) k_rdf_list(const int *__restrict__ verlet, const double *__restrict__ dist,
+                                                  const int *__restrict__ nn, int N, int M,
+                                                  const int *__restrict__ types, int ntype, double rc, int nbin,
+                                                  unsigned long long *__restrict__ hist)
+{
+    extern __shared__ unsigned sh[];
+    const int nslot = (types ? ntype * ntype : 1) * nbin;
+    const bool use_sh = nslot <= RDF_SMEM_BINS;
+    if (use_sh) {
+        for (int t = threadIdx.x; t < nslot; t += blockDim.x) sh[t] = 0;
+        __syncthreads();
+    }
+    const double dr = rc / nbin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int cnt = min(nn[i], M);
+        const int it = types ? types[i] : 0;
+        for (int q = 0; q < cnt; ++q) {
+            const double d = dist[(size_t)i * M + q];
+            if (!(d < rc)) continue;
+            const int j = verlet[(size_t)i * M + q];
+            const int k = (int)(d / dr);
+            if (k >= nbin || k < 0) continue;
+            if (types)
+                hist_add(sh, hist, use_sh, (it * ntype + types[j]) * nbin + k, 1u);
+            else if (j > i)
+                hist_add(sh, hist, use_sh, k, 2u);
+        }
+    }
+    if (use_sh) hist_flush(sh, hist, nslot);
+}
+
+__device__ __forceinline__ SortedAtom load_sorted2(const SortedAtom *__restrict__ p)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 lo = __ldg(q), hi = __ldg(q + 1);
+    SortedAtom a;
+    a.x = lo.x;
+    a.y = lo.y;
+    a.z = hi.x;
+    a.idx = __double2loint(hi.y);
+    a.cell = __double2hiint(hi.y);
+    return a;
+}
+
+__global__ void __launch_bounds__(128) k_rdf_stream(const SortedAtom *__restrict__ sorted,
+                                                    const int *__restrict__ cell_start, int N, DBox box, CellGrid g,
+                                                    const int *__restrict__ types, int ntype, double rc, int nbin,
+                                                    unsigned long long *__restrict__ hist)
+{
+    extern __shared__ unsigned sh[];
+    const int nslot = ntype * ntype * nbin;
+    const bool use_sh = nslot <= RDF_SMEM_BINS;
+    if (use_sh) {
+        for (int t = threadIdx.x; t < nslot; t += blockDim.x) sh[t] = 0;
+        __syncthreads();
+    }
+    const double dr = rc / nbin, rcsq = rc * rc;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < N) {
+        const SortedAtom me = load_sorted2(sorted + s);
+        double xi = me.x, yi = me.y, zi = me.z;
+        if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
+        const int kc = me.cell % g.n[2];
+        const int jc = (me.cell / g.n[2]) % g.n[1];
+        const int ic = me.cell / (g.n[2] * g.n[1]);
+        const int it = types[me.idx];
+        for (int di = -1; di <= 1; ++di)
+            for (int dj = -1; dj <= 1; ++dj)
+                for (int dk = -1; dk <= 1; ++dk) {
+                    const int c = (wrap_cell(ic + di, g.n[0]) * g.n[1] + wrap_cell(jc + dj, g.n[1])) * g.n[2] +
+                                  wrap_cell(kc + dk, g.n[2]);
+                    const int b = __ldg(cell_start + c), e = __ldg(cell_start + c + 1);
+                    for (int q = b; q < e; ++q) {
+                        if (q == s) continue;
+                        const SortedAtom o = load_sorted2(sorted + q);
+                        double dx = o.x - xi, dy = o.y - yi, dz = o.z - zi;
+                        min_image(box, dx, dy, dz);
+                        const double r2 = dx * dx + dy * dy + dz * dz;
+                        if (r2 < rcsq) {
+                            const int k = (int)(sqrt(r2) / dr);
+                            if (k < nbin) hist_add(sh, hist, use_sh, (it * ntype + types[o.idx]) * nbin + k, 1u);
+                        }
+                    }
+                }
+    }
+    if (use_sh) hist_flush(sh, hist, nslot);
+}
+
+__global__ void __launch_bounds__(256) k_hist_accumulate(const unsigned long long *__restrict__ hist, int n,
+                                                         double *__restrict__ g)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) g[t] += (double)hist[t];
+}
+
+}  // namespace
+
+// g (device, f64) += counts.  types == nullptr selects the single-species kernel.
+void launch_rdf_list(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int N, int M,
+                     const int *types, int ntype, double rc, int nbin, double *g)
+{
+    MDB_REQUIRE(nbin > 0 && rc > 0, MDB_ERR_VALUE, "nbin and rc must be positive");
+    const int nslot = (types ? ntype * ntype : 1) * nbin;
+    unsigned long long *hist = s.scratch2.ensure<unsigned long long>(nslot);
+    cudaStream_t st = s.stream;
+    CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * nslot, st));
+    const size_t smem = nslot <= RDF_SMEM_BINS ? sizeof(unsigned) * nslot : 0;
+    int nb = (N + 255) / 256;
+    if (nb > 1184) nb = 1184;
+    MDB_LAUNCH(k_rdf_list, nb, 256, smem, st, verlet, dist, nn, N, M, types, ntype, rc, nbin, hist);
+    MDB_LAUNCH(k_hist_accumulate, (nslot + 255) / 256, 256, 0, st, hist, nslot, g);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_rdf_streaming(MdbSystem &s, const int *types, int ntype, double rc, int nbin, double *g)
+{
+    MDB_REQUIRE(nbin > 0 && rc > 0, MDB_ERR_VALUE, "nbin and rc must be positive");
+    MDB_REQUIRE(s.n_rows == s.N && !s.gid, MDB_ERR_STATE, "streaming RDF on a decomposed frame: reduce per-rank lists instead");
+    if (s.bin_rc != rc) launch_binning(s, rc);
+    const int nslot = ntype * ntype * nbin;
+    unsigned long long *hist = s.scratch2.ensure<unsigned long long>(nslot);
+    cudaStream_t st = s.stream;
+    CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * nslot, st));
+    const size_t smem = nslot <= RDF_SMEM_BINS ? sizeof(unsigned) * nslot : 0;
+    MDB_LAUNCH(k_rdf_stream, (s.N + 127) / 128, 128, smem, st, s.sorted.as<SortedAtom>(), s.cell_start.as<int>(), s.N,
+               s.box, s.grid, types, ntype, rc, nbin, hist);
+    MDB_LAUNCH(k_hist_accumulate, (nslot + 255) / 256, 256, 0, st, hist, nslot, g);
+    CUDA_TRY(cudaGetLastError());
+}

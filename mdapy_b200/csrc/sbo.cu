@@ -1,0 +1,365 @@
+// mdapy_b200/csrc/sbo.cu
+//
+// Steinhardt bond-orientational order on the device.  Replaces
+// src/steinhardt_bond_orientation.cpp:288-576 (_compute_ql), 188-224 (Clebsch-Gordan table),
+// 243-286 (Legendre / prefactor) and 578-675 (identifySolidLiquid).
+//
+// q_lm(i) = (1/W) sum_j w_ij Y_lm(r_ij) over listed neighbours with 1e-15 < r <= rc, r taken
+// from the STORED distance list and the direction from min-image(x[j]-x[i]) (Appendix A).
+// Sums run in list order with the reference's operation order (no FMA), so q_l, w_l agree with
+// the reference to the last bit for a given list.  Everything that depends only on (l, m) --
+// sqrt((2l+1)/(4 pi prod)), sqrt(4 pi/(2l+1)), the Clebsch-Gordan coefficients -- is evaluated
+// on the host with the reference's expressions and passed in.
+#include "internal.cuh"
+#include <vector>
+
+namespace {
+
+constexpr int SBO_MAX_L = 24;
+constexpr int SBO_LOCAL = 64;  // accumulators kept in registers/local memory when ndeg*(2lmax+1) <= this
+
+struct SboParams {
+    int ndeg, lmax, nz, nnn, use_voronoi, use_weight;
+    double rc;
+    int l[8];
+};
+
+__constant__ double c_norm[8][SBO_MAX_L + 1];  // sqrt((2l+1)/(4 pi prod_{i=l-m+1}^{l+m} i)) per (degree slot, m)
+
+// _associated_legendre, cpp:243-268
+__device__ __forceinline__ double assoc_legendre(int l, int m, double x)
+{
+    double p = 1.0, pm1 = 0.0, pm2 = 0.0;
+    if (m != 0) {
+        const double sqx = sqrt(1.0 - x * x);
+        for (int i = 1; i < m + 1; ++i) p *= (2 * i - 1) * sqx;
+    }
+    for (int i = m + 1; i < l + 1; ++i) {
+        pm2 = pm1;
+        pm1 = p;
+        p = ((2 * i - 1) * x * pm1 - (i + m - 1) * pm2) / (i - m);
+    }
+    return p;
+}
+
+template <bool LOCAL>
+__global__ void __launch_bounds__(128) k_qlm(const double *__restrict__ x, const double *__restrict__ y,
+                                             const double *__restrict__ z, int N, DBox box,
+                                             const int *__restrict__ verlet, const double *__restrict__ dist,
+                                             const int *__restrict__ nn, const double *__restrict__ weight, int M,
+                                             SboParams P, double *__restrict__ qr, double *__restrict__ qi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double EPS = 1e-15;
+    const int stride = P.ndeg * P.nz;
+    double *Qr = qr + (size_t)i * stride, *Qi = qi + (size_t)i * stride;
+    double ar[LOCAL ? SBO_LOCAL : 1], ai[LOCAL ? SBO_LOCAL : 1];
+    if (LOCAL) {
+        for (int t = 0; t < stride; ++t) {
+            ar[t] = Qr[t];  // caller-zeroed, but accumulate like the reference (inout arrays)
+            ai[t] = Qi[t];
+        }
+    }
+    double *R = LOCAL ? ar : Qr, *I = LOCAL ? ai : Qi;
+    const double x1 = x[i], y1 = y[i], z1 = z[i];
+    int cnt = nn[i];
+    if (!P.use_voronoi && P.nnn > 0) cnt = P.nnn;
+    double wsum = 0.0;
+    for (int jj = 0; jj < cnt; ++jj) {
+        const size_t at = (size_t)i * M + jj;
+        const int j = verlet[at];
+        if (j < 0) continue;
+        double dx = x[j] - x1, dy = y[j] - y1, dz = z[j] - z1;
+        min_image(box, dx, dy, dz);
+        const double rmag = dist[at];
+        if (!((rmag > EPS) && (rmag <= P.rc))) continue;
+        const double w = P.use_weight ? weight[at] : 1.0;
+        wsum += w;
+        const double rinv = 1.0 / rmag;
+        const double ct = dz * rinv;
+        double er = dx, ei = dy;
+        const double rxy2 = er * er + ei * ei;
+        if (rxy2 < EPS * EPS) {
+            er = 1.0;
+            ei = 0.0;
+        } else {
+            const double inv = 1.0 / sqrt(rxy2);
+            er *= inv;
+            ei *= inv;
+        }
+        for (int il = 0; il < P.ndeg; ++il) {
+            const int l = P.l[il];
+            double *Rl = R + il * P.nz, *Il = I + il * P.nz;
+            Rl[l] += w * (c_norm[il][0] * assoc_legendre(l, 0, ct));
+            double pr = er, pi = ei;
+            for (int m = 1; m < l + 1; ++m) {
+                const double pf = c_norm[il][m] * assoc_legendre(l, m, ct);
+                const double cr = pf * pr, ci = pf * pi;
+                const double wr = w * cr, wi = w * ci;
+                Rl[l + m] += wr;
+                Il[l + m] += wi;
+                if (m & 1) {
+                    Rl[l - m] -= wr;
+                    Il[l - m] += wi;
+                } else {
+                    Rl[l - m] += wr;
+                    Il[l - m] -= wi;
+                }
+                const double tr = pr * er - pi * ei;
+                const double ti = pr * ei + pi * er;
+                pr = tr;
+                pi = ti;
+            }
+        }
+    }
+    const double fac = 1.0 / wsum;
+    for (int il = 0; il < P.ndeg; ++il) {
+        const int mm = 2 * P.l[il] + 1;
+        for (int m = 0; m < mm; ++m) {
+            Qr[il * P.nz + m] = R[il * P.nz + m] * fac;
+            Qi[il * P.nz + m] = I[il * P.nz + m] * fac;
+        }
+    }
+}
+
+// neighbour averaging (Lechner-Dellago), cpp:439-503: every listed neighbour counts, no rc filter
+__global__ void __launch_bounds__(128) k_qlm_average(int N, const int *__restrict__ verlet,
+                                                     const int *__restrict__ nn, int M, SboParams P,
+                                                     const double *__restrict__ aqr, const double *__restrict__ aqi,
+                                                     double *__restrict__ qr, double *__restrict__ qi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int stride = P.ndeg * P.nz;
+    int cnt = nn[i];
+    if (!P.use_voronoi && P.nnn > 0) cnt = P.nnn;
+    int used = 1;
+    double *Qr = qr + (size_t)i * stride, *Qi = qi + (size_t)i * stride;
+    for (int jj = 0; jj < cnt; ++jj) {
+        const int j = verlet[(size_t)i * M + jj];
+        if (j < 0) continue;
+        const double *Ar = aqr + (size_t)j * stride, *Ai = aqi + (size_t)j * stride;
+        for (int il = 0; il < P.ndeg; ++il) {
+            const int mm = 2 * P.l[il] + 1;
+            for (int m = 0; m < mm; ++m) {
+                Qr[il * P.nz + m] += Ar[il * P.nz + m];
+                Qi[il * P.nz + m] += Ai[il * P.nz + m];
+            }
+        }
+        ++used;
+    }
+    const double inv = 1.0 / used;
+    for (int il = 0; il < P.ndeg; ++il) {
+        const int mm = 2 * P.l[il] + 1;
+        for (int m = 0; m < mm; ++m) {
+            Qr[il * P.nz + m] *= inv;
+            Qi[il * P.nz + m] *= inv;
+        }
+    }
+}
+
+// q_l, w_l, w_l-hat, cpp:506-575
+__global__ void __launch_bounds__(128) k_ql_wl(int N, SboParams P, const double *__restrict__ qr,
+                                               const double *__restrict__ qi, const double *__restrict__ qnormfac,
+                                               const double *__restrict__ cg, const double *__restrict__ sqrt2l1,
+                                               int wl, int wlhat, int ncol, double *__restrict__ qn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double EPS = 1e-15;
+    const int stride = P.ndeg * P.nz;
+    const double *Qr = qr + (size_t)i * stride, *Qi = qi + (size_t)i * stride;
+    double *out = qn + (size_t)i * ncol;
+    for (int il = 0; il < P.ndeg; ++il) {
+        const int mm = 2 * P.l[il] + 1;
+        double s = 0.0;
+        for (int m = 0; m < mm; ++m) s += Qr[il * P.nz + m] * Qr[il * P.nz + m] + Qi[il * P.nz + m] * Qi[il * P.nz + m];
+        out[il] = qnormfac[il] * sqrt(s);
+    }
+    if (wl | wlhat) {
+        int t = 0;
+        for (int il = 0; il < P.ndeg; ++il) {
+            const int l = P.l[il];
+            const double *R = Qr + il * P.nz, *I = Qi + il * P.nz;
+            double ws = 0.0;
+            for (int m1 = 0; m1 < 2 * l + 1; ++m1) {
+                const int b = max(0, l - m1), e = min(2 * l + 1, 3 * l - m1 + 1);
+                for (int m2 = b; m2 < e; ++m2, ++t) {
+                    const int m = m1 + m2 - l;
+                    const double pr = R[m1] * R[m2] - I[m1] * I[m2];
+                    const double pi = R[m1] * I[m2] + I[m1] * R[m2];
+                    ws += (pr * R[m] + pi * I[m]) * cg[t];
+                }
+            }
+            const double wf = ws / sqrt2l1[il];
+            if (wl) out[il + P.ndeg] = wf;
+            if (wlhat) {
+                const double qv = out[il];
+                if (qv > EPS) {
+                    const double q = qnormfac[il] / qv;
+                    out[il + (wl ? 1 : 0) * P.ndeg + P.ndeg] = wf * (q * q * q);
+                }
+            }
+        }
+    }
+}
+
+// first sweep of identifySolidLiquid, cpp:605-644
+__global__ void __launch_bounds__(128) k_solid_bonds(int N, const int *__restrict__ verlet,
+                                                     const double *__restrict__ dist, const int *__restrict__ nn,
+                                                     int M, const double *__restrict__ qr,
+                                                     const double *__restrict__ qi, int stride, int off,
+                                                     const double *__restrict__ Q6, double threshold, int n_bond,
+                                                     int use_voronoi, int nnn, double rc,
+                                                     int *__restrict__ solid, int *__restrict__ nbond)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double PI = 3.14159265358979323846;
+    int cnt = nn[i];
+    if (!use_voronoi && nnn > 0) cnt = nnn;
+    const double *ar = qr + (size_t)i * stride + off, *ai = qi + (size_t)i * stride + off;
+    int ns = 0;
+    for (int jj = 0; jj < cnt; ++jj) {
+        const int j = verlet[(size_t)i * M + jj];
+        if (j < 0) continue;
+        if (dist[(size_t)i * M + jj] > rc) continue;
+        const double *br = qr + (size_t)j * stride + off, *bi = qi + (size_t)j * stride + off;
+        double s = 0.0;
+        for (int m = 0; m < 13; ++m) s += ar[m] * br[m] + ai[m] * bi[m];
+        s = s / Q6[i] / Q6[j] * 4 * PI / 13;
+        if (s > threshold) ++ns;
+    }
+    if (ns >= n_bond) solid[i] = 1;
+    nbond[i] = ns;
+}
+
+// second sweep, cpp:645-674, on a snapshot of the first sweep (the reference reads flags that other
+// threads may be clearing; for symmetric lists the outcome is the same)
+__global__ void __launch_bounds__(128) k_solid_isolated(int N, const int *__restrict__ verlet,
+                                                        const int *__restrict__ nn, int M, int use_voronoi, int nnn,
+                                                        const int *__restrict__ snap, int *__restrict__ solid)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N || snap[i] != 1) return;
+    int cnt = nn[i];
+    if (!use_voronoi && nnn > 0) cnt = nnn;
+    for (int jj = 0; jj < cnt; ++jj) {
+        const int j = verlet[(size_t)i * M + jj];
+        if (j < 0) continue;
+        if (snap[j] == 1) return;
+    }
+    solid[i] = 0;
+}
+
+// n! as the reference tabulates it (15 significant digits, cpp:12-181); exact for n <= 78
+double fact15(int n)
+{
+    long double f = 1.0L;
+    for (int i = 2; i <= n; ++i) f *= i;
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.15Lg", f);
+    return strtod(buf, nullptr);
+}
+
+}  // namespace
+
+void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M,
+                       const double *weight, const int *llist, int ndeg, int nnn, int lmax, bool wl, bool wlhat,
+                       bool average, bool use_voronoi, double rc, bool use_weight, double *qr, double *qi, double *qn)
+{
+    MDB_REQUIRE(ndeg >= 1 && ndeg <= 8, MDB_ERR_VALUE, "1 to 8 degrees supported, got %d", ndeg);
+    MDB_REQUIRE(lmax >= 0 && lmax <= SBO_MAX_L, MDB_ERR_VALUE, "lmax=%d exceeds the device limit %d", lmax, SBO_MAX_L);
+    const double PI = 3.14159265358979323846;
+    SboParams P{};
+    P.ndeg = ndeg;
+    P.lmax = lmax;
+    P.nz = 2 * lmax + 1;
+    P.nnn = nnn;
+    P.use_voronoi = use_voronoi;
+    P.use_weight = use_weight;
+    P.rc = rc;
+    double norm[8][SBO_MAX_L + 1] = {};
+    std::vector<double> qnf(ndeg), s2l1(ndeg);
+    for (int il = 0; il < ndeg; ++il) {
+        const int l = llist[il];
+        MDB_REQUIRE(l >= 0 && l <= lmax, MDB_ERR_VALUE, "degree %d outside [0, lmax=%d]", l, lmax);
+        P.l[il] = l;
+        for (int m = 0; m <= l; ++m) {  // _polar_prefactor, cpp:270-286
+            double pf = 1.0;
+            for (int i = l - m + 1; i < l + m + 1; ++i) pf *= i;
+            norm[il][m] = std::sqrt((2 * l + 1) / (4 * PI * pf));
+        }
+        qnf[il] = std::sqrt(4 * PI / (2 * l + 1));
+        s2l1[il] = std::sqrt(2 * l + 1.0);
+    }
+    cudaStream_t st = s.stream;
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_norm, norm, sizeof(norm), 0, cudaMemcpyHostToDevice, st));
+    const int N = s.n_rows;
+    const int nb = (N + 127) / 128;
+    if (P.ndeg * P.nz <= SBO_LOCAL)
+        MDB_LAUNCH(k_qlm<true>, nb, 128, 0, st, s.x, s.y, s.z, N, s.box, verlet, dist, nn, weight, M, P, qr, qi);
+    else
+        MDB_LAUNCH(k_qlm<false>, nb, 128, 0, st, s.x, s.y, s.z, N, s.box, verlet, dist, nn, weight, M, P, qr, qi);
+    if (average) {
+        const size_t tot = (size_t)N * P.ndeg * P.nz;
+        double *ar = s.scratch.ensure<double>(tot), *ai = s.scratch2.ensure<double>(tot);
+        CUDA_TRY(cudaMemcpyAsync(ar, qr, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ai, qi, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
+        MDB_LAUNCH(k_qlm_average, nb, 128, 0, st, N, verlet, nn, M, P, ar, ai, qr, qi);
+    }
+    // Clebsch-Gordan table, cpp:188-224
+    std::vector<double> cg(1, 0.0);
+    if (wl || wlhat) {
+        cg.clear();
+        for (int il = 0; il < ndeg; ++il) {
+            const int l = llist[il];
+            for (int m1 = 0; m1 < 2 * l + 1; ++m1) {
+                const int aa = m1 - l;
+                for (int m2 = std::max(0, l - m1); m2 < std::min(2 * l + 1, 3 * l - m1 + 1); ++m2) {
+                    const int bb = m2 - l, m = aa + bb + l;
+                    double sums = 0.0;
+                    for (int zz = std::max(0, std::max(-aa, bb)); zz < std::min(l, std::min(l - aa, l + bb)) + 1; ++zz) {
+                        const int ifac = (zz % 2) ? -1 : 1;
+                        sums += ifac / (fact15(zz) * fact15(l - zz) * fact15(l - aa - zz) * fact15(l + bb - zz) *
+                                        fact15(aa + zz) * fact15(-bb + zz));
+                    }
+                    const int cc = m - l;
+                    const double sfaccg = std::sqrt(fact15(l + aa) * fact15(l - aa) * fact15(l + bb) * fact15(l - bb) *
+                                                    fact15(l + cc) * fact15(l - cc) * (2 * l + 1));
+                    const double sfac1 = fact15(3 * l + 1), sfac2 = fact15(l);
+                    const double dcg = std::sqrt(sfac2 * sfac2 * sfac2 / sfac1);
+                    cg.push_back(sums * dcg * sfaccg);
+                }
+            }
+        }
+    }
+    const size_t ncg = cg.size();
+    double *dtab = s.out_f64c.ensure<double>(ncg + 2 * ndeg);
+    std::vector<double> tab(cg);
+    tab.insert(tab.end(), qnf.begin(), qnf.end());
+    tab.insert(tab.end(), s2l1.begin(), s2l1.end());
+    CUDA_TRY(cudaMemcpyAsync(dtab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // tab is a host temporary
+    const int ncol = ndeg * (1 + (wl ? 1 : 0) + (wlhat ? 1 : 0));
+    MDB_LAUNCH(k_ql_wl, nb, 128, 0, st, N, P, qr, qi, dtab + ncg, dtab, dtab + ncg + ndeg, wl ? 1 : 0, wlhat ? 1 : 0,
+               ncol, qn);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_solid_liquid(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, int q6index,
+                         const double *Q6, const double *qr, const double *qi, int ndeg, int nz, double threshold,
+                         int n_bond, bool use_voronoi, int nnn, double rc, int *solid, int *nbond)
+{
+    MDB_REQUIRE(nz >= 13, MDB_ERR_VALUE, "q_6m needs 2*lmax+1 >= 13 columns, got %d", nz);
+    const int N = s.n_rows;
+    const int nb = (N + 127) / 128;
+    cudaStream_t st = s.stream;
+    MDB_LAUNCH(k_solid_bonds, nb, 128, 0, st, N, verlet, dist, nn, M, qr, qi, ndeg * nz, q6index * nz, Q6, threshold,
+               n_bond, use_voronoi ? 1 : 0, nnn, rc, solid, nbond);
+    int *snap = s.scratch.ensure<int>(N);
+    CUDA_TRY(cudaMemcpyAsync(snap, solid, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
+    MDB_LAUNCH(k_solid_isolated, nb, 128, 0, st, N, verlet, nn, M, use_voronoi ? 1 : 0, nnn, snap, solid);
+    CUDA_TRY(cudaGetLastError());
+}

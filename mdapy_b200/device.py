@@ -138,6 +138,39 @@ class DeviceSystem:
         L.check(self._lib.mdb_system_aja(self._h, L.iptr(out) if fetch else None))
         return out
 
+    def steinhardt(self, llist, nnn=0, rc=-1.0, average=False, wl=False, wlhat=False, use_voronoi=False,
+                   weight=None, fetch_qlm=False):
+        ll = L.i32(llist)
+        ndeg = ll.shape[0]
+        lmax = int(ll.max())
+        ncol = ndeg * (1 + int(bool(wl)) + int(bool(wlhat)))
+        qn = np.empty((self.n_rows, ncol), np.float64)
+        qr = np.empty((self.n_rows, ndeg, 2 * lmax + 1), np.float64) if fetch_qlm else None
+        qi = np.empty_like(qr) if fetch_qlm else None
+        w = L.f64(weight) if weight is not None else None
+        if w is not None:
+            assert w.shape == (self.n_rows, self.M)
+        L.check(self._lib.mdb_system_steinhardt(
+            self._h, L.iptr(ll), ndeg, int(nnn), float(rc), int(bool(average)), int(bool(wl)), int(bool(wlhat)),
+            int(bool(use_voronoi)), L.dptr(w) if w is not None else None, L.dptr(qn),
+            L.dptr(qr) if fetch_qlm else None, L.dptr(qi) if fetch_qlm else None))
+        return qn, qr, qi
+
+    def solid_liquid(self, q6index, threshold, n_bond, nnn=0, rc=-1.0, use_voronoi=False):
+        sl = np.empty(self.n_rows, np.int32)
+        nb = np.empty(self.n_rows, np.int32)
+        L.check(self._lib.mdb_system_solid_liquid(self._h, int(q6index), float(threshold), int(n_bond),
+                                                  int(bool(use_voronoi)), int(nnn), float(rc), L.iptr(sl), L.iptr(nb)))
+        return sl, nb
+
+    def rdf_counts(self, rc, nbin, type_list=None, ntype=1, streaming=False):
+        """Raw pair counts: (ntype, ntype, nbin) with a type list, (nbin,) for the single-species list kernel."""
+        t = L.i32(type_list) if type_list is not None else None
+        g = np.zeros((ntype, ntype, nbin) if t is not None else (nbin,), np.float64)
+        L.check(self._lib.mdb_system_rdf(self._h, L.iptr(t) if t is not None else None, int(ntype), float(rc),
+                                         int(nbin), int(bool(streaming)), L.dptr(g)))
+        return g
+
     def result_device(self):
         """Raw device pointers (int) of the latest int32 / f64 per-atom result."""
         a, b = C.c_void_p(), C.c_void_p()
