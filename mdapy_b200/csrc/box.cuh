@@ -9,11 +9,14 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define MDB_HD __host__ __device__ __forceinline__
+#define MDB_COLD __host__ __device__ __noinline__
 #else
 #define MDB_HD inline
+#define MDB_COLD inline
 #endif
 
 struct DBox {
@@ -24,7 +27,87 @@ struct DBox {
     int pbc[3];
     int triclinic;
     int any_pbc;
+    // steps of n(x) = floor(x/L + 0.5) per orthogonal periodic axis, see ortho_image_axis() below
+    double img_t[3][4];
+    // steps of floor(dx/L) for the wrap, see ortho_wrap_axis()
+    double wrap_t[3][4];
 };
+
+
+// ---------------------------------------------------------------------------------------------
+// Division-free orthogonal minimum image.
+//
+// The reference evaluates xij -= L * floor(xij / L + 0.5) (src/box.h:119-124).  n(x) =
+// floor(fl(fl(x/L) + 0.5)) is a monotone step function of x, so it is fully described by the
+// doubles at which it steps.  The host finds those steps EXACTLY (bisection over the ordered bit
+// patterns, evaluating the very same expression), and the device picks n in {-1, 0, +1} with
+// comparisons; L*n is then exact and xij - L*n is the same single rounding as the reference's.
+// Anything outside [t0, t3) (a neighbour more than 1.5 box lengths away in raw coordinates) takes
+// the literal expression.  Bit-identical by construction (verified on 16 M samples per box length
+// including +-4 ulp around every step); tests/test_gpu_neighbor.py exercises both branches.
+static inline long long ord_bits(double v)
+{
+    long long b;
+    memcpy(&b, &v, 8);
+    return b < 0 ? (long long)0x8000000000000000ull - b : b;
+}
+static inline double ord_double(long long k)
+{
+    long long b = k < 0 ? (long long)0x8000000000000000ull - k : k;
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+}
+
+// smallest double x with floor(x / L + 0.5) >= k
+static inline double image_step(double L, int k)
+{
+    long long lo = ord_bits((k - 1.0) * L), hi = ord_bits((k + 0.5) * L);  // n(lo) < k <= n(hi)
+    while ((__int128)hi - lo > 1) {
+        const long long mid = (long long)(((__int128)lo + hi) >> 1);  // hi - lo can exceed 2^63
+        if (std::floor(ord_double(mid) / L + 0.5) >= k) hi = mid;
+        else lo = mid;
+    }
+    return ord_double(hi);
+}
+
+// t[0]: x >= t0 <=> n >= -1,  t[1]: n >= 0,  t[2]: n >= 1,  t[3]: n >= 2
+// rarely taken literal forms, kept out of line so the IEEE division sequences are not replicated
+// into every inlined call site
+static MDB_COLD double image_far(double x, double L) { return x - L * floor(x / L + 0.5); }
+static MDB_COLD double wrap_far(double origin, double dx, double L) { return origin + dx - L * floor(dx / L); }
+
+MDB_HD double ortho_image_axis(double x, const double *t, double L)
+{
+    if (x < t[0] || !(x < t[3])) return image_far(x, L);  // far image (or NaN): literal expression
+    // n = -1: x - (L * -1.0) == x + L exactly;  n = 0: x - L*0 == x;  n = +1: x - L
+    const double shifted = x + (x < t[1] ? L : -L);
+    return (x >= t[1] && x < t[2]) ? x : shifted;
+}
+
+// Division-free wrap of dx = x - origin: the reference computes origin + dx - L * floor(dx / L)
+// (src/box.h:160-174).  floor(fl(dx / L)) is again a monotone step function of dx; w[k+1] is the
+// smallest dx with floor(dx / L) >= k for k = -1, 0, 1, 2 (exact, found by bisection on the host).
+static inline double wrap_step(double L, int k)
+{
+    long long lo = ord_bits((k - 1.5) * L), hi = ord_bits((k + 0.5) * L);  // floor(lo/L) < k <= floor(hi/L)
+    while ((__int128)hi - lo > 1) {
+        const long long mid = (long long)(((__int128)lo + hi) >> 1);
+        if (std::floor(ord_double(mid) / L) >= k) hi = mid;
+        else lo = mid;
+    }
+    return ord_double(hi);
+}
+
+MDB_HD double ortho_wrap_axis(double x, double origin, const double *w, double L)
+{
+    const double dx = x - origin;
+    if (dx < w[0] || !(dx < w[3])) return wrap_far(origin, dx, L);
+    // n = 0 -> L*0 = 0: origin + dx - 0;  n = -1 -> origin + dx - (-L);  n = 1 -> origin + dx - L
+    const double s = origin + dx;
+    const double shifted = dx < w[1] ? s + L : s - L;
+    return (dx >= w[1] && dx < w[2]) ? s : shifted;
+}
 
 // ---- host construction: src/box.h:208-245 (get_box), 182-203, 54-89 --------
 static inline double dbox_volume(const DBox &b)
@@ -96,6 +179,13 @@ static inline int dbox_make(DBox &b, const double *box9, const double *origin3, 
         }
         b.thick[dir] = V / std::sqrt(m * m + n * n + k * k);
     }
+    for (int d = 0; d < 3; ++d)
+        for (int k = -1; k <= 2; ++k)
+        {
+            const bool on = b.pbc[d] && !b.triclinic && b.h[4 * d] > 0;
+            b.img_t[d][k + 1] = on ? image_step(b.h[4 * d], k) : 0.0;
+            b.wrap_t[d][k + 1] = on ? wrap_step(b.h[4 * d], k) : 0.0;
+        }
     return 0;
 }
 
@@ -114,9 +204,9 @@ MDB_HD void min_image(const DBox &b, double &xij, double &yij, double &zij)
         yij = x * b.h[1] + y * b.h[4] + z * b.h[7];
         zij = x * b.h[2] + y * b.h[5] + z * b.h[8];
     } else {
-        if (b.pbc[0]) xij -= b.h[0] * floor(xij / b.h[0] + 0.5);
-        if (b.pbc[1]) yij -= b.h[4] * floor(yij / b.h[4] + 0.5);
-        if (b.pbc[2]) zij -= b.h[8] * floor(zij / b.h[8] + 0.5);
+        if (b.pbc[0]) xij = ortho_image_axis(xij, b.img_t[0], b.h[0]);
+        if (b.pbc[1]) yij = ortho_image_axis(yij, b.img_t[1], b.h[4]);
+        if (b.pbc[2]) zij = ortho_image_axis(zij, b.img_t[2], b.h[8]);
     }
 }
 
@@ -137,18 +227,9 @@ MDB_HD void wrap_into_box(const DBox &b, double &x, double &y, double &z)
         y = b.origin[1] + nx * b.h[1] + ny * b.h[4] + nz * b.h[7];
         z = b.origin[2] + nx * b.h[2] + ny * b.h[5] + nz * b.h[8];
     } else {
-        if (b.pbc[0]) {
-            const double dx = x - b.origin[0];
-            x = b.origin[0] + dx - b.h[0] * floor(dx / b.h[0]);
-        }
-        if (b.pbc[1]) {
-            const double dy = y - b.origin[1];
-            y = b.origin[1] + dy - b.h[4] * floor(dy / b.h[4]);
-        }
-        if (b.pbc[2]) {
-            const double dz = z - b.origin[2];
-            z = b.origin[2] + dz - b.h[8] * floor(dz / b.h[8]);
-        }
+        if (b.pbc[0]) x = ortho_wrap_axis(x, b.origin[0], b.wrap_t[0], b.h[0]);
+        if (b.pbc[1]) y = ortho_wrap_axis(y, b.origin[1], b.wrap_t[1], b.h[4]);
+        if (b.pbc[2]) z = ortho_wrap_axis(z, b.origin[2], b.wrap_t[2], b.h[8]);
     }
 }
 
@@ -217,11 +298,24 @@ MDB_HD int wrap_cell(int a, int n)
     return r < 0 ? r + n : r;
 }
 
-// stored linear id of global cell (ci, cj, ck), ci already wrapped into [0, n0); -1 outside the window
+// Stored linear id of global cell (ci, cj, ck), ci already wrapped into [0, n0); -1 outside the
+// window.  Inside a z-pencil the cells are stored in DESCENDING ck: together with ascending original
+// index inside a cell, ONE backward walk over the three consecutive cells ck-1, ck, ck+1 visits the
+// atoms exactly in the reference's order (cells ck-1, ck, ck+1, each in descending index -- the
+// head-insertion chains of src/neighbor.cpp:97-98 walked by the loops of 147-181).
 MDB_HD int cell_linear(const CellGrid &g, int ci, int cj, int ck)
 {
     int p = ci - g.x0;
     if (p < 0) p += g.n[0];
     if (p >= g.nxl) return -1;
-    return (p * g.n[1] + cj) * g.n[2] + ck;
+    return (p * g.n[1] + cj) * g.n[2] + (g.n[2] - 1 - ck);
 }
+
+// inverse of cell_linear: global x plane, y and z cell of a stored cell id
+MDB_HD void cell_decode(const CellGrid &g, int cell, int &ic, int &jc, int &kc)
+{
+    kc = g.n[2] - 1 - cell % g.n[2];
+    jc = (cell / g.n[2]) % g.n[1];
+    ic = wrap_cell(cell / (g.n[2] * g.n[1]) + g.x0, g.n[0]);
+}
+

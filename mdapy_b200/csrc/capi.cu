@@ -66,39 +66,45 @@ static void prof_mark(MdbSystem &s, int k)
     if (s.profile) CUDA_TRY(cudaEventRecord(s.ev[k], s.stream));
 }
 
-// cut-off list into s.verlet/s.dist/s.nn.  max_neigh <= 0 -> automatic width.
+// cut-off list into s.verlet/s.dist/s.nn.  max_neigh <= 0 -> automatic width M = max(count, 1)
+// (neighbor.cpp:189-349).  Orthogonal frames with enough cells run the cell-tile kernel
+// (neighbor_tiled.cu), everything else the direct kernel (neighbor.cu); both produce identical rows.
 static void build_neighbor(MdbSystem &s, double rc, int max_neigh)
 {
     MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "rc must be positive, got %g.", rc);
     prof_mark(s, 0);
     if (s.bin_rc != rc) launch_binning(s, rc);
     prof_mark(s, 1);
+    int T = 0;
+    const bool tiled = tiled_neighbor_plan(s, T);
+    auto fill = [&](int M) {
+        prof_mark(s, 1);
+        if (tiled) launch_neighbor_tiled(s, rc, M, T, false, 1);
+        else launch_neighbor(s, rc, M, false);
+        prof_mark(s, 2);
+        return tiled ? neighbor_tiled_max(s) : device_max_int(s, s.nn.as<int>(), s.n_rows);
+    };
     if (max_neigh > 0) {
-        launch_neighbor(s, rc, max_neigh, false);
+        s.max_count = fill(max_neigh);
         s.M = max_neigh;
-        prof_mark(s, 2);
-        s.max_count = device_max_int(s, s.nn.as<int>(), s.n_rows);
     } else {
-        // Guess the width from the mean density (x1.5 + 8), fill once, then
-        // shrink (or redo if the guess was short).  Equivalent to the
-        // reference's count-then-copy (neighbor.cpp:290-343) without a
-        // second search in the common case.
-        const double vol = fabs(dbox_volume(s.box));
-        const double mean = vol > 0 ? (double)s.N / vol * 4.18879020478639 * rc * rc * rc : 16.0;
-        int guess = (int)(mean * 1.5) + 8;
-        if (guess > 256) guess = 256;
-        if ((double)guess * s.N * 12.0 > 24e9) guess = (int)(24e9 / 12.0 / s.N) > 1 ? (int)(24e9 / 12.0 / s.N) : 1;
-        launch_neighbor(s, rc, guess, false);
-        prof_mark(s, 2);
-        int mx = device_max_int(s, s.nn.as<int>(), s.n_rows);
-        const int want = mx > 1 ? mx : 1;
-        if (mx > guess) {
-            launch_neighbor(s, rc, want, false);
-            prof_mark(s, 2);
-        } else if (want < guess) {
-            launch_compact_rows(s, guess, want);
+        // width estimate: exact count pass (direct) or a count-only pass over every 16th tile (tiled);
+        // the fill pass reports the true maximum, and is repeated in the rare case the sample missed it
+        int est;
+        if (tiled) {
+            launch_neighbor_tiled(s, rc, 0, T, true, 16);
+            est = neighbor_tiled_max(s);
+        } else {
+            launch_neighbor(s, rc, 0, true);
+            est = device_max_int(s, s.nn.as<int>(), s.n_rows);
         }
-        s.M = want;
+        if (est < 1) est = 1;
+        int mx = fill(est);
+        if (mx > est) {
+            est = mx;
+            mx = fill(est);
+        }
+        s.M = est;
         s.max_count = mx;
     }
     s.list_kind = LIST_CUTOFF;

@@ -44,9 +44,8 @@ __global__ void __launch_bounds__(128) k_neighbor_direct(const SortedAtom *__res
     if (me.idx >= n_rows) return;  // ghost atom of a decomposed frame: neighbour only
     double xi = me.x, yi = me.y, zi = me.z;
     if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
-    const int kc = me.cell % g.n[2];
-    const int jc = (me.cell / g.n[2]) % g.n[1];
-    const int ic = wrap_cell(me.cell / (g.n[2] * g.n[1]) + g.x0, g.n[0]);  // global x plane
+    int ic, jc, kc;
+    cell_decode(g, me.cell, ic, jc, kc);
     int *vrow = verlet + (size_t)me.idx * M;
     double *drow = dist + (size_t)me.idx * M;
     int cnt = 0;

@@ -1,0 +1,532 @@
+// mdapy_b200/csrc/neighbor_tiled.cu
+//
+// Cell-tile neighbour build: the production kernel for orthogonal boxes (src/neighbor.cpp:102-187
+// semantics, rows bit-identical to k_neighbor_direct and to the reference, including row order).
+//
+// One CTA owns a T x T x T block of cells.  The sorted records of the (T+2)^3 surrounding cells are
+// staged in shared memory pencil by pencil -- every z-pencil of cells is one contiguous run of
+// 32-byte SortedAtom records, copied with cp.async.bulk (TMA 1-D, mbarrier completion).  Each staged
+// atom also gets an fp32 copy of its position relative to the tile centre (nearest periodic image).
+// One thread per owned atom then walks its 27 cells in the reference's order:
+//   phase 1  fp32 distance test against rc^2 * (1 + guard): a conservative pre-filter (no false
+//            negatives: the guard is >50x the fp32 error bound), survivors are queued per thread;
+//   phase 2  the queued survivors take the exact f64 test of the reference (xi wrapped, x[j] raw,
+//            division-free min-image, left-to-right sum, <= rc^2) and are written in queue order.
+// Only ~20 % of the 27-cell candidates survive phase 1, so the f64 pipe sees ~13 pairs per atom
+// instead of ~67.  Rows are padded by the writing thread (-1 / rc+1), so no prefill pass is needed.
+#include "internal.cuh"
+
+namespace {
+
+constexpr int TILE_THREADS = 256;
+constexpr int SURV_CAP = 24;      // per-thread survivor queue (uint16 staged indices)
+constexpr int SURV_RESERVE = 12;  // warp drains when any lane holds more than this at a pencil boundary
+
+struct TileArgs {
+    const SortedAtom *sorted;
+    const int *cell_start;
+    DBox box;
+    CellGrid g;
+    double rcsq;
+    double pad;     // rc + 1.0
+    float rcsq_hi;  // fp32 acceptance bound of the pre-filter
+    int M;
+    int n_rows;
+    int *verlet;
+    double *dist;
+    int *nn;
+    int *max_count;  // atomicMax of the true neighbour count
+    int cap;         // staged-atom capacity of the shared buffers
+    int p_lo, p_hi;  // owned range of stored x planes
+    int wrap_x;      // 1: planes wrap around (single GPU), 0: slab window with ghost planes
+    int tiles_y, tiles_z;
+    int tile_stride, tile_offset, n_tiles;  // sampling of the tile list (count-only estimate)
+    int count_only;
+    int use_tma;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA 1-D); bytes multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void load_rec(const SortedAtom *p, double &x, double &y, double &z, int &idx, int &cell)
+{
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 lo = q[0], hi = q[1];
+    x = lo.x;
+    y = lo.y;
+    z = hi.x;
+    idx = __double2loint(hi.y);
+    cell = __double2hiint(hi.y);
+}
+
+// exclusive scan of v[0..n) in shared memory by warp 0 (n <= 1024); total written to v[n]
+__device__ __forceinline__ void warp0_exclusive_scan(int *v, int n)
+{
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int carry = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const int x = i < n ? v[i] : 0;
+            int incl = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (i < n) v[i] = carry + incl - x;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) v[n] = carry;
+    }
+}
+
+// unwrapped cell coordinate u along an axis with n cells -> stored cell (or -1 when not needed/absent)
+__device__ __forceinline__ int map_axis(int u, int n)
+{
+    if (u >= 0 && u < n) return u;
+    if (u == -1) return n - 1;
+    if (u == n) return 0;
+    return -1;
+}
+
+template <int T, int TZ>
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const TileArgs A)
+{
+    constexpr int P = T + 2;     // block edge in x, y
+    constexpr int PZ = TZ + 2;   // block edge in z (the contiguous direction of the sorted copy)
+    constexpr int NPEN = P * P;
+    constexpr int NCELL = NPEN * PZ;
+    constexpr int CSW = PZ + 1;  // row width of the per-pencil offset table
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    SortedAtom *raw = reinterpret_cast<SortedAtom *>(smem);
+    float4 *f4 = reinterpret_cast<float4 *>(smem + (size_t)A.cap * sizeof(SortedAtom));
+    unsigned short *surv = reinterpret_cast<unsigned short *>(f4 + A.cap);  // [SURV_CAP][TILE_THREADS], interleaved
+    int *cs = reinterpret_cast<int *>(surv + TILE_THREADS * SURV_CAP);      // [NPEN][PZ+1] staged offsets
+    int *gstart = cs + NPEN * CSW;                                           // [NPEN][PZ] global start per cell (-1 absent)
+    int *ptot = gstart + NCELL;                                              // [NPEN+1]
+    int *opref = ptot + NPEN + 1;                                            // [T*T+1]
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(
+        (reinterpret_cast<uintptr_t>(opref + T * T + 2) + 7) & ~static_cast<uintptr_t>(7));
+
+    const int tid = threadIdx.x;
+    const CellGrid &g = A.g;
+    int tl = blockIdx.x * A.tile_stride + A.tile_offset;
+    if (tl >= A.n_tiles) return;
+    const int tz = tl % A.tiles_z;
+    tl /= A.tiles_z;
+    const int ty = tl % A.tiles_y;
+    const int tx = tl / A.tiles_y;
+    const int u0x = A.p_lo + tx * T - 1, u0y = ty * T - 1, u0z = tz * TZ - 1;  // unwrapped coords of position 0
+    // owned positions inside the block: 1..amax x 1..bmax x 1..kmax (edge tiles are cut at the grid end;
+    // positions beyond it only serve as wrapped candidates)
+    const int amax = min(T, A.p_hi - (u0x + 1)), bmax = min(T, g.n[1] - (u0y + 1)), kmax = min(TZ, g.n[2] - (u0z + 1));
+
+    if (tid == 0) mbar_init(bar, 1);
+
+    // ---- A. population and global start of every cell of the block
+    // z slots are in MEMORY order: slot ks holds z position kk = PZ-1-ks (cells are stored in descending z)
+    for (int c = tid; c < NCELL; c += TILE_THREADS) {
+        const int ks = c % PZ, b = (c / PZ) % P, a = c / (PZ * P);
+        const int kk = PZ - 1 - ks;
+        int px;
+        const int ux = u0x + a;
+        if (A.wrap_x) px = (ux >= A.p_lo - 1 && ux <= A.p_hi) ? map_axis(ux, g.n[0]) : -1;
+        else px = (ux >= A.p_lo - 1 && ux <= A.p_hi && ux >= 0 && ux < g.nxl) ? ux : -1;
+        const int py = map_axis(u0y + b, g.n[1]);
+        const int pz = map_axis(u0z + kk, g.n[2]);
+        int beg = -1, cnt = 0;
+        if (px >= 0 && py >= 0 && pz >= 0) {
+            const int cell = (px * g.n[1] + py) * g.n[2] + (g.n[2] - 1 - pz);
+            beg = __ldg(A.cell_start + cell);
+            cnt = __ldg(A.cell_start + cell + 1) - beg;
+        }
+        gstart[c] = beg;
+        cs[(a * P + b) * CSW + ks + 1] = cnt;  // counts for now
+    }
+    __syncthreads();
+    for (int p = tid; p < NPEN; p += TILE_THREADS) {
+        int s = 0;
+        for (int kk = 0; kk < PZ; ++kk) s += cs[p * CSW + kk + 1];
+        ptot[p] = s;
+    }
+    __syncthreads();
+    warp0_exclusive_scan(ptot, NPEN);
+    __syncthreads();
+    for (int p = tid; p < NPEN; p += TILE_THREADS) {
+        int off = ptot[p];
+        cs[p * CSW] = off;
+        for (int kk = 0; kk < PZ; ++kk) {
+            off += cs[p * CSW + kk + 1];
+            cs[p * CSW + kk + 1] = off;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < T * T; i += TILE_THREADS) {
+        const int a = i / T + 1, b = i % T + 1;
+        const int p = a * P + b;
+        // owned z positions 1..kmax are memory slots PZ-1-kmax .. PZ-2
+        opref[i] = (a <= amax && b <= bmax) ? cs[p * CSW + PZ - 1] - cs[p * CSW + PZ - 1 - kmax] : 0;
+    }
+    __syncthreads();
+    warp0_exclusive_scan(opref, T * T);
+    __syncthreads();
+    const int n_staged = ptot[NPEN];
+    const int n_owned = opref[T * T];
+    if (n_owned == 0) return;
+    const bool staged_ok = n_staged <= A.cap;
+
+    const double rcsq = A.rcsq;
+    const DBox &box = A.box;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (staged_ok) {
+        // ---- B. stage the records: one bulk copy per run of consecutive global cells of a pencil
+        if (A.use_tma) {
+            if (tid == 0) mbar_expect_tx(bar, (unsigned)n_staged * (unsigned)sizeof(SortedAtom));
+            __syncthreads();
+            for (int p = tid; p < NPEN; p += TILE_THREADS) {
+                int kk = 0;
+                while (kk < PZ) {
+                    const int beg = gstart[p * PZ + kk];
+                    const int dst0 = cs[p * CSW + kk];
+                    int total = cs[p * CSW + kk + 1] - dst0;
+                    int k2 = kk + 1;
+                    if (beg >= 0) {
+                        while (k2 < PZ && gstart[p * PZ + k2] == beg + total) {
+                            total += cs[p * CSW + k2 + 1] - cs[p * CSW + k2];
+                            ++k2;
+                        }
+                        if (total > 0)
+                            bulk_g2s(raw + dst0, A.sorted + beg, (unsigned)total * (unsigned)sizeof(SortedAtom), bar);
+                    }
+                    kk = k2;
+                }
+            }
+            mbar_wait(bar, 0);
+        } else {
+            for (int c = warp; c < NCELL; c += TILE_THREADS / 32) {
+                const int beg = gstart[c];
+                if (beg < 0) continue;
+                const int p = c / PZ, kk = c % PZ;
+                const int dst0 = cs[p * CSW + kk];
+                const int chunks = (cs[p * CSW + kk + 1] - dst0) * 2;  // 16-byte chunks
+                const double2 *src = reinterpret_cast<const double2 *>(A.sorted + beg);
+                double2 *dst = reinterpret_cast<double2 *>(raw + dst0);
+                for (int t = lane; t < chunks; t += 32) dst[t] = __ldg(src + t);
+            }
+            __syncthreads();
+        }
+
+        // ---- C. fp32 positions relative to the tile centre (nearest periodic image) + cell tag.
+        // One warp per pencil, lanes over the pencil's atoms.
+        const double rcw = 1.0 / g.rc_inv;
+        const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0);  // global x cell of the first owned plane
+        const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
+                     ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
+        for (int p = warp; p < NPEN; p += TILE_THREADS / 32) {
+            const int *row = cs + p * CSW;
+            const int beg = row[0], end = row[PZ];
+            for (int s = beg + lane; s < end; s += 32) {
+                int kk = 0;
+#pragma unroll
+                for (int t = 1; t < PZ; ++t) kk += (row[t] <= s);
+                const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
+                const double zr = reinterpret_cast<const double *>(raw + s)[2];
+                double d0 = lo.x - ctr0, d1 = lo.y - ctr1, d2 = zr - ctr2;
+                if (box.pbc[0]) d0 -= box.h[0] * rint(d0 * box.hinv[0]);
+                if (box.pbc[1]) d1 -= box.h[4] * rint(d1 * box.hinv[4]);
+                if (box.pbc[2]) d2 -= box.h[8] * rint(d2 * box.hinv[8]);
+                f4[s] = make_float4((float)d0, (float)d1, (float)d2, __int_as_float(kk));
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- D. one thread per owned atom
+    unsigned short *my_surv = surv + tid;  // entry u at my_surv[u * TILE_THREADS]
+    int local_max = 0;
+#pragma unroll 1
+    for (int base = 0; base < n_owned; base += TILE_THREADS) {
+        const int t = base + tid;
+        const bool active = t < n_owned;
+        int pi = 0;
+        if (active) {
+            int lo = 0, hi = T * T;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (opref[mid] <= t) lo = mid;
+                else hi = mid;
+            }
+            pi = lo;
+        }
+        const int a = pi / T + 1, b = pi % T + 1;
+        const int p = a * P + b;
+        const int off = active ? t - opref[pi] : 0;
+
+        double xi = 0, yi = 0, zi = 0;
+        int my_idx = 0, my_cell = 0, cnt = 0;
+        int *vrow = nullptr;
+        double *drow = nullptr;
+        bool live = false;
+
+        if (!staged_ok) {
+            // ---- overflow tile (too many atoms for the shared buffers): walk global memory directly
+            if (active) {
+                const int sg = gstart[p * PZ + PZ - 1 - kmax] + off;  // owned cells of a pencil are one global run
+                load_rec(A.sorted + sg, xi, yi, zi, my_idx, my_cell);
+                live = my_idx < A.n_rows;
+                if (live) {
+                    if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
+                    vrow = A.verlet + (size_t)my_idx * A.M;
+                    drow = A.dist + (size_t)my_idx * A.M;
+                    int ic, jc, kc;
+                    cell_decode(g, my_cell, ic, jc, kc);
+#pragma unroll 1
+                    for (int di = -1; di <= 1; ++di)
+#pragma unroll 1
+                        for (int dj = -1; dj <= 1; ++dj)
+#pragma unroll 1
+                            for (int dk = -1; dk <= 1; ++dk) {
+                                const int c = cell_linear(g, wrap_cell(ic + di, g.n[0]), wrap_cell(jc + dj, g.n[1]),
+                                                          wrap_cell(kc + dk, g.n[2]));
+                                if (c < 0) continue;
+                                const int cb = __ldg(A.cell_start + c), ce = __ldg(A.cell_start + c + 1);
+                                for (int q = ce - 1; q >= cb; --q) {
+                                    if (q == sg) continue;
+                                    double xj, yj, zj;
+                                    int jdx, jcell;
+                                    load_rec(A.sorted + q, xj, yj, zj, jdx, jcell);
+                                    double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+                                    min_image(box, dx, dy, dz);
+                                    const double d2 = dx * dx + dy * dy + dz * dz;
+                                    if (d2 <= rcsq) {
+                                        if (!A.count_only && cnt < A.M) {
+                                            vrow[cnt] = jdx;
+                                            drow[cnt] = sqrt(d2);
+                                        }
+                                        ++cnt;
+                                    }
+                                }
+                            }
+                }
+            }
+        } else {
+            int s_i = 0, kk = 1, ns = 0;
+            float fx = 0, fy = 0, fz = 0;
+            if (active) {
+                s_i = cs[p * CSW + PZ - 1 - kmax] + off;
+                load_rec(raw + s_i, xi, yi, zi, my_idx, my_cell);
+                live = my_idx < A.n_rows;
+                if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
+                const float4 me = f4[s_i];
+                fx = me.x;
+                fy = me.y;
+                fz = me.z;
+                kk = __float_as_int(me.w);
+                vrow = A.verlet + (size_t)my_idx * A.M;
+                drow = A.dist + (size_t)my_idx * A.M;
+            }
+            const float rc2hi = A.rcsq_hi;
+
+            // phase 2: exact test of the queued survivors, in queue (= reference) order
+            auto drain = [&]() {
+                for (int u = 0; u < ns; ++u) {
+                    const int q = my_surv[u * TILE_THREADS];
+                    double xj, yj, zj;
+                    int jdx, jcell;
+                    load_rec(raw + q, xj, yj, zj, jdx, jcell);
+                    double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+                    min_image(box, dx, dy, dz);
+                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    if (d2 <= rcsq) {
+                        if (!A.count_only && cnt < A.M) {
+                            vrow[cnt] = jdx;
+                            drow[cnt] = sqrt(d2);
+                        }
+                        ++cnt;
+                    }
+                }
+                ns = 0;
+            };
+
+            // phase 1: the 9 pencils of the stencil in (x, y) order.  The three z cells of a pencil are
+            // one contiguous staged run stored in descending z, so a single backward walk yields
+            // cell z-1, z, z+1, each in descending original index: the reference's order.
+#pragma unroll 1
+            for (int pen = 0; pen < 9; ++pen) {
+                if (live) {
+                    const int da = pen / 3 - 1, db = pen % 3 - 1;
+                    const int *row = cs + ((a + da) * P + (b + db)) * CSW + kk;  // kk = my memory slot
+                    const int cb = row[-1], ce = row[2];
+                    for (int q = ce - 1; q >= cb; --q) {
+                        const float4 o = f4[q];
+                        const float dx = o.x - fx, dy = o.y - fy, dz = o.z - fz;
+                        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                        if (d2 <= rc2hi && q != s_i) {
+                            if (ns == SURV_CAP) drain();  // rare: a very crowded pencil
+                            my_surv[ns * TILE_THREADS] = (unsigned short)q;
+                            ++ns;
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, ns > SURV_RESERVE) || pen == 8) drain();
+            }
+        }
+
+        if (active && live) {
+            A.nn[my_idx] = cnt;
+            local_max = max(local_max, cnt);
+            if (!A.count_only) {
+                for (int u = cnt; u < A.M; ++u) {
+                    vrow[u] = -1;
+                    drow[u] = A.pad;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, d));
+    if (lane == 0 && local_max > 0) atomicMax(A.max_count, local_max);
+}
+
+template <int T, int TZ> size_t tile_smem_bytes(int cap)
+{
+    constexpr int P = T + 2, PZ = TZ + 2, NPEN = P * P, NCELL = NPEN * PZ;
+    return (size_t)cap * (sizeof(SortedAtom) + sizeof(float4)) + sizeof(unsigned short) * TILE_THREADS * SURV_CAP +
+           sizeof(int) * (NPEN * (PZ + 1) + NCELL + NPEN + 1 + T * T + 2) + 16;
+}
+
+template <int T, int TZ> void launch_T(const TileArgs &A, int nblocks, cudaStream_t st)
+{
+    const size_t smem = tile_smem_bytes<T, TZ>(A.cap);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_tiled<T, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    MDB_LAUNCH((k_neighbor_tiled<T, TZ>), nblocks, TILE_THREADS, smem, st, A);
+}
+
+}  // namespace
+
+// Returns false when the frame is not eligible (triclinic, or too few cells along a periodic axis for
+// an unambiguous nearest image); the caller then uses the direct kernel.
+bool tiled_neighbor_plan(const MdbSystem &s, int &T)
+{
+    if (s.box.triclinic) return false;
+    const CellGrid &g = s.grid;
+    const double rho = (double)s.N / ((double)g.nxl * g.n[1] * g.n[2]);  // atoms per cell
+    // tile shape code: T*16 + TZ.  ~240 owned atoms per 256-thread CTA, <= ~900 staged atoms
+    int code = rho <= 0.45 ? (8 * 16 + 8) : (rho <= 1.6 ? (4 * 16 + 8) : (rho <= 3.6 ? (4 * 16 + 6) : (rho <= 8.0 ? (2 * 16 + 4)
+                                                                                       : (rho <= 14.0 ? (2 * 16 + 2) : (1 * 16 + 1)))));
+    if (rho > 24.0) return false;  // a single cell may exceed the survivor queue: direct kernel
+    for (int d = 0; d < 3; ++d) {
+        if (!s.box.pbc[d]) continue;
+        for (;;) {  // shrink the tile until the nearest-image rule holds along every periodic axis
+            const int t = d == 2 ? (code & 15) : (code >> 4);
+            if (g.n[d] >= t + 6) break;
+            if (code == 1 * 16 + 1) return false;
+            code = code == 8 * 16 + 8 ? 4 * 16 + 8 : (code == 4 * 16 + 8 ? 4 * 16 + 6 : (code == 4 * 16 + 6 ? 2 * 16 + 4
+                   : (code == 2 * 16 + 4 ? 2 * 16 + 2 : 1 * 16 + 1)));
+        }
+    }
+    const char *env = getenv("MDB_NEIGHBOR");
+    if (env && !strcmp(env, "direct")) return false;
+    T = code;
+    return true;
+}
+
+// count_only + sample_stride > 1: estimate of the maximum count from every sample_stride-th tile.
+void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_only, int sample_stride)
+{
+    TileArgs A{};
+    const CellGrid &g = s.grid;
+    A.sorted = s.sorted.as<SortedAtom>();
+    A.cell_start = s.cell_start.as<int>();
+    A.box = s.box;
+    A.g = g;
+    A.rcsq = rc * rc;
+    A.pad = rc + 1.0;
+    A.rcsq_hi = (float)(rc * rc * (1.0 + 2e-4)) * (1.0f + 1e-6f);
+    A.M = M;
+    A.n_rows = s.n_rows;
+    A.nn = s.nn.ensure<int>(s.n_rows);
+    if (!count_only) {
+        A.verlet = s.verlet.ensure<int>((size_t)s.n_rows * M);
+        A.dist = s.dist.ensure<double>((size_t)s.n_rows * M);
+    }
+    int *counters = s.counters.ensure<int>(8);
+    A.max_count = counters + 6;
+    CUDA_TRY(cudaMemsetAsync(A.max_count, 0, sizeof(int), s.stream));
+    const bool slab = s.slab_nx > 0;
+    A.wrap_x = slab ? 0 : 1;
+    A.p_lo = slab ? 1 : 0;
+    A.p_hi = slab ? g.nxl - 1 : g.n[0];
+    const int TT = T >> 4, TZ = T & 15;
+    const int tiles_x = (A.p_hi - A.p_lo + TT - 1) / TT;
+    A.tiles_y = (g.n[1] + TT - 1) / TT;
+    A.tiles_z = (g.n[2] + TZ - 1) / TZ;
+    A.n_tiles = tiles_x * A.tiles_y * A.tiles_z;
+    A.tile_stride = sample_stride > 1 ? sample_stride : 1;
+    A.tile_offset = 0;
+    A.count_only = count_only ? 1 : 0;
+    const char *env = getenv("MDB_STAGE");
+    A.use_tma = !(env && !strcmp(env, "ldg"));
+    {   // staged-atom capacity from the mean cell population (tiles above it take the in-kernel direct path)
+        const double rho = (double)s.N / ((double)g.nxl * g.n[1] * g.n[2]);
+        int cap = (int)(rho * (TT + 2) * (TT + 2) * (TZ + 2) * 1.35) + 64;
+        cap = (cap + 31) / 32 * 32;
+        A.cap = cap < 256 ? 256 : (cap > 2048 ? 2048 : cap);
+    }
+    const int nblocks = (A.n_tiles + A.tile_stride - 1) / A.tile_stride;
+    if (nblocks <= 0) return;
+    switch (T) {
+        case 8 * 16 + 8: launch_T<8, 8>(A, nblocks, s.stream); break;
+        case 4 * 16 + 8: launch_T<4, 8>(A, nblocks, s.stream); break;
+        case 4 * 16 + 6: launch_T<4, 6>(A, nblocks, s.stream); break;
+        case 2 * 16 + 4: launch_T<2, 4>(A, nblocks, s.stream); break;
+        case 2 * 16 + 2: launch_T<2, 2>(A, nblocks, s.stream); break;
+        default: launch_T<1, 1>(A, nblocks, s.stream); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+int neighbor_tiled_max(MdbSystem &s)
+{
+    int v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, s.counters.as<int>() + 6, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return v;
+}

@@ -99,15 +99,14 @@ __global__ void __launch_bounds__(128) k_rdf_stream(const SortedAtom *__restrict
         const SortedAtom me = load_sorted2(sorted + s);
         double xi = me.x, yi = me.y, zi = me.z;
         if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
-        const int kc = me.cell % g.n[2];
-        const int jc = (me.cell / g.n[2]) % g.n[1];
-        const int ic = me.cell / (g.n[2] * g.n[1]);
+        int ic, jc, kc;
+        cell_decode(g, me.cell, ic, jc, kc);
         const int it = types[me.idx];
         for (int di = -1; di <= 1; ++di)
             for (int dj = -1; dj <= 1; ++dj)
                 for (int dk = -1; dk <= 1; ++dk) {
-                    const int c = (wrap_cell(ic + di, g.n[0]) * g.n[1] + wrap_cell(jc + dj, g.n[1])) * g.n[2] +
-                                  wrap_cell(kc + dk, g.n[2]);
+                    const int c = cell_linear(g, wrap_cell(ic + di, g.n[0]), wrap_cell(jc + dj, g.n[1]),
+                                              wrap_cell(kc + dk, g.n[2]));
                     const int b = __ldg(cell_start + c), e = __ldg(cell_start + c + 1);
                     for (int q = b; q < e; ++q) {
                         if (q == s) continue;
