@@ -210,6 +210,22 @@ MDB_HD void min_image(const DBox &b, double &xij, double &yij, double &zij)
     }
 }
 
+// Orthogonal-only forms (no triclinic branch in the instruction stream) for kernels that are
+// dispatched on orthogonal frames only.
+MDB_HD void min_image_ortho(const DBox &b, double &xij, double &yij, double &zij)
+{
+    if (b.pbc[0]) xij = ortho_image_axis(xij, b.img_t[0], b.h[0]);
+    if (b.pbc[1]) yij = ortho_image_axis(yij, b.img_t[1], b.h[4]);
+    if (b.pbc[2]) zij = ortho_image_axis(zij, b.img_t[2], b.h[8]);
+}
+
+MDB_HD void wrap_ortho(const DBox &b, double &x, double &y, double &z)
+{
+    if (b.pbc[0]) x = ortho_wrap_axis(x, b.origin[0], b.wrap_t[0], b.h[0]);
+    if (b.pbc[1]) y = ortho_wrap_axis(y, b.origin[1], b.wrap_t[1], b.h[4]);
+    if (b.pbc[2]) z = ortho_wrap_axis(z, b.origin[2], b.wrap_t[2], b.h[8]);
+}
+
 // Wrap into the primary cell, src/box.h:131-176.
 MDB_HD void wrap_into_box(const DBox &b, double &x, double &y, double &z)
 {

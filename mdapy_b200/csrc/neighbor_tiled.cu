@@ -78,6 +78,40 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  : "memory");
 }
 
+__device__ __forceinline__ float4 lds_f4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned addr, unsigned v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u16(unsigned addr)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void lds_rec(unsigned addr, double &x, double &y, double &z, int &idx)
+{
+    double w;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(z), "=d"(w) : "r"(addr + 16));
+    idx = __double2loint(w);
+}
+
+// Exact min-image for a pair that already passed the fp32 pre-filter on a frame with >= 7 cells per
+// periodic axis: the nearest-image displacement is < 0.15 L, so n = floor(x/L + 0.5) of the reference
+// (src/box.h:119-124) is simply the integer nearest to x/L -- far from every rounding boundary, hence
+// rint(x * (1/L)) yields the same integer -- and x - L*n is evaluated with the reference's two roundings.
+__device__ __forceinline__ double near_image(double x, double L, double invL)
+{
+    const double n = rint(x * invL);
+    return x - L * n;
+}
+
 __device__ __forceinline__ void load_rec(const SortedAtom *p, double &x, double &y, double &z, int &idx, int &cell)
 {
     const double2 *q = reinterpret_cast<const double2 *>(p);
@@ -120,8 +154,56 @@ __device__ __forceinline__ int map_axis(int u, int n)
     return -1;
 }
 
-template <int T, int TZ>
-__global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const TileArgs A)
+// Overflow tile (more atoms than the shared buffers hold): the owned atom at sorted position sg walks
+// global memory directly, like k_neighbor_direct.  Out of line: it is cold and large.
+template <bool COUNT_ONLY>
+__device__ __noinline__ int direct_atom(const TileArgs &A, int sg)
+{
+    const CellGrid &g = A.g;
+    const DBox &box = A.box;
+    double xi, yi, zi;
+    int my_idx, my_cell, cnt = 0;
+    load_rec(A.sorted + sg, xi, yi, zi, my_idx, my_cell);
+    if (my_idx >= A.n_rows) return -1;
+    wrap_ortho(box, xi, yi, zi);
+    int *vrow = A.verlet + (size_t)my_idx * A.M;
+    double *drow = A.dist + (size_t)my_idx * A.M;
+    int ic, jc, kc;
+    cell_decode(g, my_cell, ic, jc, kc);
+#pragma unroll 1
+    for (int st = 0; st < 27; ++st) {
+        const int di = st / 9 - 1, dj = (st / 3) % 3 - 1, dk = st % 3 - 1;
+        const int c = cell_linear(g, wrap_cell(ic + di, g.n[0]), wrap_cell(jc + dj, g.n[1]), wrap_cell(kc + dk, g.n[2]));
+        if (c < 0) continue;
+        const int cb = __ldg(A.cell_start + c), ce = __ldg(A.cell_start + c + 1);
+        for (int q = ce - 1; q >= cb; --q) {
+            if (q == sg) continue;
+            double xj, yj, zj;
+            int jdx, jcell;
+            load_rec(A.sorted + q, xj, yj, zj, jdx, jcell);
+            double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+            min_image_ortho(box, dx, dy, dz);
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 <= A.rcsq) {
+                if (!COUNT_ONLY && cnt < A.M) {
+                    vrow[cnt] = jdx;
+                    drow[cnt] = sqrt(d2);
+                }
+                ++cnt;
+            }
+        }
+    }
+    A.nn[my_idx] = cnt;
+    if (!COUNT_ONLY)
+        for (int u = cnt; u < A.M; ++u) {
+            vrow[u] = -1;
+            drow[u] = A.pad;
+        }
+    return cnt;
+}
+
+template <int T, int TZ, bool COUNT_ONLY>
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid_constant__ TileArgs A)
 {
     constexpr int P = T + 2;     // block edge in x, y
     constexpr int PZ = TZ + 2;   // block edge in z (the contiguous direction of the sorted copy)
@@ -210,6 +292,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const TileAr
     const double rcsq = A.rcsq;
     const DBox &box = A.box;
     const int warp = tid >> 5, lane = tid & 31;
+    (void)box;
 
     if (staged_ok) {
         // ---- B. stage the records: one bulk copy per run of consecutive global cells of a pencil
@@ -275,110 +358,89 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const TileAr
     }
 
     // ---- D. one thread per owned atom
-    unsigned short *my_surv = surv + tid;  // entry u at my_surv[u * TILE_THREADS]
     int local_max = 0;
+    if (!staged_ok) {
 #pragma unroll 1
-    for (int base = 0; base < n_owned; base += TILE_THREADS) {
-        const int t = base + tid;
-        const bool active = t < n_owned;
-        int pi = 0;
-        if (active) {
+        for (int t = tid; t < n_owned; t += TILE_THREADS) {
             int lo = 0, hi = T * T;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
                 if (opref[mid] <= t) lo = mid;
                 else hi = mid;
             }
-            pi = lo;
+            const int p = (lo / T + 1) * P + (lo % T + 1);
+            const int sg = gstart[p * PZ + PZ - 1 - kmax] + (t - opref[lo]);  // owned cells of a pencil: one global run
+            local_max = max(local_max, direct_atom<COUNT_ONLY>(A, sg));
         }
-        const int a = pi / T + 1, b = pi % T + 1;
-        const int p = a * P + b;
-        const int off = active ? t - opref[pi] : 0;
-
-        double xi = 0, yi = 0, zi = 0;
-        int my_idx = 0, my_cell = 0, cnt = 0;
-        int *vrow = nullptr;
-        double *drow = nullptr;
-        bool live = false;
-
-        if (!staged_ok) {
-            // ---- overflow tile (too many atoms for the shared buffers): walk global memory directly
+    } else {
+        const unsigned f4_base = smem_u32(f4), raw_base = smem_u32(raw);
+        const unsigned q_base = smem_u32(surv) + 2u * tid;  // entry u at q_base + u * 2 * TILE_THREADS
+        const float rc2hi = A.rcsq_hi;
+        const double Lx = box.h[0], Ly = box.h[4], Lz = box.h[8];
+        const double iLx = box.hinv[0], iLy = box.hinv[4], iLz = box.hinv[8];
+        const bool px = box.pbc[0] != 0, py = box.pbc[1] != 0, pz = box.pbc[2] != 0;
+#pragma unroll 1
+        for (int base = 0; base < n_owned; base += TILE_THREADS) {
+            const int t = base + tid;
+            const bool active = t < n_owned;
+            int pi = 0;
             if (active) {
-                const int sg = gstart[p * PZ + PZ - 1 - kmax] + off;  // owned cells of a pencil are one global run
-                load_rec(A.sorted + sg, xi, yi, zi, my_idx, my_cell);
-                live = my_idx < A.n_rows;
-                if (live) {
-                    if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
-                    vrow = A.verlet + (size_t)my_idx * A.M;
-                    drow = A.dist + (size_t)my_idx * A.M;
-                    int ic, jc, kc;
-                    cell_decode(g, my_cell, ic, jc, kc);
-#pragma unroll 1
-                    for (int di = -1; di <= 1; ++di)
-#pragma unroll 1
-                        for (int dj = -1; dj <= 1; ++dj)
-#pragma unroll 1
-                            for (int dk = -1; dk <= 1; ++dk) {
-                                const int c = cell_linear(g, wrap_cell(ic + di, g.n[0]), wrap_cell(jc + dj, g.n[1]),
-                                                          wrap_cell(kc + dk, g.n[2]));
-                                if (c < 0) continue;
-                                const int cb = __ldg(A.cell_start + c), ce = __ldg(A.cell_start + c + 1);
-                                for (int q = ce - 1; q >= cb; --q) {
-                                    if (q == sg) continue;
-                                    double xj, yj, zj;
-                                    int jdx, jcell;
-                                    load_rec(A.sorted + q, xj, yj, zj, jdx, jcell);
-                                    double dx = xj - xi, dy = yj - yi, dz = zj - zi;
-                                    min_image(box, dx, dy, dz);
-                                    const double d2 = dx * dx + dy * dy + dz * dz;
-                                    if (d2 <= rcsq) {
-                                        if (!A.count_only && cnt < A.M) {
-                                            vrow[cnt] = jdx;
-                                            drow[cnt] = sqrt(d2);
-                                        }
-                                        ++cnt;
-                                    }
-                                }
-                            }
+                int lo = 0, hi = T * T;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (opref[mid] <= t) lo = mid;
+                    else hi = mid;
                 }
+                pi = lo;
             }
-        } else {
-            int s_i = 0, kk = 1, ns = 0;
+            const int a = pi / T + 1, b = pi % T + 1;
+            const int p = a * P + b;
+            double xi = 0, yi = 0, zi = 0;
+            int my_idx = 0, my_cell = 0, cnt = 0, s_i = 0, kk = 1;
+            int *vrow = nullptr;
+            double *drow = nullptr;
             float fx = 0, fy = 0, fz = 0;
+            bool live = false;
             if (active) {
-                s_i = cs[p * CSW + PZ - 1 - kmax] + off;
+                s_i = cs[p * CSW + PZ - 1 - kmax] + (t - opref[pi]);
                 load_rec(raw + s_i, xi, yi, zi, my_idx, my_cell);
                 live = my_idx < A.n_rows;
-                if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
+                wrap_ortho(box, xi, yi, zi);
                 const float4 me = f4[s_i];
                 fx = me.x;
                 fy = me.y;
                 fz = me.z;
-                kk = __float_as_int(me.w);
+                kk = __float_as_int(me.w);  // my memory slot along z
                 vrow = A.verlet + (size_t)my_idx * A.M;
                 drow = A.dist + (size_t)my_idx * A.M;
             }
-            const float rc2hi = A.rcsq_hi;
+            unsigned q_top = q_base;                            // queue write pointer
+            const unsigned q_full = q_base + 2u * TILE_THREADS * SURV_CAP;
+            const unsigned q_warn = q_base + 2u * TILE_THREADS * SURV_RESERVE;
+            const unsigned self_addr = f4_base + 16u * (unsigned)s_i;
 
             // phase 2: exact test of the queued survivors, in queue (= reference) order
             auto drain = [&]() {
-                for (int u = 0; u < ns; ++u) {
-                    const int q = my_surv[u * TILE_THREADS];
+#pragma unroll 1
+                for (unsigned qa = q_base; qa < q_top; qa += 2u * TILE_THREADS) {
+                    const unsigned q = lds_u16(qa);
                     double xj, yj, zj;
-                    int jdx, jcell;
-                    load_rec(raw + q, xj, yj, zj, jdx, jcell);
+                    int jdx;
+                    lds_rec(raw_base + 32u * q, xj, yj, zj, jdx);
                     double dx = xj - xi, dy = yj - yi, dz = zj - zi;
-                    min_image(box, dx, dy, dz);
+                    if (px) dx = near_image(dx, Lx, iLx);
+                    if (py) dy = near_image(dy, Ly, iLy);
+                    if (pz) dz = near_image(dz, Lz, iLz);
                     const double d2 = dx * dx + dy * dy + dz * dz;
                     if (d2 <= rcsq) {
-                        if (!A.count_only && cnt < A.M) {
+                        if (!COUNT_ONLY && cnt < A.M) {
                             vrow[cnt] = jdx;
                             drow[cnt] = sqrt(d2);
                         }
                         ++cnt;
                     }
                 }
-                ns = 0;
+                q_top = q_base;
             };
 
             // phase 1: the 9 pencils of the stencil in (x, y) order.  The three z cells of a pencil are
@@ -388,30 +450,37 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const TileAr
             for (int pen = 0; pen < 9; ++pen) {
                 if (live) {
                     const int da = pen / 3 - 1, db = pen % 3 - 1;
-                    const int *row = cs + ((a + da) * P + (b + db)) * CSW + kk;  // kk = my memory slot
-                    const int cb = row[-1], ce = row[2];
-                    for (int q = ce - 1; q >= cb; --q) {
-                        const float4 o = f4[q];
-                        const float dx = o.x - fx, dy = o.y - fy, dz = o.z - fz;
-                        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-                        if (d2 <= rc2hi && q != s_i) {
-                            if (ns == SURV_CAP) drain();  // rare: a very crowded pencil
-                            my_surv[ns * TILE_THREADS] = (unsigned short)q;
-                            ++ns;
+                    const int *row = cs + ((a + da) * P + (b + db)) * CSW + kk;
+                    const unsigned abeg = f4_base + 16u * (unsigned)row[-1];
+                    unsigned aq = f4_base + 16u * (unsigned)row[2];  // one past the last candidate
+#pragma unroll 1
+                    while (aq > abeg) {
+                        // scan at most as many candidates as the queue has room for, then (rarely) drain
+                        const unsigned room = (q_full - q_top) / (2u * TILE_THREADS);
+                        const unsigned astop = (aq - abeg > 16u * room) ? aq - 16u * room : abeg;
+                        while (aq > astop) {
+                            aq -= 16u;
+                            const float4 o = lds_f4(aq);
+                            const float dx = o.x - fx, dy = o.y - fy, dz = o.z - fz;
+                            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                            if (d2 <= rc2hi && aq != self_addr) {
+                                sts_u16(q_top, (aq - f4_base) >> 4);
+                                q_top += 2u * TILE_THREADS;
+                            }
                         }
+                        if (aq > abeg) drain();
                     }
                 }
-                if (__any_sync(0xffffffffu, ns > SURV_RESERVE) || pen == 8) drain();
+                if (__any_sync(0xffffffffu, q_top > q_warn) || pen == 8) drain();
             }
-        }
-
-        if (active && live) {
-            A.nn[my_idx] = cnt;
-            local_max = max(local_max, cnt);
-            if (!A.count_only) {
-                for (int u = cnt; u < A.M; ++u) {
-                    vrow[u] = -1;
-                    drow[u] = A.pad;
+            if (active && live) {
+                A.nn[my_idx] = cnt;
+                local_max = max(local_max, cnt);
+                if (!COUNT_ONLY) {
+                    for (int u = cnt; u < A.M; ++u) {
+                        vrow[u] = -1;
+                        drow[u] = A.pad;
+                    }
                 }
             }
         }
@@ -433,10 +502,14 @@ template <int T, int TZ> void launch_T(const TileArgs &A, int nblocks, cudaStrea
     const size_t smem = tile_smem_bytes<T, TZ>(A.cap);
     static bool configured = false;
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_tiled<T, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_tiled<T, TZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_tiled<T, TZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
         configured = true;
     }
-    MDB_LAUNCH((k_neighbor_tiled<T, TZ>), nblocks, TILE_THREADS, smem, st, A);
+    if (A.count_only) MDB_LAUNCH((k_neighbor_tiled<T, TZ, true>), nblocks, TILE_THREADS, smem, st, A);
+    else MDB_LAUNCH((k_neighbor_tiled<T, TZ, false>), nblocks, TILE_THREADS, smem, st, A);
 }
 
 }  // namespace
