@@ -297,14 +297,17 @@ def run_b200(args):
         e2e_step()
         torch.cuda.synchronize()
         reps = max(1, min(args.steps, 3))
+        per_rep = []
         t0 = time.perf_counter()
         for _ in range(reps):
+            t1 = time.perf_counter()
             cna = e2e_step()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            per_rep.append((time.perf_counter() - t1) * 1e3)
         dt = (time.perf_counter() - t0) / reps
         assert int(np.asarray(cna).min()) == 1 and int(np.asarray(cna).max()) == 1
         e2e = {"value": N_total / dt, "unit": "atoms/s", "h2d_bytes_per_step": 24 * N_total,
-               "d2h_bytes_per_step": 4 * N_total, "ms_per_step": dt * 1e3,
+               "d2h_bytes_per_step": 4 * N_total, "ms_per_step": dt * 1e3, "ms_each": [round(v, 2) for v in per_rep],
                "api": "System(data, box).cal_common_neighbor_analysis(rc) -> data['cna'] (host)"}
     else:
         # every rank uploads its own slab from pinned host memory and reads its labels back

@@ -61,7 +61,7 @@ class CommonNeighborAnalysis:
             assert self.rc is None or self.neighbor_number is not None
             dev = DeviceSystem(self._device)
             dev.set_atoms(data["x"], data["y"], data["z"], box.box, box.origin, box.boundary)
-            dev.put_neighbor(self.verlet_list, None, self.neighbor_number,
-                             rc=self.rc if self.rc is not None else -1.0,
+            # a caller-supplied list carries no distance bound the fast bond test could rely on: rc=-1
+            dev.put_neighbor(self.verlet_list, None, self.neighbor_number, rc=-1.0,
                              kind=LIST_CUTOFF if self.rc is not None else LIST_KNN)
         self.pattern = dev.acna() if self.rc is None else dev.fcna(self.rc)

@@ -637,7 +637,8 @@ int mdb_fcna(const double *x, const double *y, const double *z, int N, const dou
     ScopedSystem s;
     set_box(*s, box9, origin3, boundary3);
     upload_atoms(*s, x, y, z, N);
-    int rcode = mdb_system_put_neighbor(s.s, verlet, nullptr, nn, M, rc, LIST_CUTOFF);
+    // a caller-supplied list carries no trustworthy distance bound (rc = -1): exact bond tests
+    int rcode = mdb_system_put_neighbor(s.s, verlet, nullptr, nn, M, -1.0, LIST_CUTOFF);
     if (rcode != MDB_OK) return rcode;
     rcode = mdb_system_fcna(s.s, rc, pattern);
     if (rcode != MDB_OK) return rcode;

@@ -156,11 +156,145 @@ __global__ void __launch_bounds__(128) k_acna(const double *__restrict__ x, cons
     if (p) pattern[i] = p;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast fixed-cutoff CNA for orthogonal frames whose periodic edges exceed 4.2 * rc.
+// Neighbour vectors r_a = min_image(x_a - x_i) are formed exactly in f64, rounded to fp32, and the
+// 66 / 91 bond tests run on |r_a - r_b|^2 in fp32.  With every periodic edge > 4 rc the difference of
+// two nearest-image vectors IS the minimum image of x_b - x_a, so the fp32 value only differs from the
+// reference's f64 d2 by rounding (< 1e-5 rc^2); a pair whose fp32 d2 lies within 1e-4 rc^2 of the
+// threshold is re-evaluated with the reference's exact expression on raw coordinates
+// (cna.cpp:149-161), so the bond matrix -- and therefore every label -- is identical.
+// Bond rows live in shared memory (interleaved per thread) because the signature code indexes them
+// dynamically.
+constexpr int CNA_THREADS = 128;
+
+__device__ __forceinline__ CnaCounts cna_signatures_smem(const unsigned short *nb, int nn)
+{
+    // nb[v * CNA_THREADS]: bond row of neighbour v
+    CnaCounts c{0, 0, 0, 0, 0};
+    for (int ni = 0; ni < nn; ++ni) {
+        const unsigned common = nb[ni * CNA_THREADS];
+        const int ncommon = __popc(common);
+        if (ncommon < 4 || ncommon > 6) continue;  // no signature of interest
+        int twice_bonds = 0;
+        for (unsigned m = common; m; m &= m - 1) twice_bonds += __popc(nb[(__ffs(m) - 1) * CNA_THREADS] & common);
+        const int nbonds = twice_bonds >> 1;
+        if (!((ncommon == 4 && (nbonds == 2 || nbonds == 4)) || (ncommon == 5 && nbonds == 5) ||
+              (ncommon == 6 && nbonds == 6)))
+            continue;
+        int longest = 0;
+        unsigned remaining = common;
+        while (remaining) {
+            const int v0 = __ffs(remaining) - 1;
+            unsigned comp = 1u << v0, frontier = comp;
+            while (frontier) {
+                unsigned next = 0;
+                for (unsigned m = frontier; m; m &= m - 1) next |= nb[(__ffs(m) - 1) * CNA_THREADS] & common;
+                next &= ~comp;
+                comp |= next;
+                frontier = next;
+            }
+            int e2 = 0;
+            for (unsigned m = comp; m; m &= m - 1) e2 += __popc(nb[(__ffs(m) - 1) * CNA_THREADS] & common);
+            longest = max(longest, e2 >> 1);
+            remaining &= ~comp;
+        }
+        if (ncommon == 4 && nbonds == 2) {
+            if (longest == 1) ++c.n421;
+            else if (longest == 2) ++c.n422;
+        } else if (ncommon == 5 && nbonds == 5 && longest == 5) ++c.n555;
+        else if (ncommon == 4 && nbonds == 4 && longest == 4) ++c.n444;
+        else if (ncommon == 6 && nbonds == 6 && longest == 6) ++c.n666;
+    }
+    return c;
+}
+
+template <int NN>
+__device__ __forceinline__ int fcna_fast_body(const double *__restrict__ x, const double *__restrict__ y,
+                                              const double *__restrict__ z, const DBox &box, int i,
+                                              const int *__restrict__ row, double cutsq, float cut_lo, float cut_hi,
+                                              unsigned short *nb)
+{
+    const double xi = x[i], yi = y[i], zi = z[i];
+    float rx[NN], ry[NN], rz[NN];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+        const int j = __ldg(row + a);
+        double dx = __ldg(x + j) - xi, dy = __ldg(y + j) - yi, dz = __ldg(z + j) - zi;
+        min_image_ortho(box, dx, dy, dz);
+        rx[a] = (float)dx;
+        ry[a] = (float)dy;
+        rz[a] = (float)dz;
+    }
+    unsigned rows[NN];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) rows[a] = 0;
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+#pragma unroll
+        for (int b = a + 1; b < NN; ++b) {
+            const float dx = rx[b] - rx[a], dy = ry[b] - ry[a], dz = rz[b] - rz[a];
+            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+            bool bonded = d2 < cut_lo;
+            if (!bonded && d2 <= cut_hi) {  // ambiguous in fp32: the reference's exact expression decides
+                const int ja = __ldg(row + a), jb = __ldg(row + b);
+                bonded = pbc_dist_sq(box, x[ja], y[ja], z[ja], x[jb], y[jb], z[jb]) <= cutsq;
+            }
+            if (bonded) {
+                rows[a] |= 1u << b;
+                rows[b] |= 1u << a;
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < NN; ++a) nb[a * CNA_THREADS] = (unsigned short)rows[a];
+    const CnaCounts c = cna_signatures_smem(nb, NN);
+    if (c.n421 == 12) return 1;
+    if (c.n421 == 6 && c.n422 == 6) return 2;
+    if (c.n555 == 12) return 4;
+    if (c.n666 == 8 && c.n444 == 6) return 3;
+    return 0;
+}
+
+__global__ void __launch_bounds__(CNA_THREADS) k_fcna_fast(const double *__restrict__ x, const double *__restrict__ y,
+                                                           const double *__restrict__ z, int N, DBox box,
+                                                           const int *__restrict__ verlet,
+                                                           const int *__restrict__ nnum, int M, double cutsq,
+                                                           float cut_lo, float cut_hi, int *__restrict__ pattern)
+{
+    __shared__ unsigned short nb_s[14 * CNA_THREADS];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int nn = nnum[i];
+    if ((nn != 12 && nn != 14) || nn > M) return;
+    const int *row = verlet + (size_t)i * M;
+    unsigned short *nb = nb_s + threadIdx.x;
+    const int p = nn == 12 ? fcna_fast_body<12>(x, y, z, box, i, row, cutsq, cut_lo, cut_hi, nb)
+                           : fcna_fast_body<14>(x, y, z, box, i, row, cutsq, cut_lo, cut_hi, nb);
+    if (p) pattern[i] = p;
+}
+
 }  // namespace
 
 void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern)
 {
     const int N = s.n_rows;
+    // fast path: orthogonal frame, the list's own cut-off bounds the neighbour distances (cut-off list
+    // built with list_rc >= every stored distance) and every periodic edge exceeds 4.2 * that bound
+    bool fast = !s.box.triclinic && s.list_kind == LIST_CUTOFF && s.list_rc > 0;
+    const double rb = s.list_rc > rc ? s.list_rc : rc;
+    for (int d = 0; d < 3 && fast; ++d)
+        if (s.box.pbc[d] && !(s.box.h[4 * d] > 4.2 * rb)) fast = false;
+    const char *env = getenv("MDB_CNA");
+    if (env && !strcmp(env, "exact")) fast = false;
+    if (fast) {
+        const double c2 = rc * rc;
+        MDB_LAUNCH(k_fcna_fast, (N + CNA_THREADS - 1) / CNA_THREADS, CNA_THREADS, 0, s.stream, s.x, s.y, s.z, N, s.box,
+                   verlet, nn, M, c2, (float)(c2 * (1.0 - 1e-4)), (float)(c2 * (1.0 + 1e-4)), pattern);
+        CUDA_TRY(cudaGetLastError());
+        return;
+    }
     MDB_LAUNCH(k_fcna, (N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, nn, M, rc * rc, pattern);
     CUDA_TRY(cudaGetLastError());
 }
