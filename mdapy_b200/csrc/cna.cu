@@ -169,25 +169,47 @@ __global__ void __launch_bounds__(128) k_acna(const double *__restrict__ x, cons
 // dynamically.
 constexpr int CNA_THREADS = 128;
 
+// Signature counts from bond rows in shared memory (nb[v * CNA_THREADS] = row of neighbour v).
+// The reference's "longest chain" (cna.cpp:97-147) is the bond count of the largest connected
+// component of the common-neighbour bond graph.  For the signatures that are counted it reduces to:
+//   (4 common, 2 bonds): chain 2 iff some common neighbour has degree 2, else 1 (two disjoint bonds);
+//   (5,5) and (4,4):     the bonds are necessarily connected (two bond-carrying components on 5 / 4
+//                        vertices hold at most 4 / 2 bonds), so the chain is 5 / 4;
+//   (6,6):               connected unless the bonds split 3+3, 4+2 or 5+1: one flood decides.
 __device__ __forceinline__ CnaCounts cna_signatures_smem(const unsigned short *nb, int nn)
 {
-    // nb[v * CNA_THREADS]: bond row of neighbour v
     CnaCounts c{0, 0, 0, 0, 0};
+#pragma unroll 1
     for (int ni = 0; ni < nn; ++ni) {
         const unsigned common = nb[ni * CNA_THREADS];
         const int ncommon = __popc(common);
-        if (ncommon < 4 || ncommon > 6) continue;  // no signature of interest
-        int twice_bonds = 0;
-        for (unsigned m = common; m; m &= m - 1) twice_bonds += __popc(nb[(__ffs(m) - 1) * CNA_THREADS] & common);
-        const int nbonds = twice_bonds >> 1;
-        if (!((ncommon == 4 && (nbonds == 2 || nbonds == 4)) || (ncommon == 5 && nbonds == 5) ||
-              (ncommon == 6 && nbonds == 6)))
-            continue;
-        int longest = 0;
-        unsigned remaining = common;
-        while (remaining) {
-            const int v0 = __ffs(remaining) - 1;
-            unsigned comp = 1u << v0, frontier = comp;
+        if (ncommon < 4 || ncommon > 6) continue;
+        int twice = 0, maxdeg = 0;
+        unsigned first_row = 0;
+        int first_v = -1;
+        for (unsigned m = common; m; m &= m - 1) {
+            const int v = __ffs(m) - 1;
+            const unsigned r = nb[v * CNA_THREADS] & common;
+            const int d = __popc(r);
+            twice += d;
+            maxdeg = max(maxdeg, d);
+            if (first_v < 0 && d > 0) {
+                first_v = v;
+                first_row = r;
+            }
+        }
+        const int nbonds = twice >> 1;
+        if (ncommon == 4) {
+            if (nbonds == 2) {
+                if (maxdeg == 2) ++c.n422;
+                else ++c.n421;
+            } else if (nbonds == 4)
+                ++c.n444;
+        } else if (ncommon == 5) {
+            if (nbonds == 5) ++c.n555;
+        } else if (nbonds == 6) {
+            // flood the component of the first bonded vertex; all 6 bonds must lie inside it
+            unsigned comp = (1u << first_v) | first_row, frontier = first_row;
             while (frontier) {
                 unsigned next = 0;
                 for (unsigned m = frontier; m; m &= m - 1) next |= nb[(__ffs(m) - 1) * CNA_THREADS] & common;
@@ -197,17 +219,39 @@ __device__ __forceinline__ CnaCounts cna_signatures_smem(const unsigned short *n
             }
             int e2 = 0;
             for (unsigned m = comp; m; m &= m - 1) e2 += __popc(nb[(__ffs(m) - 1) * CNA_THREADS] & common);
-            longest = max(longest, e2 >> 1);
-            remaining &= ~comp;
+            if (e2 == 12) ++c.n666;
         }
-        if (ncommon == 4 && nbonds == 2) {
-            if (longest == 1) ++c.n421;
-            else if (longest == 2) ++c.n422;
-        } else if (ncommon == 5 && nbonds == 5 && longest == 5) ++c.n555;
-        else if (ncommon == 4 && nbonds == 4 && longest == 4) ++c.n444;
-        else if (ncommon == 6 && nbonds == 6 && longest == 6) ++c.n666;
     }
     return c;
+}
+
+__device__ __forceinline__ int cna_label(const CnaCounts &c)
+{
+    if (c.n421 == 12) return 1;
+    if (c.n421 == 6 && c.n422 == 6) return 2;
+    if (c.n555 == 12) return 4;
+    if (c.n666 == 8 && c.n444 == 6) return 3;
+    return 0;
+}
+
+// slow path of the fast kernel: every bond from the reference's exact expression (cna.cpp:149-161)
+__device__ __noinline__ int fcna_exact_atom(const double *__restrict__ x, const double *__restrict__ y,
+                                            const double *__restrict__ z, const DBox &box,
+                                            const int *__restrict__ row, int nn, double cutsq, unsigned short *nb)
+{
+    for (int a = 0; a < nn; ++a) nb[a * CNA_THREADS] = 0;
+    for (int a = 0; a < nn; ++a) {
+        const int ja = row[a];
+        const double xa = x[ja], ya = y[ja], za = z[ja];
+        for (int b = a + 1; b < nn; ++b) {
+            const int jb = row[b];
+            if (pbc_dist_sq(box, xa, ya, za, x[jb], y[jb], z[jb]) <= cutsq) {
+                nb[a * CNA_THREADS] |= (unsigned short)(1u << b);
+                nb[b * CNA_THREADS] |= (unsigned short)(1u << a);
+            }
+        }
+    }
+    return cna_label(cna_signatures_smem(nb, nn));
 }
 
 template <int NN>
@@ -217,12 +261,18 @@ __device__ __forceinline__ int fcna_fast_body(const double *__restrict__ x, cons
                                               unsigned short *nb)
 {
     const double xi = x[i], yi = y[i], zi = z[i];
+    const double Lx = box.h[0], Ly = box.h[4], Lz = box.h[8];
+    const double iLx = box.hinv[0], iLy = box.hinv[4], iLz = box.hinv[8];
     float rx[NN], ry[NN], rz[NN];
 #pragma unroll
     for (int a = 0; a < NN; ++a) {
         const int j = __ldg(row + a);
         double dx = __ldg(x + j) - xi, dy = __ldg(y + j) - yi, dz = __ldg(z + j) - zi;
-        min_image_ortho(box, dx, dy, dz);
+        // listed neighbours lie within rc << L/2 of atom i: nearest integer of d/L is the image count
+        // (only fp32 bond screening uses these vectors; anything near the threshold is redone exactly)
+        if (box.pbc[0]) dx -= Lx * rint(dx * iLx);
+        if (box.pbc[1]) dy -= Ly * rint(dy * iLy);
+        if (box.pbc[2]) dz -= Lz * rint(dz * iLz);
         rx[a] = (float)dx;
         ry[a] = (float)dy;
         rz[a] = (float)dz;
@@ -230,35 +280,29 @@ __device__ __forceinline__ int fcna_fast_body(const double *__restrict__ x, cons
     unsigned rows[NN];
 #pragma unroll
     for (int a = 0; a < NN; ++a) rows[a] = 0;
+    bool ambiguous = false;
 #pragma unroll
     for (int a = 0; a < NN; ++a) {
 #pragma unroll
         for (int b = a + 1; b < NN; ++b) {
             const float dx = rx[b] - rx[a], dy = ry[b] - ry[a], dz = rz[b] - rz[a];
             const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-            bool bonded = d2 < cut_lo;
-            if (!bonded && d2 <= cut_hi) {  // ambiguous in fp32: the reference's exact expression decides
-                const int ja = __ldg(row + a), jb = __ldg(row + b);
-                bonded = pbc_dist_sq(box, x[ja], y[ja], z[ja], x[jb], y[jb], z[jb]) <= cutsq;
-            }
-            if (bonded) {
+            if (d2 < cut_lo) {
                 rows[a] |= 1u << b;
                 rows[b] |= 1u << a;
-            }
+            } else if (d2 <= cut_hi)
+                ambiguous = true;
         }
     }
+    if (ambiguous) return fcna_exact_atom(x, y, z, box, row, NN, cutsq, nb);
 #pragma unroll
     for (int a = 0; a < NN; ++a) nb[a * CNA_THREADS] = (unsigned short)rows[a];
-    const CnaCounts c = cna_signatures_smem(nb, NN);
-    if (c.n421 == 12) return 1;
-    if (c.n421 == 6 && c.n422 == 6) return 2;
-    if (c.n555 == 12) return 4;
-    if (c.n666 == 8 && c.n444 == 6) return 3;
-    return 0;
+    return cna_label(cna_signatures_smem(nb, NN));
 }
 
 __global__ void __launch_bounds__(CNA_THREADS) k_fcna_fast(const double *__restrict__ x, const double *__restrict__ y,
-                                                           const double *__restrict__ z, int N, DBox box,
+                                                           const double *__restrict__ z, int N,
+                                                           const __grid_constant__ DBox box,
                                                            const int *__restrict__ verlet,
                                                            const int *__restrict__ nnum, int M, double cutsq,
                                                            float cut_lo, float cut_hi, int *__restrict__ pattern)
