@@ -84,6 +84,16 @@ int mdb_compute_aja(const double *x, const double *y, const double *z, int N, co
                     const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
                     int Md, int *aja, int num_t);
 
+/* _ptm.get_ptm, src/polyhedral_template_matching.cpp:135.  verlet rows: nearest neighbours in ascending
+ * distance (18 wanted).  output (N, ocols): type, ordering, rmsd, interatomic distance, qw, qx, qy, qz;
+ * ptm_indices (N, icols): the atom, then its matched neighbours, -1 padded.  Structures sc / fcc / hcp /
+ * ico / bcc; dcub / dhex / graphene are ignored when combined with those and rejected on their own.
+ * ptm_indices follow THIS library's template point order. */
+int mdb_get_ptm(const char *structure, const double *x, const double *y, const double *z, int N, const double *box9,
+                const double *origin3, const int *boundary3, const int *verlet, int M, const int *atom_types,
+                int ntypes, double rmsd_threshold, double *output, int ocols, int *ptm_indices, int icols,
+                int num_t);
+
 /* _sbo.get_sq, src/steinhardt_bond_orientation.cpp:677.  qlm_r/qlm_i (N, ndeg, 2*lmax+1) are inout
  * (zeroed by the caller, steinhardt_bond_orientation.py:228-229), qnarray (N, ncol) is out; rc is the
  * value the Python wrapper passes (1e9 / 1e10 for the nnn / voronoi neighbour sources).  llist is
@@ -175,6 +185,9 @@ int mdb_system_solid_liquid(mdb_system *s, int q6index, double threshold, int n_
  * or straight from positions (streaming = 1) */
 int mdb_system_rdf(mdb_system *s, const int *types_host, int ntype, double rc, int nbin, int streaming,
                    double *g_host);
+/* PTM on the cached (sorted, >= 18 wide) list; types_host may be NULL; outputs (n_rows, 8) / (n_rows, 18) */
+int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, double rmsd_threshold,
+                   double *output_host, int *indices_host);
 /* device pointers to the most recent int32 / f64 per-atom result */
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 

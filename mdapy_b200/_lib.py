@@ -41,6 +41,8 @@ PROTOTYPES = {
     "mdb_acna": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_ip, C.c_int]),
     "mdb_get_csp": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, C.c_int, c_dp, C.c_int]),
     "mdb_compute_aja": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, C.c_int, c_ip, C.c_int]),
+    "mdb_get_ptm": (C.c_int, [C.c_char_p] + _XYZN + _BOX + [c_ip, C.c_int, c_ip, C.c_int, C.c_double, c_dp, C.c_int, c_ip,
+                                             C.c_int, C.c_int]),
     "mdb_get_sq": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, c_ip, c_dp, c_ip] + [C.c_int] * 7 +
                    [C.c_double, C.c_int, c_dp, c_dp, c_dp, C.c_int, C.c_int]),
     "mdb_identify_solid_liquid": (C.c_int, [C.c_int, c_dp, c_ip, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_dp, C.c_int,
@@ -74,6 +76,7 @@ PROTOTYPES = {
     "mdb_system_solid_liquid": (C.c_int, [c_vp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, c_ip,
                                           c_ip]),
     "mdb_system_rdf": (C.c_int, [c_vp, c_ip, C.c_int, C.c_double, C.c_int, C.c_int, c_dp]),
+    "mdb_system_ptm": (C.c_int, [c_vp, C.c_char_p, c_ip, C.c_double, c_dp, c_ip]),
     "mdb_system_result_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "mdb_system_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_last_times": (C.c_int, [c_vp, c_fp, c_fp, c_fp]),

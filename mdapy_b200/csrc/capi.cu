@@ -173,7 +173,7 @@ void mdb_system_destroy(mdb_system *s)
     if (!s) return;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
-    DevBuf *more[] = {&s->wx, &s->wy, &s->wz, &s->qlm_r, &s->qlm_i, &s->qn, &s->types, &s->weight};
+    DevBuf *more[] = {&s->wx, &s->wy, &s->wz, &s->qlm_r, &s->qlm_i, &s->qn, &s->types, &s->weight, &s->ptm_out, &s->ptm_idx};
     for (DevBuf *b : more) b->release();
     DevBuf *bufs[] = {&s->bx, &s->by, &s->bz, &s->cell_count, &s->cell_start, &s->perm, &s->perm_tmp, &s->sorted,
                       &s->scan_tmp, &s->big_cells, &s->counters, &s->verlet, &s->dist, &s->nn, &s->verlet_tmp,
@@ -511,6 +511,26 @@ int mdb_system_rdf(mdb_system *s, const int *types_host, int ntype, double rc, i
     API_END
 }
 
+// PTM on the cached list (>= 18 sorted neighbours per row, or fewer for open clusters).  output_host:
+// (n_rows, 8) = type, ordering, rmsd, interatomic distance, qw, qx, qy, qz; indices_host: (n_rows, 18).
+int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, double rmsd_threshold,
+                   double *output_host, int *indices_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    const int R = s->n_rows;
+    const int *types = nullptr;
+    if (types_host) types = h2d(*s, s->types, types_host, (size_t)s->N);
+    double *out = s->ptm_out.ensure<double>((size_t)R * 8);
+    int *idx = s->ptm_idx.ensure<int>((size_t)R * 18);
+    launch_ptm(*s, ptm_parse_flags(structure), s->verlet.as<int>(), s->M, types, rmsd_threshold, out, 8, idx, 18);
+    d2h(*s, output_host, out, (size_t)R * 8);
+    d2h(*s, indices_host, idx, (size_t)R * 18);
+    if (output_host || indices_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64)
 {
     API_BEGIN
@@ -687,6 +707,29 @@ int mdb_compute_aja(const double *x, const double *y, const double *z, int N, co
     if (rcode != MDB_OK) return rcode;
     rcode = mdb_system_aja(s.s, aja);
     if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_get_ptm(const char *structure, const double *x, const double *y, const double *z, int N, const double *box9,
+                const double *origin3, const int *boundary3, const int *verlet, int M, const int *atom_types,
+                int ntypes, double rmsd_threshold, double *output, int ocols, int *ptm_indices, int icols,
+                int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(output && ocols >= 1, MDB_ERR_VALUE, "output array required");
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, nullptr, nullptr, M, -1.0, LIST_KNN);
+    if (rcode != MDB_OK) return rcode;
+    // atom types are used only when one per atom is given (polyhedral_template_matching.cpp:160-162)
+    const int *types = (atom_types && ntypes == N) ? h2d(*s, s->types, atom_types, (size_t)N) : nullptr;
+    double *out = s->ptm_out.ensure<double>((size_t)N * ocols);
+    int *idx = ptm_indices ? s->ptm_idx.ensure<int>((size_t)N * icols) : nullptr;
+    launch_ptm(*s, ptm_parse_flags(structure), s->verlet.as<int>(), M, types, rmsd_threshold, out, ocols, idx, icols);
+    d2h(*s, output, out, (size_t)N * ocols);
+    if (ptm_indices) d2h(*s, ptm_indices, idx, (size_t)N * icols);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
 }
 

@@ -122,7 +122,7 @@ struct MdbSystem {
     DevBuf out_i32, out_f64, out_f64b, out_f64c, scratch, scratch2;
     DevBuf wx, wy, wz;  // kNN: wrapped coordinates (fast_knn.cpp wrap arithmetic)
     // Steinhardt state kept for identifySolidLiquid / repeated reads
-    DevBuf qlm_r, qlm_i, qn, types, weight;
+    DevBuf qlm_r, qlm_i, qn, types, weight, ptm_out, ptm_idx;
     int sbo_ndeg{0}, sbo_nz{0}, sbo_ncol{0};
 
     // timing of the last call, per kernel (ms), filled when profiling is on
@@ -157,5 +157,8 @@ void launch_solid_liquid(MdbSystem &s, const int *verlet, const double *dist, co
 void launch_rdf_list(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int N, int M,
                      const int *types, int ntype, double rc, int nbin, double *g);
 void launch_rdf_streaming(MdbSystem &s, const int *types, int ntype, double rc, int nbin, double *g);
+int ptm_parse_flags(const char *structure);
+void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
+                double *output, int ocols, int *indices, int icols);
 int device_max_int(MdbSystem &s, const int *v, size_t n);
 int device_min_int(MdbSystem &s, const int *v, size_t n);

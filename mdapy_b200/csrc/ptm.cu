@@ -1,0 +1,144 @@
+// mdapy_b200/csrc/ptm.cu -- polyhedral template matching on the device.
+// Replaces _ptm.get_ptm (src/polyhedral_template_matching.cpp:135-319): the serial Voronoi pre-ordering
+// stage (211-255) and the OpenMP ptm_index loop (258-318) become ONE kernel, one thread per atom, running
+// the per-atom core of ptm_core.cuh.  Look-up tables are generated on the host at first use
+// (ptm_tables.h) and kept in device memory.
+#include "internal.cuh"
+#include "ptm_tables.h"
+#include <mutex>
+
+namespace {
+
+struct DeviceTables {
+    ptm::Tables *d_tables{nullptr};
+    void *d_hash{nullptr}, *d_aut_begin{nullptr}, *d_aut_label{nullptr}, *d_gen{nullptr};
+    bool ready{false};
+};
+DeviceTables g_dev[16];
+std::mutex g_mu;
+
+const ptm::Tables *device_tables(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    MDB_REQUIRE(device >= 0 && device < 16, MDB_ERR_VALUE, "device index %d out of range", device);
+    DeviceTables &D = g_dev[device];
+    if (D.ready) return D.d_tables;
+    ptm::HostTables H;
+    ptm::build_tables(H);
+    ptm::Tables T = H.t;
+    auto up = [](const void *src, size_t bytes, void **dst) {
+        CUDA_TRY(cudaMalloc(dst, bytes ? bytes : 8));
+        CUDA_TRY(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    };
+    up(H.hash.data(), H.hash.size() * sizeof(unsigned long long), &D.d_hash);
+    up(H.aut_begin.data(), H.aut_begin.size() * sizeof(int), &D.d_aut_begin);
+    up(H.aut_label.data(), H.aut_label.size(), &D.d_aut_label);
+    up(H.gen.data(), H.gen.size() * sizeof(double), &D.d_gen);
+    T.hash = static_cast<const unsigned long long *>(D.d_hash);
+    T.aut_begin = static_cast<const int *>(D.d_aut_begin);
+    T.aut_label = static_cast<const signed char *>(D.d_aut_label);
+    T.gen = static_cast<const double *>(D.d_gen);
+    void *dt = nullptr;
+    up(&T, sizeof(T), &dt);
+    D.d_tables = static_cast<ptm::Tables *>(dt);
+    D.ready = true;
+    return D.d_tables;
+}
+
+__global__ void __launch_bounds__(64) k_ptm(const double *__restrict__ x, const double *__restrict__ y,
+                                            const double *__restrict__ z, int N, int n_rows,
+                                            const __grid_constant__ DBox box, const int *__restrict__ verlet, int M,
+                                            const int *__restrict__ types, int flags, double rmsd_threshold,
+                                            const ptm::Tables *__restrict__ tables, double *__restrict__ output,
+                                            int ocols, int *__restrict__ indices, int icols)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    double pts[ptm::MAX_IN][3];
+    int nbr[ptm::MAX_IN], ty[ptm::MAX_IN + 1];
+    int num = 0;
+    const double xi = x[i], yi = y[i], zi = z[i];
+    ty[0] = types ? types[i] : 0;
+    // neighbour collection: polyhedral_template_matching.cpp:222-248
+    for (int k = 0; k < M && num < ptm::MAX_IN; ++k) {
+        const int j = verlet[(size_t)i * M + k];
+        if (j < 0 || j >= N) break;
+        if (j == i) continue;
+        double dx = x[j] - xi, dy = y[j] - yi, dz = z[j] - zi;
+        min_image(box, dx, dy, dz);
+        pts[num][0] = dx;
+        pts[num][1] = dy;
+        pts[num][2] = dz;
+        nbr[num] = j;
+        ty[1 + num] = types ? types[j] : 0;
+        ++num;
+    }
+    ptm::Result r;
+    int order[ptm::MAX_IN];
+    ptm::index_atom(*tables, flags, num, pts, ty, r, order);
+    // outputs: polyhedral_template_matching.cpp:265-314
+    int type = r.type, ordering = r.ordering;
+    if (r.rmsd > rmsd_threshold || type == 0) {
+        type = 0;
+        ordering = 0;
+    }
+    double vals[8] = {(double)type, (double)ordering, r.rmsd, r.interatomic_distance, r.q[0], r.q[1], r.q[2], r.q[3]};
+    double *o = output + (size_t)i * ocols;
+    for (int c = 0; c < ocols; ++c) o[c] = c < 8 ? vals[c] : 0.0;
+    if (indices) {
+        int *ind = indices + (size_t)i * icols;
+        const int n = r.struct_index >= 0 ? tables->n_nbrs[r.struct_index] : -1;
+        for (int c = 0; c < icols; ++c) {
+            int v = -1;
+            if (n >= 0 && c == 0) v = i;
+            else if (n >= 0 && c <= n) v = nbr[order[r.mapping[c] - 1]];
+            ind[c] = v;
+        }
+    }
+}
+
+}  // namespace
+
+// structure string -> flag set, same grammar as polyhedral_template_matching.cpp:168-206
+int ptm_parse_flags(const char *structure)
+{
+    static const char *names[] = {"fcc", "hcp", "bcc", "ico", "sc", "dcub", "dhex", "graphene", "all", "default"};
+    static const int flags[] = {ptm::CHECK_FCC, ptm::CHECK_HCP, ptm::CHECK_BCC, ptm::CHECK_ICO, ptm::CHECK_SC,
+                                ptm::CHECK_DCUB, ptm::CHECK_DHEX, ptm::CHECK_GRAPHENE, 255,
+                                ptm::CHECK_FCC | ptm::CHECK_HCP | ptm::CHECK_BCC | ptm::CHECK_ICO};
+    auto sep = [](char c) { return c == '\0' || c == ' ' || c == ',' || c == '-' || c == '_' || c == '|'; };
+    int out = 0;
+    const char *p = structure ? structure : "";
+    while (*p) {
+        if (sep(*p)) {
+            ++p;
+            continue;
+        }
+        bool found = false;
+        for (int k = 0; k < 10; ++k) {
+            const size_t len = strlen(names[k]);
+            if (strncmp(p, names[k], len) == 0 && sep(p[len])) {
+                out |= flags[k];
+                p += len;
+                found = true;
+                break;
+            }
+        }
+        if (!found) ++p;
+    }
+    if (out == 0) out = ptm::CHECK_FCC | ptm::CHECK_HCP | ptm::CHECK_BCC | ptm::CHECK_ICO;
+    return out;
+}
+
+void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
+                double *output, int ocols, int *indices, int icols)
+{
+    const int unsupported = flags & (ptm::CHECK_DCUB | ptm::CHECK_DHEX | ptm::CHECK_GRAPHENE);
+    MDB_REQUIRE(!(unsupported && !(flags & 31)), MDB_ERR_VALUE,
+                "PTM structures dcub / dhex / graphene need neighbours of neighbours and are not built yet");
+    const ptm::Tables *T = device_tables(s.device);
+    const int R = s.n_rows;
+    MDB_LAUNCH(k_ptm, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, types, flags & 31,
+               rmsd_threshold, T, output, ocols, indices, icols);
+    CUDA_TRY(cudaGetLastError());
+}

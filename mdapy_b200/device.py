@@ -171,6 +171,15 @@ class DeviceSystem:
                                          int(nbin), int(bool(streaming)), L.dptr(g)))
         return g
 
+    def ptm(self, structure="fcc-hcp-bcc", rmsd_threshold=0.1, types=None):
+        """(output[n_rows, 8], ptm_indices[n_rows, 18]) on the cached sorted list."""
+        out = np.empty((self.n_rows, 8), np.float64)
+        ind = np.empty((self.n_rows, 18), np.int32)
+        t = L.i32(types) if types is not None else None
+        L.check(self._lib.mdb_system_ptm(self._h, structure.encode(), L.iptr(t) if t is not None else None,
+                                         float(rmsd_threshold), L.dptr(out), L.iptr(ind)))
+        return out, ind
+
     def result_device(self):
         """Raw device pointers (int) of the latest int32 / f64 per-atom result."""
         a, b = C.c_void_p(), C.c_void_p()

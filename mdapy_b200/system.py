@@ -25,6 +25,7 @@ from .device import LIST_CUTOFF, LIST_KNN, DeviceSystem
 from .frame import Frame
 from .knn import NearestNeighbor
 from .neighbor import Neighbor
+from .polyhedral_template_matching import PolyhedralTemplateMatching
 from .radial_distribution_function import RadialDistributionFunction
 from .steinhardt_bond_orientation import SteinhardtBondOrientation
 
@@ -343,3 +344,31 @@ class System:
                                              device=self._device)
         rdf.compute()
         return rdf
+
+    def cal_polyhedral_template_matching(self, structure="fcc-hcp-bcc", rmsd_threshold=0.1, return_ordering=False,
+                                         return_rmsd=False, return_atomic_distance=False, return_orientation=False,
+                                         identify_fcc_planar_faults=False, identify_esf=True):
+        if identify_fcc_planar_faults:
+            raise NotImplementedError("FCC planar-fault identification is outside the hot path (SURVEY.md 8f.1)")
+        use_cached = False
+        repeat = self._safe_repeat()
+        if sum(repeat) == 3 and self._has_list and self._min_neighbor_number() >= 18:
+            self._sort_neighbor(18)
+            use_cached = True
+        box, data = self._get_compute_view()
+        ptm = PolyhedralTemplateMatching(structure, data, box, rmsd_threshold,
+                                         dev=self._device_list() if use_cached else None, device=self._device)
+        ptm.compute()
+        output = ptm.output[: self.N]
+        cols = {"ptm": output[:, 0].astype(np.int32)}
+        if output.shape[1] >= 8:
+            if return_ordering:
+                cols["ordering"] = output[:, 1].copy()
+            if return_rmsd:
+                cols["rmsd"] = output[:, 2].copy()
+            if return_atomic_distance:
+                cols["interatomic_distance"] = output[:, 3].copy()
+            if return_orientation:
+                cols.update(qx=output[:, 5].copy(), qy=output[:, 6].copy(), qz=output[:, 7].copy(), qw=output[:, 4].copy())
+        self.update_data(self._data.with_columns(**cols))
+        return ptm
