@@ -123,7 +123,9 @@ __global__ void __launch_bounds__(128) k_qlm(const double *__restrict__ x, const
     }
 }
 
-// neighbour averaging (Lechner-Dellago), cpp:439-503: every listed neighbour counts, no rc filter
+// neighbour averaging (Lechner-Dellago), cpp:439-503: every listed neighbour counts, no rc filter.
+// Same summation order as the reference (own q_lm first, then neighbours in list order).
+template <bool LOCAL>
 __global__ void __launch_bounds__(128) k_qlm_average(int N, const int *__restrict__ verlet,
                                                      const int *__restrict__ nn, int M, SboParams P,
                                                      const double *__restrict__ aqr, const double *__restrict__ aqi,
@@ -136,6 +138,13 @@ __global__ void __launch_bounds__(128) k_qlm_average(int N, const int *__restric
     if (!P.use_voronoi && P.nnn > 0) cnt = P.nnn;
     int used = 1;
     double *Qr = qr + (size_t)i * stride, *Qi = qi + (size_t)i * stride;
+    double ar[LOCAL ? SBO_LOCAL : 1], ai[LOCAL ? SBO_LOCAL : 1];
+    if (LOCAL)
+        for (int t = 0; t < stride; ++t) {
+            ar[t] = Qr[t];
+            ai[t] = Qi[t];
+        }
+    double *R = LOCAL ? ar : Qr, *I = LOCAL ? ai : Qi;
     for (int jj = 0; jj < cnt; ++jj) {
         const int j = verlet[(size_t)i * M + jj];
         if (j < 0) continue;
@@ -143,8 +152,8 @@ __global__ void __launch_bounds__(128) k_qlm_average(int N, const int *__restric
         for (int il = 0; il < P.ndeg; ++il) {
             const int mm = 2 * P.l[il] + 1;
             for (int m = 0; m < mm; ++m) {
-                Qr[il * P.nz + m] += Ar[il * P.nz + m];
-                Qi[il * P.nz + m] += Ai[il * P.nz + m];
+                R[il * P.nz + m] += __ldg(Ar + il * P.nz + m);
+                I[il * P.nz + m] += __ldg(Ai + il * P.nz + m);
             }
         }
         ++used;
@@ -153,8 +162,8 @@ __global__ void __launch_bounds__(128) k_qlm_average(int N, const int *__restric
     for (int il = 0; il < P.ndeg; ++il) {
         const int mm = 2 * P.l[il] + 1;
         for (int m = 0; m < mm; ++m) {
-            Qr[il * P.nz + m] *= inv;
-            Qi[il * P.nz + m] *= inv;
+            Qr[il * P.nz + m] = R[il * P.nz + m] * inv;
+            Qi[il * P.nz + m] = I[il * P.nz + m] * inv;
         }
     }
 }
@@ -307,7 +316,8 @@ void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, cons
         double *ar = s.scratch.ensure<double>(tot), *ai = s.scratch2.ensure<double>(tot);
         CUDA_TRY(cudaMemcpyAsync(ar, qr, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ai, qi, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
-        MDB_LAUNCH(k_qlm_average, nb, 128, 0, st, N, verlet, nn, M, P, ar, ai, qr, qi);
+        if (P.ndeg * P.nz <= SBO_LOCAL) MDB_LAUNCH(k_qlm_average<true>, nb, 128, 0, st, N, verlet, nn, M, P, ar, ai, qr, qi);
+        else MDB_LAUNCH(k_qlm_average<false>, nb, 128, 0, st, N, verlet, nn, M, P, ar, ai, qr, qi);
     }
     // Clebsch-Gordan table, cpp:188-224
     std::vector<double> cg(1, 0.0);

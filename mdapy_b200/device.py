@@ -139,12 +139,12 @@ class DeviceSystem:
         return out
 
     def steinhardt(self, llist, nnn=0, rc=-1.0, average=False, wl=False, wlhat=False, use_voronoi=False,
-                   weight=None, fetch_qlm=False):
+                   weight=None, fetch_qlm=False, fetch=True):
         ll = L.i32(llist)
         ndeg = ll.shape[0]
         lmax = int(ll.max())
         ncol = ndeg * (1 + int(bool(wl)) + int(bool(wlhat)))
-        qn = np.empty((self.n_rows, ncol), np.float64)
+        qn = np.empty((self.n_rows, ncol), np.float64) if fetch else None
         qr = np.empty((self.n_rows, ndeg, 2 * lmax + 1), np.float64) if fetch_qlm else None
         qi = np.empty_like(qr) if fetch_qlm else None
         w = L.f64(weight) if weight is not None else None
@@ -152,7 +152,7 @@ class DeviceSystem:
             assert w.shape == (self.n_rows, self.M)
         L.check(self._lib.mdb_system_steinhardt(
             self._h, L.iptr(ll), ndeg, int(nnn), float(rc), int(bool(average)), int(bool(wl)), int(bool(wlhat)),
-            int(bool(use_voronoi)), L.dptr(w) if w is not None else None, L.dptr(qn),
+            int(bool(use_voronoi)), L.dptr(w) if w is not None else None, L.dptr(qn) if fetch else None,
             L.dptr(qr) if fetch_qlm else None, L.dptr(qi) if fetch_qlm else None))
         return qn, qr, qi
 
@@ -171,13 +171,14 @@ class DeviceSystem:
                                          int(nbin), int(bool(streaming)), L.dptr(g)))
         return g
 
-    def ptm(self, structure="fcc-hcp-bcc", rmsd_threshold=0.1, types=None):
+    def ptm(self, structure="fcc-hcp-bcc", rmsd_threshold=0.1, types=None, fetch=True):
         """(output[n_rows, 8], ptm_indices[n_rows, 18]) on the cached sorted list."""
-        out = np.empty((self.n_rows, 8), np.float64)
-        ind = np.empty((self.n_rows, 18), np.int32)
+        out = np.empty((self.n_rows, 8), np.float64) if fetch else None
+        ind = np.empty((self.n_rows, 18), np.int32) if fetch else None
         t = L.i32(types) if types is not None else None
         L.check(self._lib.mdb_system_ptm(self._h, structure.encode(), L.iptr(t) if t is not None else None,
-                                         float(rmsd_threshold), L.dptr(out), L.iptr(ind)))
+                                         float(rmsd_threshold), L.dptr(out) if fetch else None,
+                                         L.iptr(ind) if fetch else None))
         return out, ind
 
     def result_device(self):
