@@ -23,6 +23,7 @@
 extern "C" {
 #endif
 #if defined(__GNUC__)
+#include <stddef.h>
 #pragma GCC visibility push(default)
 #endif
 
@@ -37,6 +38,12 @@ const char *mdb_version(void);
 /* number of kernels launched by this library since load (bench.py "gpu_launches") */
 long long mdb_launch_count(void);
 int mdb_device_count(int *count);
+/* Released device blocks and pinned host blocks are cached for the next frame; this returns them to the
+ * driver.  mdb_host_alloc/mdb_host_free hand out page-locked host memory for result columns (device ->
+ * host copies into it run at full PCIe rate and need no staging). */
+int mdb_trim_cache(void);
+int mdb_host_alloc(size_t bytes, void **ptr);
+void mdb_host_free(void *ptr);
 
 /* ------------------------------------------------------------------------
  * Section A: host-pointer drop-ins, one per reference nanobind function
@@ -73,6 +80,10 @@ int mdb_fcna(const double *x, const double *y, const double *z, int N, const dou
 /* _cna.acna, src/cna.cpp:289.  verlet rows: >= 14 neighbours, ascending distance. */
 int mdb_acna(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
              const int *boundary3, const int *verlet, int M, int *pattern, int num_t);
+/* _cna.ids, src/cna.cpp:163 (IdentifyDiamond).  verlet rows: >= 4 neighbours, ascending distance.
+ * new_verlet (N x 12, may be NULL) receives the second-shell list; pattern is fully written (0-6). */
+int mdb_ids(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+            const int *boundary3, const int *verlet, int M, int *new_verlet, int *pattern, int num_t);
 
 /* _csp.get_csp, src/centro_symmetry_parameter.cpp:12. */
 int mdb_get_csp(const double *x, const double *y, const double *z, int N, const double *box9,
@@ -172,6 +183,7 @@ int mdb_system_neighbor_device(mdb_system *s, int **verlet, double **dist, int *
 /* descriptors on the cached list; results stay on the device when out == NULL */
 int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host);
 int mdb_system_acna(mdb_system *s, int *pattern_host);
+int mdb_system_ids(mdb_system *s, int *pattern_host);
 int mdb_system_csp(mdb_system *s, int nnei, double *csp_host);
 int mdb_system_aja(mdb_system *s, int *aja_host);
 /* Steinhardt q_l (+ w_l, w_l-hat) on the cached list; q_lm stay on the device for solid_liquid.

@@ -18,8 +18,13 @@ def __getattr__(name):
         "Neighbor": ("neighbor", "Neighbor"),
         "NearestNeighbor": ("knn", "NearestNeighbor"),
         "DeviceSystem": ("device", "DeviceSystem"),
+        "IdentifyDiamondStructure": ("identify_diamond_structure", "IdentifyDiamondStructure"),
         "build_crystal": ("lattice", "build_crystal"),
     }
+    if name == "empty_cache":
+        from ._lib import empty_cache
+
+        return empty_cache
     if name in table:
         mod, attr = table[name]
         return getattr(importlib.import_module(f"{__name__}.{mod}"), attr)

@@ -31,6 +31,9 @@ PROTOTYPES = {
     "mdb_version": (C.c_char_p, []),
     "mdb_launch_count": (C.c_longlong, []),
     "mdb_device_count": (C.c_int, [c_ip]),
+    "mdb_trim_cache": (C.c_int, []),
+    "mdb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(c_vp)]),
+    "mdb_host_free": (None, [c_vp]),
     "mdb_build_neighbor": (C.c_int, _XYZN + _BOX + [C.c_double, c_ip, c_dp, c_ip, C.c_int, C.c_int]),
     "mdb_build_neighbor_without_max_neigh": (
         C.c_int, _XYZN + _BOX + [C.c_double, C.c_int, C.POINTER(c_vp), c_ip]),
@@ -39,6 +42,7 @@ PROTOTYPES = {
     "mdb_sort_verlet_by_distance": (C.c_int, [c_ip, c_dp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mdb_fcna": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_ip, c_ip, C.c_double, C.c_int]),
     "mdb_acna": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_ip, C.c_int]),
+    "mdb_ids": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_ip, c_ip, C.c_int]),
     "mdb_get_csp": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, C.c_int, c_dp, C.c_int]),
     "mdb_compute_aja": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, C.c_int, c_ip, C.c_int]),
     "mdb_get_ptm": (C.c_int, [C.c_char_p] + _XYZN + _BOX + [c_ip, C.c_int, c_ip, C.c_int, C.c_double, c_dp, C.c_int, c_ip,
@@ -69,6 +73,7 @@ PROTOTYPES = {
     "mdb_system_neighbor_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), c_ip]),
     "mdb_system_fcna": (C.c_int, [c_vp, C.c_double, c_ip]),
     "mdb_system_acna": (C.c_int, [c_vp, c_ip]),
+    "mdb_system_ids": (C.c_int, [c_vp, c_ip]),
     "mdb_system_csp": (C.c_int, [c_vp, C.c_int, c_dp]),
     "mdb_system_aja": (C.c_int, [c_vp, c_ip]),
     "mdb_system_steinhardt": (C.c_int, [c_vp, c_ip, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -134,3 +139,39 @@ def box_args(box, origin, boundary):
     o = f64(origin).reshape(3)
     p = i32(boundary).reshape(3)
     return b, o, p
+
+
+class _PinnedBlock:
+    """Page-locked host block from the library's cache, exposed through the array interface."""
+
+    def __init__(self, nbytes: int, shape, dtype):
+        ptr = c_vp()
+        check(lib().mdb_host_alloc(nbytes, C.byref(ptr)))
+        self._ptr = ptr.value
+        self.__array_interface__ = {"shape": tuple(shape), "typestr": np.dtype(dtype).str,
+                                    "data": (self._ptr, False), "version": 3}
+
+    def __del__(self):
+        if getattr(self, "_ptr", None) and _lib is not None:
+            _lib.mdb_host_free(c_vp(self._ptr))
+            self._ptr = None
+
+
+PINNED_MIN_BYTES = 1 << 20
+PINNED_MAX_BYTES = 4 << 30
+
+
+def result_empty(shape, dtype) -> np.ndarray:
+    """Uninitialised host array for a result column.  Between 1 MiB and 4 GiB it lives in page-locked
+    memory from the library's cache, so the device -> host copy runs at PCIe rate without a staging
+    pass and without first-touch page faults; the block returns to the cache when the array dies."""
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+    if nbytes < PINNED_MIN_BYTES or nbytes > PINNED_MAX_BYTES:
+        return np.empty(shape, dtype)
+    return np.asarray(_PinnedBlock(nbytes, shape, dtype))
+
+
+def empty_cache() -> None:
+    """Return the cached device and pinned-host blocks to the driver."""
+    check(lib().mdb_trim_cache())

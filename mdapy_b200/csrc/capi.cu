@@ -3,6 +3,10 @@
 #include "../../include/mdapy_b200.h"
 #include <cstdarg>
 #include <new>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 
 long long g_mdb_launches = 0;
 static thread_local char g_err[1024] = "";
@@ -131,6 +135,141 @@ template <class T> static T *h2d(MdbSystem &s, DevBuf &buf, const T *host, size_
 static void require_list(MdbSystem &s)
 {
     MDB_REQUIRE(s.list_kind != LIST_NONE, MDB_ERR_STATE, "no neighbour list on the device; build one first");
+}
+
+// ---------------------------------------------------------------- block caches
+namespace {
+std::mutex g_pool_mu;
+std::map<std::pair<int, size_t>, std::vector<void *>> g_dev_free;  // (device, bytes) -> blocks
+size_t g_dev_cached = 0;
+std::multimap<size_t, void *> g_host_free;                         // bytes -> pinned block
+std::unordered_map<void *, size_t> g_host_live;
+size_t g_host_cached = 0;
+constexpr size_t HOST_CACHE_LIMIT = (size_t)12 << 30;
+
+size_t round_block(size_t bytes)
+{   // 2 MiB granules below 1 GiB, 64 MiB above: keeps successive frames of similar size on the same blocks
+    const size_t g = bytes < ((size_t)1 << 30) ? ((size_t)2 << 20) : ((size_t)64 << 20);
+    return bytes < 65536 ? ((bytes + 511) & ~(size_t)511) : (bytes + g - 1) / g * g;
+}
+
+void trim_device_locked(int device)
+{
+    for (auto it = g_dev_free.begin(); it != g_dev_free.end();) {
+        if (device < 0 || it->first.first == device) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            cudaSetDevice(it->first.first);
+            for (void *q : it->second) {
+                cudaFree(q);
+                g_dev_cached -= it->first.second;
+            }
+            cudaSetDevice(cur);
+            it = g_dev_free.erase(it);
+        } else ++it;
+    }
+}
+}  // namespace
+
+void *mdb_pool_alloc(size_t bytes, size_t *got)
+{
+    int device = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+    const size_t want = round_block(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        // smallest cached block that fits without wasting more than half of it
+        auto it = g_dev_free.lower_bound({device, want});
+        while (it != g_dev_free.end() && it->first.first == device && it->first.second <= want + want / 2 + (1 << 20)) {
+            if (!it->second.empty()) {
+                void *q = it->second.back();
+                it->second.pop_back();
+                g_dev_cached -= it->first.second;
+                *got = it->first.second;
+                return q;
+            }
+            ++it;
+        }
+    }
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, want);
+    if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once
+        cudaGetLastError();
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            trim_device_locked(device);
+        }
+        e = cudaMalloc(&q, want);
+    }
+    CUDA_TRY(e);
+    *got = want;
+    return q;
+}
+
+void mdb_pool_free(void *p, size_t bytes)
+{
+    if (!p) return;
+    int device = 0;
+    cudaGetDevice(&device);
+    static const bool off = getenv("MDB_NO_CACHE") != nullptr;
+    if (off) {
+        cudaFree(p);
+        return;
+    }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_dev_free[{device, bytes}].push_back(p);
+    g_dev_cached += bytes;
+}
+
+int mdb_trim_cache(void)
+{
+    API_BEGIN
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    trim_device_locked(-1);
+    for (auto &kv : g_host_free) cudaFreeHost(kv.second);
+    g_host_free.clear();
+    g_host_cached = 0;
+    API_END
+}
+
+int mdb_host_alloc(size_t bytes, void **ptr)
+{
+    API_BEGIN
+    MDB_REQUIRE(ptr, MDB_ERR_VALUE, "ptr is required");
+    const size_t want = round_block(bytes ? bytes : 1);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = g_host_free.lower_bound(want);
+        if (it != g_host_free.end() && it->first <= want + want / 2 + (1 << 20)) {
+            *ptr = it->second;
+            g_host_live[it->second] = it->first;
+            g_host_cached -= it->first;
+            g_host_free.erase(it);
+            return MDB_OK;
+        }
+    }
+    void *q = nullptr;
+    CUDA_TRY(cudaHostAlloc(&q, want, cudaHostAllocPortable));
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_host_live[q] = want;
+    *ptr = q;
+    API_END
+}
+
+void mdb_host_free(void *ptr)
+{
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_host_live.find(ptr);
+    if (it == g_host_live.end()) return;
+    const size_t bytes = it->second;
+    g_host_live.erase(it);
+    if (g_host_cached + bytes > HOST_CACHE_LIMIT) {
+        cudaFreeHost(ptr);
+        return;
+    }
+    g_host_free.emplace(bytes, ptr);
+    g_host_cached += bytes;
 }
 
 extern "C" {
@@ -391,6 +530,20 @@ int mdb_system_acna(mdb_system *s, int *pattern_host)
     int *pat = s->out_i32.ensure<int>(s->n_rows);
     CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->n_rows, s->stream));
     launch_acna(*s, s->verlet.as<int>(), s->M, pat);
+    d2h(*s, pattern_host, pat, (size_t)s->n_rows);
+    if (pattern_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_system_ids(mdb_system *s, int *pattern_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(s->slab_nx == 0, MDB_ERR_STATE, "diamond identification is not available on a decomposed frame");
+    int *pat = s->out_i32.ensure<int>(s->n_rows);
+    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->n_rows, s->stream));
+    launch_ids(*s, s->verlet.as<int>(), s->M, nullptr, pat);
     d2h(*s, pattern_host, pat, (size_t)s->n_rows);
     if (pattern_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
@@ -676,6 +829,25 @@ int mdb_acna(const double *x, const double *y, const double *z, int N, const dou
     if (rcode != MDB_OK) return rcode;
     rcode = mdb_system_acna(s.s, pattern);
     if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_ids(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+            const int *boundary3, const int *verlet, int M, int *new_verlet, int *pattern, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, nullptr, nullptr, M, -1.0, LIST_KNN);
+    if (rcode != MDB_OK) return rcode;
+    int *pat = s->out_i32.ensure<int>(N);
+    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * N, s->stream));
+    int *second = new_verlet ? s->scratch2.ensure<int>((size_t)N * 12) : nullptr;
+    launch_ids(*s, s->verlet.as<int>(), M, second, pat);
+    d2h(*s, pattern, pat, (size_t)N);
+    d2h(*s, new_verlet, second, (size_t)N * 12);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
 }
 

@@ -319,6 +319,94 @@ __global__ void __launch_bounds__(CNA_THREADS) k_fcna_fast(const double *__restr
     if (p) pattern[i] = p;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Diamond structure identification, cna.cpp:163-287.  verlet rows: >= 4 neighbours, ascending distance.
+// k_ids_classify = the reference's parallel loop (second-shell list, CNA over 12 with the local
+// cut-off).  The two serial sweeps that follow in the reference (cna.cpp:251-286) visit atoms in
+// ascending index and label still-unlabelled first neighbours, so the label an atom receives is the
+// one of the LOWEST-index labelled atom that lists it: k_ids_claim records that index with atomicMin,
+// k_ids_assign applies it -- deterministic and identical to the serial result.
+__global__ void __launch_bounds__(128) k_ids_classify(const double *__restrict__ x, const double *__restrict__ y,
+                                                      const double *__restrict__ z, int N, DBox box,
+                                                      const int *__restrict__ verlet, int M,
+                                                      int *__restrict__ second_out, int *__restrict__ pattern)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int second[12];
+    int count = 0;
+    const int *row = verlet + (size_t)i * M;
+    bool ok = true;
+    for (int m = 0; m < 4; ++m) {
+        const int j = row[m];
+        if (j < 0 || j >= N) {
+            ok = false;
+            break;
+        }
+        const int *rj = verlet + (size_t)j * M;
+        int taken = 0;
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = rj[kk];
+            if (k != i && taken < 3) {
+                second[count++] = k;
+                ++taken;
+            }
+        }
+    }
+    for (int m = 0; m < 12 && ok; ++m)
+        if (m >= count || second[m] < 0 || second[m] >= N) ok = false;
+    if (second_out)
+        for (int m = 0; m < 12; ++m) second_out[(size_t)i * 12 + m] = m < count ? second[m] : 0;
+    if (!ok) return;  // short / padded rows: the reference would read out of bounds; leave 0
+    const double xi = x[i], yi = y[i], zi = z[i];
+    double px[12], py[12], pz[12];
+    double rsum = 0.0;
+    for (int m = 0; m < 12; ++m) {
+        const int j = second[m];
+        px[m] = x[j];
+        py[m] = y[j];
+        pz[m] = z[j];
+        rsum += sqrt(pbc_dist_sq(box, xi, yi, zi, px[m], py[m], pz[m]));
+    }
+    rsum /= 12.0;
+    const double cut = rsum * 1.2071068;
+    unsigned nb[12];
+    bond_matrix(box, px, py, pz, 12, cut * cut, nb);
+    const CnaCounts c = cna_signatures(nb, 12);
+    if (c.n421 == 12) pattern[i] = 1;
+    else if (c.n421 == 6 && c.n422 == 6) pattern[i] = 4;
+}
+
+__global__ void k_ids_claim(int N, const int *__restrict__ verlet, int M, const int *__restrict__ pattern, int ta, int tb,
+                            int *__restrict__ owner)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int t = pattern[i];
+    if (t != ta && t != tb) return;
+    for (int jj = 0; jj < 4; ++jj) {
+        const int j = verlet[(size_t)i * M + jj];
+        if (j >= 0 && j < N && pattern[j] == 0) atomicMin(owner + j, i);
+    }
+}
+
+__global__ void k_ids_assign(int N, int *__restrict__ pattern, int *__restrict__ owner)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const int o = owner[j];
+    if (o != INT_MAX) {
+        pattern[j] = pattern[o] + 1;  // owners carry 1/4 (or 2/5), receivers were 0: no read/write overlap
+        owner[j] = INT_MAX;
+    }
+}
+
+__global__ void k_fill_int(int n, int v, int *__restrict__ p)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 }  // namespace
 
 void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern)
@@ -349,5 +437,21 @@ void launch_acna(MdbSystem &s, const int *verlet, int M, int *pattern)
     MDB_REQUIRE(M >= 14, MDB_ERR_VALUE, "adaptive CNA needs >= 14 sorted neighbours per atom, row width is %d", M);
     const double f = 1.0 + std::sqrt(2.0);
     MDB_LAUNCH(k_acna, (N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, M, f, pattern);
+    CUDA_TRY(cudaGetLastError());
+}
+
+// pattern must be pre-zeroed; second_out (N x 12, may be null) receives the reference's new_verlet_list
+void launch_ids(MdbSystem &s, const int *verlet, int M, int *second_out, int *pattern)
+{
+    const int N = s.n_rows;
+    MDB_REQUIRE(M >= 4, MDB_ERR_VALUE, "diamond identification needs >= 4 sorted neighbours per atom, row width is %d", M);
+    const int nb = (N + 127) / 128;
+    MDB_LAUNCH(k_ids_classify, nb, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, M, second_out, pattern);
+    int *owner = s.scratch.ensure<int>(N);
+    MDB_LAUNCH(k_fill_int, (N + 255) / 256, 256, 0, s.stream, N, INT_MAX, owner);
+    for (int pass = 0; pass < 2; ++pass) {
+        MDB_LAUNCH(k_ids_claim, (N + 255) / 256, 256, 0, s.stream, N, verlet, M, pattern, pass ? 2 : 1, pass ? 5 : 4, owner);
+        MDB_LAUNCH(k_ids_assign, (N + 255) / 256, 256, 0, s.stream, N, pattern, owner);
+    }
     CUDA_TRY(cudaGetLastError());
 }

@@ -52,6 +52,13 @@ struct MdbError {
         }                                                                                           \
     } while (0)
 
+// Device / pinned-host block caches (capi.cu).  A System is created per frame by the Python layer
+// (system.py mirrors the reference's one-System-per-file usage); cudaMalloc/cudaFree of ~20 GB of
+// buffers per frame would dominate the end-to-end time, so released blocks are parked per device and
+// reused by the next System.  mdb_trim_cache() returns everything to the driver.
+void *mdb_pool_alloc(size_t bytes, size_t *got);
+void mdb_pool_free(void *p, size_t bytes);
+
 // grow-only device buffer; allocation cost is paid once per high-water mark
 struct DevBuf {
     void *p{nullptr};
@@ -60,19 +67,15 @@ struct DevBuf {
     {
         const size_t bytes = count * sizeof(T);
         if (bytes > cap) {
-            if (p) CUDA_TRY(cudaFree(p));
-            p = nullptr;
-            cap = 0;
-            size_t want = bytes + bytes / 16 + 256;
-            CUDA_TRY(cudaMalloc(&p, want));
-            cap = want;
+            release();
+            p = mdb_pool_alloc(bytes + bytes / 16 + 256, &cap);
         }
         return static_cast<T *>(p);
     }
     template <class T> T *as() const { return static_cast<T *>(p); }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) mdb_pool_free(p, cap);
         p = nullptr;
         cap = 0;
     }
@@ -146,6 +149,7 @@ int neighbor_tiled_max(MdbSystem &s);
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k);
 void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern);
 void launch_acna(MdbSystem &s, const int *verlet, int M, int *pattern);
+void launch_ids(MdbSystem &s, const int *verlet, int M, int *second_out, int *pattern);
 void launch_csp(MdbSystem &s, const int *verlet, int M, int nnei, double *csp);
 void launch_aja(MdbSystem &s, const int *verlet, int M, const double *dist, int Md, int *aja);
 void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M,

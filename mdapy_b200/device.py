@@ -99,9 +99,9 @@ class DeviceSystem:
         return v.value
 
     def fetch_neighbor(self, want_verlet=True, want_dist=True, want_nn=True):
-        verlet = np.empty((self.n_rows, self.M), np.int32) if want_verlet else None
-        dist = np.empty((self.n_rows, self.M), np.float64) if want_dist else None
-        nn = np.empty(self.n_rows, np.int32) if want_nn else None
+        verlet = L.result_empty((self.n_rows, self.M), np.int32) if want_verlet else None
+        dist = L.result_empty((self.n_rows, self.M), np.float64) if want_dist else None
+        nn = L.result_empty(self.n_rows, np.int32) if want_nn else None
         L.check(self._lib.mdb_system_fetch_neighbor(
             self._h, L.iptr(verlet) if want_verlet else None, L.dptr(dist) if want_dist else None,
             L.iptr(nn) if want_nn else None))
@@ -119,22 +119,27 @@ class DeviceSystem:
 
     # -- descriptors ---------------------------------------------------------
     def fcna(self, rc: float, fetch=True):
-        out = np.empty(self.n_rows, np.int32) if fetch else None
+        out = L.result_empty(self.n_rows, np.int32) if fetch else None
         L.check(self._lib.mdb_system_fcna(self._h, float(rc), L.iptr(out) if fetch else None))
         return out
 
     def acna(self, fetch=True):
-        out = np.empty(self.n_rows, np.int32) if fetch else None
+        out = L.result_empty(self.n_rows, np.int32) if fetch else None
         L.check(self._lib.mdb_system_acna(self._h, L.iptr(out) if fetch else None))
         return out
 
+    def ids(self, fetch=True):
+        out = L.result_empty(self.n_rows, np.int32) if fetch else None
+        L.check(self._lib.mdb_system_ids(self._h, L.iptr(out) if fetch else None))
+        return out
+
     def csp(self, nnei: int, fetch=True):
-        out = np.empty(self.n_rows, np.float64) if fetch else None
+        out = L.result_empty(self.n_rows, np.float64) if fetch else None
         L.check(self._lib.mdb_system_csp(self._h, int(nnei), L.dptr(out) if fetch else None))
         return out
 
     def aja(self, fetch=True):
-        out = np.empty(self.n_rows, np.int32) if fetch else None
+        out = L.result_empty(self.n_rows, np.int32) if fetch else None
         L.check(self._lib.mdb_system_aja(self._h, L.iptr(out) if fetch else None))
         return out
 
@@ -144,9 +149,9 @@ class DeviceSystem:
         ndeg = ll.shape[0]
         lmax = int(ll.max())
         ncol = ndeg * (1 + int(bool(wl)) + int(bool(wlhat)))
-        qn = np.empty((self.n_rows, ncol), np.float64) if fetch else None
-        qr = np.empty((self.n_rows, ndeg, 2 * lmax + 1), np.float64) if fetch_qlm else None
-        qi = np.empty_like(qr) if fetch_qlm else None
+        qn = L.result_empty((self.n_rows, ncol), np.float64) if fetch else None
+        qr = L.result_empty((self.n_rows, ndeg, 2 * lmax + 1), np.float64) if fetch_qlm else None
+        qi = L.result_empty(qr.shape, np.float64) if fetch_qlm else None
         w = L.f64(weight) if weight is not None else None
         if w is not None:
             assert w.shape == (self.n_rows, self.M)
@@ -157,8 +162,8 @@ class DeviceSystem:
         return qn, qr, qi
 
     def solid_liquid(self, q6index, threshold, n_bond, nnn=0, rc=-1.0, use_voronoi=False):
-        sl = np.empty(self.n_rows, np.int32)
-        nb = np.empty(self.n_rows, np.int32)
+        sl = L.result_empty(self.n_rows, np.int32)
+        nb = L.result_empty(self.n_rows, np.int32)
         L.check(self._lib.mdb_system_solid_liquid(self._h, int(q6index), float(threshold), int(n_bond),
                                                   int(bool(use_voronoi)), int(nnn), float(rc), L.iptr(sl), L.iptr(nb)))
         return sl, nb
@@ -173,8 +178,8 @@ class DeviceSystem:
 
     def ptm(self, structure="fcc-hcp-bcc", rmsd_threshold=0.1, types=None, fetch=True):
         """(output[n_rows, 8], ptm_indices[n_rows, 18]) on the cached sorted list."""
-        out = np.empty((self.n_rows, 8), np.float64) if fetch else None
-        ind = np.empty((self.n_rows, 18), np.int32) if fetch else None
+        out = L.result_empty((self.n_rows, 8), np.float64) if fetch else None
+        ind = L.result_empty((self.n_rows, 18), np.int32) if fetch else None
         t = L.i32(types) if types is not None else None
         L.check(self._lib.mdb_system_ptm(self._h, structure.encode(), L.iptr(t) if t is not None else None,
                                          float(rmsd_threshold), L.dptr(out) if fetch else None,

@@ -21,6 +21,7 @@ from .ackland_jones_analysis import AcklandJonesAnalysis
 from .box import Box
 from .centro_symmetry_parameter import CentroSymmetryParameter
 from .common_neighbor_analysis import CommonNeighborAnalysis
+from .identify_diamond_structure import IdentifyDiamondStructure
 from .device import LIST_CUTOFF, LIST_KNN, DeviceSystem
 from .frame import Frame
 from .knn import NearestNeighbor
@@ -230,6 +231,23 @@ class System:
                                      device=self._device)
         cna.compute()
         self.update_data(self._data.with_columns(cna=cna.pattern[: self.N]))
+
+    def cal_identify_diamond_structure(self):
+        """system.py:1493-1529 -> data['ids'] (0 other, 1-3 cubic diamond + shells, 4-6 hexagonal)."""
+        dev = None
+        safe_L = 15
+        repeat = np.ceil(safe_L / self.box.get_thickness()).astype(int)
+        for i in range(3):
+            if self.box.boundary[i] == 0:
+                repeat[i] = 1
+        if sum(repeat) == 3 and self._has_list and "rc" in self.__dict__:
+            if self._min_neighbor_number() >= 4:
+                self._sort_neighbor(4)
+                dev = self._device_list()
+        box, data = self._get_compute_view()
+        ids = IdentifyDiamondStructure(data, box, dev=dev, device=self._device)
+        ids.compute()
+        self.update_data(self._data.with_columns(ids=ids.pattern[: self.N]))
 
     def cal_centro_symmetry_parameter(self, N: int):
         assert N % 2 == 0 and N > 0, f"N must be a positive even number: {N}."

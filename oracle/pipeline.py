@@ -127,6 +127,17 @@ def cal_cna(K, fr: Frame, rc=None):
     return K.fcna(*f3.geom(), v, n, rc)[:N]
 
 
+def cal_ids(K, fr: Frame):
+    """system.py:1493-1529 + identify_diamond_structure.py:75-124, fresh system (kNN path, safe_L = 15)."""
+    N = fr.N
+    if fr.boundary.sum() == 0 and N <= 4:
+        return np.zeros(N, np.int32)
+    rep = safe_repeat(fr.box, fr.boundary, safe_L=15)
+    f2 = fr.replicate(K, *rep) if rep.sum() != 3 else fr
+    f3, idx, _ = nearest(K, f2, 4)
+    return K.ids(*f3.geom(), idx)[:N]
+
+
 def cal_csp(K, fr: Frame, nnei):
     """system.py:1972-2003, fresh system (kNN path)."""
     if fr.N <= nnei and fr.boundary.sum() == 0:

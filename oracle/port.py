@@ -140,6 +140,19 @@ def acna(x, y, z, box, origin, boundary, verlet, nt=None):
     return pattern
 
 
+def ids(x, y, z, box, origin, boundary, verlet, nt=None):
+    """cna.cpp:163 IdentifyDiamond."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet = _i32(verlet)
+    N, M = verlet.shape
+    new_verlet = np.zeros((N, 12), np.int32)
+    pattern = np.zeros(N, np.int32)
+    _lib("cna").port_ids(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _i(verlet), C.c_int(M),
+                        _i(new_verlet), _i(pattern), C.c_int(nt or num_threads()))
+    return pattern
+
+
 # --------------------------------------------------------------------------
 # src/centro_symmetry_parameter.cpp, src/ackland_jones_analysis.cpp
 # --------------------------------------------------------------------------

@@ -457,6 +457,54 @@ void port_acna(const double *x, const double *y, const double *z, int N, const d
     }
 }
 
+/* ------------------------------------------------------------------ diamond structure
+ * cna.cpp:163-287 IdentifyDiamond.  verlet rows hold >= 4 neighbours sorted by distance.  Second-shell
+ * list = for each of the 4 first neighbours j, the first 3 entries of j's row that are not i; CNA on
+ * those 12 with cutoff 1.2071068 * mean distance; then two serial sweeps spread the labels to first
+ * and second neighbours (lowest atom index wins, cna.cpp:251-286). */
+void port_ids(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+              const int *boundary3, const int *verlet, int M, int *new_verlet, int *pattern, int num_t)
+{
+    cell_t c;
+    cell_init(&c, box9, origin3, boundary3);
+#pragma omp parallel for num_threads(num_t)
+    for (int i = 0; i < N; ++i) {
+        int *second = new_verlet + (size_t)i * 12;
+        int count = 0;
+        for (int m = 0; m < 4; ++m) {
+            const int j = verlet[(size_t)i * M + m];
+            int taken = 0;
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = verlet[(size_t)j * M + kk];
+                if (k != i && taken < 3) {
+                    second[count++] = k;
+                    ++taken;
+                }
+            }
+        }
+        double sum = 0.0;
+        for (int m = 0; m < 12; ++m) sum += sqrt(raw_dist_sq(&c, x, y, z, i, second[m]));
+        sum /= 12.0;
+        const double cut = sum * 1.2071068; /* cna.cpp:208 */
+        unsigned nb[32];
+        bonds(&c, x, y, z, second, 12, cut * cut, nb);
+        sig_t s = signatures(nb, 12);
+        if (s.n421 == 12) pattern[i] = 1;
+        else if (s.n421 == 6 && s.n422 == 6) pattern[i] = 4;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        const int a = pass ? 2 : 1, b = pass ? 5 : 4;
+        for (int i = 0; i < N; ++i) {
+            const int t = pattern[i];
+            if (t != a && t != b) continue;
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = verlet[(size_t)i * M + jj];
+                if (pattern[j] == 0) pattern[j] = t + 1;
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ centro-symmetry
  * centro_symmetry_parameter.cpp:12-92: all pair sums |r_j + r_k|^2, the nnei/2 smallest
  * added in ascending order. */

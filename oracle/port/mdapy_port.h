@@ -15,6 +15,8 @@ void port_fcna(const double *x, const double *y, const double *z, int N, const d
                const int *boundary3, const int *verlet, int M, const int *nn, int *pattern, double rc, int num_t);
 void port_acna(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
                const int *boundary3, const int *verlet, int M, int *pattern, int num_t);
+void port_ids(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+              const int *boundary3, const int *verlet, int M, int *new_verlet, int *pattern, int num_t);
 void port_csp(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
               const int *boundary3, const int *verlet, int M, int nnei, double *csp, int num_t);
 void port_aja(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,

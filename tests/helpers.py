@@ -53,3 +53,25 @@ def same_rows_as_sets(v1, n1, v2, n2):
         if sorted(v1[i, :k].tolist()) != sorted(v2[i, :k].tolist()):
             return False
     return True
+
+
+DIAMOND = np.concatenate([FCC, FCC + 0.25])
+
+
+def diamond(a=3.567, n=5):
+    return lattice(DIAMOND, a, n, n, n)
+
+
+def hex_diamond(a=2.52, nx=6, ny=4, nz=4):
+    """Lonsdaleite in its 8-atom orthogonal cell (a, sqrt(3) a, c = sqrt(8/3) a)."""
+    c = np.sqrt(8.0 / 3.0) * a
+    frac = []
+    for (u, v) in ((0.0, 0.0), (0.5, 0.5)):            # the two hexagonal cells of the orthogonal cell
+        for (fx, fy, fz) in ((0.0, 1 / 3, 0.0), (0.5, 1 / 6, 0.5), (0.0, 1 / 3, 3 / 8), (0.5, 1 / 6, 7 / 8)):
+            frac.append(((fx + u) % 1.0, (fy + v) % 1.0, fz))
+    frac = np.array(frac)
+    cell = np.array([a, np.sqrt(3.0) * a, c])
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    shift = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1).astype(float)
+    pos = ((frac[None, :, :] + shift[:, None, :]) * cell).reshape(-1, 3)
+    return np.ascontiguousarray(pos), np.diag(cell * np.array([nx, ny, nz]))

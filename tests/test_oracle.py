@@ -37,6 +37,7 @@ def test_golden_labels_and_csp(K, path):
     if "cna" in d.files:
         assert np.array_equal(P.cal_cna(K, fr, float(d["cna_cutoff"])), d["cna"])
     assert np.array_equal(P.cal_aja(K, fr), d["aja"])
+    assert np.array_equal(P.cal_ids(K, fr), d["ids"])
     assert np.array_equal(P.cal_cna(K, fr, None), d["ref_acna"])
     if "csp" in d.files:
         got = P.cal_csp(K, fr, int(d["csp_num_neighbors"]))
@@ -160,3 +161,19 @@ def test_port_equals_reference(case):
     assert np.array_equal(ref.rdf_streaming(x, y, z, t, 2, box, o, bnd, rc, 40),
                           port.rdf_streaming(x, y, z, t, 2, box, o, bnd, rc, 40))
     assert np.array_equal(ref.repeat_cell(box, pos[:50], 2, 3, 2), port.repeat_cell(box, pos[:50], 2, 3, 2))
+
+
+def test_port_ids_equals_reference_on_defective_diamond():
+    """cna.cpp:163-287 incl. the order-dependent label sweeps, on inputs with all seven labels."""
+    if not ref.available():
+        pytest.skip("_ref not prebuilt")
+    import helpers as H
+
+    pc, bc = H.diamond(3.567, 4)
+    ph, bh = H.hex_diamond(2.522, 5, 3, 3)
+    pos = np.concatenate([pc, ph + np.array([bc[0, 0] + 0.9, 0.3, 0.2])])
+    pos = H.rattle(pos[np.random.default_rng(5).permutation(len(pos))], 0.03, 6)
+    box = np.diag(pos.max(0) - pos.min(0) + 4.0)
+    fr = P.Frame(pos - pos.min(0) + 2.0, box, [0, 0, 0])
+    a, b = P.cal_ids(ref, fr), P.cal_ids(port, fr)
+    assert np.array_equal(a, b) and (np.bincount(a, minlength=7) > 0).all()

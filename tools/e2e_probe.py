@@ -3,8 +3,10 @@ sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import helpers as H
 import mdapy_b200 as mp
 from mdapy_b200.device import DeviceSystem
-pos, box = H.fcc(4.05, 136)
-x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 136
+pos, box = H.fcc(4.05, n)
+x, y, z = (torch.from_numpy(np.ascontiguousarray(pos[:, k])).pin_memory().numpy() for k in range(3))
+del pos
 rc = 0.8536 * 4.05
 def T(): torch.cuda.synchronize(); return time.perf_counter()
 for rep in range(3):
