@@ -8,8 +8,10 @@
 // 32-byte SortedAtom records, copied with cp.async.bulk (TMA 1-D, mbarrier completion).  Each staged
 // atom also gets an fp32 copy of its position relative to the tile centre (nearest periodic image).
 // One thread per owned atom then walks its 27 cells in the reference's order:
-//   phase 1  fp32 distance test against rc^2 * (1 + guard): a conservative pre-filter (no false
-//            negatives: the guard is >50x the fp32 error bound), survivors are queued per thread;
+//   phase 1  fp32 test |rj|^2 - 2 ri.rj <= rc^2 (1 + guard) - |ri|^2 (three FMAs per candidate): a
+//            conservative pre-filter (no false negatives: the guard is > 5x the fp32 error bound for
+//            staged positions inside the radius limit; a tile holding an atom beyond the limit takes
+//            the exact direct path), survivors are queued per thread;
 //   phase 2  the queued survivors take the exact f64 test of the reference (xi wrapped, x[j] raw,
 //            division-free min-image, left-to-right sum, <= rc^2) and are written in queue order.
 // Only ~20 % of the 27-cell candidates survive phase 1, so the f64 pipe sees ~13 pairs per atom
@@ -30,6 +32,7 @@ struct TileArgs {
     double rcsq;
     double pad;     // rc + 1.0
     float rcsq_hi;  // fp32 acceptance bound of the pre-filter
+    float w_limit;  // largest |r|^2 (relative to the tile centre) the fp32 error bound was derived for
     int M;
     int n_rows;
     int *verlet;
@@ -203,7 +206,7 @@ __device__ __noinline__ int direct_atom(const TileArgs &A, int sg)
 }
 
 template <int T, int TZ, bool COUNT_ONLY>
-__global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid_constant__ TileArgs A)
+__global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid_constant__ TileArgs A)
 {
     constexpr int P = T + 2;     // block edge in x, y
     constexpr int PZ = TZ + 2;   // block edge in z (the contiguous direction of the sorted copy)
@@ -219,6 +222,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
     int *gstart = cs + NPEN * CSW;                                           // [NPEN][PZ] global start per cell (-1 absent)
     int *ptot = gstart + NCELL;                                              // [NPEN+1]
     int *opref = ptot + NPEN + 1;                                            // [T*T+1]
+    int *far_flag = opref + T * T + 1;                                       // [1]
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(
         (reinterpret_cast<uintptr_t>(opref + T * T + 2) + 7) & ~static_cast<uintptr_t>(7));
 
@@ -235,7 +239,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
     // positions beyond it only serve as wrapped candidates)
     const int amax = min(T, A.p_hi - (u0x + 1)), bmax = min(T, g.n[1] - (u0y + 1)), kmax = min(TZ, g.n[2] - (u0z + 1));
 
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        *far_flag = 0;
+    }
 
     // ---- A. population and global start of every cell of the block
     // z slots are in MEMORY order: slot ks holds z position kk = PZ-1-ks (cells are stored in descending z)
@@ -287,14 +294,14 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
     const int n_staged = ptot[NPEN];
     const int n_owned = opref[T * T];
     if (n_owned == 0) return;
-    const bool staged_ok = n_staged <= A.cap;
+    const bool fits = n_staged <= A.cap;
 
     const double rcsq = A.rcsq;
     const DBox &box = A.box;
     const int warp = tid >> 5, lane = tid & 31;
     (void)box;
 
-    if (staged_ok) {
+    if (fits) {
         // ---- B. stage the records: one bulk copy per run of consecutive global cells of a pencil
         if (A.use_tma) {
             if (tid == 0) mbar_expect_tx(bar, (unsigned)n_staged * (unsigned)sizeof(SortedAtom));
@@ -342,20 +349,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
             const int *row = cs + p * CSW;
             const int beg = row[0], end = row[PZ];
             for (int s = beg + lane; s < end; s += 32) {
-                int kk = 0;
-#pragma unroll
-                for (int t = 1; t < PZ; ++t) kk += (row[t] <= s);
                 const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
                 const double zr = reinterpret_cast<const double *>(raw + s)[2];
                 double d0 = lo.x - ctr0, d1 = lo.y - ctr1, d2 = zr - ctr2;
                 if (box.pbc[0]) d0 -= box.h[0] * rint(d0 * box.hinv[0]);
                 if (box.pbc[1]) d1 -= box.h[4] * rint(d1 * box.hinv[4]);
                 if (box.pbc[2]) d2 -= box.h[8] * rint(d2 * box.hinv[8]);
-                f4[s] = make_float4((float)d0, (float)d1, (float)d2, __int_as_float(kk));
+                const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
+                const float w = __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0));
+                if (!(w <= A.w_limit)) *far_flag = 1;  // outside the radius the fp32 bound covers (or NaN)
+                f4[s] = make_float4(f0, f1, f2, w);
             }
         }
         __syncthreads();
     }
+    const bool staged_ok = fits && *far_flag == 0;
 
     // ---- D. one thread per owned atom
     int local_max = 0;
@@ -399,7 +407,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
             int my_idx = 0, my_cell = 0, cnt = 0, s_i = 0, kk = 1;
             int *vrow = nullptr;
             double *drow = nullptr;
-            float fx = 0, fy = 0, fz = 0;
+            float fx = 0, fy = 0, fz = 0, thr = 0;
             bool live = false;
             if (active) {
                 s_i = cs[p * CSW + PZ - 1 - kmax] + (t - opref[pi]);
@@ -407,23 +415,28 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
                 live = my_idx < A.n_rows;
                 wrap_ortho(box, xi, yi, zi);
                 const float4 me = f4[s_i];
-                fx = me.x;
-                fy = me.y;
-                fz = me.z;
-                kk = __float_as_int(me.w);  // my memory slot along z
+                fx = -2.0f * me.x;
+                fy = -2.0f * me.y;
+                fz = -2.0f * me.z;
+                thr = rc2hi - me.w;
+                // my memory slot along z: owned slots are PZ-1-kmax .. PZ-2
+                kk = PZ - 1 - kmax;
+                const int *prow = cs + p * CSW;
+                while (kk < PZ - 2 && prow[kk + 1] <= s_i) ++kk;
                 vrow = A.verlet + (size_t)my_idx * A.M;
                 drow = A.dist + (size_t)my_idx * A.M;
             }
             unsigned q_top = q_base;                            // queue write pointer
             const unsigned q_full = q_base + 2u * TILE_THREADS * SURV_CAP;
             const unsigned q_warn = q_base + 2u * TILE_THREADS * SURV_RESERVE;
-            const unsigned self_addr = f4_base + 16u * (unsigned)s_i;
+            const unsigned self_q = (unsigned)s_i;
 
             // phase 2: exact test of the queued survivors, in queue (= reference) order
             auto drain = [&]() {
 #pragma unroll 1
                 for (unsigned qa = q_base; qa < q_top; qa += 2u * TILE_THREADS) {
                     const unsigned q = lds_u16(qa);
+                    if (q == self_q) continue;
                     double xj, yj, zj;
                     int jdx;
                     lds_rec(raw_base + 32u * q, xj, yj, zj, jdx);
@@ -446,11 +459,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
             // phase 1: the 9 pencils of the stencil in (x, y) order.  The three z cells of a pencil are
             // one contiguous staged run stored in descending z, so a single backward walk yields
             // cell z-1, z, z+1, each in descending original index: the reference's order.
+            int pen_off = -P - 1, pen_y = 0;  // pencil offsets of the 3 x 3 stencil in (x, y) order
 #pragma unroll 1
             for (int pen = 0; pen < 9; ++pen) {
                 if (live) {
-                    const int da = pen / 3 - 1, db = pen % 3 - 1;
-                    const int *row = cs + ((a + da) * P + (b + db)) * CSW + kk;
+                    const int *row = cs + (p + pen_off) * CSW + kk;
                     const unsigned abeg = f4_base + 16u * (unsigned)row[-1];
                     unsigned aq = f4_base + 16u * (unsigned)row[2];  // one past the last candidate
 #pragma unroll 1
@@ -458,12 +471,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
                         // scan at most as many candidates as the queue has room for, then (rarely) drain
                         const unsigned room = (q_full - q_top) / (2u * TILE_THREADS);
                         const unsigned astop = (aq - abeg > 16u * room) ? aq - 16u * room : abeg;
+#pragma unroll 2
                         while (aq > astop) {
                             aq -= 16u;
                             const float4 o = lds_f4(aq);
-                            const float dx = o.x - fx, dy = o.y - fy, dz = o.z - fz;
-                            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-                            if (d2 <= rc2hi && aq != self_addr) {
+                            // |rj|^2 - 2 ri.rj  <=  rc^2 (1 + guard) - |ri|^2   (the atom itself passes; phase 2 drops it)
+                            const float t2 = __fmaf_rn(fx, o.x, __fmaf_rn(fy, o.y, __fmaf_rn(fz, o.z, o.w)));
+                            if (t2 <= thr) {
                                 sts_u16(q_top, (aq - f4_base) >> 4);
                                 q_top += 2u * TILE_THREADS;
                             }
@@ -471,6 +485,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
                         if (aq > abeg) drain();
                     }
                 }
+                if (++pen_y == 3) {
+                    pen_y = 0;
+                    pen_off += P - 2;
+                } else ++pen_off;
                 if (__any_sync(0xffffffffu, q_top > q_warn) || pen == 8) drain();
             }
             if (active && live) {
@@ -552,7 +570,11 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     A.g = g;
     A.rcsq = rc * rc;
     A.pad = rc + 1.0;
-    A.rcsq_hi = (float)(rc * rc * (1.0 + 2e-4)) * (1.0f + 1e-6f);
+    // fp32 error of the dot-product form: <= ~8 ulp of the largest partial sum, i.e. 8 * 6e-8 * w_limit
+    // = 7.7e-5 rc^2 at w_limit = 160 rc^2 (a (T+2)-cell block with cells <= 1.34 rc stays below 135 rc^2);
+    // the guard of 4e-4 rc^2 leaves a factor 5
+    A.rcsq_hi = (float)(rc * rc * (1.0 + 4e-4)) * (1.0f + 1e-6f);
+    A.w_limit = (float)(160.0 * rc * rc);
     A.M = M;
     A.n_rows = s.n_rows;
     A.nn = s.nn.ensure<int>(s.n_rows);

@@ -45,23 +45,15 @@ const ptm::Tables *device_tables(int device)
     return D.d_tables;
 }
 
-__global__ void __launch_bounds__(64) k_ptm(const double *__restrict__ x, const double *__restrict__ y,
-                                            const double *__restrict__ z, int N, int n_rows,
-                                            const __grid_constant__ DBox box, const int *__restrict__ verlet, int M,
-                                            const int *__restrict__ types, int flags, double rmsd_threshold,
-                                            const ptm::Tables *__restrict__ tables, double *__restrict__ output,
-                                            int ocols, int *__restrict__ indices, int icols)
+// neighbour vectors of atom i in list order: polyhedral_template_matching.cpp:222-248
+__device__ __forceinline__ int gather_points(const double *__restrict__ x, const double *__restrict__ y,
+                                             const double *__restrict__ z, int N, const DBox &box,
+                                             const int *__restrict__ row, int M, int i, double (*pts)[3], int *nbr)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rows) return;
-    double pts[ptm::MAX_IN][3];
-    int nbr[ptm::MAX_IN], ty[ptm::MAX_IN + 1];
-    int num = 0;
     const double xi = x[i], yi = y[i], zi = z[i];
-    ty[0] = types ? types[i] : 0;
-    // neighbour collection: polyhedral_template_matching.cpp:222-248
+    int num = 0;
     for (int k = 0; k < M && num < ptm::MAX_IN; ++k) {
-        const int j = verlet[(size_t)i * M + k];
+        const int j = row[k];
         if (j < 0 || j >= N) break;
         if (j == i) continue;
         double dx = x[j] - xi, dy = y[j] - yi, dz = z[j] - zi;
@@ -70,12 +62,52 @@ __global__ void __launch_bounds__(64) k_ptm(const double *__restrict__ x, const 
         pts[num][1] = dy;
         pts[num][2] = dz;
         nbr[num] = j;
-        ty[1 + num] = types ? types[j] : 0;
         ++num;
     }
-    ptm::Result r;
+    return num;
+}
+
+// Pass 1 (the reference's pre-ordering loop, polyhedral_template_matching.cpp:213-252): Voronoi solid-angle
+// ranking of every atom's listed neighbours.  order[i][r] = list position of the rank-r neighbour.
+__global__ void __launch_bounds__(64) k_ptm_order(const double *__restrict__ x, const double *__restrict__ y,
+                                                  const double *__restrict__ z, int N, int n_rows,
+                                                  const __grid_constant__ DBox box, const int *__restrict__ verlet, int M,
+                                                  unsigned char *__restrict__ order_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    double pts[ptm::MAX_IN][3];
+    int nbr[ptm::MAX_IN];
+    const int num = gather_points(x, y, z, N, box, verlet + (size_t)i * M, M, i, pts, nbr);
     int order[ptm::MAX_IN];
-    ptm::index_atom(*tables, flags, num, pts, ty, r, order);
+    // Voronoi face polygons of this thread: shared memory, one column per thread (conflict-free)
+    __shared__ double poly[4 * ptm::MAX_POLY2 * 64];
+    ptm::preorder_neighbours<64>(num, pts, order, poly + threadIdx.x);
+    unsigned char *o = order_out + (size_t)i * ptm::MAX_IN;
+    for (int k = 0; k < ptm::MAX_IN; ++k) o[k] = (unsigned char)(k < num ? order[k] : 255);
+}
+
+// Pass 2 (polyhedral_template_matching.cpp:255-316): template matching on the ranked neighbours.
+__global__ void __launch_bounds__(64) k_ptm_match(const double *__restrict__ x, const double *__restrict__ y,
+                                                  const double *__restrict__ z, int N, int n_rows,
+                                                  const __grid_constant__ DBox box, const int *__restrict__ verlet, int M,
+                                                  const unsigned char *__restrict__ order_in,
+                                                  const int *__restrict__ types, int flags, double rmsd_threshold,
+                                                  const ptm::Tables *__restrict__ tables, double *__restrict__ output,
+                                                  int ocols, int *__restrict__ indices, int icols)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    double pts[ptm::MAX_IN][3];
+    int nbr[ptm::MAX_IN], ty[ptm::MAX_IN + 1], order[ptm::MAX_IN];
+    const int num = gather_points(x, y, z, N, box, verlet + (size_t)i * M, M, i, pts, nbr);
+    ty[0] = types ? types[i] : 0;
+    for (int k = 0; k < num; ++k) {
+        ty[1 + k] = types ? types[nbr[k]] : 0;
+        order[k] = order_in[(size_t)i * ptm::MAX_IN + k];
+    }
+    ptm::Result r;
+    ptm::match_atom(*tables, flags, num, pts, order, ty, r);
     // outputs: polyhedral_template_matching.cpp:265-314
     int type = r.type, ordering = r.ordering;
     if (r.rmsd > rmsd_threshold || type == 0) {
@@ -138,7 +170,9 @@ void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *ty
                 "PTM structures dcub / dhex / graphene need neighbours of neighbours and are not built yet");
     const ptm::Tables *T = device_tables(s.device);
     const int R = s.n_rows;
-    MDB_LAUNCH(k_ptm, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, types, flags & 31,
-               rmsd_threshold, T, output, ocols, indices, icols);
+    unsigned char *order = s.scratch.ensure<unsigned char>((size_t)R * ptm::MAX_IN);
+    MDB_LAUNCH(k_ptm_order, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order);
+    MDB_LAUNCH(k_ptm_match, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
+               flags & 31, rmsd_threshold, T, output, ocols, indices, icols);
     CUDA_TRY(cudaGetLastError());
 }

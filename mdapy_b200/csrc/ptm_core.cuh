@@ -30,13 +30,21 @@
 #include <cstdint>
 #include "box.cuh"
 
+// large cold-ish building blocks are kept out of line on the device: the fully inlined kernel was 460 KB
+// of SASS and stalled on instruction fetch
+#ifdef __CUDACC__
+#define MDB_HDN __host__ __device__ __noinline__
+#else
+#define MDB_HDN inline
+#endif
+
 namespace ptm {
 
 constexpr int MAX_IN = 18;      // neighbours offered per atom (PTM_MAX_INPUT_POINTS - 1)
 constexpr int MAX_NB = 14;      // neighbours of the largest supported structure (BCC)
 constexpr int MAX_FACETS = 24;  // 2n - 4 for n = 14
 constexpr int MAX_CODE = 72;    // 3 * facets = 2 * edges
-constexpr int MAX_POLY = 40;    // vertices of one Voronoi face during clipping
+constexpr int MAX_POLY = 28;    // vertices of one Voronoi face during clipping (<= 17 bisectors + 4 + cube corners)
 
 enum { S_SC = 0, S_FCC = 1, S_HCP = 2, S_ICO = 3, S_BCC = 4, NSTRUCT = 5 };
 // reference structure ids (ptm_constants.h): FCC 1, HCP 2, BCC 3, ICO 4, SC 5
@@ -68,14 +76,6 @@ MDB_HD void cross3(const double *a, const double *b, double *c)
 
 // ---------------------------------------------------------------------------------------------
 // 2. Voronoi solid angles
-MDB_HD double solid_angle_tri(const double *r1, const double *r2, const double *r3)
-{
-    double c[3];
-    cross3(r2, r3, c);
-    const double num = dot3(r1, c);
-    const double den = 1 + dot3(r1, r2) + dot3(r3, r1) + dot3(r2, r3);
-    return fabs(2 * atan2(num, den));
-}
 
 // clip polygon (n vertices, in order) by the half-space nrm.x <= d; returns new vertex count
 MDB_HD int clip_poly(const double (*in)[3], int n, const double *nrm, double d, double (*out)[3])
@@ -107,8 +107,25 @@ MDB_HD int clip_poly(const double (*in)[3], int n, const double *nrm, double d, 
     return m;
 }
 
-// solid angle subtended at the origin by the Voronoi face of point k (0 when the face is empty)
-MDB_HD double voronoi_face_solid_angle(int num, const double (*pts)[3], const double *normsq, double box_half, int k)
+// 0: the plane cuts nothing (polygon unchanged), 1: it cuts, 2: nothing is left
+MDB_HD int clip_class(const double (*in)[3], int n, const double *nrm, double d)
+{
+    bool out = false, in_ = false;
+    for (int i = 0; i < n; ++i) {
+        const double sc = dot3(in[i], nrm) - d;
+        if (sc <= 0) in_ = true;
+        else out = true;
+    }
+    return !out ? 0 : (in_ ? 1 : 2);
+}
+
+// solid angle subtended at the origin by the Voronoi face of point k (0 when the face is empty).
+// The face is the bisector plane of k clipped by the other bisectors (nearest first: the polygon shrinks
+// to its final size after a few planes and the remaining ones are rejected by clip_class without touching
+// it) and finally by the bounding cube of the reference's cell (+-10 r_max), which only matters for atoms
+// whose cell is open.  The solid angle of the fan is the argument of the product of the triangles'
+// (den + i num) terms (Van Oosterom-Strackee per triangle): one atan2 per face.
+MDB_HDN double voronoi_face_solid_angle(int num, const double (*pts)[3], const double *normsq, double box_half, int k)
 {
     double bufa[MAX_POLY][3], bufb[MAX_POLY][3];
     // a large square on the bisector plane of point k
@@ -137,23 +154,26 @@ MDB_HD double voronoi_face_solid_angle(int num, const double (*pts)[3], const do
     int n = 4;
     double(*src)[3] = bufa;
     double(*dst)[3] = bufb;
-    // the bounding cube of the reference's cell (+-10 r_max)
-    for (int d = 0; d < 3 && n; ++d) {
-        double nrm[3] = {0, 0, 0};
-        nrm[d] = 1;
-        n = clip_poly(src, n, nrm, box_half, dst);
-        double(*t)[3] = src;
-        src = dst;
-        dst = t;
-        nrm[d] = -1;
-        n = clip_poly(src, n, nrm, box_half, dst);
-        t = src;
-        src = dst;
-        dst = t;
-    }
-    for (int j = 0; j < num && n; ++j) {
+    for (int j = 0; j < num + 6 && n; ++j) {
         if (j == k) continue;
-        n = clip_poly(src, n, pts[j], 0.5 * normsq[j], dst);
+        double cube[3] = {0, 0, 0};
+        const double *nrm;
+        double d;
+        if (j < num) {
+            nrm = pts[j];
+            d = 0.5 * normsq[j];
+        } else {
+            cube[(j - num) >> 1] = ((j - num) & 1) ? -1.0 : 1.0;
+            nrm = cube;
+            d = box_half;
+        }
+        const int cls = clip_class(src, n, nrm, d);
+        if (cls == 0) continue;
+        if (cls == 2) {
+            n = 0;
+            break;
+        }
+        n = clip_poly(src, n, nrm, d, dst);
         double(*t)[3] = src;
         src = dst;
         dst = t;
@@ -166,13 +186,153 @@ MDB_HD double voronoi_face_solid_angle(int num, const double (*pts)[3], const do
         src[i][1] /= nr;
         src[i][2] /= nr;
     }
-    double sa = 0;
-    for (int i = 2; i < n; ++i) sa += solid_angle_tri(src[0], src[i - 1], src[i]);
-    return sa;
+    double re = 1.0, im = 0.0;
+    for (int i = 2; i < n; ++i) {
+        double c[3];
+        cross3(src[i - 1], src[i], c);
+        const double tn = dot3(src[0], c);
+        const double td = 1 + dot3(src[0], src[i - 1]) + dot3(src[i], src[0]) + dot3(src[i - 1], src[i]);
+        const double r2 = re * td - im * tn;
+        im = re * tn + im * td;
+        re = r2;
+    }
+    return fabs(2 * atan2(im, re));
 }
 
-// order[0..num) = input indices ranked by (solid angle desc, distance asc, input order)
-MDB_HD void preorder_neighbours(int num, const double (*pts)[3], int *order)
+// The same face in the 2-D coordinates (a, b) of its own plane, x = p/2 + a u + b v: a clipping plane
+// becomes the line s0 + a su + b sv <= 0 (three dot products per plane, two multiply-adds per vertex), and
+// the two small vertex buffers fit in shared memory on the device (element i of a buffer lives at
+// buf[i * STRIDE]; STRIDE = 1 on the host, = block size on the device with buf offset by the thread).
+// Returns -1 when a polygon outgrows the buffers: the caller then uses the 3-D routine above.
+constexpr int MAX_POLY2 = 16;
+
+template <int STRIDE>
+MDB_HD double voronoi_face_solid_angle_2d(int num, const double (*pts)[3], const double *normsq, double box_half, int k,
+                                          double *buf)
+{
+    const double *p = pts[k];
+    const double pn = sqrt(normsq[k]);
+    double u[3], v[3], e[3] = {0, 0, 0};
+    int ax = 0;
+    if (fabs(p[1]) < fabs(p[ax])) ax = 1;
+    if (fabs(p[2]) < fabs(p[ax])) ax = 2;
+    e[ax] = 1;
+    cross3(p, e, u);
+    const double un = sqrt(dot3(u, u));
+    u[0] /= un;
+    u[1] /= un;
+    u[2] /= un;
+    cross3(p, u, v);
+    v[0] /= pn;
+    v[1] /= pn;
+    v[2] /= pn;
+    const double c0[3] = {0.5 * p[0], 0.5 * p[1], 0.5 * p[2]};
+    const double S = 4 * box_half;
+    // buffer layout: [which (2)][coordinate (2)][vertex (MAX_POLY2)]
+    double *A0 = buf, *B0 = buf + MAX_POLY2 * STRIDE, *A1 = buf + 2 * MAX_POLY2 * STRIDE, *B1 = buf + 3 * MAX_POLY2 * STRIDE;
+    A0[0] = S;
+    B0[0] = S;
+    A0[STRIDE] = -S;
+    B0[STRIDE] = S;
+    A0[2 * STRIDE] = -S;
+    B0[2 * STRIDE] = -S;
+    A0[3 * STRIDE] = S;
+    B0[3 * STRIDE] = -S;
+    int n = 4;
+    double *sa = A0, *sb = B0, *da = A1, *db = B1;
+    for (int j = 0; j < num + 6 && n; ++j) {
+        if (j == k) continue;
+        double s0, su, sv;
+        if (j < num) {
+            const double *q = pts[j];
+            s0 = dot3(c0, q) - 0.5 * normsq[j];
+            su = dot3(u, q);
+            sv = dot3(v, q);
+        } else {
+            const int d = (j - num) >> 1;
+            const double sg = ((j - num) & 1) ? -1.0 : 1.0;
+            s0 = sg * c0[d] - box_half;
+            su = sg * u[d];
+            sv = sg * v[d];
+        }
+        bool any_out = false, any_in = false;
+        for (int i = 0; i < n; ++i) {
+            const double sc = s0 + sa[i * STRIDE] * su + sb[i * STRIDE] * sv;
+            if (sc <= 0) any_in = true;
+            else any_out = true;
+        }
+        if (!any_out) continue;
+        if (!any_in) {
+            n = 0;
+            break;
+        }
+        double pa = sa[(n - 1) * STRIDE], pb = sb[(n - 1) * STRIDE];
+        double sp = s0 + pa * su + pb * sv;
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const double ca = sa[i * STRIDE], cb = sb[i * STRIDE];
+            const double sc = s0 + ca * su + cb * sv;
+            if ((sc <= 0) != (sp <= 0)) {
+                if (m >= MAX_POLY2) return -1.0;
+                const double t = sp / (sp - sc);
+                da[m * STRIDE] = pa + t * (ca - pa);
+                db[m * STRIDE] = pb + t * (cb - pb);
+                ++m;
+            }
+            if (sc <= 0) {
+                if (m >= MAX_POLY2) return -1.0;
+                da[m * STRIDE] = ca;
+                db[m * STRIDE] = cb;
+                ++m;
+            }
+            pa = ca;
+            pb = cb;
+            sp = sc;
+        }
+        n = m;
+        double *t1 = sa;
+        sa = da;
+        da = t1;
+        t1 = sb;
+        sb = db;
+        db = t1;
+    }
+    if (n < 3) return 0.0;
+    // fan of spherical triangles from vertex 0; product of the (den + i num) terms, one atan2
+    double f0[3], fp[3], fc[3];
+    auto unit = [&](int i, double *o) {
+        const double a = sa[i * STRIDE], b = sb[i * STRIDE];
+        o[0] = c0[0] + a * u[0] + b * v[0];
+        o[1] = c0[1] + a * u[1] + b * v[1];
+        o[2] = c0[2] + a * u[2] + b * v[2];
+        const double nr = sqrt(dot3(o, o));
+        o[0] /= nr;
+        o[1] /= nr;
+        o[2] /= nr;
+    };
+    unit(0, f0);
+    unit(1, fp);
+    double re = 1.0, im = 0.0;
+    for (int i = 2; i < n; ++i) {
+        unit(i, fc);
+        double c[3];
+        cross3(fp, fc, c);
+        const double tn = dot3(f0, c);
+        const double td = 1 + dot3(f0, fp) + dot3(fc, f0) + dot3(fp, fc);
+        const double r2 = re * td - im * tn;
+        im = re * tn + im * td;
+        re = r2;
+        fp[0] = fc[0];
+        fp[1] = fc[1];
+        fp[2] = fc[2];
+    }
+    return fabs(2 * atan2(im, re));
+}
+
+// order[0..num) = input indices ranked by (solid angle desc, distance asc, input order).
+// buf: 4 * MAX_POLY2 doubles of scratch per caller, strided by STRIDE (see above).
+template <int STRIDE>
+MDB_HD void preorder_neighbours(int num, const double (*pts)[3], int *order, double *buf)
 {
     double normsq[MAX_IN], area[MAX_IN];
     double mx = 0;
@@ -181,7 +341,11 @@ MDB_HD void preorder_neighbours(int num, const double (*pts)[3], int *order)
         mx = mx > normsq[i] ? mx : normsq[i];
     }
     const double box_half = 10 * sqrt(mx);
-    for (int i = 0; i < num; ++i) area[i] = voronoi_face_solid_angle(num, pts, normsq, box_half, i);
+    for (int i = 0; i < num; ++i) {
+        double a = voronoi_face_solid_angle_2d<STRIDE>(num, pts, normsq, box_half, i, buf);
+        if (a < 0) a = voronoi_face_solid_angle(num, pts, normsq, box_half, i);
+        area[i] = a;
+    }
     // stable insertion sort
     for (int i = 0; i < num; ++i) order[i] = i;
     for (int i = 1; i < num; ++i) {
@@ -202,7 +366,7 @@ MDB_HD void preorder_neighbours(int num, const double (*pts)[3], int *order)
 // 3a. incremental convex hull of points[0..np) (0 = central atom).  Facets are returned over the
 // neighbour indices 0..np-2, counter-clockwise seen from outside.  Returns the facet count, or a
 // negative value when the point set is degenerate, the hull overflows or the centre lies on it.
-MDB_HD int convex_hull(int np, const double (*P)[3], signed char (*facets)[3])
+MDB_HDN int convex_hull(int np, const double (*P)[3], signed char (*facets)[3])
 {
     const double TOL = 1e-12;
     signed char F[2 * MAX_NB + 8][3];
@@ -387,8 +551,12 @@ MDB_HD bool build_rotation(int n, int nf, const signed char (*facets)[3], Rotati
     return true;
 }
 
-// code for one start dart; returns false when the walk breaks (malformed surface)
-MDB_HD bool dart_code(int n, const Rotation &R, int s, int t, signed char *label, signed char *code, int &len)
+// Code for one start dart, compared on the fly with the best code so far (best_len < 0: none yet).
+// Returns 1 when the new code is lexicographically smaller (code[0..len) is then complete), 0 when it
+// equals the best, -1 as soon as it is known to be larger (the walk stops there), -2 when the walk breaks
+// (malformed surface).  All codes of one graph have the same length (one entry per dart).
+MDB_HD int dart_code(int n, const Rotation &R, int s, int t, signed char *label, signed char *code, int &len,
+                     const signed char *best, int best_len)
 {
     signed char ref[MAX_NB], byl[MAX_NB];
     for (int u = 0; u < n; ++u) label[u] = -1;
@@ -399,25 +567,40 @@ MDB_HD bool dart_code(int n, const Rotation &R, int s, int t, signed char *label
     ref[s] = (signed char)t;
     ref[t] = (signed char)s;
     int count = 2;
-    len = 0;
-    for (int k = 0; k < n; ++k) {
-        if (k >= count) return false;  // disconnected
-        const int v = byl[k];
-        int w = ref[v];
-        for (int j = 0; j < R.deg[v]; ++j) {
-            if (w < 0) return false;
-            if (label[w] < 0) {
-                label[w] = (signed char)count;
-                byl[count] = (signed char)w;
-                ref[w] = (signed char)v;
-                ++count;
+    int state = best_len < 0 ? 1 : 0;
+    int total = 0;
+    for (int u = 0; u < n; ++u) total += R.deg[u];
+    if (total > MAX_CODE) return -2;
+    // one flat loop over the darts (same trip count for every atom of a shell: SIMT friendly);
+    // (k, v, j, w) = position in the label-ordered vertex list, that vertex, neighbours listed so far, next neighbour
+    int k = 0, v = s, j = 0, w = t, dv = R.deg[s];
+    for (len = 0; len < total; ++len) {
+        if (w < 0) return -2;
+        if (label[w] < 0) {
+            label[w] = (signed char)count;
+            byl[count] = (signed char)w;
+            ref[w] = (signed char)v;
+            ++count;
+        }
+        const signed char c = label[w];
+        if (state == 0) {
+            if (c > best[len]) return -1;
+            if (c < best[len]) state = 1;
+        }
+        code[len] = c;
+        w = R.nxt[v][w];
+        if (++j == dv) {
+            if (++k >= count) {
+                if (len + 1 < total) return -2;  // disconnected
+                continue;
             }
-            if (len >= MAX_CODE) return false;
-            code[len++] = label[w];
-            w = R.nxt[v][w];
+            v = byl[k];
+            w = ref[v];
+            j = 0;
+            dv = R.deg[v];
         }
     }
-    return count == n;
+    return count == n ? state : -2;
 }
 
 MDB_HD unsigned long long code_hash(const signed char *code, int len)
@@ -430,33 +613,44 @@ MDB_HD unsigned long long code_hash(const signed char *code, int len)
     return h ^ ((unsigned long long)len << 56);
 }
 
-// canonical code + ONE canonical labelling of an environment graph
-MDB_HD bool canonical_form(int n, int nf, const signed char (*facets)[3], const Rotation &R, signed char *best_label,
+// Start darts are restricted to those whose (deg s, deg t, deg third-vertex-of-the-facet) triple is the
+// largest in the graph -- an isomorphism-invariant choice (the reference prunes the same way,
+// ptm_canonical_coloured.cpp:120-167), which leaves a handful of darts instead of 3 * facets.
+MDB_HD int dart_key(const Rotation &R, int s, int t, int w) { return (R.deg[s] << 16) | (R.deg[t] << 8) | R.deg[w]; }
+
+// canonical code + ONE canonical labelling of an environment graph (the first start dart, in facet order,
+// that attains the minimum)
+MDB_HDN bool canonical_form(int n, int nf, const signed char (*facets)[3], const Rotation &R, signed char *best_label,
                            unsigned long long &hash)
 {
-    signed char best[MAX_CODE], cur[MAX_CODE], lab[MAX_NB];
+    signed char bufa[MAX_CODE], bufb[MAX_CODE], laba[MAX_NB], labb[MAX_NB];
+    signed char *best = bufa, *cur = bufb, *blab = laba, *clab = labb;
     int best_len = -1;
+    int top = 0;
+    for (int f = 0; f < nf; ++f)
+        for (int e = 0; e < 3; ++e) {
+            const int k = dart_key(R, facets[f][e], facets[f][(e + 1) % 3], facets[f][(e + 2) % 3]);
+            top = top > k ? top : k;
+        }
     for (int f = 0; f < nf; ++f)
         for (int e = 0; e < 3; ++e) {
             const int s = facets[f][e], t = facets[f][(e + 1) % 3];
+            if (dart_key(R, s, t, facets[f][(e + 2) % 3]) != top) continue;
             int len;
-            if (!dart_code(n, R, s, t, lab, cur, len)) return false;
-            bool better = best_len < 0;
-            if (!better) {
-                for (int i = 0; i < len; ++i) {
-                    if (cur[i] != best[i]) {
-                        better = cur[i] < best[i];
-                        break;
-                    }
-                }
-            }
-            if (better) {
+            const int r = dart_code(n, R, s, t, clab, cur, len, best, best_len);
+            if (r == -2) return false;
+            if (r == 1) {
                 best_len = len;
-                for (int i = 0; i < len; ++i) best[i] = cur[i];
-                for (int u = 0; u < n; ++u) best_label[u] = lab[u];
+                signed char *x = best;
+                best = cur;
+                cur = x;
+                x = blab;
+                blab = clab;
+                clab = x;
             }
         }
     if (best_len < 0) return false;
+    for (int u = 0; u < n; ++u) best_label[u] = blab[u];
     hash = code_hash(best, best_len);
     return true;
 }
@@ -465,7 +659,7 @@ MDB_HD bool canonical_form(int n, int nf, const signed char (*facets)[3], const 
 // 3c. optimal rotation (unit quaternion, w first) taking template points onto observed points.
 // A[3*a+b] = sum_i tpl_i[a] * obs_i[b].  Largest eigenvalue of Horn's 4x4 matrix by Newton iteration on
 // its characteristic quartic, eigenvector from the adjugate (Theobald's QCP formulation).
-MDB_HD void optimal_rotation(const double *A, double E0, double *q)
+MDB_HDN void optimal_rotation(const double *A, double E0, double *q)
 {
     const double Sxx = A[0], Sxy = A[1], Sxz = A[2], Syx = A[3], Syy = A[4], Syz = A[5], Szx = A[6], Szy = A[7],
                  Szz = A[8];
@@ -593,7 +787,7 @@ struct Result {
 };
 
 // try every template triangulation of structure s whose hash matches
-MDB_HD void check_structure(const Tables &T, int s, unsigned long long hash, const signed char *env_label,
+MDB_HDN void check_structure(const Tables &T, int s, unsigned long long hash, const signed char *env_label,
                             const double (*centred)[3], Result &res)
 {
     const int n = T.n_nbrs[s], np = n + 1;
@@ -659,7 +853,7 @@ MDB_HD void check_structure(const Tables &T, int s, unsigned long long hash, con
 }
 
 // hull + canonical form of the first n ordered points, then the listed structures (all with n neighbours)
-MDB_HD void match_shell(const Tables &T, const int *structs, int ns, const double (*hull_pts)[3],
+MDB_HDN void match_shell(const Tables &T, const int *structs, int ns, const double (*hull_pts)[3],
                         const double (*raw_pts)[3], Result &res)
 {
     const int s0 = structs[0];
@@ -689,10 +883,11 @@ MDB_HD void match_shell(const Tables &T, const int *structs, int ns, const doubl
     for (int k = 0; k < ns; ++k) check_structure(T, structs[k], hash, label, centred, res);
 }
 
-// full per-atom analysis.  pts[0..num): neighbour vectors in list (distance) order; types: atom type of
-// the centre (types[0]) and of each listed neighbour (types[1 + k]).
-MDB_HD void index_atom(const Tables &T, int flags, int num, const double (*pts)[3], const int *types, Result &res,
-                       int *order_out)
+// full per-atom analysis.  pts[0..num): neighbour vectors in list (distance) order; order[0..num): their
+// ranking from preorder_neighbours; types: atom type of the centre (types[0]) and of each listed
+// neighbour (types[1 + k]).
+MDB_HD void match_atom(const Tables &T, int flags, int num, const double (*pts)[3], const int *order, const int *types,
+                       Result &res)
 {
     res.type = 0;
     res.ordering = 0;
@@ -701,9 +896,6 @@ MDB_HD void index_atom(const Tables &T, int flags, int num, const double (*pts)[
     res.interatomic_distance = 0;
     res.struct_index = -1;
     res.q[0] = res.q[1] = res.q[2] = res.q[3] = 0;
-    int order[MAX_IN];
-    preorder_neighbours(num, pts, order);
-    for (int i = 0; i < num; ++i) order_out[i] = order[i];
     // ordered points, 0 = centre
     double raw[MAX_IN + 1][3];
     raw[0][0] = raw[0][1] = raw[0][2] = 0;
@@ -777,6 +969,14 @@ MDB_HD void index_atom(const Tables &T, int flags, int num, const double (*pts)[
     } else if (s == S_BCC) {
         if (diff == 0x1feu) res.ordering = 5;  // first shell unlike, second shell like
     }
+}
+
+MDB_HD void index_atom(const Tables &T, int flags, int num, const double (*pts)[3], const int *types, Result &res,
+                       int *order_out)
+{
+    double buf[4 * MAX_POLY2];
+    preorder_neighbours<1>(num, pts, order_out, buf);
+    match_atom(T, flags, num, pts, order_out, types, res);
 }
 
 }  // namespace ptm

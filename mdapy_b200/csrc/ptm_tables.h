@@ -292,11 +292,16 @@ inline void build_tables(HostTables &H)
             // all start darts: minimal code and every labelling attaining it
             std::vector<signed char> best;
             std::vector<std::array<signed char, MAX_NB>> labs;
+            int top = 0;
+            for (int f = 0; f < nf; ++f)
+                for (int e = 0; e < 3; ++e)
+                    top = std::max(top, dart_key(R, facets[f][e], facets[f][(e + 1) % 3], facets[f][(e + 2) % 3]));
             for (int f = 0; f < nf; ++f)
                 for (int e = 0; e < 3; ++e) {
+                    if (dart_key(R, facets[f][e], facets[f][(e + 1) % 3], facets[f][(e + 2) % 3]) != top) continue;
                     signed char lab[MAX_NB], code[MAX_CODE];
                     int len;
-                    if (!dart_code(n, R, facets[f][e], facets[f][(e + 1) % 3], lab, code, len)) continue;
+                    if (dart_code(n, R, facets[f][e], facets[f][(e + 1) % 3], lab, code, len, nullptr, -1) != 1) continue;
                     std::vector<signed char> c(code, code + len);
                     std::array<signed char, MAX_NB> la{};
                     for (int u = 0; u < n; ++u) la[u] = lab[u];
