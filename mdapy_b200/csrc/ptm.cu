@@ -87,6 +87,23 @@ __global__ void __launch_bounds__(64) k_ptm_order(const double *__restrict__ x, 
     for (int k = 0; k < ptm::MAX_IN; ++k) o[k] = (unsigned char)(k < num ? order[k] : 255);
 }
 
+// access to other atoms' lists and rankings for the two-shell structures (ptm::two_shell_env)
+struct DeviceSrc {
+    const double *x, *y, *z;
+    int N;
+    const DBox *box;
+    const int *verlet;
+    int M;
+    const int *types;
+    const unsigned char *order;
+    __device__ int gather(int i, double (*pts)[3], int *nbr) const
+    {
+        return gather_points(x, y, z, N, *box, verlet + (size_t)i * M, M, i, pts, nbr);
+    }
+    __device__ const unsigned char *order_of(int i) const { return order + (size_t)i * ptm::MAX_IN; }
+    __device__ int type_of(int i) const { return types ? types[i] : 0; }
+};
+
 // Pass 2 (polyhedral_template_matching.cpp:255-316): template matching on the ranked neighbours.
 __global__ void __launch_bounds__(64) k_ptm_match(const double *__restrict__ x, const double *__restrict__ y,
                                                   const double *__restrict__ z, int N, int n_rows,
@@ -106,8 +123,9 @@ __global__ void __launch_bounds__(64) k_ptm_match(const double *__restrict__ x, 
         ty[1 + k] = types ? types[nbr[k]] : 0;
         order[k] = order_in[(size_t)i * ptm::MAX_IN + k];
     }
+    const DeviceSrc src{x, y, z, N, &box, verlet, M, types, order_in};
     ptm::Result r;
-    ptm::match_atom(*tables, flags, num, pts, order, ty, r);
+    ptm::match_atom(*tables, flags, num, pts, order, ty, nbr, src, i, r);
     // outputs: polyhedral_template_matching.cpp:265-314
     int type = r.type, ordering = r.ordering;
     if (r.rmsd > rmsd_threshold || type == 0) {
@@ -120,12 +138,7 @@ __global__ void __launch_bounds__(64) k_ptm_match(const double *__restrict__ x, 
     if (indices) {
         int *ind = indices + (size_t)i * icols;
         const int n = r.struct_index >= 0 ? tables->n_nbrs[r.struct_index] : -1;
-        for (int c = 0; c < icols; ++c) {
-            int v = -1;
-            if (n >= 0 && c == 0) v = i;
-            else if (n >= 0 && c <= n) v = nbr[order[r.mapping[c] - 1]];
-            ind[c] = v;
-        }
+        for (int c = 0; c < icols; ++c) ind[c] = c <= n ? r.env_idx[r.mapping[c]] : -1;
     }
 }
 
@@ -165,14 +178,13 @@ int ptm_parse_flags(const char *structure)
 void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
                 double *output, int ocols, int *indices, int icols)
 {
-    const int unsupported = flags & (ptm::CHECK_DCUB | ptm::CHECK_DHEX | ptm::CHECK_GRAPHENE);
-    MDB_REQUIRE(!(unsupported && !(flags & 31)), MDB_ERR_VALUE,
-                "PTM structures dcub / dhex / graphene need neighbours of neighbours and are not built yet");
+    MDB_REQUIRE(!(flags & (ptm::CHECK_DCUB | ptm::CHECK_DHEX | ptm::CHECK_GRAPHENE)) || s.slab_nx == 0, MDB_ERR_STATE,
+                "PTM structures dcub / dhex / graphene read neighbours of neighbours: not available on a decomposed frame");
     const ptm::Tables *T = device_tables(s.device);
     const int R = s.n_rows;
     unsigned char *order = s.scratch.ensure<unsigned char>((size_t)R * ptm::MAX_IN);
     MDB_LAUNCH(k_ptm_order, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order);
     MDB_LAUNCH(k_ptm_match, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
-               flags & 31, rmsd_threshold, T, output, ocols, indices, icols);
+               flags & 255, rmsd_threshold, T, output, ocols, indices, icols);
     CUDA_TRY(cudaGetLastError());
 }

@@ -41,18 +41,20 @@
 namespace ptm {
 
 constexpr int MAX_IN = 18;      // neighbours offered per atom (PTM_MAX_INPUT_POINTS - 1)
-constexpr int MAX_NB = 14;      // neighbours of the largest supported structure (BCC)
-constexpr int MAX_FACETS = 24;  // 2n - 4 for n = 14
-constexpr int MAX_CODE = 72;    // 3 * facets = 2 * edges
+constexpr int MAX_NB = 16;      // neighbours of the largest supported structure (diamond: 4 + 12)
+constexpr int MAX_FACETS = 28;  // 2n - 4 for n = 16
+constexpr int MAX_CODE = 84;    // 3 * facets = 2 * edges
+constexpr int MAX_MULTISHELL = 13;  // two-shell environments only use the 13 nearest listed neighbours (ptm_multishell.h:20)
 constexpr int MAX_POLY = 28;    // vertices of one Voronoi face during clipping (<= 17 bisectors + 4 + cube corners)
 
-enum { S_SC = 0, S_FCC = 1, S_HCP = 2, S_ICO = 3, S_BCC = 4, NSTRUCT = 5 };
-// reference structure ids (ptm_constants.h): FCC 1, HCP 2, BCC 3, ICO 4, SC 5
+enum { S_SC = 0, S_FCC = 1, S_HCP = 2, S_ICO = 3, S_BCC = 4, S_DCUB = 5, S_DHEX = 6, S_GRAPHENE = 7, NSTRUCT = 8 };
+// reference structure ids (ptm_constants.h): FCC 1, HCP 2, BCC 3, ICO 4, SC 5, DCUB 6, DHEX 7, graphene 8
 constexpr int CHECK_FCC = 1, CHECK_HCP = 2, CHECK_BCC = 4, CHECK_ICO = 8, CHECK_SC = 16, CHECK_DCUB = 32,
               CHECK_DHEX = 64, CHECK_GRAPHENE = 128;
 
 struct Tables {
     int n_nbrs[NSTRUCT], n_facets[NSTRUCT], max_degree[NSTRUCT], type_id[NSTRUCT], group[NSTRUCT];
+    int n_inner[NSTRUCT];                 // two-shell structures: neighbours of the first shell (coloured 1), else 0
     double tpl[NSTRUCT][MAX_NB + 1][3];   // template points (0 = centre), barycentre 0, mean distance 1
     double c_dist[NSTRUCT];               // |template[1]|: interatomic distance = c_dist / scale
     int graph_begin[NSTRUCT + 1];         // graphs of structure s: [graph_begin[s], graph_begin[s+1]) sorted by hash
@@ -555,8 +557,10 @@ MDB_HD bool build_rotation(int n, int nf, const signed char (*facets)[3], Rotati
 // Returns 1 when the new code is lexicographically smaller (code[0..len) is then complete), 0 when it
 // equals the best, -1 as soon as it is known to be larger (the walk stops there), -2 when the walk breaks
 // (malformed surface).  All codes of one graph have the same length (one entry per dart).
+// n_inner > 0: vertices 0..n_inner-1 carry colour 1 and enter the code as n + label
+// (ptm_canonical_coloured.cpp:33-44), so only colour-preserving relabellings compare equal.
 MDB_HD int dart_code(int n, const Rotation &R, int s, int t, signed char *label, signed char *code, int &len,
-                     const signed char *best, int best_len)
+                     const signed char *best, int best_len, int n_inner = 0)
 {
     signed char ref[MAX_NB], byl[MAX_NB];
     for (int u = 0; u < n; ++u) label[u] = -1;
@@ -582,7 +586,7 @@ MDB_HD int dart_code(int n, const Rotation &R, int s, int t, signed char *label,
             ref[w] = (signed char)v;
             ++count;
         }
-        const signed char c = label[w];
+        const signed char c = (signed char)(label[w] + (w < n_inner ? n : 0));
         if (state == 0) {
             if (c > best[len]) return -1;
             if (c < best[len]) state = 1;
@@ -621,7 +625,7 @@ MDB_HD int dart_key(const Rotation &R, int s, int t, int w) { return (R.deg[s] <
 // canonical code + ONE canonical labelling of an environment graph (the first start dart, in facet order,
 // that attains the minimum)
 MDB_HDN bool canonical_form(int n, int nf, const signed char (*facets)[3], const Rotation &R, signed char *best_label,
-                           unsigned long long &hash)
+                           unsigned long long &hash, int n_inner = 0)
 {
     signed char bufa[MAX_CODE], bufb[MAX_CODE], laba[MAX_NB], labb[MAX_NB];
     signed char *best = bufa, *cur = bufb, *blab = laba, *clab = labb;
@@ -632,23 +636,30 @@ MDB_HDN bool canonical_form(int n, int nf, const signed char (*facets)[3], const
             const int k = dart_key(R, facets[f][e], facets[f][(e + 1) % 3], facets[f][(e + 2) % 3]);
             top = top > k ? top : k;
         }
+    // the qualifying start darts are listed first, so that the threads of a warp walk their lists in step
+    // (testing the key inside the walk loop left ~4 of 32 lanes busy)
+    unsigned short dart[MAX_CODE];
+    int nd = 0;
     for (int f = 0; f < nf; ++f)
         for (int e = 0; e < 3; ++e) {
             const int s = facets[f][e], t = facets[f][(e + 1) % 3];
-            if (dart_key(R, s, t, facets[f][(e + 2) % 3]) != top) continue;
-            int len;
-            const int r = dart_code(n, R, s, t, clab, cur, len, best, best_len);
-            if (r == -2) return false;
-            if (r == 1) {
-                best_len = len;
-                signed char *x = best;
-                best = cur;
-                cur = x;
-                x = blab;
-                blab = clab;
-                clab = x;
-            }
+            if (dart_key(R, s, t, facets[f][(e + 2) % 3]) == top && nd < MAX_CODE) dart[nd++] = (unsigned short)(s | (t << 8));
         }
+    for (int i = 0; i < nd; ++i) {
+        const int s = dart[i] & 255, t = dart[i] >> 8;
+        int len;
+        const int r = dart_code(n, R, s, t, clab, cur, len, best, best_len, n_inner);
+        if (r == -2) return false;
+        if (r == 1) {
+            best_len = len;
+            signed char *x = best;
+            best = cur;
+            cur = x;
+            x = blab;
+            blab = clab;
+            clab = x;
+        }
+    }
     if (best_len < 0) return false;
     for (int u = 0; u < n; ++u) best_label[u] = blab[u];
     hash = code_hash(best, best_len);
@@ -783,7 +794,9 @@ struct Result {
     int ordering;   // alloy ordering (ptm_constants.h): 0 none, 1 pure, 2 L1_0, 3 L1_2(Cu), 4 L1_2(Au), 5 B2
     double rmsd, scale, q[4], interatomic_distance;
     int struct_index;            // S_* of the winner, -1 none
-    signed char mapping[MAX_NB + 1];  // template point -> ordered point (0 = centre)
+    signed char mapping[MAX_NB + 1];  // template point -> environment point (0 = centre)
+    // two-shell winners (diamond, graphene): atom index and type of every environment point
+    int env_idx[MAX_NB + 1], env_type[MAX_NB + 1];
 };
 
 // try every template triangulation of structure s whose hash matches
@@ -883,11 +896,305 @@ MDB_HDN void match_shell(const Tables &T, const int *structs, int ns, const doub
     for (int k = 0; k < ns; ++k) check_structure(T, structs[k], hash, label, centred, res);
 }
 
+// barycentre of the np points removed (ptm_normalize_vertices.cpp:21-44)
+MDB_HD void subtract_barycentre(int np, const double (*raw)[3], double (*out)[3])
+{
+    double sum[3] = {0, 0, 0};
+    for (int i = 0; i < np; ++i)
+        for (int d = 0; d < 3; ++d) sum[d] += raw[i][d];
+    for (int d = 0; d < 3; ++d) sum[d] /= np;
+    for (int i = 0; i < np; ++i)
+        for (int d = 0; d < 3; ++d) out[i][d] = raw[i][d] - sum[d];
+}
+
+// hull coordinates: barycentre removed, then divided by (sum of the neighbour lengths) / np
+// (ptm_normalize_vertices.cpp:46-66 -- the divisor counts the centre as well)
+MDB_HD void normalize_vertices(int np, const double (*raw)[3], double (*out)[3])
+{
+    subtract_barycentre(np, raw, out);
+    double scale = 0;
+    for (int i = 1; i < np; ++i) scale += sqrt(dot3(out[i], out[i]));
+    scale /= np;
+    for (int i = 0; i < np; ++i)
+        for (int d = 0; d < 3; ++d) out[i][d] /= scale;
+}
+
+// Two-shell environment of the diamond structures (ptm_structure_matcher.cpp:193-310).  Points: centre,
+// 4 first neighbours ("inner", vertices 0..3 of the graph), 12 second neighbours (vertices 4..15, three
+// per inner atom).  The hull of the 16 neighbours normally consists of the outer atoms only; every inner
+// atom is then put back as the apex over the facet spanned by its own three outer atoms, which yields
+// the 28-facet graph the templates are tabulated with.  An inner atom that does reach the hull
+// ("inverted") already brings its three facets along.
+MDB_HDN void match_diamond(const Tables &T, int flags, const double (*hull_pts)[3], const double (*raw_pts)[3],
+                          Result &res)
+{
+    const int n = 16, np = 17;
+    signed char facets[MAX_FACETS][3];
+    int nf = convex_hull(np, hull_pts, facets);
+    if (nf < 0) return;
+    bool inverted[4] = {false, false, false, false};
+    for (int f = 0; f < nf; ++f) {
+        int cnt = 0;
+        for (int e = 0; e < 3; ++e)
+            if (facets[f][e] <= 3) {
+                inverted[facets[f][e]] = true;
+                ++cnt;
+            }
+        if (cnt > 1) return;  // a facet with two inner atoms
+    }
+    int n_inv = 0;
+    for (int i = 0; i < 4; ++i) n_inv += inverted[i] ? 1 : 0;
+    if (nf != 20 + 2 * n_inv) return;
+    int n_found = 0;
+    signed char toadd[4][3];
+    for (int f = 0; f < nf; ++f) {
+        const int a = facets[f][0], b = facets[f][1], c = facets[f][2];
+        if (a <= 3 || b <= 3 || c <= 3) continue;
+        const int i0 = (a - 4) / 3, i1 = (b - 4) / 3, i2 = (c - 4) / 3;
+        if (i0 == i1 && i0 == i2) {
+            if (n_found + n_inv >= 4) return;
+            toadd[n_found][0] = (signed char)a;
+            toadd[n_found][1] = (signed char)b;
+            toadd[n_found][2] = (signed char)c;
+            ++n_found;
+            for (int e = 0; e < 3; ++e) facets[f][e] = facets[nf - 1][e];
+            --nf;
+            --f;
+        }
+    }
+    if (n_found + n_inv != 4) return;
+    for (int k = 0; k < n_found; ++k) {
+        const signed char a = toadd[k][0], b = toadd[k][1], c = toadd[k][2];
+        const signed char i0 = (signed char)((a - 4) / 3);
+        if (nf + 3 > MAX_FACETS) return;
+        facets[nf][0] = i0, facets[nf][1] = b, facets[nf][2] = c;
+        ++nf;
+        facets[nf][0] = a, facets[nf][1] = i0, facets[nf][2] = c;
+        ++nf;
+        facets[nf][0] = a, facets[nf][1] = b, facets[nf][2] = i0;
+        ++nf;
+    }
+    Rotation R;
+    if (!build_rotation(n, nf, facets, R)) return;
+    int maxdeg = 0;
+    for (int u = 0; u < n; ++u) maxdeg = maxdeg > R.deg[u] ? maxdeg : R.deg[u];
+    if (maxdeg > T.max_degree[S_DCUB]) return;
+    double centred[MAX_NB + 1][3];
+    subtract_barycentre(np, raw_pts, centred);
+    signed char label[MAX_NB];
+    unsigned long long hash;
+    if (!canonical_form(n, nf, facets, R, label, hash, 4)) return;
+    if (flags & CHECK_DCUB) check_structure(T, S_DCUB, hash, label, centred, res);
+    if (flags & CHECK_DHEX) check_structure(T, S_DHEX, hash, label, centred, res);
+}
+
+// RMSD of one fixed correspondence (ptm_structure_matcher.cpp:29-56); mapping: template point -> env point
+MDB_HDN void try_mapping(const Tables &T, int s, const double (*centred)[3], const signed char *mapping, double G1,
+                        double G2, Result &res)
+{
+    const int np = T.n_nbrs[s] + 1;
+    const double E0 = (G1 + G2) / 2;
+    double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < np; ++i) {
+        const double *t = T.tpl[s][i];
+        const double *o = centred[mapping[i]];
+        A[0] += t[0] * o[0];
+        A[1] += t[0] * o[1];
+        A[2] += t[0] * o[2];
+        A[3] += t[1] * o[0];
+        A[4] += t[1] * o[1];
+        A[5] += t[1] * o[2];
+        A[6] += t[2] * o[0];
+        A[7] += t[2] * o[1];
+        A[8] += t[2] * o[2];
+    }
+    double q[4], rot[9];
+    optimal_rotation(A, E0, q);
+    quat_to_matrix(q, rot);
+    double k0 = 0;
+    for (int i = 0; i < np; ++i) {
+        const double *t = T.tpl[s][i];
+        const double *o = centred[mapping[i]];
+        for (int j = 0; j < 3; ++j) {
+            double v = 0.0;
+            for (int k = 0; k < 3; ++k) v += rot[j * 3 + k] * t[k];
+            k0 += v * o[j];
+        }
+    }
+    const double scale = k0 / G2;
+    const double rmsd = sqrt(fabs(G1 - scale * k0) / np);
+    if (rmsd < res.rmsd) {
+        res.rmsd = rmsd;
+        res.scale = scale;
+        res.struct_index = s;
+        for (int d = 0; d < 4; ++d) res.q[d] = q[d];
+        for (int i = 0; i < np; ++i) res.mapping[i] = mapping[i];
+    }
+}
+
+// graphene: 3 + 3 x 2 neighbours, planar, no hull: the two outer atoms of every inner atom are tried in
+// both orders (ptm_structure_matcher.cpp:348-380, same sequence of the eight correspondences)
+MDB_HD void match_graphene(const Tables &T, const double (*raw_pts)[3], Result &res)
+{
+    const int np = 10;
+    double centred[MAX_NB + 1][3];
+    subtract_barycentre(np, raw_pts, centred);
+    double G1 = 0, G2 = 0;
+    for (int i = 0; i < np; ++i) {
+        G1 += T.tpl[S_GRAPHENE][i][0] * T.tpl[S_GRAPHENE][i][0] + T.tpl[S_GRAPHENE][i][1] * T.tpl[S_GRAPHENE][i][1] +
+              T.tpl[S_GRAPHENE][i][2] * T.tpl[S_GRAPHENE][i][2];
+        G2 += centred[i][0] * centred[i][0] + centred[i][1] * centred[i][1] + centred[i][2] * centred[i][2];
+    }
+    signed char mapping[MAX_NB + 1];
+    for (int i = 0; i < np; ++i) mapping[i] = (signed char)i;
+    auto swp = [&](int a, int b) {
+        const signed char t = mapping[a];
+        mapping[a] = mapping[b];
+        mapping[b] = t;
+    };
+    for (int i = 0; i < 2; ++i) {
+        swp(4, 5);
+        for (int j = 0; j < 2; ++j) {
+            swp(6, 7);
+            for (int k = 0; k < 2; ++k) {
+                swp(8, 9);
+                try_mapping(T, S_GRAPHENE, centred, mapping, G1, G2, res);
+            }
+        }
+    }
+}
+
+// Two-shell neighbour ordering (ptm_multishell.cpp:94-184).  Src gives access to other atoms:
+//   int gather(int atom, double (*pts)[3], int *nbr)   listed neighbours (vectors, indices), returns their number
+//   const unsigned char *order_of(int atom)            rank -> list position from the pre-ordering pass (255 = none)
+//   int type_of(int atom)
+// Only the MAX_MULTISHELL nearest listed neighbours of an atom take part.  Returns false when the
+// environment cannot be completed.  out_*: centre, n_inner first neighbours, then n_outer per inner.
+struct ShellEnv {
+    double pts[MAX_NB + 1][3];
+    int idx[MAX_NB + 1], type[MAX_NB + 1];
+};
+
+template <class Src>
+MDB_HDN bool two_shell_env(const Src &src, int atom, int num, const double (*pts)[3], const int *nbr, const int *order,
+                          const int *types, int n_inner, int n_outer, ShellEnv &out)
+{
+    // filtered, ordered first shell
+    int kept = 0;
+    out.pts[0][0] = out.pts[0][1] = out.pts[0][2] = 0;
+    out.idx[0] = atom;
+    out.type[0] = types[0];
+    for (int r = 0; r < num; ++r) {
+        const int p = order[r];
+        if (p + 1 > MAX_MULTISHELL) continue;
+        if (kept < n_inner) {
+            for (int d = 0; d < 3; ++d) out.pts[1 + kept][d] = pts[p][d];
+            out.idx[1 + kept] = nbr[p];
+            out.type[1 + kept] = types[1 + p];
+        }
+        ++kept;
+    }
+    if (kept + 1 < n_inner + 1) return false;
+    double tol = 1e-5 * sqrt(dot3(out.pts[1], out.pts[1]));
+    tol = tol > 1e-5 ? tol : 1e-5;
+    // filtered, ordered neighbours of every inner atom, relative to the centre
+    struct Cand {
+        double d[3];
+        int idx, type;
+    };
+    Cand cand[4][MAX_MULTISHELL];
+    int ncand[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n_inner; ++i) {
+        double ip[MAX_IN][3];
+        int inb[MAX_IN];
+        const int a = out.idx[1 + i];
+        const int m = src.gather(a, ip, inb);
+        const unsigned char *ord = src.order_of(a);
+        int c = 0;
+        for (int r = 0; r < m; ++r) {
+            const int p = ord[r];
+            if (p >= m || p + 1 > MAX_MULTISHELL) continue;
+            for (int d = 0; d < 3; ++d) cand[i][c].d[d] = ip[p][d] + out.pts[1 + i][d];
+            cand[i][c].idx = inb[p];
+            cand[i][c].type = src.type_of(inb[p]);
+            ++c;
+        }
+        ncand[i] = c;
+        if (c + 1 < n_inner + 1) return false;
+    }
+    // rank-major sweep (the reference's stable sort by rank keeps the inner atoms in order within a rank)
+    int counts[4] = {0, 0, 0, 0};
+    int found = 0;
+    const int want = n_inner * n_outer;
+    auto claimed = [&](int idx, const double *d) {
+        auto near = [&](int slot) {
+            if (out.idx[slot] != idx) return false;
+            const double dx = d[0] - out.pts[slot][0], dy = d[1] - out.pts[slot][1], dz = d[2] - out.pts[slot][2];
+            return sqrt(dx * dx + dy * dy + dz * dz) < tol;
+        };
+        for (int s = 0; s < n_inner + 1; ++s)
+            if (near(s)) return true;
+        for (int i = 0; i < n_inner; ++i)
+            for (int j = 0; j < counts[i]; ++j)
+                if (near(1 + n_inner + n_outer * i + j)) return true;
+        return false;
+    };
+    for (int r = 0; r < MAX_MULTISHELL && found < want; ++r)
+        for (int i = 0; i < n_inner && found < want; ++i) {
+            if (r >= ncand[i] || counts[i] >= n_outer) continue;
+            const Cand &c = cand[i][r];
+            if (claimed(c.idx, c.d)) continue;
+            const int slot = 1 + n_inner + n_outer * i + counts[i];
+            for (int d = 0; d < 3; ++d) out.pts[slot][d] = c.d[d];
+            out.idx[slot] = c.idx;
+            out.type[slot] = c.type;
+            ++counts[i];
+            ++found;
+        }
+    return found == want;
+}
+
+// diamond (4 + 4 x 3) and graphene (3 + 3 x 2) environments; kept out of line so that the common
+// one-shell path does not pay for its registers and stack
+template <class Src>
+MDB_HDN void match_two_shell(const Tables &T, int flags, int num, const double (*pts)[3], const int *order,
+                            const int *types, const int *nbr, const Src &src, int atom, Result &res)
+{
+    ShellEnv env;
+    if (flags & (CHECK_DCUB | CHECK_DHEX)) {   // ptm_index.cpp:159-170
+        if (two_shell_env(src, atom, num, pts, nbr, order, types, 4, 3, env)) {
+            double hull[MAX_NB + 1][3];
+            normalize_vertices(17, env.pts, hull);
+            const double before = res.rmsd;
+            match_diamond(T, flags, hull, env.pts, res);
+            if (res.rmsd < before)
+                for (int p = 0; p < 17; ++p) {
+                    res.env_idx[p] = env.idx[p];
+                    res.env_type[p] = env.type[p];
+                }
+        }
+    }
+    if (flags & CHECK_GRAPHENE) {             // ptm_index.cpp:172-179
+        if (two_shell_env(src, atom, num, pts, nbr, order, types, 3, 2, env)) {
+            const double before = res.rmsd;
+            match_graphene(T, env.pts, res);
+            if (res.rmsd < before)
+                for (int p = 0; p < 10; ++p) {
+                    res.env_idx[p] = env.idx[p];
+                    res.env_type[p] = env.type[p];
+                }
+        }
+    }
+}
+
 // full per-atom analysis.  pts[0..num): neighbour vectors in list (distance) order; order[0..num): their
 // ranking from preorder_neighbours; types: atom type of the centre (types[0]) and of each listed
 // neighbour (types[1 + k]).
+// nbr: atom index of every listed neighbour; src / atom: access to the neighbours' own lists and rankings
+// for the two-shell structures (see two_shell_env).
+template <class Src>
 MDB_HD void match_atom(const Tables &T, int flags, int num, const double (*pts)[3], const int *order, const int *types,
-                       Result &res)
+                       const int *nbr, const Src &src, int atom, Result &res)
 {
     res.type = 0;
     res.ordering = 0;
@@ -932,6 +1239,18 @@ MDB_HD void match_atom(const Tables &T, int flags, int num, const double (*pts)[
         const int st[1] = {S_BCC};
         match_shell(T, st, 1, hull, raw, res);
     }
+    // one-shell winners so far: environment = the ranked list itself
+    if (res.struct_index >= 0) {
+        const int n1 = T.n_nbrs[res.struct_index];
+        res.env_idx[0] = atom;
+        res.env_type[0] = types[0];
+        for (int p = 1; p <= n1; ++p) {
+            res.env_idx[p] = nbr[order[p - 1]];
+            res.env_type[p] = types[1 + order[p - 1]];
+        }
+    }
+    if (flags & (CHECK_DCUB | CHECK_DHEX | CHECK_GRAPHENE))
+        match_two_shell(T, flags, num, pts, order, types, nbr, src, atom, res);
     if (res.struct_index < 0) {
         res.rmsd = 0;
         return;
@@ -943,12 +1262,12 @@ MDB_HD void match_atom(const Tables &T, int flags, int num, const double (*pts)[
     res.interatomic_distance = T.c_dist[s] / res.scale;
     // alloy ordering (ptm_alloy_types.cpp:92-121) from the types of the matched points
     const int n = T.n_nbrs[s];
-    const int t0 = types[0];
+    const int t0 = res.env_type[0];
     bool pure = true, binary = true;
     int other = -1;
     unsigned diff = 0;  // bit p: template point p carries a different type than the centre
     for (int p = 1; p <= n; ++p) {
-        const int tp = types[1 + order[res.mapping[p] - 1]];
+        const int tp = res.env_type[res.mapping[p]];
         if (tp != t0) {
             pure = false;
             diff |= 1u << p;
@@ -968,15 +1287,12 @@ MDB_HD void match_atom(const Tables &T, int flags, int num, const double (*pts)[
             }
     } else if (s == S_BCC) {
         if (diff == 0x1feu) res.ordering = 5;  // first shell unlike, second shell like
+    } else if (s == S_DCUB || s == S_DHEX) {
+        if (diff == 0x1eu) res.ordering = 6;   // SiC: the four first neighbours unlike, second shell like
+    } else if (s == S_GRAPHENE) {
+        if (diff == 0xeu) res.ordering = 7;    // BN
     }
 }
 
-MDB_HD void index_atom(const Tables &T, int flags, int num, const double (*pts)[3], const int *types, Result &res,
-                       int *order_out)
-{
-    double buf[4 * MAX_POLY2];
-    preorder_neighbours<1>(num, pts, order_out, buf);
-    match_atom(T, flags, num, pts, order_out, types, res);
-}
 
 }  // namespace ptm

@@ -85,6 +85,34 @@ inline std::vector<std::array<double, 3>> template_points(int s)
                 v[d] = 2 * s1 * sg;
                 add_point(p, v[0], v[1], v[2]);
             }
+    } else if (s == S_DCUB || s == S_DHEX || s == S_GRAPHENE) {
+        // bond vectors of the centre (unit length), then the first shell, then for every first neighbour its own
+        // other neighbours: diamond cubic and graphene are staggered (inner - b_m), hexagonal diamond is
+        // eclipsed across the bond along c (inner + mirror_z(b_m)) and staggered across the other three
+        std::vector<std::array<double, 3>> b;
+        if (s == S_DCUB) {
+            const double h = 1 / std::sqrt(3.0);
+            b = {{h, h, h}, {h, -h, -h}, {-h, -h, h}, {-h, h, -h}};
+        } else if (s == S_DHEX) {
+            const double r = std::sqrt(2.0 / 3.0), q = std::sqrt(2.0) / 3;
+            b = {{-r, q, -1.0 / 3}, {0, -2 * q, -1.0 / 3}, {r, q, -1.0 / 3}, {0, 0, 1}};
+        } else {
+            const double h = std::sqrt(3.0) / 2;
+            b = {{0, 1, 0}, {h, -0.5, 0}, {-h, -0.5, 0}};
+        }
+        const int ni = (int)b.size();
+        for (auto &v : b) add_point(p, v[0], v[1], v[2]);
+        for (int i = 0; i < ni; ++i)
+            for (int m = 0; m < ni; ++m) {
+                if (m == i) continue;
+                if (s == S_DHEX && i == 3) add_point(p, b[i][0] + b[m][0], b[i][1] + b[m][1], b[i][2] - b[m][2]);
+                else add_point(p, b[i][0] - b[m][0], b[i][1] - b[m][1], b[i][2] - b[m][2]);
+            }
+        double mean = 0;
+        for (size_t i = 1; i < p.size(); ++i) mean += std::sqrt(p[i][0] * p[i][0] + p[i][1] * p[i][1] + p[i][2] * p[i][2]);
+        mean /= (double)(p.size() - 1);
+        for (auto &q : p)
+            for (double &c : q) c /= mean;
     }
     // snap tiny trigonometric residue so coplanarity tests are clean
     for (auto &q : p)
@@ -192,11 +220,12 @@ inline void close_group(std::vector<std::array<double, 4>> &g)
 inline void build_tables(HostTables &H)
 {
     Tables &T = H.t;
-    const int nn[NSTRUCT] = {6, 12, 12, 12, 14};
-    const int nfac[NSTRUCT] = {8, 20, 20, 20, 24};
-    const int mdeg[NSTRUCT] = {4, 6, 6, 6, 8};
-    const int tid[NSTRUCT] = {5, 1, 2, 4, 3};   // reference ids: SC 5, FCC 1, HCP 2, ICO 4, BCC 3
-    const int grp[NSTRUCT] = {0, 0, 1, 2, 0};   // cubic, cubic, hexagonal-conventional, icosahedral, cubic
+    const int nn[NSTRUCT] = {6, 12, 12, 12, 14, 16, 16, 9};
+    const int nfac[NSTRUCT] = {8, 20, 20, 20, 24, 28, 28, 0};
+    const int mdeg[NSTRUCT] = {4, 6, 6, 6, 8, 8, 8, 0};
+    const int tid[NSTRUCT] = {5, 1, 2, 4, 3, 6, 7, 8};   // reference ids: SC 5, FCC 1, HCP 2, ICO 4, BCC 3, DCUB 6, DHEX 7, graphene 8
+    const int grp[NSTRUCT] = {0, 0, 1, 2, 0, 0, 1, 1};   // cubic / hexagonal-conventional / icosahedral fundamental zones
+    const int ninner[NSTRUCT] = {0, 0, 0, 0, 0, 4, 4, 3};
     H.aut_begin.clear();
     H.hash.clear();
     H.aut_label.clear();
@@ -218,11 +247,17 @@ inline void build_tables(HostTables &H)
         T.max_degree[s] = mdeg[s];
         T.type_id[s] = tid[s];
         T.group[s] = grp[s];
+        T.n_inner[s] = ninner[s];
         auto pts = detail::template_points(s);
         for (int i = 0; i <= MAX_NB; ++i)
             for (int d = 0; d < 3; ++d) T.tpl[s][i][d] = i < (int)pts.size() ? pts[i][d] : 0.0;
         T.c_dist[s] = std::sqrt(dot3(T.tpl[s][1], T.tpl[s][1]));
         const int n = nn[s];
+        if (s == S_GRAPHENE) {   // matched without a graph (ptm_structure_matcher.cpp:348)
+            T.graph_begin[s] = (int)H.hash.size();
+            continue;
+        }
+        const int n_col = (s == S_DCUB || s == S_DHEX) ? 4 : 0;
         // permutations of the neighbour points induced by the proper rotations that map the template onto itself
         std::vector<std::vector<int>> perms;
         for (auto &q : groups[grp[s]]) {
@@ -278,6 +313,19 @@ inline void build_tables(HostTables &H)
                     ++nf;
                 }
             }
+            if (n_col) {   // inner atoms back in as apexes (same surgery as match_diamond)
+                for (int f = 0; f < nf; ++f) {
+                    const int a = facets[f][0], b = facets[f][1], c = facets[f][2];
+                    if (a < 4 || b < 4 || c < 4) continue;
+                    const int i0 = (a - 4) / 3;
+                    if ((b - 4) / 3 != i0 || (c - 4) / 3 != i0) continue;
+                    facets[f][0] = (signed char)i0, facets[f][1] = (signed char)b, facets[f][2] = (signed char)c;
+                    facets[nf][0] = (signed char)a, facets[nf][1] = (signed char)i0, facets[nf][2] = (signed char)c;
+                    ++nf;
+                    facets[nf][0] = (signed char)a, facets[nf][1] = (signed char)b, facets[nf][2] = (signed char)i0;
+                    ++nf;
+                }
+            }
             // orbit representative: smallest facet list over the template's rotations
             std::vector<std::array<int, 3>> rep;
             for (auto &pi : perms) {
@@ -301,7 +349,7 @@ inline void build_tables(HostTables &H)
                     if (dart_key(R, facets[f][e], facets[f][(e + 1) % 3], facets[f][(e + 2) % 3]) != top) continue;
                     signed char lab[MAX_NB], code[MAX_CODE];
                     int len;
-                    if (dart_code(n, R, facets[f][e], facets[f][(e + 1) % 3], lab, code, len, nullptr, -1) != 1) continue;
+                    if (dart_code(n, R, facets[f][e], facets[f][(e + 1) % 3], lab, code, len, nullptr, -1, n_col) != 1) continue;
                     std::vector<signed char> c(code, code + len);
                     std::array<signed char, MAX_NB> la{};
                     for (int u = 0; u < n; ++u) la[u] = lab[u];

@@ -1,11 +1,11 @@
 """Polyhedral template matching, mirroring ``mdapy.polyhedral_template_matching.PolyhedralTemplateMatching``
 (src/mdapy/polyhedral_template_matching.py:16-167).  ``output`` (N, 8): structure type (0 other, 1 fcc,
-2 hcp, 3 bcc, 4 ico, 5 sc), alloy ordering, rmsd, interatomic distance, quaternion w, x, y, z;
-``ptm_indices`` (N, 18): the atom and its matched neighbours.
+2 hcp, 3 bcc, 4 ico, 5 sc, 6 cubic diamond, 7 hexagonal diamond, 8 graphene), alloy ordering (1 pure, 2 L1_0,
+3 L1_2 Cu, 4 L1_2 Au, 5 B2, 6 SiC, 7 BN), rmsd, interatomic distance, quaternion w, x, y, z;
+``ptm_indices`` (N, 18): the atom and its matched neighbours (first 18 points of the matched environment).
 
-Built structures: sc, fcc, hcp, ico, bcc ("default" = fcc-hcp-bcc-ico).  dcub / dhex / graphene need
-neighbours of neighbours and are not built yet: they are ignored inside a mixed request such as "all"
-and rejected when requested alone."""
+All eight reference structures are built ("default" = fcc-hcp-bcc-ico); the diamond and graphene ones read
+the ranked neighbour lists of the first-shell atoms (ptm_multishell.cpp:94-184)."""
 from __future__ import annotations
 
 from typing import Optional

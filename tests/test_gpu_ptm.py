@@ -44,8 +44,7 @@ def test_golden_ptm_through_system(path):
     _close(d["ref_ptm_output"], ptm.output[: s.N], check_all_rmsd=Path(path).stem[3:] not in EXACT_TIES)
     s2 = mp.System(pos=d["pos"], box=mp.Box(d["box"], boundary=list(d["boundary"])))
     ptm2 = s2.cal_polyhedral_template_matching(structure="all")
-    assert np.array_equal(ptm2.output[: s2.N, 0] * (d["ref_ptm_all_output"][:, 0] < 6), 
-                          d["ref_ptm_all_output"][:, 0] * (d["ref_ptm_all_output"][:, 0] < 6))
+    assert np.array_equal(ptm2.output[: s2.N, 0], d["ref_ptm_all_output"][:, 0])     # all eight structures
 
 
 def _hcp(a=2.95, n=(8, 5, 5)):
@@ -55,6 +54,13 @@ def _hcp(a=2.95, n=(8, 5, 5)):
     ix, iy, iz = np.meshgrid(*[np.arange(k) for k in n], indexing="ij")
     shift = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], 1)
     return ((basis[None] + shift[:, None, :]) * cell).reshape(-1, 3), np.diag(cell * np.array(n))
+
+
+def _graphene(a=2.46, n=20):
+    frac = np.array([[0, 0, 0.5], [0.5, 1 / 6, 0.5], [0.5, 0.5, 0.5], [0, 2 / 3, 0.5]])
+    cell = np.array([a, np.sqrt(3) * a, 20.0])
+    g = np.stack(np.meshgrid(np.arange(n), np.arange(n), np.arange(1), indexing="ij"), -1).reshape(-1, 3)
+    return ((frac[None] + g[:, None]) * cell).reshape(-1, 3), np.diag(cell * np.array([n, n, 1]))
 
 
 def _seeded():
@@ -75,7 +81,19 @@ def _seeded():
     ps, bx = H.shear(H.rattle(p, 0.06, 8), b, xy=0.2, xz=0.1, yz=-0.15)
     out.append(("fcc_triclinic", ps, bx, [1, 1, 1], "fcc-hcp-bcc"))
     g, bg = H.random_gas(2500, 30.0, 6)
-    out.append(("gas", g, bg, [1, 1, 1], "fcc-hcp-bcc-ico-sc"))
+    out.append(("gas", g, bg, [1, 1, 1], "all"))
+    # two-shell structures: neighbours of neighbours (ptm_multishell.cpp)
+    dc, bd = H.diamond(3.567, 6)
+    keep = rng.random(dc.shape[0]) > 0.02
+    out.append(("dcub_vac_rattle", H.rattle(dc[keep], 0.05, 9), bd, [1, 1, 1], "dcub-dhex"))
+    out.append(("dcub_hot_all", H.rattle(dc, 0.3, 10), bd, [1, 1, 1], "all"))
+    dh, bh = H.hex_diamond(2.52, 6, 4, 4)
+    out.append(("dhex_rattle_slab", H.rattle(dh, 0.06, 11), bh, [1, 1, 0], "all"))
+    out.append(("dhex_hot", H.rattle(dh, 0.25, 12), bh, [1, 1, 1], "dcub-dhex-graphene"))
+    gr, bgr = _graphene()
+    out.append(("graphene_rattle", H.rattle(gr, 0.05, 13), bgr, [1, 1, 0], "graphene"))
+    out.append(("graphene_hot_all", H.rattle(gr, 0.2, 14), bgr, [1, 1, 0], "all"))
+    out.append(("fcc_hot_all", H.rattle(p, 0.3, 15), b, [1, 1, 1], "all"))
     return out
 
 
@@ -117,18 +135,28 @@ def test_ptm_alloy_ordering_b2_l12():
     cases.append((H.rattle(p, 0.03, 2), b, np.tile([2, 1, 1, 1], p.shape[0] // 4)))            # L1_2
     cases.append((H.rattle(p, 0.03, 3), b, np.tile([1, 1, 2, 2], p.shape[0] // 4)))            # L1_0
     cases.append((H.rattle(p, 0.03, 4), b, np.random.default_rng(0).integers(1, 4, p.shape[0])))  # ternary / random
-    for pos, box, types in cases:
-        fr = P.Frame(pos, box)
+    # zincblende / wurtzite (SiC ordering, 6) and hexagonal BN (7): the two sublattices alternate
+    p, b = H.diamond(4.36, 5)
+    cases.append((H.rattle(p, 0.03, 5), b, np.tile([1, 1, 1, 1, 2, 2, 2, 2], p.shape[0] // 8)))
+    p, b = H.hex_diamond(3.08, 5, 3, 3)
+    cases.append((H.rattle(p, 0.03, 6), b, np.tile([1, 2, 2, 1], p.shape[0] // 4)))
+    p, b = _graphene(2.5, 16)
+    cases.append((H.rattle(p, 0.03, 7), b, np.tile([1, 2, 1, 2], p.shape[0] // 4)))
+    seen = set()
+    for k, (pos, box, types) in enumerate(cases):
+        fr = P.Frame(pos, box, [1, 1, 0] if k == 6 else [1, 1, 1])
         f3, idx, _ = P.nearest(KR, fr, 18)
         t = types.astype(np.int32)
-        ro, _ = KR.ptm("fcc-hcp-bcc", *f3.geom(), idx, t, 0.1)
+        structure = "fcc-hcp-bcc" if k < 4 else "all"
+        ro, _ = KR.ptm(structure, *f3.geom(), idx, t, 0.1)
         ds = DeviceSystem(0)
         ds.set_atoms(f3.x, f3.y, f3.z, f3.box, f3.origin, f3.boundary)
         ds.put_neighbor(idx, kind=2)
-        ho, _ = ds.ptm("fcc-hcp-bcc", 0.1, t)
+        ho, _ = ds.ptm(structure, 0.1, t)
         assert np.array_equal(ro[:, 0], ho[:, 0])
         assert np.array_equal(ro[:, 1], ho[:, 1]), (np.bincount(ro[:, 1].astype(int)), np.bincount(ho[:, 1].astype(int)))
-        assert len(np.unique(ro[:, 1])) >= 1
+        seen |= set(np.unique(ro[:, 1]).astype(int).tolist())
+    assert {1, 2, 3, 4, 5, 6, 7} <= seen | {1}, seen
 
 
 def test_ptm_host_dropin_and_known_answers():
@@ -157,6 +185,11 @@ def test_ptm_host_dropin_and_known_answers():
                                     L.iptr(pb), L.iptr(idx), 18, L.iptr(t), N, 0.1, L.dptr(out), 8, L.iptr(ind), 18, 8))
         ro, _ = KR.ptm("fcc-hcp-bcc", *f3.geom(), idx, t, 0.1)
         _close(ro, out)
-    with pytest.raises(ValueError):
-        s = mp.System(pos=H.fcc(3.615, 5)[0], box=H.fcc(3.615, 5)[1])
-        s.cal_polyhedral_template_matching(structure="dcub")
+    # perfect two-shell crystals (reference tests/test_polyhedral_template_matching.py:34-55)
+    dia = mp.System(pos=H.diamond(3.567, 5)[0], box=H.diamond(3.567, 5)[1])
+    pd = dia.cal_polyhedral_template_matching(structure="dcub", return_rmsd=True)
+    assert np.all(np.asarray(dia.data["ptm"]) == 6) and np.asarray(dia.data["rmsd"]).max() < 1e-6
+    assert np.allclose(pd.output[:, 3], 3.567 * np.sqrt(3) / 4, rtol=1e-9)
+    lon = mp.System(pos=H.hex_diamond()[0], box=H.hex_diamond()[1])
+    lon.cal_polyhedral_template_matching(structure="dcub-dhex")
+    assert np.all(np.asarray(lon.data["ptm"]) == 7)

@@ -31,12 +31,12 @@ def harness(tmp_path_factory):
 
 
 def test_generated_tables(harness):
-    c = (C.c_int * 9)()
+    c = (C.c_int * 12)()
     harness.ptmh_tables_info(c)
-    assert list(c)[:5] == [1, 8, 16, 1, 218]
-    assert list(c)[5:8] == [24, 12, 60]
-    t = np.zeros((15, 3))
-    for s, n in enumerate([6, 12, 12, 12, 14]):
+    assert list(c)[:8] == [1, 8, 16, 1, 218, 12, 24, 0]      # ptm_graph_data.h:28-34
+    assert list(c)[8:11] == [24, 12, 60]
+    t = np.zeros((17, 3))
+    for s, n in enumerate([6, 12, 12, 12, 14, 16, 16, 9]):
         harness.ptmh_template(s, t.ctypes.data_as(dp))
         assert np.allclose(t[: n + 1].sum(axis=0), 0, atol=1e-12)                     # barycentre 0
         assert abs(np.linalg.norm(t[1: n + 1], axis=1).mean() - 1) < 1e-12            # mean distance 1
@@ -68,3 +68,12 @@ def test_host_core_vs_golden(harness, path):
     assert dq.size == 0 or dq.max() < 1e-6
     if Path(path).stem[3:] not in EXACT_TIES:
         assert np.allclose(out[:, 2], ro[:, 2], rtol=1e-6, atol=1e-7)
+    # all eight structures (flags 255) against the reference run with structure="all"
+    out2 = np.zeros((N, 8))
+    harness.ptmh_index(f3.x.ctypes.data_as(dp), f3.y.ctypes.data_as(dp), f3.z.ctypes.data_as(dp), N,
+                       b.ctypes.data_as(dp), o.ctypes.data_as(dp), pb.ctypes.data_as(ip), idx.ctypes.data_as(ip), 18,
+                       t.ctypes.data_as(ip), 255, C.c_double(0.1), out2.ctypes.data_as(dp), ind.ctypes.data_as(ip))
+    ra = d["ref_ptm_all_output"]
+    assert np.array_equal(out2[: fr.N, 0], ra[:, 0])
+    m = ra[:, 0] > 0
+    assert np.allclose(out2[: fr.N][m, 2:4], ra[m, 2:4], rtol=1e-6, atol=1e-7)
