@@ -17,6 +17,7 @@
 // Only ~20 % of the 27-cell candidates survive phase 1, so the f64 pipe sees ~13 pairs per atom
 // instead of ~67.  Rows are padded by the writing thread (-1 / rc+1), so no prefill pass is needed.
 #include "internal.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -222,9 +223,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid
     int *gstart = cs + NPEN * CSW;                                           // [NPEN][PZ] global start per cell (-1 absent)
     int *ptot = gstart + NCELL;                                              // [NPEN+1]
     int *opref = ptot + NPEN + 1;                                            // [T*T+1]
-    int *far_flag = opref + T * T + 1;                                       // [1]
+    int *far_flag = opref + T * T + 1;                                       // [2]: beyond the fp32 radius / periodic shift used
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(
-        (reinterpret_cast<uintptr_t>(opref + T * T + 2) + 7) & ~static_cast<uintptr_t>(7));
+        (reinterpret_cast<uintptr_t>(opref + T * T + 3) + 7) & ~static_cast<uintptr_t>(7));
 
     const int tid = threadIdx.x;
     const CellGrid &g = A.g;
@@ -241,7 +242,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid
 
     if (tid == 0) {
         mbar_init(bar, 1);
-        *far_flag = 0;
+        far_flag[0] = 0;
+        far_flag[1] = 0;
     }
 
     // ---- A. population and global start of every cell of the block
@@ -352,18 +354,24 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid
                 const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
                 const double zr = reinterpret_cast<const double *>(raw + s)[2];
                 double d0 = lo.x - ctr0, d1 = lo.y - ctr1, d2 = zr - ctr2;
-                if (box.pbc[0]) d0 -= box.h[0] * rint(d0 * box.hinv[0]);
-                if (box.pbc[1]) d1 -= box.h[4] * rint(d1 * box.hinv[4]);
-                if (box.pbc[2]) d2 -= box.h[8] * rint(d2 * box.hinv[8]);
+                double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+                if (box.pbc[0]) n0 = rint(d0 * box.hinv[0]);
+                if (box.pbc[1]) n1 = rint(d1 * box.hinv[4]);
+                if (box.pbc[2]) n2 = rint(d2 * box.hinv[8]);
+                d0 -= box.h[0] * n0;
+                d1 -= box.h[4] * n1;
+                d2 -= box.h[8] * n2;
+                if ((n0 != 0.0) | (n1 != 0.0) | (n2 != 0.0)) far_flag[1] = 1;  // some staged atom is a periodic image
                 const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
                 const float w = __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0));
-                if (!(w <= A.w_limit)) *far_flag = 1;  // outside the radius the fp32 bound covers (or NaN)
+                if (!(w <= A.w_limit)) far_flag[0] = 1;  // outside the radius the fp32 bound covers (or NaN)
                 f4[s] = make_float4(f0, f1, f2, w);
             }
         }
         __syncthreads();
     }
-    const bool staged_ok = fits && *far_flag == 0;
+    const bool staged_ok = fits && far_flag[0] == 0;
+    const bool tile_shifted = far_flag[1] != 0;
 
     // ---- D. one thread per owned atom
     int local_max = 0;
@@ -387,6 +395,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid
         const double Lx = box.h[0], Ly = box.h[4], Lz = box.h[8];
         const double iLx = box.hinv[0], iLy = box.hinv[4], iLz = box.hinv[8];
         const bool px = box.pbc[0] != 0, py = box.pbc[1] != 0, pz = box.pbc[2] != 0;
+        const int M = A.M;
+        const bool vec4 = !COUNT_ONLY && (M & 3) == 0;  // rows are 16-byte aligned: int4 / double2 stores
+        // odd lanes read the two halves of a 32-byte record in swapped order, which spreads the
+        // gathered records over all shared-memory banks (halves the conflicts of the two LDS.128)
+        const unsigned sw = (unsigned)(lane & 1) << 4;
 #pragma unroll 1
         for (int base = 0; base < n_owned; base += TILE_THREADS) {
             const int t = base + tid;
@@ -409,10 +422,19 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid
             double *drow = nullptr;
             float fx = 0, fy = 0, fz = 0, thr = 0;
             bool live = false;
+            // img: the exact test needs the minimum-image step.  When no staged atom of the tile is a
+            // periodic image and this atom lies inside the box, every pre-filter survivor has
+            // |dx| <= ~rc << L/2, so n = floor(dx/L + 0.5) = 0 and dx - L*0 == dx: the step is skipped.
+            bool img = tile_shifted;
+            int i0 = 0, i1 = 0, i2 = 0, i3 = 0;  // last four accepted indices (shift register)
+            double e0 = 0.0, e1 = 0.0;            // last two accepted distances
             if (active) {
                 s_i = cs[p * CSW + PZ - 1 - kmax] + (t - opref[pi]);
                 load_rec(raw + s_i, xi, yi, zi, my_idx, my_cell);
                 live = my_idx < A.n_rows;
+                if (px) { const double d = xi - box.origin[0]; img |= !(d >= box.wrap_t[0][1] && d < box.wrap_t[0][2]); }
+                if (py) { const double d = yi - box.origin[1]; img |= !(d >= box.wrap_t[1][1] && d < box.wrap_t[1][2]); }
+                if (pz) { const double d = zi - box.origin[2]; img |= !(d >= box.wrap_t[2][1] && d < box.wrap_t[2][2]); }
                 wrap_ortho(box, xi, yi, zi);
                 const float4 me = f4[s_i];
                 fx = -2.0f * me.x;
@@ -423,8 +445,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid
                 kk = PZ - 1 - kmax;
                 const int *prow = cs + p * CSW;
                 while (kk < PZ - 2 && prow[kk + 1] <= s_i) ++kk;
-                vrow = A.verlet + (size_t)my_idx * A.M;
-                drow = A.dist + (size_t)my_idx * A.M;
+                vrow = A.verlet + (size_t)my_idx * M;
+                drow = A.dist + (size_t)my_idx * M;
             }
             unsigned q_top = q_base;                            // queue write pointer
             const unsigned q_full = q_base + 2u * TILE_THREADS * SURV_CAP;
@@ -432,28 +454,49 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid
             const unsigned self_q = (unsigned)s_i;
 
             // phase 2: exact test of the queued survivors, in queue (= reference) order
-            auto drain = [&]() {
+            auto drain_t = [&](auto IMG) {
 #pragma unroll 1
                 for (unsigned qa = q_base; qa < q_top; qa += 2u * TILE_THREADS) {
                     const unsigned q = lds_u16(qa);
                     if (q == self_q) continue;
-                    double xj, yj, zj;
-                    int jdx;
-                    lds_rec(raw_base + 32u * q, xj, yj, zj, jdx);
+                    const unsigned ra = raw_base + 32u * q;
+                    double a0, a1, b0, b1;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a0), "=d"(a1) : "r"(ra + sw));
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(b0), "=d"(b1) : "r"(ra + (sw ^ 16u)));
+                    const double xj = sw ? b0 : a0, yj = sw ? b1 : a1, zj = sw ? a0 : b0;
+                    const int jdx = __double2loint(sw ? a1 : b1);
                     double dx = xj - xi, dy = yj - yi, dz = zj - zi;
-                    if (px) dx = near_image(dx, Lx, iLx);
-                    if (py) dy = near_image(dy, Ly, iLy);
-                    if (pz) dz = near_image(dz, Lz, iLz);
+                    if (decltype(IMG)::value) {
+                        if (px) dx = near_image(dx, Lx, iLx);
+                        if (py) dy = near_image(dy, Ly, iLy);
+                        if (pz) dz = near_image(dz, Lz, iLz);
+                    }
                     const double d2 = dx * dx + dy * dy + dz * dz;
                     if (d2 <= rcsq) {
-                        if (!COUNT_ONLY && cnt < A.M) {
-                            vrow[cnt] = jdx;
-                            drow[cnt] = sqrt(d2);
+                        if (!COUNT_ONLY && cnt < M) {
+                            const double dd = sqrt(d2);
+                            if (vec4) {
+                                i0 = i1;
+                                i1 = i2;
+                                i2 = i3;
+                                i3 = jdx;
+                                e0 = e1;
+                                e1 = dd;
+                                if (cnt & 1) *reinterpret_cast<double2 *>(drow + cnt - 1) = make_double2(e0, e1);
+                                if ((cnt & 3) == 3) *reinterpret_cast<int4 *>(vrow + cnt - 3) = make_int4(i0, i1, i2, i3);
+                            } else {
+                                vrow[cnt] = jdx;
+                                drow[cnt] = dd;
+                            }
                         }
                         ++cnt;
                     }
                 }
                 q_top = q_base;
+            };
+            auto drain = [&]() {
+                if (img) drain_t(std::true_type{});
+                else drain_t(std::false_type{});
             };
 
             // phase 1: the 9 pencils of the stencil in (x, y) order.  The three z cells of a pencil are
@@ -495,7 +538,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid
                 A.nn[my_idx] = cnt;
                 local_max = max(local_max, cnt);
                 if (!COUNT_ONLY) {
-                    for (int u = cnt; u < A.M; ++u) {
+                    if (vec4 && cnt < M) {
+                        // still in the shift registers: the last (cnt & 3) indices and (cnt & 1) distance
+                        const int r = cnt & 3;
+                        if (r >= 3) vrow[cnt - 3] = i1;
+                        if (r >= 2) vrow[cnt - 2] = i2;
+                        if (r >= 1) vrow[cnt - 1] = i3;
+                        if (cnt & 1) drow[cnt - 1] = e1;
+                    }
+                    for (int u = cnt; u < M; ++u) {
                         vrow[u] = -1;
                         drow[u] = A.pad;
                     }
@@ -512,7 +563,7 @@ template <int T, int TZ> size_t tile_smem_bytes(int cap)
 {
     constexpr int P = T + 2, PZ = TZ + 2, NPEN = P * P, NCELL = NPEN * PZ;
     return (size_t)cap * (sizeof(SortedAtom) + sizeof(float4)) + sizeof(unsigned short) * TILE_THREADS * SURV_CAP +
-           sizeof(int) * (NPEN * (PZ + 1) + NCELL + NPEN + 1 + T * T + 2) + 16;
+           sizeof(int) * (NPEN * (PZ + 1) + NCELL + NPEN + 1 + T * T + 3) + 16;
 }
 
 template <int T, int TZ> void launch_T(const TileArgs &A, int nblocks, cudaStream_t st)
