@@ -22,8 +22,8 @@
 namespace {
 
 constexpr int TILE_THREADS = 256;
-constexpr int SURV_CAP = 24;      // per-thread survivor queue (uint16 staged indices)
-constexpr int SURV_RESERVE = 12;  // warp drains when any lane holds more than this at a pencil boundary
+constexpr int SURV_CAP = 20;      // per-thread survivor queue (uint16 staged indices)
+constexpr int SURV_RESERVE = 10;  // warp drains when any lane holds more than this at a pencil boundary
 
 struct TileArgs {
     const SortedAtom *sorted;
@@ -207,7 +207,7 @@ __device__ __noinline__ int direct_atom(const TileArgs &A, int sg)
 }
 
 template <int T, int TZ, bool COUNT_ONLY>
-__global__ void __launch_bounds__(TILE_THREADS, 3) k_neighbor_tiled(const __grid_constant__ TileArgs A)
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid_constant__ TileArgs A)
 {
     constexpr int P = T + 2;     // block edge in x, y
     constexpr int PZ = TZ + 2;   // block edge in z (the contiguous direction of the sorted copy)
@@ -652,7 +652,7 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     A.use_tma = !(env && !strcmp(env, "ldg"));
     {   // staged-atom capacity from the mean cell population (tiles above it take the in-kernel direct path)
         const double rho = (double)s.N / ((double)g.nxl * g.n[1] * g.n[2]);
-        int cap = (int)(rho * (TT + 2) * (TT + 2) * (TZ + 2) * 1.35) + 64;
+        int cap = (int)(rho * (TT + 2) * (TT + 2) * (TZ + 2) * 1.15) + 64;
         cap = (cap + 31) / 32 * 32;
         A.cap = cap < 256 ? 256 : (cap > 2048 ? 2048 : cap);
     }
