@@ -373,7 +373,10 @@ def run_b200(args):
         line["roofline"] = {
             "kernel": "k_neighbor (cut-off neighbour build)", "bound": "hbm", "achieved": alg / (tn * 1e-3) / 1e9,
             "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if pk.exists() else "fallback",
-            "unit": "GB/s", "frac": alg / (tn * 1e-3) / 1e9 / peak, "traffic": None,
+            "unit": "GB/s", "frac": alg / (tn * 1e-3) / 1e9 / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default size, from the
+            # ncu --set full capture summarised in profiles/r1_s7_n292_ncu_full.txt (6.58 GB + 15.89 GB)
+            "traffic": 22.47e9 if n == 292 else None,
             "algorithmic_bytes_per_atom": 28 + 12 * M, "kernel_ms": tn,
             "step_breakdown_ms": {"binning": float(np.mean(t_bin)), "neighbor": tn, "cna": float(np.mean(t_cna))},
         }
