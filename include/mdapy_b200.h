@@ -156,6 +156,9 @@ int mdb_system_set_atoms_device(mdb_system *s, const double *dx, const double *d
 int mdb_system_set_slab_device(mdb_system *s, const double *dx, const double *dy, const double *dz,
                                const int *dgid, int n_local, int n_owned, int plane0, int nplanes,
                                const double *box9, const double *origin3, const int *boundary3);
+/* Decomposed frame: fraction (0, 1] of the box volume the local atoms occupy.  A density hint only
+ * (cell size of the k-nearest search grid); results do not depend on it. */
+int mdb_system_set_local_fraction(mdb_system *s, double fraction);
 /* cell grid of the cut-off search for (box, rc): src/neighbor.cpp:367-370 */
 int mdb_cell_grid(const double *box9, const double *origin3, const int *boundary3, double rc, int *n3);
 /* global x cell plane of each atom (device arrays), same arithmetic as src/neighbor.cpp:30-62 */

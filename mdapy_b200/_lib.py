@@ -62,6 +62,7 @@ PROTOTYPES = {
     "mdb_system_set_atoms": (C.c_int, [c_vp] + _XYZN + _BOX),
     "mdb_system_set_atoms_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int] + _BOX),
     "mdb_system_set_slab_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int] + _BOX),
+    "mdb_system_set_local_fraction": (C.c_int, [c_vp, C.c_double]),
     "mdb_cell_grid": (C.c_int, _BOX + [C.c_double, c_ip]),
     "mdb_cell_planes_device": (C.c_int, [c_vp, c_vp, c_vp, C.c_int] + _BOX + [C.c_double, c_vp, c_vp]),
     "mdb_system_build_neighbor": (C.c_int, [c_vp, C.c_double, C.c_int, c_ip, c_ip]),

@@ -62,6 +62,7 @@ static void upload_atoms(MdbSystem &s, const double *x, const double *y, const d
     s.n_rows = N;
     s.gid = nullptr;
     s.slab_x0 = s.slab_nx = 0;
+    s.local_frac = 1.0;
     invalidate(s);
 }
 
@@ -390,7 +391,16 @@ int mdb_system_set_slab_device(mdb_system *s, const double *dx, const double *dy
     s->n_rows = n_owned;
     s->slab_x0 = plane0;
     s->slab_nx = nplanes;
+    s->local_frac = 1.0;
     invalidate(*s);
+    API_END
+}
+
+int mdb_system_set_local_fraction(mdb_system *s, double fraction)
+{
+    API_BEGIN
+    MDB_REQUIRE(fraction > 0.0 && fraction <= 1.0, MDB_ERR_VALUE, "fraction must be in (0, 1], got %g", fraction);
+    s->local_frac = fraction;
     API_END
 }
 
@@ -540,9 +550,10 @@ int mdb_system_ids(mdb_system *s, int *pattern_host)
     API_BEGIN
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
-    MDB_REQUIRE(s->slab_nx == 0, MDB_ERR_STATE, "diamond identification is not available on a decomposed frame");
-    int *pat = s->out_i32.ensure<int>(s->n_rows);
-    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->n_rows, s->stream));
+    MDB_REQUIRE(s->n_rows == s->N || s->list_kind == LIST_KNN, MDB_ERR_STATE,
+                "diamond identification on a decomposed frame needs the k-nearest list (rows for ghosts too)");
+    int *pat = s->out_i32.ensure<int>(s->N);
+    CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->N, s->stream));
     launch_ids(*s, s->verlet.as<int>(), s->M, nullptr, pat);
     d2h(*s, pattern_host, pat, (size_t)s->n_rows);
     if (pattern_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -587,11 +598,14 @@ int mdb_system_steinhardt(mdb_system *s, const int *llist, int ndeg, int nnn, do
     const int nz = 2 * lmax + 1, R = s->n_rows;
     const int ncol = ndeg * (1 + (wl ? 1 : 0) + (wlhat ? 1 : 0));
     const size_t nq = (size_t)R * ndeg * nz;
-    double *qr = s->qlm_r.ensure<double>(nq), *qi = s->qlm_i.ensure<double>(nq);
-    double *qn = s->qn.ensure<double>((size_t)R * ncol);
-    CUDA_TRY(cudaMemsetAsync(qr, 0, sizeof(double) * nq, s->stream));
-    CUDA_TRY(cudaMemsetAsync(qi, 0, sizeof(double) * nq, s->stream));
-    CUDA_TRY(cudaMemsetAsync(qn, 0, sizeof(double) * (size_t)R * ncol, s->stream));
+    // arrays indexed by NEIGHBOUR ids cover every local atom (s->N >= n_rows: ghosts of a decomposed
+    // frame keep zero rows), results are read back for the n_rows row atoms
+    const size_t nq_all = (size_t)s->N * ndeg * nz;
+    double *qr = s->qlm_r.ensure<double>(nq_all), *qi = s->qlm_i.ensure<double>(nq_all);
+    double *qn = s->qn.ensure<double>((size_t)s->N * ncol);
+    CUDA_TRY(cudaMemsetAsync(qr, 0, sizeof(double) * nq_all, s->stream));
+    CUDA_TRY(cudaMemsetAsync(qi, 0, sizeof(double) * nq_all, s->stream));
+    CUDA_TRY(cudaMemsetAsync(qn, 0, sizeof(double) * (size_t)s->N * ncol, s->stream));
     const double *w = nullptr;
     if (weight_host) w = h2d(*s, s->weight, weight_host, (size_t)R * s->M);
     // steinhardt_bond_orientation.py:238-245: a huge rc for the voronoi / nnn neighbour sources
@@ -625,12 +639,13 @@ int mdb_system_solid_liquid(mdb_system *s, int q6index, double threshold, int n_
     if (use_voronoi) rc_eff = 10000000000.0;
     else if (nnn > 0) rc_eff = 1000000000.0;
     // contiguous copy of the q6 column (np.ascontiguousarray(qnarray[:, Q6index]) in the reference wrapper)
-    double *q6 = s->out_f64.ensure<double>(R);
+    const int NA = s->N;  // arrays indexed by neighbour ids cover the ghosts of a decomposed frame too
+    double *q6 = s->out_f64.ensure<double>(NA);
     CUDA_TRY(cudaMemcpy2DAsync(q6, sizeof(double), s->qn.as<double>() + q6index, sizeof(double) * s->sbo_ncol,
-                               sizeof(double), R, cudaMemcpyDeviceToDevice, s->stream));
-    int *solid = s->out_i32.ensure<int>((size_t)2 * R);
-    int *nbond = solid + R;
-    CUDA_TRY(cudaMemsetAsync(solid, 0, sizeof(int) * 2 * (size_t)R, s->stream));
+                               sizeof(double), NA, cudaMemcpyDeviceToDevice, s->stream));
+    int *solid = s->out_i32.ensure<int>((size_t)2 * NA);
+    int *nbond = solid + NA;
+    CUDA_TRY(cudaMemsetAsync(solid, 0, sizeof(int) * 2 * (size_t)NA, s->stream));
     launch_solid_liquid(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, q6index, q6,
                         s->qlm_r.as<double>(), s->qlm_i.as<double>(), s->sbo_ndeg, s->sbo_nz, threshold, n_bond,
                         use_voronoi != 0, nnn, rc_eff, solid, nbond);

@@ -327,10 +327,12 @@ __global__ void __launch_bounds__(CNA_THREADS) k_fcna_fast(const double *__restr
 // one of the LOWEST-index labelled atom that lists it: k_ids_claim records that index with atomicMin,
 // k_ids_assign applies it -- deterministic and identical to the serial result.
 __global__ void __launch_bounds__(128) k_ids_classify(const double *__restrict__ x, const double *__restrict__ y,
-                                                      const double *__restrict__ z, int N, DBox box,
+                                                      const double *__restrict__ z, int N, int NA, DBox box,
                                                       const int *__restrict__ verlet, int M,
                                                       int *__restrict__ second_out, int *__restrict__ pattern)
 {
+    // N rows are classified; neighbour ids are valid below NA (NA > N: ghosts of a decomposed frame,
+    // whose k-nearest rows exist as well)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int second[12];
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(128) k_ids_classify(const double *__restrict__
     bool ok = true;
     for (int m = 0; m < 4; ++m) {
         const int j = row[m];
-        if (j < 0 || j >= N) {
+        if (j < 0 || j >= NA) {
             ok = false;
             break;
         }
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(128) k_ids_classify(const double *__restrict__
         }
     }
     for (int m = 0; m < 12 && ok; ++m)
-        if (m >= count || second[m] < 0 || second[m] >= N) ok = false;
+        if (m >= count || second[m] < 0 || second[m] >= NA) ok = false;
     if (second_out)
         for (int m = 0; m < 12; ++m) second_out[(size_t)i * 12 + m] = m < count ? second[m] : 0;
     if (!ok) return;  // short / padded rows: the reference would read out of bounds; leave 0
@@ -377,28 +379,37 @@ __global__ void __launch_bounds__(128) k_ids_classify(const double *__restrict__
     else if (c.n421 == 6 && c.n422 == 6) pattern[i] = 4;
 }
 
+// owner[j] = (order key of the claiming atom << 32) | its local index; the order key is the GLOBAL id in
+// a decomposed frame (the reference's sweeps run in ascending original index), the index itself otherwise
 __global__ void k_ids_claim(int N, const int *__restrict__ verlet, int M, const int *__restrict__ pattern, int ta, int tb,
-                            int *__restrict__ owner)
+                            const int *__restrict__ gid, unsigned long long *__restrict__ owner)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int t = pattern[i];
     if (t != ta && t != tb) return;
+    const unsigned long long key = ((unsigned long long)(unsigned)(gid ? gid[i] : i) << 32) | (unsigned)i;
     for (int jj = 0; jj < 4; ++jj) {
         const int j = verlet[(size_t)i * M + jj];
-        if (j >= 0 && j < N && pattern[j] == 0) atomicMin(owner + j, i);
+        if (j >= 0 && j < N && pattern[j] == 0) atomicMin(owner + j, key);
     }
 }
 
-__global__ void k_ids_assign(int N, int *__restrict__ pattern, int *__restrict__ owner)
+__global__ void k_ids_assign(int N, int *__restrict__ pattern, unsigned long long *__restrict__ owner)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
-    const int o = owner[j];
-    if (o != INT_MAX) {
-        pattern[j] = pattern[o] + 1;  // owners carry 1/4 (or 2/5), receivers were 0: no read/write overlap
-        owner[j] = INT_MAX;
+    const unsigned long long o = owner[j];
+    if (o != ~0ull) {
+        pattern[j] = pattern[(int)(o & 0xffffffffu)] + 1;  // owners carry 1/4 (or 2/5), receivers were 0: no read/write overlap
+        owner[j] = ~0ull;
     }
+}
+
+__global__ void k_fill_u64(int n, unsigned long long v, unsigned long long *__restrict__ p)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 __global__ void k_fill_int(int n, int v, int *__restrict__ p)
@@ -446,11 +457,12 @@ void launch_ids(MdbSystem &s, const int *verlet, int M, int *second_out, int *pa
     const int N = s.n_rows;
     MDB_REQUIRE(M >= 4, MDB_ERR_VALUE, "diamond identification needs >= 4 sorted neighbours per atom, row width is %d", M);
     const int nb = (N + 127) / 128;
-    MDB_LAUNCH(k_ids_classify, nb, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, M, second_out, pattern);
-    int *owner = s.scratch.ensure<int>(N);
-    MDB_LAUNCH(k_fill_int, (N + 255) / 256, 256, 0, s.stream, N, INT_MAX, owner);
+    MDB_LAUNCH(k_ids_classify, nb, 128, 0, s.stream, s.x, s.y, s.z, N, s.N, s.box, verlet, M, second_out, pattern);
+    unsigned long long *owner = s.scratch.ensure<unsigned long long>(N);
+    MDB_LAUNCH(k_fill_u64, (N + 255) / 256, 256, 0, s.stream, N, ~0ull, owner);
     for (int pass = 0; pass < 2; ++pass) {
-        MDB_LAUNCH(k_ids_claim, (N + 255) / 256, 256, 0, s.stream, N, verlet, M, pattern, pass ? 2 : 1, pass ? 5 : 4, owner);
+        MDB_LAUNCH(k_ids_claim, (N + 255) / 256, 256, 0, s.stream, N, verlet, M, pattern, pass ? 2 : 1, pass ? 5 : 4, s.gid,
+                   owner);
         MDB_LAUNCH(k_ids_assign, (N + 255) / 256, 256, 0, s.stream, N, pattern, owner);
     }
     CUDA_TRY(cudaGetLastError());

@@ -108,6 +108,7 @@ struct MdbSystem {
     int n_rows{0};
     const int *gid{nullptr};  // optional global ids (order inside a cell, exported lists)
     int slab_x0{0}, slab_nx{0};  // stored window of global x cell planes (0,0 = whole grid)
+    double local_frac{1.0};      // fraction of the box volume the local atoms occupy (density hint, kNN grid)
 
     // cell binning for a given rc
     double bin_rc{-1.0};

@@ -275,7 +275,9 @@ void launch_knn(MdbSystem &s, int k)
 {
     MDB_REQUIRE(k >= 1 && k <= KNN_MAX_K, MDB_ERR_VALUE, "k must be in [1, %d], got %d.", KNN_MAX_K, k);
     MDB_REQUIRE(s.N > 0 && s.x, MDB_ERR_STATE, "no atoms uploaded");
-    MDB_REQUIRE(s.n_rows == s.N && !s.gid, MDB_ERR_STATE, "kNN on a decomposed frame is not supported yet");
+    // Decomposed frame: the search runs over ALL local atoms (owned + ghosts) with the global box, so
+    // wrapped coordinates, image shifts and distances are the single-GPU ones; a row is complete iff its
+    // k-th distance does not reach past the halo (checked by mdapy_b200/distributed.py).
     const int N = s.N;
     cudaStream_t st = s.stream;
     const DBox &b = s.box;
@@ -320,7 +322,8 @@ void launch_knn(MdbSystem &s, int k)
         frac *= range[d] / full;
         len[d] = std::fabs(b.thick[d]) * (range[d] / std::fabs(full));  // perpendicular extent along d
     }
-    const double vol = std::fabs(dbox_volume(b)) * std::fabs(frac);
+    // a slab occupies only local_frac of the (periodic) box: keep the cell size tied to the LOCAL density
+    const double vol = std::fabs(dbox_volume(b)) * std::fabs(frac) * (s.local_frac > 0 && s.local_frac < 1 ? s.local_frac : 1.0);
     const double rho = vol > 0 ? N / vol : 1.0;
     double wt = 1.1 * std::cbrt(3.0 * (k + 1) / (4.0 * 3.14159265358979323846 * rho));
     // thin (quasi 2-D / 1-D) extents: do not let a degenerate axis inflate the density estimate

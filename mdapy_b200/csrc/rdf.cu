@@ -40,8 +40,10 @@ __device__ __forceinline__ void hist_flush(unsigned *sh, unsigned long long *gl,
 __global__ void __launch_bounds__(256) k_rdf_list(const int *__restrict__ verlet, const double *__restrict__ dist,
                                                   const int *__restrict__ nn, int N, int M,
                                                   const int *__restrict__ types, int ntype, double rc, int nbin,
-                                                  unsigned long long *__restrict__ hist)
+                                                  const int *__restrict__ gid, unsigned long long *__restrict__ hist)
 {
+    // gid: global ids of a decomposed frame -- the single-species "j > i counts twice" rule compares
+    // ORIGINAL indices, so every unordered pair is counted by exactly one rank
     extern __shared__ unsigned sh[];
     const int nslot = (types ? ntype * ntype : 1) * nbin;
     const bool use_sh = nslot <= RDF_SMEM_BINS;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256) k_rdf_list(const int *__restrict__ verlet
             if (k >= nbin || k < 0) continue;
             if (types)
                 hist_add(sh, hist, use_sh, (it * ntype + types[j]) * nbin + k, 1u);
-            else if (j > i)
+            else if (gid ? gid[j] > gid[i] : j > i)
                 hist_add(sh, hist, use_sh, k, 2u);
         }
     }
@@ -82,7 +84,8 @@ __device__ __forceinline__ SortedAtom load_sorted2(const SortedAtom *__restrict_
 }
 
 __global__ void __launch_bounds__(128) k_rdf_stream(const SortedAtom *__restrict__ sorted,
-                                                    const int *__restrict__ cell_start, int N, DBox box, CellGrid g,
+                                                    const int *__restrict__ cell_start, int N, int n_rows, DBox box,
+                                                    CellGrid g,
                                                     const int *__restrict__ types, int ntype, double rc, int nbin,
                                                     unsigned long long *__restrict__ hist)
 {
@@ -95,8 +98,8 @@ __global__ void __launch_bounds__(128) k_rdf_stream(const SortedAtom *__restrict
     }
     const double dr = rc / nbin, rcsq = rc * rc;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < N) {
-        const SortedAtom me = load_sorted2(sorted + s);
+    const SortedAtom me = s < N ? load_sorted2(sorted + s) : SortedAtom{};
+    if (s < N && me.idx < n_rows) {  // ghosts of a decomposed frame are neighbours only
         double xi = me.x, yi = me.y, zi = me.z;
         if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
         int ic, jc, kc;
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(128) k_rdf_stream(const SortedAtom *__restrict
                 for (int dk = -1; dk <= 1; ++dk) {
                     const int c = cell_linear(g, wrap_cell(ic + di, g.n[0]), wrap_cell(jc + dj, g.n[1]),
                                               wrap_cell(kc + dk, g.n[2]));
+                    if (c < 0) continue;  // outside the stored slab window (never for an owned atom)
                     const int b = __ldg(cell_start + c), e = __ldg(cell_start + c + 1);
                     for (int q = b; q < e; ++q) {
                         if (q == s) continue;
@@ -145,7 +149,7 @@ void launch_rdf_list(MdbSystem &s, const int *verlet, const double *dist, const 
     const size_t smem = nslot <= RDF_SMEM_BINS ? sizeof(unsigned) * nslot : 0;
     int nb = (N + 255) / 256;
     if (nb > 1184) nb = 1184;
-    MDB_LAUNCH(k_rdf_list, nb, 256, smem, st, verlet, dist, nn, N, M, types, ntype, rc, nbin, hist);
+    MDB_LAUNCH(k_rdf_list, nb, 256, smem, st, verlet, dist, nn, N, M, types, ntype, rc, nbin, s.gid, hist);
     MDB_LAUNCH(k_hist_accumulate, (nslot + 255) / 256, 256, 0, st, hist, nslot, g);
     CUDA_TRY(cudaGetLastError());
 }
@@ -153,7 +157,6 @@ void launch_rdf_list(MdbSystem &s, const int *verlet, const double *dist, const 
 void launch_rdf_streaming(MdbSystem &s, const int *types, int ntype, double rc, int nbin, double *g)
 {
     MDB_REQUIRE(nbin > 0 && rc > 0, MDB_ERR_VALUE, "nbin and rc must be positive");
-    MDB_REQUIRE(s.n_rows == s.N && !s.gid, MDB_ERR_STATE, "streaming RDF on a decomposed frame: reduce per-rank lists instead");
     if (s.bin_rc != rc) launch_binning(s, rc);
     const int nslot = ntype * ntype * nbin;
     unsigned long long *hist = s.scratch2.ensure<unsigned long long>(nslot);
@@ -161,7 +164,7 @@ void launch_rdf_streaming(MdbSystem &s, const int *types, int ntype, double rc, 
     CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * nslot, st));
     const size_t smem = nslot <= RDF_SMEM_BINS ? sizeof(unsigned) * nslot : 0;
     MDB_LAUNCH(k_rdf_stream, (s.N + 127) / 128, 128, smem, st, s.sorted.as<SortedAtom>(), s.cell_start.as<int>(), s.N,
-               s.box, s.grid, types, ntype, rc, nbin, hist);
+               s.n_rows, s.box, s.grid, types, ntype, rc, nbin, hist);
     MDB_LAUNCH(k_hist_accumulate, (nslot + 255) / 256, 256, 0, st, hist, nslot, g);
     CUDA_TRY(cudaGetLastError());
 }

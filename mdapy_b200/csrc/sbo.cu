@@ -312,7 +312,9 @@ void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, cons
     else
         MDB_LAUNCH(k_qlm<false>, nb, 128, 0, st, s.x, s.y, s.z, N, s.box, verlet, dist, nn, weight, M, P, qr, qi);
     if (average) {
-        const size_t tot = (size_t)N * P.ndeg * P.nz;
+        // the snapshot is indexed by neighbour ids: it covers every local atom (qr/qi hold s.N rows, the
+        // ghost rows of a decomposed frame are zero)
+        const size_t tot = (size_t)s.N * P.ndeg * P.nz;
         double *ar = s.scratch.ensure<double>(tot), *ai = s.scratch2.ensure<double>(tot);
         CUDA_TRY(cudaMemcpyAsync(ar, qr, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ai, qi, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
@@ -368,8 +370,8 @@ void launch_solid_liquid(MdbSystem &s, const int *verlet, const double *dist, co
     cudaStream_t st = s.stream;
     MDB_LAUNCH(k_solid_bonds, nb, 128, 0, st, N, verlet, dist, nn, M, qr, qi, ndeg * nz, q6index * nz, Q6, threshold,
                n_bond, use_voronoi ? 1 : 0, nnn, rc, solid, nbond);
-    int *snap = s.scratch.ensure<int>(N);
-    CUDA_TRY(cudaMemcpyAsync(snap, solid, sizeof(int) * N, cudaMemcpyDeviceToDevice, st));
+    int *snap = s.scratch.ensure<int>(s.N);  // indexed by neighbour ids (solid holds s.N entries)
+    CUDA_TRY(cudaMemcpyAsync(snap, solid, sizeof(int) * s.N, cudaMemcpyDeviceToDevice, st));
     MDB_LAUNCH(k_solid_isolated, nb, 128, 0, st, N, verlet, nn, M, use_voronoi ? 1 : 0, nnn, snap, solid);
     CUDA_TRY(cudaGetLastError());
 }

@@ -76,6 +76,16 @@ class DeviceSystem:
         self._keep = (dx, dy, dz, dgid)
         self.M = 0
 
+    def set_local_fraction(self, fraction: float):
+        """Decomposed frame: fraction of the box volume the local atoms occupy (density hint only)."""
+        L.check(self._lib.mdb_system_set_local_fraction(self._h, float(fraction)))
+
+    def neighbor_device(self):
+        """Raw device pointers (int) of verlet / distance / count arrays and the row width."""
+        v, d, n, M = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int(0)
+        L.check(self._lib.mdb_system_neighbor_device(self._h, C.byref(v), C.byref(d), C.byref(n), C.byref(M)))
+        return v.value, d.value, n.value, M.value
+
     def synchronize(self):
         L.check(self._lib.mdb_system_synchronize(self._h))
 
