@@ -2,7 +2,7 @@
 """Multi-GPU parity check of the decomposed path (run under torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/dist_check.py [--n 40]
+        tools/dist_check.py [--cells 40]
 
 Every rank starts with an arbitrary interleaved share of a rattled crystal, the frame is migrated to its
 slab owners over NCCL, halos are exchanged, and every descriptor is compared -- on each rank, for its OWNED
@@ -34,7 +34,7 @@ def main():
     from mdapy_b200.distributed import KnnDecomposition, SlabDecomposition
 
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=40, help="FCC supercell edge (40 -> 256,000 atoms)")
+    ap.add_argument("--cells", dest="n", type=int, default=40, help="FCC supercell edge (40 -> 256,000 atoms)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
