@@ -93,23 +93,32 @@ static void build_neighbor(MdbSystem &s, double rc, int max_neigh)
         s.max_count = fill(max_neigh);
         s.M = max_neigh;
     } else {
-        // width estimate: exact count pass (direct) or a count-only pass over every 16th tile (tiled);
-        // the fill pass reports the true maximum, and is repeated in the rare case the sample missed it
-        int est;
+        // Width: exact count pass (direct kernel), or a count-only pass over every 16th tile (tiled).
+        // A sample with min == max is a uniform frame (perfect lattice): the fill uses exactly that
+        // width.  Otherwise the true maximum is an extreme value the sample probably missed: the fill
+        // uses the next multiple of 4 above estimate + 1 (rows then leave in 16-byte stores) and the
+        // rows are compacted to the true maximum afterwards -- one streaming pass instead of a second
+        // search.  Only when even that margin was too small is the fill repeated.
+        int est, est_min = 0;
+        bool exact = !tiled;
         if (tiled) {
             launch_neighbor_tiled(s, rc, 0, T, true, 16);
-            est = neighbor_tiled_max(s);
+            est = neighbor_tiled_max(s, &est_min);
+            if (est == est_min) exact = true;
         } else {
             launch_neighbor(s, rc, 0, true);
             est = device_max_int(s, s.nn.as<int>(), s.n_rows);
         }
         if (est < 1) est = 1;
-        int mx = fill(est);
-        if (mx > est) {
-            est = mx;
-            mx = fill(est);
+        int width = exact ? est : (est + 1 + 3) / 4 * 4;
+        int mx = fill(width);
+        if (mx > width) {
+            width = exact ? mx : (mx + 3) / 4 * 4;
+            mx = fill(width);
         }
-        s.M = est;
+        const int M = mx < 1 ? 1 : mx;
+        if (M < width) launch_compact_rows(s, width, M);
+        s.M = M;
         s.max_count = mx;
     }
     s.list_kind = LIST_CUTOFF;

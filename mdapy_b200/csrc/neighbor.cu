@@ -94,9 +94,18 @@ __global__ void __launch_bounds__(256) k_compact_rows(const int *__restrict__ vi
                                                       int *__restrict__ vout, double *__restrict__ dout, int N,
                                                       int M_from, int M_to)
 {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)N * M_to;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (total < 0xffffffffull) {  // 32-bit index arithmetic (the common case)
+        const unsigned mt = (unsigned)M_to;
+        for (; t < total; t += stride) {
+            const unsigned i = (unsigned)t / mt, k = (unsigned)t - i * mt;
+            vout[t] = vin[(size_t)i * M_from + k];
+            dout[t] = din[(size_t)i * M_from + k];
+        }
+        return;
+    }
     for (; t < total; t += stride) {
         const size_t i = t / M_to, k = t % M_to;
         vout[t] = vin[i * M_from + k];

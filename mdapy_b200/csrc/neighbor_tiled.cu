@@ -40,6 +40,7 @@ struct TileArgs {
     double *dist;
     int *nn;
     int *max_count;  // atomicMax of the true neighbour count
+    int *min_count;  // atomicMin of the true neighbour count (tells uniform frames from disordered ones)
     int cap;         // staged-atom capacity of the shared buffers
     int p_lo, p_hi;  // owned range of stored x planes
     int wrap_x;      // 1: planes wrap around (single GPU), 0: slab window with ghost planes
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
     const bool tile_shifted = far_flag[1] != 0;
 
     // ---- D. one thread per owned atom
-    int local_max = 0;
+    int local_max = 0, local_min = INT_MAX;
     if (!staged_ok) {
 #pragma unroll 1
         for (int t = tid; t < n_owned; t += TILE_THREADS) {
@@ -386,7 +387,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
             }
             const int p = (lo / T + 1) * P + (lo % T + 1);
             const int sg = gstart[p * PZ + PZ - 1 - kmax] + (t - opref[lo]);  // owned cells of a pencil: one global run
-            local_max = max(local_max, direct_atom<COUNT_ONLY>(A, sg));
+            const int c = direct_atom<COUNT_ONLY>(A, sg);
+            local_max = max(local_max, c);
+            if (c >= 0) local_min = min(local_min, c);
         }
     } else {
         const unsigned f4_base = smem_u32(f4), raw_base = smem_u32(raw);
@@ -537,6 +540,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
             if (active && live) {
                 A.nn[my_idx] = cnt;
                 local_max = max(local_max, cnt);
+                local_min = min(local_min, cnt);
                 if (!COUNT_ONLY) {
                     if (vec4 && cnt < M) {
                         // still in the shift registers: the last (cnt & 3) indices and (cnt & 1) distance
@@ -555,8 +559,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
         }
     }
 #pragma unroll
-    for (int d = 16; d; d >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, d));
+    for (int d = 16; d; d >>= 1) {
+        local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, d));
+        local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, d));
+    }
     if (lane == 0 && local_max > 0) atomicMax(A.max_count, local_max);
+    if (lane == 0 && local_min != INT_MAX) atomicMin(A.min_count, local_min);
 }
 
 template <int T, int TZ> size_t tile_smem_bytes(int cap)
@@ -635,7 +643,9 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     }
     int *counters = s.counters.ensure<int>(8);
     A.max_count = counters + 6;
-    CUDA_TRY(cudaMemsetAsync(A.max_count, 0, sizeof(int), s.stream));
+    A.min_count = counters + 7;
+    const int init[2] = {0, INT_MAX};
+    CUDA_TRY(cudaMemcpyAsync(A.max_count, init, sizeof(init), cudaMemcpyHostToDevice, s.stream));
     const bool slab = s.slab_nx > 0;
     A.wrap_x = slab ? 0 : 1;
     A.p_lo = slab ? 1 : 0;
@@ -669,10 +679,11 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     CUDA_TRY(cudaGetLastError());
 }
 
-int neighbor_tiled_max(MdbSystem &s)
+int neighbor_tiled_max(MdbSystem &s, int *min_count)
 {
-    int v = 0;
-    CUDA_TRY(cudaMemcpyAsync(&v, s.counters.as<int>() + 6, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    int v[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(v, s.counters.as<int>() + 6, sizeof(v), cudaMemcpyDeviceToHost, s.stream));
     CUDA_TRY(cudaStreamSynchronize(s.stream));
-    return v;
+    if (min_count) *min_count = v[1];
+    return v[0];
 }
