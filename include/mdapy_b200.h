@@ -130,6 +130,21 @@ int mdb_rdf_streaming(const double *x, const double *y, const double *z, int N, 
                       const double *box9, const double *origin3, const int *boundary3, double *g, int ntype,
                       double rc, int nbin, int num_t);
 
+/* ---- further neighbour-list consumers ---- */
+/* _cnp.compute_cnp(x,y,z,box,origin,boundary,verlet_list,distance_list,neighbor_number,cnp,rc,num_t)
+ * -- src/common_neighbor_parameter.cpp:10 */
+int mdb_compute_cnp(const double *x, const double *y, const double *z, int N, const double *box9,
+                    const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                    const int *nn, double *cnp, double rc, int num_t);
+/* _wcp.get_wcp(verlet_list, neighbor_number, type_list, Ntype, WCP[Ntype,Ntype], num_t)
+ * -- src/warren_cowley_parameter.cpp:9 */
+int mdb_get_wcp(const int *verlet, int N, int M, const int *nn, const int *type_list, int Ntype, double *WCP,
+                int num_t);
+/* _neighbor.average_by_neighbor(rc, verlet_list, distance_list, neighbor_number, value, value_ave,
+ * include_self, num_t) -- src/neighbor.cpp:704 */
+int mdb_average_by_neighbor(double rc, const int *verlet, int N, int M, const double *dist, const int *nn,
+                            const double *value, double *value_ave, int include_self, int num_t);
+
 /* ------------------------------------------------------------------------
  * Section B: device-resident system handle
  * ---------------------------------------------------------------------- */
@@ -204,6 +219,11 @@ int mdb_system_rdf(mdb_system *s, const int *types_host, int ntype, double rc, i
 int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, double rmsd_threshold,
                    double *output_host, int *indices_host);
 /* device pointers to the most recent int32 / f64 per-atom result */
+/* list consumers of SURVEY.md 8f.1 on the cached list (results copied to the host arrays) */
+int mdb_system_cnp(mdb_system *s, double rc, double *cnp_host);
+int mdb_system_wcp(mdb_system *s, const int *types_host, int ntype, double *wcp_host);
+int mdb_system_average_by_neighbor(mdb_system *s, double rc, const double *value_host, int include_self,
+                                   double *value_ave_host);
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 
 /* per-kernel device times (ms) of the most recent build_neighbor / fcna, measured with CUDA events */

@@ -689,6 +689,65 @@ int mdb_system_rdf(mdb_system *s, const int *types_host, int ntype, double rc, i
 }
 
 // PTM on the cached list (>= 18 sorted neighbours per row, or fewer for open clusters).  output_host:
+int mdb_system_cnp(mdb_system *s, double rc, double *cnp_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "rc must be positive, got %g.", rc);
+    MDB_REQUIRE(s->n_rows == s->N, MDB_ERR_STATE, "the common neighbour parameter reads its neighbours' rows: use a halo >= 2 frame "
+                                                   "through distributed.py (rows for the inner ghost layer)");
+    double *out = s->out_f64.ensure<double>(s->n_rows);
+    launch_cnp(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, rc, out);
+    d2h(*s, cnp_host, out, (size_t)s->n_rows);
+    if (cnp_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+// WCP[i][j] = 1 - Z_ij / (alpha_j * Z_i) from integer counts, normalised on the host with the
+// reference's expressions (warren_cowley_parameter.cpp:67-79)
+int mdb_system_wcp(mdb_system *s, const int *types_host, int ntype, double *wcp_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(types_host && wcp_host && ntype >= 1, MDB_ERR_VALUE, "type list, Ntype and WCP are required");
+    const int *types = h2d(*s, s->types, types_host, (size_t)s->N);
+    const int nslot = ntype * ntype + 2 * ntype;
+    unsigned long long *counts = s->scratch2.ensure<unsigned long long>(nslot);
+    launch_wcp_counts(*s, s->verlet.as<int>(), s->nn.as<int>(), s->M, types, ntype, counts);
+    std::vector<unsigned long long> h(nslot);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), counts, sizeof(unsigned long long) * nslot, cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    const unsigned long long *Zmn = h.data(), *Zm = Zmn + ntype * ntype, *pop = Zm + ntype;
+    const int N = s->n_rows;
+    for (int i = 0; i < ntype; ++i)
+        for (int j = 0; j < ntype; ++j) {
+            const double alpha_j = (double)pop[j] / N;
+            const int zm_i = (int)Zm[i];
+            if (alpha_j > 0 && zm_i > 0)
+                wcp_host[i * ntype + j] = 1.0 - static_cast<double>((int)Zmn[i * ntype + j]) / (alpha_j * zm_i);
+            else wcp_host[i * ntype + j] = 0.0;
+        }
+    API_END
+}
+
+int mdb_system_average_by_neighbor(mdb_system *s, double rc, const double *value_host, int include_self,
+                                   double *value_ave_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(value_host, MDB_ERR_VALUE, "value is required");
+    const double *val = h2d(*s, s->out_f64b, value_host, (size_t)s->N);
+    double *out = s->out_f64.ensure<double>(s->n_rows);
+    launch_average_by_neighbor(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, rc, val,
+                               include_self != 0, out);
+    d2h(*s, value_ave_host, out, (size_t)s->n_rows);
+    if (value_ave_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 // (n_rows, 8) = type, ordering, rmsd, interatomic distance, qw, qx, qy, qz; indices_host: (n_rows, 18).
 int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, double rmsd_threshold,
                    double *output_host, int *indices_host)
@@ -886,6 +945,55 @@ int mdb_get_csp(const double *x, const double *y, const double *z, int N, const 
     int rcode = mdb_system_put_neighbor(s.s, verlet, nullptr, nullptr, M, -1.0, LIST_KNN);
     if (rcode != MDB_OK) return rcode;
     rcode = mdb_system_csp(s.s, nnei, csp);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_compute_cnp(const double *x, const double *y, const double *z, int N, const double *box9,
+                    const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                    const int *nn, double *cnp, double rc, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nn, M, rc, LIST_CUTOFF);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_cnp(s.s, rc, cnp);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+// no coordinates on this path: the list alone (a placeholder frame carries the row count)
+static int list_only_system(MdbSystem &s, int N, const int *verlet, const double *dist, const int *nn, int M, double rc)
+{
+    MDB_REQUIRE(N > 0 && verlet && nn, MDB_ERR_VALUE, "verlet_list and neighbor_number are required");
+    s.N = s.n_rows = N;
+    s.x = s.y = s.z = nullptr;
+    return mdb_system_put_neighbor(&s, verlet, dist, nn, M, rc, LIST_CUTOFF);
+}
+
+int mdb_get_wcp(const int *verlet, int N, int M, const int *nn, const int *type_list, int Ntype, double *WCP,
+                int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    int rcode = list_only_system(*s, N, verlet, nullptr, nn, M, -1.0);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_wcp(s.s, type_list, Ntype, WCP);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_average_by_neighbor(double rc, const int *verlet, int N, int M, const double *dist, const int *nn,
+                            const double *value, double *value_ave, int include_self, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(dist && value_ave, MDB_ERR_VALUE, "distance_list and value_ave are required");
+    ScopedSystem s;
+    int rcode = list_only_system(*s, N, verlet, dist, nn, M, rc);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_average_by_neighbor(s.s, rc, value, include_self, value_ave);
     if (rcode != MDB_OK) return rcode;
     API_END
 }

@@ -152,6 +152,102 @@ __global__ void __launch_bounds__(128) k_aja(const double *__restrict__ x, const
     aja[i] = t;
 }
 
+
+// Common neighbour parameter, src/common_neighbor_parameter.cpp:40-136: for every listed neighbour j
+// within rc, R_ij = sum over common neighbours k (within rc of both) of (r_ik + r_jk), each a
+// min-image vector; cnp_i = sum_j |R_ij|^2 / N_i, 1000 when no neighbour lies within rc.  Same loop
+// nesting and summation order as the reference.
+__global__ void __launch_bounds__(128) k_cnp(const double *__restrict__ x, const double *__restrict__ y,
+                                             const double *__restrict__ z, int N, DBox box,
+                                             const int *__restrict__ verlet, const double *__restrict__ dist,
+                                             const int *__restrict__ nn, int M, double rc, double *__restrict__ cnp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int ni = min(nn[i], M);
+    const int *vi = verlet + (size_t)i * M;
+    const double *di = dist + (size_t)i * M;
+    const double xi = x[i], yi = y[i], zi = z[i];
+    int cnt = 0;
+    double acc = 0.0;
+    for (int m = 0; m < ni; ++m) {
+        if (!(di[m] <= rc)) continue;
+        const int j = vi[m];
+        ++cnt;
+        double rx = 0.0, ry = 0.0, rz = 0.0;
+        const int nj = min(nn[j], M);
+        const int *vj = verlet + (size_t)j * M;
+        const double *dj = dist + (size_t)j * M;
+        const double xj = x[j], yj = y[j], zj = z[j];
+        for (int s = 0; s < nj; ++s) {
+            const int k = vj[s];
+            for (int h = 0; h < ni; ++h) {
+                if (vi[h] != k) continue;
+                if (dj[s] <= rc && di[h] <= rc) {
+                    const double xk = x[k], yk = y[k], zk = z[k];
+                    double ax = xi - xk, ay = yi - yk, az = zi - zk;
+                    double bx = xj - xk, by = yj - yk, bz = zj - zk;
+                    min_image(box, ax, ay, az);
+                    min_image(box, bx, by, bz);
+                    rx += ax + bx;
+                    ry += ay + by;
+                    rz += az + bz;
+                }
+                break;  // the reference leaves the h loop at the first index match
+            }
+        }
+        acc += rx * rx + ry * ry + rz * rz;
+    }
+    cnp[i] = cnt > 0 ? acc / cnt : 1000.0;
+}
+
+// Warren-Cowley counts, src/warren_cowley_parameter.cpp:33-49: Z_mn (neighbour-type pairs), Z_m (listed
+// neighbours per central type), population per type.  counts = [Zmn (T*T) | Zm (T) | pop (T)], 64-bit.
+__global__ void __launch_bounds__(256) k_wcp_counts(const int *__restrict__ verlet, const int *__restrict__ nn, int N,
+                                                    int M, const int *__restrict__ types, int T,
+                                                    unsigned long long *__restrict__ counts)
+{
+    extern __shared__ unsigned sh_w[];
+    const int nslot = T * T + 2 * T;
+    for (int t = threadIdx.x; t < nslot; t += blockDim.x) sh_w[t] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int it = types[i];
+        const int c = nn[i];
+        atomicAdd(sh_w + T * T + T + it, 1u);
+        atomicAdd(sh_w + T * T + it, (unsigned)c);
+        for (int q = 0; q < c; ++q) atomicAdd(sh_w + it * T + types[verlet[(size_t)i * M + q]], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nslot; t += blockDim.x)
+        if (sh_w[t]) atomicAdd(counts + t, (unsigned long long)sh_w[t]);
+}
+
+// average_by_neighbor, src/neighbor.cpp:704-743: own value first (include_self), then the listed
+// neighbours within rc in list order.
+__global__ void __launch_bounds__(128) k_average_by_neighbor(const int *__restrict__ verlet,
+                                                             const double *__restrict__ dist,
+                                                             const int *__restrict__ nn, int N, int M, double rc,
+                                                             const double *__restrict__ value, int include_self,
+                                                             double *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double sum = 0.0;
+    int n = 0;
+    if (include_self) {
+        sum += value[i];
+        ++n;
+    }
+    const int c = nn[i];
+    for (int q = 0; q < c; ++q)
+        if (dist[(size_t)i * M + q] <= rc) {
+            sum += value[verlet[(size_t)i * M + q]];
+            ++n;
+        }
+    out[i] = n > 0 ? sum / n : 0.0;
+}
+
 }  // namespace
 
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k)
@@ -174,5 +270,36 @@ void launch_aja(MdbSystem &s, const int *verlet, int M, const double *dist, int 
 {
     MDB_REQUIRE(M >= 14 && Md >= 14, MDB_ERR_VALUE, "Ackland-Jones needs >= 14 sorted neighbours, row width is %d", M);
     MDB_LAUNCH(k_aja, (s.n_rows + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, s.n_rows, s.box, verlet, M, dist, Md, aja);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_cnp(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc, double *cnp)
+{
+    const int N = s.n_rows;
+    MDB_LAUNCH(k_cnp, (N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, dist, nn, M, rc, cnp);
+    CUDA_TRY(cudaGetLastError());
+}
+
+// counts (device, 64-bit): [T*T | T | T] as described at k_wcp_counts; zeroed here
+void launch_wcp_counts(MdbSystem &s, const int *verlet, const int *nn, int M, const int *types, int T,
+                       unsigned long long *counts)
+{
+    const int N = s.n_rows;
+    const int nslot = T * T + 2 * T;
+    MDB_REQUIRE(T >= 1 && nslot <= 8192, MDB_ERR_VALUE, "Ntype=%d is outside the supported range", T);
+    CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * nslot, s.stream));
+    int nb = (N + 255) / 256;
+    // a block's 32-bit shared counters see at most 256 * ceil(N / (nb*256)) * M increments: keep that < 2^32
+    if (nb > 1184) nb = 1184;
+    MDB_LAUNCH(k_wcp_counts, nb, 256, sizeof(unsigned) * nslot, s.stream, verlet, nn, N, M, types, T, counts);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_average_by_neighbor(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc,
+                                const double *value, bool include_self, double *out)
+{
+    const int N = s.n_rows;
+    MDB_LAUNCH(k_average_by_neighbor, (N + 127) / 128, 128, 0, s.stream, verlet, dist, nn, N, M, rc, value,
+               include_self ? 1 : 0, out);
     CUDA_TRY(cudaGetLastError());
 }

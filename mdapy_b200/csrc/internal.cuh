@@ -162,6 +162,11 @@ void launch_solid_liquid(MdbSystem &s, const int *verlet, const double *dist, co
 void launch_rdf_list(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int N, int M,
                      const int *types, int ntype, double rc, int nbin, double *g);
 void launch_rdf_streaming(MdbSystem &s, const int *types, int ntype, double rc, int nbin, double *g);
+void launch_cnp(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc, double *cnp);
+void launch_wcp_counts(MdbSystem &s, const int *verlet, const int *nn, int M, const int *types, int T,
+                       unsigned long long *counts);
+void launch_average_by_neighbor(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc,
+                                const double *value, bool include_self, double *out);
 int ptm_parse_flags(const char *structure);
 void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
                 double *output, int ocols, int *indices, int icols);
