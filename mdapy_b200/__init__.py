@@ -19,6 +19,8 @@ def __getattr__(name):
         "NearestNeighbor": ("knn", "NearestNeighbor"),
         "DeviceSystem": ("device", "DeviceSystem"),
         "IdentifyDiamondStructure": ("identify_diamond_structure", "IdentifyDiamondStructure"),
+        "CommonNeighborParameter": ("common_neighbor_parameter", "CommonNeighborParameter"),
+        "WarrenCowleyParameter": ("warren_cowley_parameter", "WarrenCowleyParameter"),
         "build_crystal": ("lattice", "build_crystal"),
     }
     if name == "empty_cache":

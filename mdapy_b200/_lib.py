@@ -55,6 +55,9 @@ PROTOTYPES = {
     "mdb_rdf": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, c_ip, c_dp, C.c_int, C.c_double, C.c_int]),
     "mdb_rdf_single_species": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_double, C.c_int]),
     "mdb_rdf_streaming": (C.c_int, _XYZN + [c_ip] + _BOX + [c_dp, C.c_int, C.c_double, C.c_int, C.c_int]),
+    "mdb_compute_cnp": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, c_ip, c_dp, C.c_double, C.c_int]),
+    "mdb_get_wcp": (C.c_int, [c_ip, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_dp, C.c_int]),
+    "mdb_average_by_neighbor": (C.c_int, [C.c_double, c_ip, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_dp, C.c_int, C.c_int]),
     "mdb_system_create": (C.c_int, [C.c_int, C.POINTER(c_vp)]),
     "mdb_system_destroy": (None, [c_vp]),
     "mdb_system_set_stream": (C.c_int, [c_vp, c_vp]),
@@ -83,6 +86,9 @@ PROTOTYPES = {
                                           c_ip]),
     "mdb_system_rdf": (C.c_int, [c_vp, c_ip, C.c_int, C.c_double, C.c_int, C.c_int, c_dp]),
     "mdb_system_ptm": (C.c_int, [c_vp, C.c_char_p, c_ip, C.c_double, c_dp, c_ip]),
+    "mdb_system_cnp": (C.c_int, [c_vp, C.c_double, c_dp]),
+    "mdb_system_wcp": (C.c_int, [c_vp, c_ip, C.c_int, c_dp]),
+    "mdb_system_average_by_neighbor": (C.c_int, [c_vp, C.c_double, c_dp, C.c_int, c_dp]),
     "mdb_system_result_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "mdb_system_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_last_times": (C.c_int, [c_vp, c_fp, c_fp, c_fp]),

@@ -196,6 +196,29 @@ class DeviceSystem:
                                          L.iptr(ind) if fetch else None))
         return out, ind
 
+    def cnp(self, rc: float, fetch=True):
+        """Common neighbour parameter on the cached cut-off list (common_neighbor_parameter.cpp:10)."""
+        out = L.result_empty(self.n_rows, np.float64) if fetch else None
+        L.check(self._lib.mdb_system_cnp(self._h, float(rc), L.dptr(out) if fetch else None))
+        return out
+
+    def wcp(self, type_list, ntype: int):
+        """Warren-Cowley matrix (ntype, ntype) from the cached list (warren_cowley_parameter.cpp:9)."""
+        t = L.i32(type_list)
+        assert t.shape[0] == self.N
+        out = np.zeros((int(ntype), int(ntype)), np.float64)
+        L.check(self._lib.mdb_system_wcp(self._h, L.iptr(t), int(ntype), L.dptr(out)))
+        return out
+
+    def average_by_neighbor(self, rc: float, value, include_self=True):
+        """Neighbour average of a per-atom value on the cached list (neighbor.cpp:704)."""
+        v = L.f64(value)
+        assert v.shape[0] == self.N
+        out = L.result_empty(self.n_rows, np.float64)
+        L.check(self._lib.mdb_system_average_by_neighbor(self._h, float(rc), L.dptr(v), int(bool(include_self)),
+                                                         L.dptr(out)))
+        return out
+
     def result_device(self):
         """Raw device pointers (int) of the latest int32 / f64 per-atom result."""
         a, b = C.c_void_p(), C.c_void_p()

@@ -21,6 +21,7 @@ from .ackland_jones_analysis import AcklandJonesAnalysis
 from .box import Box
 from .centro_symmetry_parameter import CentroSymmetryParameter
 from .common_neighbor_analysis import CommonNeighborAnalysis
+from .common_neighbor_parameter import CommonNeighborParameter
 from .identify_diamond_structure import IdentifyDiamondStructure
 from .device import LIST_CUTOFF, LIST_KNN, DeviceSystem
 from .frame import Frame
@@ -29,6 +30,7 @@ from .neighbor import Neighbor
 from .polyhedral_template_matching import PolyhedralTemplateMatching
 from .radial_distribution_function import RadialDistributionFunction
 from .steinhardt_bond_orientation import SteinhardtBondOrientation
+from .warren_cowley_parameter import WarrenCowleyParameter
 
 _LIST_ATTRS = ("verlet_list", "distance_list", "neighbor_number")
 
@@ -280,6 +282,47 @@ class System:
         aja = AcklandJonesAnalysis(data, box, dev=self._device_list())
         aja.compute()
         self.update_data(self._data.with_columns(aja=aja.aja[: self.N]))
+
+    # ---- further list consumers
+    def _ensure_cutoff_list(self, rc: float, max_neigh: Optional[int] = None):
+        """system.py:1591-1596 / 1666-1671: reuse the cached list when it reaches at least rc."""
+        has_neigh = "rc" in self.__dict__ and self.rc >= rc
+        if not has_neigh:
+            self.build_neighbor(rc, max_neigh)
+
+    def cal_common_neighbor_parameter(self, rc: float, max_neigh: Optional[int] = None) -> None:
+        """system.py:1572-1603 -> data['cnp']."""
+        self._ensure_cutoff_list(rc, max_neigh)
+        box, data = self._get_compute_view()
+        cnp = CommonNeighborParameter(data, box, rc, dev=self._device_list(), device=self._device)
+        cnp.compute()
+        self.update_data(self._data.with_columns(cnp=cnp.cnp[: self.N]))
+
+    def cal_warren_cowley_parameter(self, rc: float, max_neigh: Optional[int] = None) -> WarrenCowleyParameter:
+        """system.py:1638-1676: returns the object holding the (Ntype, Ntype) matrix ``WCP``."""
+        self._ensure_cutoff_list(rc, max_neigh)
+        _, data = self._get_compute_view()
+        wcp = WarrenCowleyParameter(None, None, data, dev=self._device_list(), device=self._device)
+        wcp.compute()
+        return wcp
+
+    def average_by_neighbor(self, average_rc: float, property_name: str, include_self: bool = True,
+                            output_name: Optional[str] = None, max_neigh: Optional[int] = None) -> None:
+        """system.py:2363-2414 -> data[output_name or f'{property_name}_ave']."""
+        assert property_name in self._data.columns, f"{property_name} not in data."
+        if "rc" in self.__dict__:
+            if self.rc < average_rc:
+                self.build_neighbor(average_rc, max_neigh)
+        else:
+            self.build_neighbor(average_rc, max_neigh)
+        assert "_enlarge_data" not in self.__dict__, (
+            "average_by_neighbor only supports systems whose box is large enough "
+            "that no replica was built (i.e. self._enlarge_data must not exist)."
+        )
+        value = np.asarray(self._data[property_name], np.float64)
+        ave = self._device_list().average_by_neighbor(average_rc, value, include_self)
+        name = output_name if output_name is not None else f"{property_name}_ave"
+        self.update_data(self._data.with_columns(**{name: np.asarray(ave[: self.N]).copy()}))
 
     def cal_steinhardt_bond_orientation(self, llist, use_voronoi: bool = False, nnn: int = 0, rc: float = -1.0,
                                         average: bool = False, use_weight: bool = False, weight=None,

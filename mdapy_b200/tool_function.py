@@ -53,3 +53,17 @@ def sort_neighbor(verlet_list: np.ndarray, distance_list: np.ndarray, neighbor_n
     assert verlet_list.flags.c_contiguous and distance_list.flags.c_contiguous
     N, M = verlet_list.shape
     L.check(L.lib().mdb_sort_verlet_by_distance(L.iptr(verlet_list), L.dptr(distance_list), N, M, int(k), 1))
+
+
+def average_by_neighbor(average_rc: float, data: Frame, property_name: str, verlet_list: np.ndarray,
+                        distance_list: np.ndarray, neighbor_number: np.ndarray, include_self: bool = True,
+                        output_name=None) -> Frame:
+    """tool_function.py:14-72: neighbour average of a column from HOST lists (one call through the C ABI)."""
+    assert property_name in data.columns, f"{property_name} not in data."
+    v, d, n = L.i32(verlet_list), L.f64(distance_list), L.i32(neighbor_number)
+    value = L.f64(data[property_name])
+    out = np.zeros(data.shape[0])
+    L.check(L.lib().mdb_average_by_neighbor(float(average_rc), L.iptr(v), v.shape[0], v.shape[1], L.dptr(d),
+                                            L.iptr(n), L.dptr(value), L.dptr(out), int(bool(include_self)), 1))
+    name = output_name if output_name is not None else f"{property_name}_ave"
+    return data.with_columns(**{name: out})

@@ -248,3 +248,26 @@ def cal_rdf(K, fr: Frame, rc, nbin, type_list=None, streaming=None):
     vol = np.linalg.det(f2.box)
     r, g_total, part = rdf_normalise(counts, tl, ntype, rc, nbin, vol, f2.N)
     return {"r": r, "g_total": g_total, "g_partial": part, "counts": counts, "elements": uniq}
+
+
+# --------------------------------------------------------------------------
+# further list consumers
+# --------------------------------------------------------------------------
+def cal_cnp(K, fr: Frame, rc):
+    """system.py:1572-1603: cut-off list (replicated for small boxes), compute_cnp, slice [:N]."""
+    fu, v, d, n = neighbor(K, fr, rc)
+    return K.cnp(*fu.geom(), v, d, n, rc)[: fr.N]
+
+
+def cal_average_by_neighbor(K, fr: Frame, rc, value, include_self=True):
+    """system.py:2363-2414 (big boxes only: no replica)."""
+    fu, v, d, n = neighbor(K, fr, rc)
+    assert fu.N == fr.N
+    return K.average_by_neighbor(rc, v, d, n, value, include_self)
+
+
+def cal_wcp(K, fr: Frame, rc, type_list, ntype):
+    """system.py:1638-1676."""
+    fu, v, d, n = neighbor(K, fr, rc)
+    assert fu.N == fr.N
+    return K.wcp(v, n, type_list, ntype)

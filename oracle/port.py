@@ -286,3 +286,39 @@ def repeat_cell(box, pos, nx, ny, nz, nt=None):
     _lib("repeat").port_repeat_cell(_d(out), _d(b), _d(pos), C.c_int(n), C.c_int(nx), C.c_int(ny), C.c_int(nz),
                                    C.c_int(nt or num_threads()))
     return out.reshape(-1, 3)
+
+
+# --------------------------------------------------------------------------
+# further list consumers: common neighbour parameter, Warren-Cowley, average_by_neighbor
+# --------------------------------------------------------------------------
+def cnp(x, y, z, box, origin, boundary, verlet, dist, nn, rc, nt=None):
+    """common_neighbor_parameter.cpp:10 compute_cnp."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet, dist, nn = _i32(verlet), _f64(dist), _i32(nn)
+    N, M = verlet.shape
+    out = np.zeros(N, np.float64)
+    _lib().port_cnp(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _i(verlet), C.c_int(M), _d(dist),
+                        _i(nn), _d(out), C.c_double(rc), C.c_int(nt or num_threads()))
+    return out
+
+
+def wcp(verlet, nn, type_list, ntype, nt=None):
+    """warren_cowley_parameter.cpp:9 get_wcp."""
+    verlet, nn, type_list = _i32(verlet), _i32(nn), _i32(type_list)
+    N, M = verlet.shape
+    out = np.zeros((ntype, ntype), np.float64)
+    _lib().port_wcp(_i(verlet), C.c_int(N), C.c_int(M), _i(nn), _i(type_list), C.c_int(ntype), _d(out),
+                        C.c_int(nt or num_threads()))
+    return out
+
+
+def average_by_neighbor(rc, verlet, dist, nn, value, include_self=True, nt=None):
+    """neighbor.cpp:704 average_by_neighbor."""
+    verlet, dist, nn, value = _i32(verlet), _f64(dist), _i32(nn), _f64(value)
+    N, M = verlet.shape
+    out = np.zeros(N, np.float64)
+    _lib().port_average_by_neighbor(C.c_double(rc), _i(verlet), C.c_int(N), C.c_int(M), _d(dist), _i(nn),
+                                             _d(value), _d(out), C.c_int(int(bool(include_self))),
+                                             C.c_int(nt or num_threads()))
+    return out

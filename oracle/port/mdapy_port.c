@@ -949,3 +949,95 @@ void port_repeat_cell(double *new_pos, const double *old_box, const double *old_
                         new_pos[(cellno * n_old + a) * 3 + d] = old_pos[3 * a + d] + sh[d];
             }
 }
+
+/* ------------------------------------------------------------------ common neighbour parameter
+ * common_neighbor_parameter.cpp:10-136 */
+void port_cnp(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+              const int *boundary3, const int *verlet, int M, const double *dist, const int *nn, double *cnp, double rc,
+              int num_t)
+{
+    cell_t c;
+    cell_init(&c, box9, origin3, boundary3);
+#pragma omp parallel for num_threads(num_t) schedule(dynamic, 64)
+    for (int i = 0; i < N; ++i) {
+        int cnt = 0;
+        double acc = 0.0;
+        const int ni = nn[i];
+        const int *vi = verlet + (size_t)i * M;
+        const double *di = dist + (size_t)i * M;
+        for (int m = 0; m < ni; ++m) {
+            if (!(di[m] <= rc)) continue;
+            const int j = vi[m];
+            ++cnt;
+            double rx = 0.0, ry = 0.0, rz = 0.0;
+            const int nj = nn[j];
+            const int *vj = verlet + (size_t)j * M;
+            const double *dj = dist + (size_t)j * M;
+            for (int s2 = 0; s2 < nj; ++s2) {
+                const int k = vj[s2];
+                for (int h = 0; h < ni; ++h) {
+                    if (vi[h] != k) continue;
+                    if (dj[s2] <= rc && di[h] <= rc) {
+                        double ax = x[i] - x[k], ay = y[i] - y[k], az = z[i] - z[k];
+                        double bx = x[j] - x[k], by = y[j] - y[k], bz = z[j] - z[k];
+                        min_image(&c, &ax, &ay, &az);
+                        min_image(&c, &bx, &by, &bz);
+                        rx += ax + bx;
+                        ry += ay + by;
+                        rz += az + bz;
+                    }
+                    break;
+                }
+            }
+            acc += rx * rx + ry * ry + rz * rz;
+        }
+        cnp[i] = cnt > 0 ? acc / cnt : 1000.0;
+    }
+}
+
+/* ------------------------------------------------------------------ Warren-Cowley parameter
+ * warren_cowley_parameter.cpp:9-80 */
+void port_wcp(const int *verlet, int N, int M, const int *nn, const int *type_list, int T, double *WCP, int num_t)
+{
+    (void)num_t;
+    long long *Zmn = (long long *)calloc((size_t)T * T, sizeof(long long));
+    long long *Zm = (long long *)calloc((size_t)T, sizeof(long long));
+    double *alpha = (double *)calloc((size_t)T, sizeof(double));
+    for (int i = 0; i < N; ++i) {
+        const int it = type_list[i];
+        alpha[it] += 1.0;
+        Zm[it] += nn[i];
+        for (int q = 0; q < nn[i]; ++q) Zmn[it * T + type_list[verlet[(size_t)i * M + q]]]++;
+    }
+    for (int i = 0; i < T; ++i) alpha[i] /= N;
+    for (int i = 0; i < T; ++i)
+        for (int j = 0; j < T; ++j) {
+            const int zmn = (int)Zmn[i * T + j], zm = (int)Zm[i];
+            WCP[i * T + j] = (alpha[j] > 0 && zm > 0) ? 1.0 - (double)zmn / (alpha[j] * zm) : 0.0;
+        }
+    free(Zmn);
+    free(Zm);
+    free(alpha);
+}
+
+/* ------------------------------------------------------------------ average_by_neighbor
+ * neighbor.cpp:704-743 */
+void port_average_by_neighbor(double rc, const int *verlet, int N, int M, const double *dist, const int *nn,
+                              const double *value, double *value_ave, int include_self, int num_t)
+{
+#pragma omp parallel for num_threads(num_t)
+    for (int i = 0; i < N; ++i) {
+        double sum = 0.0;
+        int n = 0;
+        if (include_self) {
+            sum += value[i];
+            ++n;
+        }
+        for (int q = 0; q < nn[i]; ++q)
+            if (dist[(size_t)i * M + q] <= rc) {
+                sum += value[verlet[(size_t)i * M + q]];
+                ++n;
+            }
+        value_ave[i] = n > 0 ? sum / n : 0.0;
+    }
+}

@@ -39,6 +39,13 @@ void port_rdf_streaming(const double *x, const double *y, const double *z, int N
 void port_repeat_cell(double *new_pos, const double *old_box, const double *old_pos, int n_old, int nx, int ny,
                       int nz, int num_t);
 
+void port_cnp(const double *x, const double *y, const double *z, int N, const double *box9, const double *origin3,
+              const int *boundary3, const int *verlet, int M, const double *dist, const int *nn, double *cnp, double rc,
+              int num_t);
+void port_wcp(const int *verlet, int N, int M, const int *nn, const int *type_list, int T, double *WCP, int num_t);
+void port_average_by_neighbor(double rc, const int *verlet, int N, int M, const double *dist, const int *nn,
+                              const double *value, double *value_ave, int include_self, int num_t);
+
 #ifdef __cplusplus
 }
 #endif

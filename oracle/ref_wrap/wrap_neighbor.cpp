@@ -32,4 +32,11 @@ void ref_wrap_positions(double *x, double *y, double *z, int N, BOXARGS, int num
 {
     wrap_positions(W1D(x, N), W1D(y, N), W1D(z, N), BOXPASS, num_t);
 }
+// neighbor.cpp:704 average_by_neighbor
+void ref_average_by_neighbor(double rc, const int *verlet, int N, int M, const double *dist, const int *nn,
+                             const double *value, double *value_ave, int include_self, int num_t)
+{
+    average_by_neighbor(rc, A2I(verlet, N, M), A2D(dist, N, M), A1I(nn, N), A1D(value, N), W1D(value_ave, N),
+                        include_self != 0, num_t);
+}
 }

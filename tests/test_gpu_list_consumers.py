@@ -1,0 +1,132 @@
+"""GPU parity of the further neighbour-list consumers: common neighbour parameter,
+Warren-Cowley parameter, average_by_neighbor -- device-resident path, host-pointer C ABI and the
+System methods, against the oracle (bit-exact) and the reference's own fixtures."""
+import glob
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import checker as K
+from oracle import pipeline as P
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+SA = sorted(glob.glob(str(GOLD / "sa_*.npz")))
+CNP = [p for p in SA if "cnp" in np.load(p).files]
+
+
+def _cases():
+    p, b = H.fcc(3.615, 8)
+    out = [("fcc_rattled", H.rattle(p, 0.1, 3), b, [1, 1, 1], 3.2),
+           ("fcc_hot_slab", H.rattle(p, 0.3, 4), b, [1, 1, 0], 3.6)]
+    ps, bs = H.shear(H.rattle(p, 0.08, 5), b, xy=0.2, xz=0.1, yz=-0.15)
+    out.append(("triclinic", ps, bs, [1, 1, 1], 3.3))
+    g, bg = H.random_gas(2500, 30.0, 6)
+    out.append(("gas", g, bg, [1, 1, 1], 4.5))
+    return out
+
+
+CASES = _cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_device_path_bit_exact(case):
+    from mdapy_b200.device import DeviceSystem
+
+    _, pos, box, bnd, rc = case
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    o = np.zeros(3)
+    v, d, n = K.build_neighbor_auto(x, y, z, box, o, bnd, rc)
+    ds = DeviceSystem(0)
+    ds.set_atoms(x, y, z, box, o, bnd)
+    ds.build_neighbor(rc)
+    for r in (rc, 0.9 * rc):
+        ref = K.cnp(x, y, z, box, o, bnd, v, d, n, r)
+        got = ds.cnp(r)
+        assert np.array_equal(got.view(np.int64), ref.view(np.int64)), np.abs(got - ref).max()
+    t = (np.random.default_rng(0).integers(0, 3, x.shape[0])).astype(np.int32)
+    assert np.array_equal(ds.wcp(t, 3), K.wcp(v, n, t, 3))
+    val = np.random.default_rng(1).normal(size=x.shape[0])
+    for inc in (True, False):
+        ref = K.average_by_neighbor(0.9 * rc, v, d, n, val, inc)
+        got = ds.average_by_neighbor(0.9 * rc, val, inc)
+        assert np.array_equal(got.view(np.int64), ref.view(np.int64))
+
+
+def test_host_pointer_dropins():
+    """Section A: same arguments as the reference's nanobind functions, host arrays in and out."""
+    from mdapy_b200 import _lib as L
+
+    _, pos, box, bnd, rc = CASES[0]
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    o = np.zeros(3)
+    v, d, n = K.build_neighbor_auto(x, y, z, box, o, bnd, rc)
+    b, oo, p = L.box_args(box, o, bnd)
+    N, M = v.shape
+    out = np.zeros(N)
+    L.check(L.lib().mdb_compute_cnp(L.dptr(x), L.dptr(y), L.dptr(z), N, L.dptr(b), L.dptr(oo), L.iptr(p), L.iptr(v), M,
+                                    L.dptr(d), L.iptr(n), L.dptr(out), rc, 1))
+    assert np.array_equal(out.view(np.int64), K.cnp(x, y, z, box, o, bnd, v, d, n, rc).view(np.int64))
+    t = (np.arange(N) % 4).astype(np.int32)
+    w = np.zeros((4, 4))
+    L.check(L.lib().mdb_get_wcp(L.iptr(v), N, M, L.iptr(n), L.iptr(t), 4, L.dptr(w), 1))
+    assert np.array_equal(w, K.wcp(v, n, t, 4))
+    ave = np.zeros(N)
+    L.check(L.lib().mdb_average_by_neighbor(rc, L.iptr(v), N, M, L.dptr(d), L.iptr(n), L.dptr(x), L.dptr(ave), 1, 1))
+    assert np.array_equal(ave.view(np.int64), K.average_by_neighbor(rc, v, d, n, x, True).view(np.int64))
+
+
+@pytest.mark.parametrize("path", CNP, ids=[Path(p).stem[3:] for p in CNP])
+def test_system_cnp_against_reference_fixture(path):
+    """tests/test_common_neighbor_parameter.py:21-30 (incl. the small boxes that are replicated)."""
+    import mdapy_b200 as mp
+
+    d = np.load(path)
+    system = mp.System(pos=d["pos"], box=mp.Box(d["box"], d["boundary"]))
+    system.cal_common_neighbor_parameter(float(d["cnp_cutoff"]))
+    got = np.asarray(system.data["cnp"])
+    assert np.allclose(got, d["cnp"], atol=1e-6, rtol=1e-6), np.abs(got - d["cnp"]).max()
+    fr = P.Frame(d["pos"], d["box"], d["boundary"])
+    ref = P.cal_cnp(K, fr, float(d["cnp_cutoff"]))
+    assert np.array_equal(got.view(np.int64), ref.view(np.int64))
+
+
+def test_system_cnp_known_answers():
+    """tests/test_common_neighbor_parameter.py:33-53."""
+    import mdapy_b200 as mp
+
+    a = 3.615
+    s = mp.build_crystal("Cu", "fcc", a, nx=4, ny=4, nz=4)
+    s.cal_common_neighbor_parameter(0.86 * a)
+    assert np.allclose(np.asarray(s.data["cnp"]).max(), 0.0)
+    s = mp.build_crystal("Cu", "bcc", a, nx=4, ny=4, nz=4)
+    s.cal_common_neighbor_parameter(1.21 * a)
+    assert np.allclose(np.asarray(s.data["cnp"]).max(), 0.0)
+
+
+@pytest.mark.parametrize("name", ["rec_box_big", "tri_box_big"])
+def test_system_average_by_neighbor_fixture(name):
+    """tests/test_average_neighbor.py:14-26."""
+    import mdapy_b200 as mp
+
+    g = np.load(GOLD / "average_neighbor.npz")
+    system = mp.System(pos=g[f"{name}__pos"], box=mp.Box(g[f"{name}__box"], [1, 1, 1], g[f"{name}__origin"]))
+    system.average_by_neighbor(float(g[f"{name}__cutoff"]), "x", include_self=True)
+    got = np.asarray(system.data["x_ave"])
+    assert np.allclose(got, g[f"{name}__x_ave"], atol=1e-6), np.abs(got - g[f"{name}__x_ave"]).max()
+
+
+def test_system_warren_cowley_fixture():
+    """tests/test_warren_cowley_parameter.py:7-23 (8788-atom CoCuFeNiPd, non-zero box origin)."""
+    import mdapy_b200 as mp
+
+    g = np.load(GOLD / "wcp_cocufenipd.npz")
+    pos = g["pos"]
+    system = mp.System(data={"x": pos[:, 0].copy(), "y": pos[:, 1].copy(), "z": pos[:, 2].copy(), "type": g["type"]},
+                       box=mp.Box(g["box"], g["boundary"], g["origin"]))
+    wcp = system.cal_warren_cowley_parameter(rc=float(g["cutoff"]))
+    assert np.allclose(wcp.WCP.round(2), g["wcp_rounded"]), wcp.WCP.round(2)
+    fr = P.Frame(pos, g["box"], g["boundary"], g["origin"])
+    assert np.array_equal(wcp.WCP, P.cal_wcp(K, fr, float(g["cutoff"]), (g["type"] - 1).astype(np.int32), 5))

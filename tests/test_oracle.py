@@ -177,3 +177,53 @@ def test_port_ids_equals_reference_on_defective_diamond():
     fr = P.Frame(pos - pos.min(0) + 2.0, box, [0, 0, 0])
     a, b = P.cal_ids(ref, fr), P.cal_ids(port, fr)
     assert np.array_equal(a, b) and (np.bincount(a, minlength=7) > 0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# further list consumers: the reference's own fixtures
+# (tests/test_common_neighbor_parameter.py:21-30, test_average_neighbor.py:14-26,
+#  test_warren_cowley_parameter.py:7-23)
+CNP = [p for p in SA if "cnp" in np.load(p).files]
+
+
+@pytest.mark.parametrize("K", BACKENDS)
+@pytest.mark.parametrize("path", CNP, ids=[Path(p).stem[3:] for p in CNP])
+def test_golden_cnp(K, path):
+    d, fr = _load(path)
+    got = P.cal_cnp(K, fr, float(d["cnp_cutoff"]))
+    assert np.allclose(got, d["cnp"], atol=1e-6, rtol=1e-6), np.abs(got - d["cnp"]).max()
+
+
+@pytest.mark.parametrize("K", BACKENDS)
+@pytest.mark.parametrize("name", ["rec_box_big", "tri_box_big"])
+def test_golden_average_by_neighbor(K, name):
+    g = np.load(GOLD / "average_neighbor.npz")
+    fr = P.Frame(g[f"{name}__pos"], g[f"{name}__box"], [1, 1, 1], g[f"{name}__origin"])
+    got = P.cal_average_by_neighbor(K, fr, float(g[f"{name}__cutoff"]), fr.x, True)
+    assert np.allclose(got, g[f"{name}__x_ave"], atol=1e-6), np.abs(got - g[f"{name}__x_ave"]).max()
+
+
+@pytest.mark.parametrize("K", BACKENDS)
+def test_golden_warren_cowley(K):
+    g = np.load(GOLD / "wcp_cocufenipd.npz")
+    fr = P.Frame(g["pos"], g["box"], g["boundary"], g["origin"])
+    t = (g["type"] - 1).astype(np.int32)
+    got = P.cal_wcp(K, fr, float(g["cutoff"]), t, 5)
+    assert np.allclose(got.round(2), g["wcp_rounded"]), got.round(2)
+
+
+@pytest.mark.skipif(not (ref.available() and port.available()), reason="needs both checkers")
+def test_port_list_consumers_equal_reference():
+    pos, box = H.fcc(3.615, 6)
+    pos = H.rattle(pos, 0.12, 21)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    o, bnd, rc = np.zeros(3), [1, 1, 1], 3.3
+    v, d, n = ref.build_neighbor_auto(x, y, z, box, o, bnd, rc)
+    for r in (rc, 2.9):
+        a, b = ref.cnp(x, y, z, box, o, bnd, v, d, n, r), port.cnp(x, y, z, box, o, bnd, v, d, n, r)
+        assert np.array_equal(a.view(np.int64), b.view(np.int64))
+    t = (np.arange(x.shape[0]) % 3).astype(np.int32)
+    assert np.array_equal(ref.wcp(v, n, t, 3), port.wcp(v, n, t, 3))
+    for inc in (True, False):
+        a, b = ref.average_by_neighbor(2.9, v, d, n, x, inc), port.average_by_neighbor(2.9, v, d, n, x, inc)
+        assert np.array_equal(a.view(np.int64), b.view(np.int64))
