@@ -145,6 +145,17 @@ int mdb_get_wcp(const int *verlet, int N, int M, const int *nn, const int *type_
 int mdb_average_by_neighbor(double rc, const int *verlet, int N, int M, const double *dist, const int *nn,
                             const double *value, double *value_ave, int include_self, int num_t);
 
+/* _cluster.get_cluster(verlet_list, distance_list, neighbor_number, rc, particleClusters) -> cluster count
+ * -- src/cluster.cpp:9;  _cluster.get_cluster_by_bond(verlet_list, neighbor_number, particleClusters) -- :62;
+ * _cluster.filter_by_type(verlet_list (inout), distance_list, neighbor_number, type_list, type1, type2, r, num_t)
+ * -- :114 */
+int mdb_get_cluster(const int *verlet, int N, int M, const double *dist, const int *nn, double rc,
+                    int *particle_clusters, int *cluster_number);
+int mdb_get_cluster_by_bond(const int *verlet, int N, int M, const int *nn, int *particle_clusters,
+                            int *cluster_number);
+int mdb_filter_by_type(int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list,
+                       const int *type1, const int *type2, const double *r, int npair, int num_t);
+
 /* ------------------------------------------------------------------------
  * Section B: device-resident system handle
  * ---------------------------------------------------------------------- */
@@ -224,6 +235,11 @@ int mdb_system_cnp(mdb_system *s, double rc, double *cnp_host);
 int mdb_system_wcp(mdb_system *s, const int *types_host, int ntype, double *wcp_host);
 int mdb_system_average_by_neighbor(mdb_system *s, double rc, const double *value_host, int include_self,
                                    double *value_ave_host);
+/* cluster ids (1-based, numbered by smallest member index) on the cached list.  npair == 0: one cut-off rc
+ * (get_cluster); npair > 0: type-pair cut-offs, bonds filtered like filter_by_type and then joined like
+ * get_cluster_by_bond (types_host: n_local ints in the units of type1/type2). */
+int mdb_system_cluster(mdb_system *s, double rc, const int *types_host, const int *type1, const int *type2,
+                       const double *r, int npair, int *cluster_host, int *cluster_number);
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 
 /* per-kernel device times (ms) of the most recent build_neighbor / fcna, measured with CUDA events */

@@ -21,6 +21,7 @@ def __getattr__(name):
         "IdentifyDiamondStructure": ("identify_diamond_structure", "IdentifyDiamondStructure"),
         "CommonNeighborParameter": ("common_neighbor_parameter", "CommonNeighborParameter"),
         "WarrenCowleyParameter": ("warren_cowley_parameter", "WarrenCowleyParameter"),
+        "ClusterAnalysis": ("cluster_analysis", "ClusterAnalysis"),
         "build_crystal": ("lattice", "build_crystal"),
     }
     if name == "empty_cache":

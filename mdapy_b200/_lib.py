@@ -58,6 +58,9 @@ PROTOTYPES = {
     "mdb_compute_cnp": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, c_ip, c_dp, C.c_double, C.c_int]),
     "mdb_get_wcp": (C.c_int, [c_ip, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_dp, C.c_int]),
     "mdb_average_by_neighbor": (C.c_int, [C.c_double, c_ip, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_dp, C.c_int, C.c_int]),
+    "mdb_get_cluster": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, C.c_double, c_ip, c_ip]),
+    "mdb_get_cluster_by_bond": (C.c_int, [c_ip, C.c_int, C.c_int, c_ip, c_ip, c_ip]),
+    "mdb_filter_by_type": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, c_ip, c_ip, c_ip, c_dp, C.c_int, C.c_int]),
     "mdb_system_create": (C.c_int, [C.c_int, C.POINTER(c_vp)]),
     "mdb_system_destroy": (None, [c_vp]),
     "mdb_system_set_stream": (C.c_int, [c_vp, c_vp]),
@@ -89,6 +92,7 @@ PROTOTYPES = {
     "mdb_system_cnp": (C.c_int, [c_vp, C.c_double, c_dp]),
     "mdb_system_wcp": (C.c_int, [c_vp, c_ip, C.c_int, c_dp]),
     "mdb_system_average_by_neighbor": (C.c_int, [c_vp, C.c_double, c_dp, C.c_int, c_dp]),
+    "mdb_system_cluster": (C.c_int, [c_vp, C.c_double, c_ip, c_ip, c_ip, c_dp, C.c_int, c_ip, c_ip]),
     "mdb_system_result_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "mdb_system_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_last_times": (C.c_int, [c_vp, c_fp, c_fp, c_fp]),

@@ -235,6 +235,14 @@ __global__ void __launch_bounds__(256) k_translate_ids(const int *__restrict__ i
 
 }  // namespace
 
+// in -> out exclusive prefix sum over n ints on the system's stream (scratch: s.scan_tmp)
+void device_exclusive_scan(MdbSystem &s, const int *in, int *out, int n)
+{
+    int *tmp = s.scan_tmp.ensure<int>(scan_tmp_ints(n));
+    exclusive_scan(in, out, n, tmp, s.stream);
+    CUDA_TRY(cudaGetLastError());
+}
+
 void launch_cell_planes(const double *x, const double *y, const double *z, int N, const DBox &b, const CellGrid &g,
                         int *plane, cudaStream_t st)
 {

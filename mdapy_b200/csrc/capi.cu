@@ -748,6 +748,40 @@ int mdb_system_average_by_neighbor(mdb_system *s, double rc, const double *value
     API_END
 }
 
+int mdb_system_cluster(mdb_system *s, double rc, const int *types_host, const int *type1, const int *type2,
+                       const double *r, int npair, int *cluster_host, int *cluster_number)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(s->n_rows == s->N, MDB_ERR_STATE, "cluster analysis needs the whole frame on one device");
+    const int R = s->n_rows, M = s->M;
+    int *out = s->out_i32.ensure<int>(R);
+    int count;
+    if (npair > 0) {
+        MDB_REQUIRE(types_host && type1 && type2 && r, MDB_ERR_VALUE, "Need type_list for multi cutoff mode.");
+        const int *types = h2d(*s, s->types, types_host, (size_t)s->N);
+        // filtered copy of the list (the reference works on verlet_list.copy(), cluster_analysis.py:66-69)
+        int *vcopy = s->verlet_tmp.ensure<int>((size_t)R * M);
+        CUDA_TRY(cudaMemcpyAsync(vcopy, s->verlet.as<int>(), sizeof(int) * (size_t)R * M, cudaMemcpyDeviceToDevice,
+                                 s->stream));
+        int *pairs = s->scratch2.ensure<int>((size_t)2 * npair + 2);
+        double *rr = s->out_f64c.ensure<double>(npair);
+        CUDA_TRY(cudaMemcpyAsync(pairs, type1, sizeof(int) * npair, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(pairs + npair, type2, sizeof(int) * npair, cudaMemcpyHostToDevice, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(rr, r, sizeof(double) * npair, cudaMemcpyHostToDevice, s->stream));
+        launch_filter_by_type(*s, vcopy, s->dist.as<double>(), s->nn.as<int>(), M, types, pairs, pairs + npair, rr, npair);
+        count = launch_cluster(*s, vcopy, nullptr, s->nn.as<int>(), M, 0.0, out);
+    } else {
+        MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "rc should be a positive number, got %g.", rc);
+        count = launch_cluster(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), M, rc, out);
+    }
+    if (cluster_number) *cluster_number = count;
+    d2h(*s, cluster_host, out, (size_t)R);
+    if (cluster_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 // (n_rows, 8) = type, ordering, rmsd, interatomic distance, qw, qx, qy, qz; indices_host: (n_rows, 18).
 int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, double rmsd_threshold,
                    double *output_host, int *indices_host)
@@ -995,6 +1029,57 @@ int mdb_average_by_neighbor(double rc, const int *verlet, int N, int M, const do
     if (rcode != MDB_OK) return rcode;
     rcode = mdb_system_average_by_neighbor(s.s, rc, value, include_self, value_ave);
     if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_get_cluster(const int *verlet, int N, int M, const double *dist, const int *nn, double rc,
+                    int *particle_clusters, int *cluster_number)
+{
+    API_BEGIN
+    MDB_REQUIRE(dist && particle_clusters, MDB_ERR_VALUE, "distance_list and particleClusters are required");
+    ScopedSystem s;
+    int rcode = list_only_system(*s, N, verlet, dist, nn, M, rc);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_cluster(s.s, rc, nullptr, nullptr, nullptr, nullptr, 0, particle_clusters, cluster_number);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_get_cluster_by_bond(const int *verlet, int N, int M, const int *nn, int *particle_clusters,
+                            int *cluster_number)
+{
+    API_BEGIN
+    MDB_REQUIRE(particle_clusters, MDB_ERR_VALUE, "particleClusters is required");
+    ScopedSystem s;
+    int rcode = list_only_system(*s, N, verlet, nullptr, nn, M, -1.0);
+    if (rcode != MDB_OK) return rcode;
+    int *out = s->out_i32.ensure<int>(N);
+    const int count = launch_cluster(*s, s->verlet.as<int>(), nullptr, s->nn.as<int>(), M, 0.0, out);
+    if (cluster_number) *cluster_number = count;
+    d2h(*s, particle_clusters, out, (size_t)N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_filter_by_type(int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list,
+                       const int *type1, const int *type2, const double *r, int npair, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(dist && type_list && type1 && type2 && r && npair > 0, MDB_ERR_VALUE,
+                "distance_list, type_list and the type-pair table are required");
+    ScopedSystem s;
+    int rcode = list_only_system(*s, N, verlet, dist, nn, M, -1.0);
+    if (rcode != MDB_OK) return rcode;
+    const int *types = h2d(*s, s->types, type_list, (size_t)N);
+    int *pairs = s->scratch2.ensure<int>((size_t)2 * npair + 2);
+    double *rr = s->out_f64c.ensure<double>(npair);
+    CUDA_TRY(cudaMemcpyAsync(pairs, type1, sizeof(int) * npair, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(pairs + npair, type2, sizeof(int) * npair, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(rr, r, sizeof(double) * npair, cudaMemcpyHostToDevice, s->stream));
+    launch_filter_by_type(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), M, types, pairs, pairs + npair,
+                          rr, npair);
+    d2h(*s, verlet, s->verlet.as<int>(), (size_t)N * M);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
 }
 

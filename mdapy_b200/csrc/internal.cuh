@@ -167,6 +167,10 @@ void launch_wcp_counts(MdbSystem &s, const int *verlet, const int *nn, int M, co
                        unsigned long long *counts);
 void launch_average_by_neighbor(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc,
                                 const double *value, bool include_self, double *out);
+void device_exclusive_scan(MdbSystem &s, const int *in, int *out, int n);
+void launch_filter_by_type(MdbSystem &s, int *verlet, const double *dist, const int *nn, int M, const int *types,
+                           const int *t1, const int *t2, const double *r, int npair);
+int launch_cluster(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc, int *cluster);
 int ptm_parse_flags(const char *structure);
 void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
                 double *output, int ocols, int *indices, int icols);

@@ -219,6 +219,20 @@ class DeviceSystem:
                                                          L.dptr(out)))
         return out
 
+    def cluster(self, rc: float, type_list=None, type1=None, type2=None, r=None):
+        """(cluster ids [n_rows], cluster count).  One cut-off, or type-pair cut-offs (cluster.cpp:9-150)."""
+        out = L.result_empty(self.n_rows, np.int32)
+        cnt = C.c_int(0)
+        if type1 is not None:
+            t, a, b, rr = L.i32(type_list), L.i32(type1), L.i32(type2), L.f64(r)
+            assert t.shape[0] == self.N
+            L.check(self._lib.mdb_system_cluster(self._h, float(rc), L.iptr(t), L.iptr(a), L.iptr(b), L.dptr(rr),
+                                                 int(a.shape[0]), L.iptr(out), C.byref(cnt)))
+        else:
+            L.check(self._lib.mdb_system_cluster(self._h, float(rc), None, None, None, None, 0, L.iptr(out),
+                                                 C.byref(cnt)))
+        return out, cnt.value
+
     def result_device(self):
         """Raw device pointers (int) of the latest int32 / f64 per-atom result."""
         a, b = C.c_void_p(), C.c_void_p()

@@ -20,6 +20,7 @@ from . import tool_function as tool
 from .ackland_jones_analysis import AcklandJonesAnalysis
 from .box import Box
 from .centro_symmetry_parameter import CentroSymmetryParameter
+from .cluster_analysis import ClusterAnalysis
 from .common_neighbor_analysis import CommonNeighborAnalysis
 from .common_neighbor_parameter import CommonNeighborParameter
 from .identify_diamond_structure import IdentifyDiamondStructure
@@ -323,6 +324,28 @@ class System:
         ave = self._device_list().average_by_neighbor(average_rc, value, include_self)
         name = output_name if output_name is not None else f"{property_name}_ave"
         self.update_data(self._data.with_columns(**{name: np.asarray(ave[: self.N]).copy()}))
+
+    def cal_cluster_analysis(self, rc=5.0, max_neigh: Optional[int] = None) -> None:
+        """system.py:2416-2478 -> data['cluster_id']; rc is a number or a dict like {'1-1': 1.5, '1-2': 1.3}."""
+        if isinstance(rc, (int, float, np.integer, np.floating)):
+            max_rc = float(rc)
+        elif isinstance(rc, dict):
+            max_rc = max([i for i in rc.values()])
+        else:
+            raise TypeError("rc should be a positive number, or a dict like {'1-1':1.5, '1-2':1.3}")
+        if "rc" in self.__dict__:
+            if self.rc < max_rc:
+                self.build_neighbor(max_rc, max_neigh)
+        else:
+            self.build_neighbor(max_rc, max_neigh)
+        type_list = None
+        if isinstance(rc, dict):
+            assert "type" in self.data.columns, "Must have type for multi rc cluster calculation."
+            _, view = self._get_compute_view()
+            type_list = np.asarray((view if "type" in view.columns else self.data)["type"]).astype(np.int32)
+        ca = ClusterAnalysis(rc, type_list=type_list, dev=self._device_list())
+        ca.compute()
+        self.update_data(self.data.with_columns(cluster_id=np.asarray(ca.particleClusters[: self.N]).copy()))
 
     def cal_steinhardt_bond_orientation(self, llist, use_voronoi: bool = False, nnn: int = 0, rc: float = -1.0,
                                         average: bool = False, use_weight: bool = False, weight=None,

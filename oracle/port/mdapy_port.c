@@ -1041,3 +1041,47 @@ void port_average_by_neighbor(double rc, const int *verlet, int N, int M, const 
         value_ave[i] = n > 0 ? sum / n : 0.0;
     }
 }
+
+/* ------------------------------------------------------------------ cluster analysis
+ * cluster.cpp:9-60 (rc > 0: bond iff distance <= rc), 62-112 (dist == NULL: bond iff entry > -1), 114-150 */
+int port_get_cluster(const int *verlet, int N, int M, const double *dist, const int *nn, double rc, int *clusters)
+{
+    int *queue = (int *)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1));
+    int id = 0;
+    for (int seed = 0; seed < N; ++seed) {
+        if (clusters[seed] != -1) continue;
+        int head = 0, tail = 0;
+        queue[tail++] = seed;
+        ++id;
+        while (head < tail) {
+            const int cur = queue[head++];
+            int nl = 0;
+            for (int q = 0; q < nn[cur]; ++q) {
+                const int j = verlet[(size_t)cur * M + q];
+                const int bond = dist ? (dist[(size_t)cur * M + q] <= rc) : (j > -1);
+                if (!bond) continue;
+                ++nl;
+                if (clusters[j] == -1) {
+                    clusters[j] = id;
+                    queue[tail++] = j;
+                }
+            }
+            if (nl == 0) clusters[cur] = id;
+        }
+    }
+    free(queue);
+    return id;
+}
+
+void port_filter_by_type(int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list,
+                         const int *t1, const int *t2, const double *r, int npair, int num_t)
+{
+    (void)num_t;
+    for (int i = 0; i < N; ++i)
+        for (int q = 0; q < nn[i]; ++q) {
+            const int j = verlet[(size_t)i * M + q];
+            for (int k = 0; k < npair; ++k)
+                if ((t1[k] == type_list[i]) & (t2[k] == type_list[j]) & (dist[(size_t)i * M + q] > r[k]))
+                    verlet[(size_t)i * M + q] = -1;
+        }
+}

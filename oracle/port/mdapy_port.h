@@ -46,6 +46,10 @@ void port_wcp(const int *verlet, int N, int M, const int *nn, const int *type_li
 void port_average_by_neighbor(double rc, const int *verlet, int N, int M, const double *dist, const int *nn,
                               const double *value, double *value_ave, int include_self, int num_t);
 
+int port_get_cluster(const int *verlet, int N, int M, const double *dist, const int *nn, double rc, int *clusters);
+void port_filter_by_type(int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list,
+                         const int *t1, const int *t2, const double *r, int npair, int num_t);
+
 #ifdef __cplusplus
 }
 #endif

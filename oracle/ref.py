@@ -352,3 +352,27 @@ def average_by_neighbor(rc, verlet, dist, nn, value, include_self=True, nt=None)
                                              _d(value), _d(out), C.c_int(int(bool(include_self))),
                                              C.c_int(nt or num_threads()))
     return out
+
+
+def cluster(verlet, nn, dist=None, rc=0.0):
+    """cluster.cpp:9 get_cluster (dist given) / :62 get_cluster_by_bond (dist None) -> (ids, count)."""
+    verlet, nn = _i32(verlet), _i32(nn)
+    N, M = verlet.shape
+    out = np.full(N, -1, np.int32)
+    if dist is None:
+        cnt = _lib("cluster").ref_get_cluster_by_bond(_i(verlet), C.c_int(N), C.c_int(M), _i(nn), _i(out))
+    else:
+        dist = _f64(dist)
+        cnt = _lib("cluster").ref_get_cluster(_i(verlet), C.c_int(N), C.c_int(M), _d(dist), _i(nn), C.c_double(rc), _i(out))
+    return out, int(cnt)
+
+
+def filter_by_type(verlet, dist, nn, type_list, type1, type2, r, nt=None):
+    """cluster.cpp:114 filter_by_type -> filtered copy of verlet."""
+    v = _i32(verlet).copy()
+    dist, nn, type_list = _f64(dist), _i32(nn), _i32(type_list)
+    t1, t2, r = _i32(type1), _i32(type2), _f64(r)
+    N, M = v.shape
+    _lib("cluster").ref_filter_by_type(_i(v), C.c_int(N), C.c_int(M), _d(dist), _i(nn), _i(type_list), _i(t1), _i(t2), _d(r),
+           C.c_int(t1.shape[0]), C.c_int(nt or num_threads()))
+    return v

@@ -130,3 +130,74 @@ def test_system_warren_cowley_fixture():
     assert np.allclose(wcp.WCP.round(2), g["wcp_rounded"]), wcp.WCP.round(2)
     fr = P.Frame(pos, g["box"], g["boundary"], g["origin"])
     assert np.array_equal(wcp.WCP, P.cal_wcp(K, fr, float(g["cutoff"]), (g["type"] - 1).astype(np.int32), 5))
+
+
+# ---------------------------------------------------------------------------------------------
+# cluster analysis (src/cluster.cpp): ids numbered like the reference's serial flood
+def _gas(n, L, seed):
+    g, bg = H.random_gas(n, L, seed)
+    return np.ascontiguousarray(g[:, 0]), np.ascontiguousarray(g[:, 1]), np.ascontiguousarray(g[:, 2]), bg
+
+
+@pytest.mark.parametrize("rc_list,rc", [(3.0, 3.0), (3.0, 2.1), (3.0, 0.8), (4.5, 4.5)])
+def test_cluster_ids_equal_reference(rc_list, rc):
+    from mdapy_b200.device import DeviceSystem
+
+    x, y, z, box = _gas(4000, 40.0, 14)
+    o, bnd = np.zeros(3), [1, 1, 0]
+    v, d, n = K.build_neighbor_auto(x, y, z, box, o, bnd, rc_list)
+    ref, cnt = K.cluster(v, n, d, rc)
+    ds = DeviceSystem(0)
+    ds.set_atoms(x, y, z, box, o, bnd)
+    ds.build_neighbor(rc_list)
+    got, c = ds.cluster(rc)
+    assert c == cnt and np.array_equal(got, ref)
+
+
+def test_cluster_type_pair_cutoffs_and_host_api():
+    import ctypes as C
+
+    from mdapy_b200 import _lib as L
+    from mdapy_b200.cluster_analysis import ClusterAnalysis, type_pair_table
+    from mdapy_b200.device import DeviceSystem
+
+    x, y, z, box = _gas(3000, 36.0, 15)
+    o, bnd = np.zeros(3), [1, 1, 1]
+    types = (np.random.default_rng(2).integers(1, 3, x.shape[0])).astype(np.int32)
+    rcd = {"1-1": 2.0, "1-2": 2.7, "2-2": 3.1}
+    v, d, n = K.build_neighbor_auto(x, y, z, box, o, bnd, 3.1)
+    t1, t2, r = type_pair_table(rcd)
+    fv = K.filter_by_type(v, d, n, types, t1, t2, r)
+    ref, cnt = K.cluster(fv, n)
+    # device-resident path
+    ds = DeviceSystem(0)
+    ds.set_atoms(x, y, z, box, o, bnd)
+    ds.build_neighbor(3.1)
+    got, c = ds.cluster(0.0, types, t1, t2, r)
+    assert c == cnt and np.array_equal(got, ref)
+    # host-pointer path through the mirrored class (filter_by_type + get_cluster_by_bond)
+    ca = ClusterAnalysis(rcd, v, d, n, types)
+    ca.compute()
+    assert np.array_equal(ca.verlet_list, fv) and ca.cluster_number == cnt and np.array_equal(ca.particleClusters, ref)
+    ca = ClusterAnalysis(2.4, v, d, n)
+    ca.compute()
+    ref2, cnt2 = K.cluster(v, n, d, 2.4)
+    assert ca.cluster_number == cnt2 and np.array_equal(ca.particleClusters, ref2)
+
+
+def test_system_cluster_analysis():
+    import mdapy_b200 as mp
+
+    x, y, z, box = _gas(3000, 36.0, 16)
+    types = (np.arange(x.shape[0]) % 2 + 1).astype(np.int32)
+    system = mp.System(data={"x": x, "y": y, "z": z, "type": types}, box=mp.Box(box))
+    system.cal_cluster_analysis(2.5)
+    v, d, n = K.build_neighbor_auto(x, y, z, box, np.zeros(3), [1, 1, 1], 2.5)
+    ref, cnt = K.cluster(v, n, d, 2.5)
+    assert np.array_equal(np.asarray(system.data["cluster_id"]), ref)
+    system.cal_cluster_analysis({"1-1": 1.8, "1-2": 2.5, "2-2": 2.2})      # reuses the cached rc = 2.5 list
+    from mdapy_b200.cluster_analysis import type_pair_table
+
+    t1, t2, r = type_pair_table({"1-1": 1.8, "1-2": 2.5, "2-2": 2.2})
+    ref, cnt = K.cluster(K.filter_by_type(v, d, n, types, t1, t2, r), n)
+    assert np.array_equal(np.asarray(system.data["cluster_id"]), ref)

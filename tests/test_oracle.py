@@ -227,3 +227,22 @@ def test_port_list_consumers_equal_reference():
     for inc in (True, False):
         a, b = ref.average_by_neighbor(2.9, v, d, n, x, inc), port.average_by_neighbor(2.9, v, d, n, x, inc)
         assert np.array_equal(a.view(np.int64), b.view(np.int64))
+
+
+@pytest.mark.skipif(not (ref.available() and port.available()), reason="needs both checkers")
+def test_port_cluster_equals_reference():
+    g, bg = H.random_gas(1500, 30.0, 12)
+    x, y, z = (np.ascontiguousarray(g[:, k]) for k in range(3))
+    o, bnd = np.zeros(3), [1, 1, 1]
+    v, d, n = ref.build_neighbor_auto(x, y, z, bg, o, bnd, 3.0)
+    for rc in (3.0, 2.2, 1.0):
+        a, ca = ref.cluster(v, n, d, rc)
+        b, cb = port.cluster(v, n, d, rc)
+        assert ca == cb and np.array_equal(a, b) and a.min() == 1 and a.max() == ca
+    t = (np.arange(x.shape[0]) % 2 + 1).astype(np.int32)
+    t1, t2, r = np.array([1, 1, 2, 2], np.int32), np.array([1, 2, 1, 2], np.int32), np.array([2.0, 2.6, 2.6, 3.0])
+    fa, fb = ref.filter_by_type(v, d, n, t, t1, t2, r), port.filter_by_type(v, d, n, t, t1, t2, r)
+    assert np.array_equal(fa, fb) and (fa == -1).sum() > (v == -1).sum()
+    a, ca = ref.cluster(fa, n)
+    b, cb = port.cluster(fb, n)
+    assert ca == cb and np.array_equal(a, b)
