@@ -313,6 +313,8 @@ int mdb_system_create(int device, mdb_system **out)
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
     for (int k = 0; k < 4; ++k) CUDA_TRY(cudaEventCreate(&s->ev[k]));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreateWithFlags(&s->chunk_ev[k], cudaEventDisableTiming));
     *out = s;
     API_END
 }
@@ -330,6 +332,12 @@ void mdb_system_destroy(mdb_system *s)
     for (DevBuf *b : bufs) b->release();
     for (int k = 0; k < 4; ++k)
         if (s->ev[k]) cudaEventDestroy(s->ev[k]);
+    for (int k = 0; k < 2; ++k)
+        if (s->chunk_ev[k]) cudaEventDestroy(s->chunk_ev[k]);
+    if (s->copy_stream) {
+        cudaStreamSynchronize(s->copy_stream);
+        cudaStreamDestroy(s->copy_stream);
+    }
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -533,9 +541,28 @@ int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host)
     int *pat = s->out_i32.ensure<int>(s->n_rows);
     CUDA_TRY(cudaMemsetAsync(pat, 0, sizeof(int) * s->n_rows, s->stream));
     prof_mark(*s, 2);
-    launch_fcna(*s, s->verlet.as<int>(), s->nn.as<int>(), s->M, rc, pat);
-    prof_mark(*s, 3);
-    d2h(*s, pattern_host, pat, (size_t)s->n_rows);
+    // Large frames with a host destination: the labels of one chunk travel to the host (copy stream) while the
+    // next chunk is classified, so only the last chunk's copy is exposed.
+    const int R = s->n_rows;
+    const int nchunk = (pattern_host && R >= (1 << 22)) ? 8 : 1;
+    if (nchunk == 1) {
+        launch_fcna(*s, s->verlet.as<int>(), s->nn.as<int>(), s->M, rc, pat);
+        prof_mark(*s, 3);
+        d2h(*s, pattern_host, pat, (size_t)R);
+    } else {
+        const int step = ((R + nchunk - 1) / nchunk + 127) / 128 * 128;
+        for (int c = 0, first = 0; first < R; ++c, first += step) {
+            const int count = first + step <= R ? step : R - first;
+            launch_fcna(*s, s->verlet.as<int>(), s->nn.as<int>(), s->M, rc, pat, first, count);
+            cudaEvent_t ev = s->chunk_ev[c & 1];
+            CUDA_TRY(cudaEventRecord(ev, s->stream));
+            CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, ev, 0));
+            CUDA_TRY(cudaMemcpyAsync(pattern_host + first, pat + first, sizeof(int) * (size_t)count,
+                                     cudaMemcpyDeviceToHost, s->copy_stream));
+        }
+        prof_mark(*s, 3);
+        CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    }
     if (pattern_host || s->profile) CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->profile) CUDA_TRY(cudaEventElapsedTime(&s->t_cna, s->ev[2], s->ev[3]));
     API_END

@@ -83,9 +83,9 @@ __device__ __forceinline__ void bond_matrix(const DBox &box, const double *px, c
 __global__ void __launch_bounds__(128) k_fcna(const double *__restrict__ x, const double *__restrict__ y,
                                               const double *__restrict__ z, int N, DBox box,
                                               const int *__restrict__ verlet, const int *__restrict__ nnum, int M,
-                                              double cutsq, int *__restrict__ pattern)
+                                              double cutsq, int *__restrict__ pattern, int first)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;  // rows [first, N)
     if (i >= N) return;
     const int nn = nnum[i];
     if ((nn != 12 && nn != 14) || nn > M) return;
@@ -305,10 +305,11 @@ __global__ void __launch_bounds__(CNA_THREADS) k_fcna_fast(const double *__restr
                                                            const __grid_constant__ DBox box,
                                                            const int *__restrict__ verlet,
                                                            const int *__restrict__ nnum, int M, double cutsq,
-                                                           float cut_lo, float cut_hi, int *__restrict__ pattern)
+                                                           float cut_lo, float cut_hi, int *__restrict__ pattern,
+                                                           int first)
 {
     __shared__ unsigned short nb_s[14 * CNA_THREADS];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;  // rows [first, N)
     if (i >= N) return;
     const int nn = nnum[i];
     if ((nn != 12 && nn != 14) || nn > M) return;
@@ -420,9 +421,12 @@ __global__ void k_fill_int(int n, int v, int *__restrict__ p)
 
 }  // namespace
 
-void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern)
+// rows [first, first + count) (count < 0: all rows)
+void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern, int first, int count)
 {
-    const int N = s.n_rows;
+    const int N = count < 0 ? s.n_rows : first + count;
+    const int span = N - first;
+    if (span <= 0) return;
     // fast path: orthogonal frame, the list's own cut-off bounds the neighbour distances (cut-off list
     // built with list_rc >= every stored distance) and every periodic edge exceeds 4.2 * that bound
     bool fast = !s.box.triclinic && s.list_kind == LIST_CUTOFF && s.list_rc > 0;
@@ -433,12 +437,13 @@ void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double r
     if (env && !strcmp(env, "exact")) fast = false;
     if (fast) {
         const double c2 = rc * rc;
-        MDB_LAUNCH(k_fcna_fast, (N + CNA_THREADS - 1) / CNA_THREADS, CNA_THREADS, 0, s.stream, s.x, s.y, s.z, N, s.box,
-                   verlet, nn, M, c2, (float)(c2 * (1.0 - 1e-4)), (float)(c2 * (1.0 + 1e-4)), pattern);
+        MDB_LAUNCH(k_fcna_fast, (span + CNA_THREADS - 1) / CNA_THREADS, CNA_THREADS, 0, s.stream, s.x, s.y, s.z, N, s.box,
+                   verlet, nn, M, c2, (float)(c2 * (1.0 - 1e-4)), (float)(c2 * (1.0 + 1e-4)), pattern, first);
         CUDA_TRY(cudaGetLastError());
         return;
     }
-    MDB_LAUNCH(k_fcna, (N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, nn, M, rc * rc, pattern);
+    MDB_LAUNCH(k_fcna, (span + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, nn, M, rc * rc, pattern,
+               first);
     CUDA_TRY(cudaGetLastError());
 }
 

@@ -96,6 +96,8 @@ struct MdbSystem {
     int device{0};
     cudaStream_t stream{nullptr};
     bool own_stream{false};
+    cudaStream_t copy_stream{nullptr};  // device -> host copies that overlap the next chunk of a kernel
+    cudaEvent_t chunk_ev[2]{};
 
     // atoms (raw coordinates, SoA as mdapy's polars columns: neighbor.py:104-106)
     int N{0};
@@ -148,7 +150,8 @@ bool tiled_neighbor_plan(const MdbSystem &s, int &T);
 void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_only, int sample_stride);
 int neighbor_tiled_max(MdbSystem &s, int *min_count = nullptr);
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k);
-void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern);
+void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern, int first = 0,
+                 int count = -1);
 void launch_acna(MdbSystem &s, const int *verlet, int M, int *pattern);
 void launch_ids(MdbSystem &s, const int *verlet, int M, int *second_out, int *pattern);
 void launch_csp(MdbSystem &s, const int *verlet, int M, int nnei, double *csp);
