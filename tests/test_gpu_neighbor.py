@@ -131,3 +131,49 @@ def test_config1_fcc_32k():
         v, d, n = ds.fetch_neighbor()
         assert np.array_equal(v, rv) and np.array_equal(n, rn) and np.array_equal(d.view(np.int64), rd.view(np.int64))
         assert np.array_equal(ds.fcna(rc), K.fcna(x, y, z, b, np.zeros(3), [1, 1, 1], rv, rn, rc))
+
+
+# ---------------------------------------------------------------------------------------------
+# Cell-tile kernel (neighbor_tiled.cu): frames large enough to take it, exercising every branch --
+# tile shapes from sparse to dense, non-zero origin (wrap is not the identity bit pattern), unwrapped
+# atoms (periodic-image path), open axes, 16-byte and scalar row stores, the automatic width with margin +
+# compaction, overflowing max_neigh.
+def _tiled_cases():
+    out = []
+    p, b = H.fcc(3.615, 12)                       # 43.4 A: 14 cells at rc = 3.08
+    r = H.rattle(p, 0.06, 31)
+    out.append(("fcc12_T4", r, b, np.zeros(3), [1, 1, 1], 3.615 * 0.8536))
+    out.append(("fcc12_origin", r + np.array([-7.3, 11.1, 0.37]), b, np.array([-7.3, 11.1, 0.37]), [1, 1, 1], 3.1))
+    shift = np.random.default_rng(5).integers(-2, 3, r.shape) * np.diag(b)
+    out.append(("fcc12_unwrapped", r + shift, b, np.zeros(3), [1, 1, 1], 3.1))
+    out.append(("fcc12_slab", r, b, np.zeros(3), [1, 1, 0], 3.3))
+    out.append(("fcc12_open", r, b, np.zeros(3), [0, 0, 0], 3.3))
+    out.append(("fcc12_dense_rc5", r, b, np.zeros(3), [1, 1, 1], 5.0))
+    out.append(("fcc12_dense_rc6", r, b, np.zeros(3), [1, 0, 1], 6.2))
+    g, bg = H.random_gas(6000, 60.0, 33)           # 0.03 atoms / A^3: sparse tiles
+    out.append(("gas_sparse", g, bg, np.zeros(3), [1, 1, 1], 2.4))
+    g2, bg2 = H.random_gas(20000, 50.0, 34)        # clustered cells, wide count distribution
+    out.append(("gas_dense", g2, bg2, np.zeros(3), [1, 1, 1], 3.3))
+    return out
+
+
+TILED = _tiled_cases()
+
+
+@pytest.mark.parametrize("case", TILED, ids=[c[0] for c in TILED])
+@pytest.mark.parametrize("max_neigh", [None, 13, 64])
+def test_tiled_kernel_rows_bit_exact(case, max_neigh):
+    name, pos, box, origin, boundary, rc = case
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    if max_neigh is None:
+        rv, rd, rn = K.build_neighbor_auto(x, y, z, box, origin, boundary, rc)
+    else:
+        rv, rd, rn = K.build_neighbor(x, y, z, box, origin, boundary, rc, max_neigh)
+    ds = _dev()
+    ds.set_atoms(x, y, z, box, origin, boundary)
+    M, mx = ds.build_neighbor(rc, max_neigh)
+    v, d, n = ds.fetch_neighbor()
+    assert M == rv.shape[1] and mx == int(rn.max())
+    assert np.array_equal(n, rn)
+    assert np.array_equal(v, rv), "row order / membership differs from the reference"
+    assert np.array_equal(d.view(np.int64), rd.view(np.int64)), "distances are not bit-identical"
