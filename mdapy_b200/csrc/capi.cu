@@ -101,7 +101,10 @@ static void build_neighbor(MdbSystem &s, double rc, int max_neigh)
         // search.  Only when even that margin was too small is the fill repeated.
         int est, est_min = 0;
         bool exact = !tiled;
-        if (tiled) {
+        if (tiled && s.hint_rc == rc && s.hint_M > 0) {
+            est = s.hint_M;             // previous frame on this handle, same cut-off
+            exact = s.hint_uniform;
+        } else if (tiled) {
             launch_neighbor_tiled(s, rc, 0, T, true, 16);
             est = neighbor_tiled_max(s, &est_min);
             if (est == est_min) exact = true;
@@ -112,14 +115,19 @@ static void build_neighbor(MdbSystem &s, double rc, int max_neigh)
         if (est < 1) est = 1;
         int width = exact ? est : (est + 1 + 3) / 4 * 4;
         int mx = fill(width);
+        bool refilled = false;
         if (mx > width) {
-            width = exact ? mx : (mx + 3) / 4 * 4;
+            width = (mx + 3) / 4 * 4;
             mx = fill(width);
+            refilled = true;
         }
         const int M = mx < 1 ? 1 : mx;
         if (M < width) launch_compact_rows(s, width, M);
         s.M = M;
         s.max_count = mx;
+        s.hint_rc = rc;
+        s.hint_M = M;
+        s.hint_uniform = exact && !refilled && M == width;
     }
     s.list_kind = LIST_CUTOFF;
     s.list_rc = rc;

@@ -123,6 +123,11 @@ struct MdbSystem {
     int M{0};
     int max_count{0};
     DevBuf verlet, dist, nn, verlet_tmp, dist_tmp;
+    // width of the previous automatic build on this handle (frames of a trajectory reuse one handle: the
+    // next frame starts from this width instead of sampling tiles again)
+    double hint_rc{-1.0};
+    int hint_M{0};
+    bool hint_uniform{false};
 
     // per-atom outputs kept on device until fetched
     DevBuf out_i32, out_f64, out_f64b, out_f64c, scratch, scratch2;

@@ -177,3 +177,21 @@ def test_tiled_kernel_rows_bit_exact(case, max_neigh):
     assert np.array_equal(n, rn)
     assert np.array_equal(v, rv), "row order / membership differs from the reference"
     assert np.array_equal(d.view(np.int64), rd.view(np.int64)), "distances are not bit-identical"
+
+
+def test_width_hint_across_frames_of_one_handle():
+    """Frames of a trajectory reuse one handle: the second frame starts from the first frame's width
+    (no sampling pass) and must still produce the reference's rows, also when its maximum grows or shrinks."""
+    p, b = H.fcc(3.615, 12)
+    rc = 3.3
+    o, bnd = np.zeros(3), [1, 1, 1]
+    ds = _dev()
+    for sigma, seed in ((0.0, 0), (0.25, 1), (0.02, 2), (0.35, 3), (0.0, 4)):
+        pos = H.rattle(p, sigma, seed) if sigma > 0 else p
+        x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+        rv, rd, rn = K.build_neighbor_auto(x, y, z, b, o, bnd, rc)
+        ds.set_atoms(x, y, z, b, o, bnd)
+        M, mx = ds.build_neighbor(rc)
+        v, d, n = ds.fetch_neighbor()
+        assert M == rv.shape[1] and np.array_equal(n, rn) and np.array_equal(v, rv)
+        assert np.array_equal(d.view(np.int64), rd.view(np.int64))
