@@ -156,6 +156,11 @@ int mdb_get_cluster_by_bond(const int *verlet, int N, int M, const int *nn, int 
 int mdb_filter_by_type(int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list,
                        const int *type1, const int *type2, const double *r, int npair, int num_t);
 
+/* _structure_entropy.calculate_structure_entropy(rc, sigma, use_local_density, volume, distance_list,
+ * neighbor_number, entropy, num_t) -- src/structure_entropy.cpp:11 */
+int mdb_calculate_structure_entropy(double rc, double sigma, int use_local_density, double volume, const double *dist,
+                                    int N, int M, const int *nn, double *entropy, int num_t);
+
 /* ------------------------------------------------------------------------
  * Section B: device-resident system handle
  * ---------------------------------------------------------------------- */
@@ -240,6 +245,10 @@ int mdb_system_average_by_neighbor(mdb_system *s, double rc, const double *value
  * get_cluster_by_bond (types_host: n_local ints in the units of type1/type2). */
 int mdb_system_cluster(mdb_system *s, double rc, const int *types_host, const int *type1, const int *type2,
                        const double *r, int npair, int *cluster_host, int *cluster_number);
+/* structure entropy on the cached list; average_rc > 0 also fills entropy_ave_host (average_by_neighbor
+ * with include_self, structure_entropy.py:133-145).  Either host pointer may be NULL. */
+int mdb_system_structure_entropy(mdb_system *s, double rc, double sigma, int use_local_density, double volume,
+                                 double average_rc, double *entropy_host, double *entropy_ave_host);
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 
 /* per-kernel device times (ms) of the most recent build_neighbor / fcna, measured with CUDA events */

@@ -22,6 +22,7 @@ def __getattr__(name):
         "CommonNeighborParameter": ("common_neighbor_parameter", "CommonNeighborParameter"),
         "WarrenCowleyParameter": ("warren_cowley_parameter", "WarrenCowleyParameter"),
         "ClusterAnalysis": ("cluster_analysis", "ClusterAnalysis"),
+        "StructureEntropy": ("structure_entropy", "StructureEntropy"),
         "build_crystal": ("lattice", "build_crystal"),
     }
     if name == "empty_cache":

@@ -61,6 +61,8 @@ PROTOTYPES = {
     "mdb_get_cluster": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, C.c_double, c_ip, c_ip]),
     "mdb_get_cluster_by_bond": (C.c_int, [c_ip, C.c_int, C.c_int, c_ip, c_ip, c_ip]),
     "mdb_filter_by_type": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, c_ip, c_ip, c_ip, c_dp, C.c_int, C.c_int]),
+    "mdb_calculate_structure_entropy": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_double, c_dp, C.c_int, C.c_int,
+                                                  c_ip, c_dp, C.c_int]),
     "mdb_system_create": (C.c_int, [C.c_int, C.POINTER(c_vp)]),
     "mdb_system_destroy": (None, [c_vp]),
     "mdb_system_set_stream": (C.c_int, [c_vp, c_vp]),
@@ -93,6 +95,8 @@ PROTOTYPES = {
     "mdb_system_wcp": (C.c_int, [c_vp, c_ip, C.c_int, c_dp]),
     "mdb_system_average_by_neighbor": (C.c_int, [c_vp, C.c_double, c_dp, C.c_int, c_dp]),
     "mdb_system_cluster": (C.c_int, [c_vp, C.c_double, c_ip, c_ip, c_ip, c_dp, C.c_int, c_ip, c_ip]),
+    "mdb_system_structure_entropy": (C.c_int, [c_vp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, c_dp,
+                                               c_dp]),
     "mdb_system_result_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "mdb_system_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_last_times": (C.c_int, [c_vp, c_fp, c_fp, c_fp]),

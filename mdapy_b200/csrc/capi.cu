@@ -817,6 +817,28 @@ int mdb_system_cluster(mdb_system *s, double rc, const int *types_host, const in
     API_END
 }
 
+int mdb_system_structure_entropy(mdb_system *s, double rc, double sigma, int use_local_density, double volume,
+                                 double average_rc, double *entropy_host, double *entropy_ave_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    const int R = s->n_rows;
+    MDB_REQUIRE(average_rc <= 0 || R == s->N, MDB_ERR_STATE, "the neighbour average needs rows for every listed atom");
+    double *ent = s->out_f64.ensure<double>((size_t)2 * R);
+    launch_structure_entropy(*s, s->dist.as<double>(), s->nn.as<int>(), s->M, rc, sigma, use_local_density != 0, volume,
+                             ent);
+    d2h(*s, entropy_host, ent, (size_t)R);
+    if (average_rc > 0) {
+        MDB_REQUIRE(average_rc <= rc, MDB_ERR_VALUE, "average_rc should be smaller than rc.");
+        launch_average_by_neighbor(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, average_rc, ent,
+                                   true, ent + R);
+        d2h(*s, entropy_ave_host, ent + R, (size_t)R);
+    }
+    if (entropy_host || entropy_ave_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 // (n_rows, 8) = type, ordering, rmsd, interatomic distance, qw, qx, qy, qz; indices_host: (n_rows, 18).
 int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, double rmsd_threshold,
                    double *output_host, int *indices_host)
@@ -1114,6 +1136,22 @@ int mdb_filter_by_type(int *verlet, int N, int M, const double *dist, const int 
     launch_filter_by_type(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), M, types, pairs, pairs + npair,
                           rr, npair);
     d2h(*s, verlet, s->verlet.as<int>(), (size_t)N * M);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_calculate_structure_entropy(double rc, double sigma, int use_local_density, double volume, const double *dist,
+                                    int N, int M, const int *nn, double *entropy, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(dist && nn && entropy && N > 0 && M > 0, MDB_ERR_VALUE, "distance_list, neighbor_number and entropy are required");
+    ScopedSystem s;
+    s->N = s->n_rows = N;
+    const double *dd = h2d(*s, s->dist, dist, (size_t)N * M);
+    const int *dn = h2d(*s, s->nn, nn, (size_t)N);
+    double *ent = s->out_f64.ensure<double>(N);
+    launch_structure_entropy(*s, dd, dn, M, rc, sigma, use_local_density != 0, volume, ent);
+    d2h(*s, entropy, ent, (size_t)N);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
 }

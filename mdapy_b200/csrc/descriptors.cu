@@ -248,6 +248,54 @@ __global__ void __launch_bounds__(128) k_average_by_neighbor(const int *__restri
     out[i] = n > 0 ? sum / n : 0.0;
 }
 
+
+// Local structural entropy (pair-entropy fingerprint), src/structure_entropy.cpp:11-103.  Per atom:
+// g_m(r_j) = sum_k exp(-(r_j - d_k)^2 / (2 sigma^2)) / prefactor_j over listed distances <= rc, optional
+// local-density rescale, integrand (g ln g - g + 1) r^2, trapezoid sum.  Same loop nesting and summation
+// order as the reference (bins outer, neighbours inner); exp / log are the device's (<= 1 ulp from libm).
+__global__ void __launch_bounds__(128) k_structure_entropy(const double *__restrict__ dist, const int *__restrict__ nn,
+                                                           int N, int M, double rc, double sigma, int use_local_density,
+                                                           double global_density, int nbins, double *__restrict__ entropy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double MY_PI = 3.14159265358979323846;
+    const double step = rc / (nbins - 1);
+    const double factor = (4. * MY_PI * global_density * sqrt(2. * MY_PI * sigma * sigma));
+    const double sigma_sq = sigma * sigma;
+    const double local_vol = 4. / 3. * MY_PI * rc * rc * rc;
+    const double *di = dist + (size_t)i * M;
+    const int c = nn[i];
+    int n_neigh = 0;
+    for (int k = 0; k < c; ++k) n_neigh += di[k] <= rc ? 1 : 0;
+    double density = global_density, fac = 1.0;
+    if (use_local_density) {
+        density = n_neigh / local_vol;
+        fac = global_density / density;
+    }
+    const double r1 = 1 * step;
+    const double pref1 = (r1 * r1) * factor;
+    double sum = 0.0, prev = 0.0;
+    for (int j = 0; j < nbins; ++j) {
+        const double rj = j * step;
+        const double rsq = rj * rj;
+        const double pref = j == 0 ? pref1 : rsq * factor;
+        double g = 0.0;
+        for (int k = 0; k < c; ++k) {
+            const double dis = di[k];
+            if (dis <= rc) {
+                const double delta = rj - dis;
+                g += exp(-(delta * delta) / (2.0 * sigma_sq)) / pref;
+            }
+        }
+        if (use_local_density) g *= fac;
+        const double integrand = g >= 1e-10 ? (g * log(g) - g + 1.0) * rsq : rsq;
+        if (j > 0) sum += prev + integrand;
+        prev = integrand;
+    }
+    entropy[i] = -MY_PI * density * sum * sigma;
+}
+
 }  // namespace
 
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k)
@@ -301,5 +349,18 @@ void launch_average_by_neighbor(MdbSystem &s, const int *verlet, const double *d
     const int N = s.n_rows;
     MDB_LAUNCH(k_average_by_neighbor, (N + 127) / 128, 128, 0, s.stream, verlet, dist, nn, N, M, rc, value,
                include_self ? 1 : 0, out);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_structure_entropy(MdbSystem &s, const double *dist, const int *nn, int M, double rc, double sigma,
+                              bool use_local_density, double volume, double *entropy)
+{
+    const int N = s.n_rows;
+    MDB_REQUIRE(rc > 0 && sigma > 0 && volume > 0, MDB_ERR_VALUE, "rc, sigma and the volume must be positive");
+    const int nbins = static_cast<int>(std::floor(rc / sigma)) + 1;
+    MDB_REQUIRE(nbins >= 2, MDB_ERR_VALUE, "sigma=%g is larger than rc=%g", sigma, rc);
+    const double global_density = N / volume;
+    MDB_LAUNCH(k_structure_entropy, (N + 127) / 128, 128, 0, s.stream, dist, nn, N, M, rc, sigma,
+               use_local_density ? 1 : 0, global_density, nbins, entropy);
     CUDA_TRY(cudaGetLastError());
 }

@@ -179,6 +179,8 @@ void device_exclusive_scan(MdbSystem &s, const int *in, int *out, int n);
 void launch_filter_by_type(MdbSystem &s, int *verlet, const double *dist, const int *nn, int M, const int *types,
                            const int *t1, const int *t2, const double *r, int npair);
 int launch_cluster(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc, int *cluster);
+void launch_structure_entropy(MdbSystem &s, const double *dist, const int *nn, int M, double rc, double sigma,
+                              bool use_local_density, double volume, double *entropy);
 int ptm_parse_flags(const char *structure);
 void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
                 double *output, int ocols, int *indices, int icols);

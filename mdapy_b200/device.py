@@ -233,6 +233,15 @@ class DeviceSystem:
                                                  C.byref(cnt)))
         return out, cnt.value
 
+    def structure_entropy(self, rc, sigma, use_local_density, volume, average_rc=0.0):
+        """(entropy, entropy_ave or None) on the cached cut-off list (structure_entropy.cpp:11)."""
+        ent = L.result_empty(self.n_rows, np.float64)
+        ave = L.result_empty(self.n_rows, np.float64) if average_rc > 0 else None
+        L.check(self._lib.mdb_system_structure_entropy(self._h, float(rc), float(sigma), int(bool(use_local_density)),
+                                                       float(volume), float(average_rc), L.dptr(ent),
+                                                       L.dptr(ave) if ave is not None else None))
+        return ent, ave
+
     def result_device(self):
         """Raw device pointers (int) of the latest int32 / f64 per-atom result."""
         a, b = C.c_void_p(), C.c_void_p()

@@ -31,6 +31,7 @@ from .neighbor import Neighbor
 from .polyhedral_template_matching import PolyhedralTemplateMatching
 from .radial_distribution_function import RadialDistributionFunction
 from .steinhardt_bond_orientation import SteinhardtBondOrientation
+from .structure_entropy import StructureEntropy
 from .warren_cowley_parameter import WarrenCowleyParameter
 
 _LIST_ATTRS = ("verlet_list", "distance_list", "neighbor_number")
@@ -346,6 +347,23 @@ class System:
         ca = ClusterAnalysis(rc, type_list=type_list, dev=self._device_list())
         ca.compute()
         self.update_data(self.data.with_columns(cluster_id=np.asarray(ca.particleClusters[: self.N]).copy()))
+
+    def cal_structure_entropy(self, rc: float, sigma: float, use_local_density: bool = False, average_rc: float = 0.0,
+                              max_neigh: Optional[int] = None) -> None:
+        """system.py:2480-2542 -> data['entropy'] (+ data['entropy_ave'] when average_rc > 0)."""
+        if "rc" in self.__dict__:
+            if self.rc < rc:
+                self.build_neighbor(rc, max_neigh)
+        else:
+            self.build_neighbor(rc, max_neigh)
+        box, _ = self._get_compute_view()
+        SE = StructureEntropy(box, rc=rc, sigma=sigma, use_local_density=use_local_density, average_rc=average_rc,
+                              dev=self._device_list())
+        SE.compute()
+        cols = {"entropy": np.asarray(SE.entropy[: self.N]).copy()}
+        if average_rc > 0:
+            cols["entropy_ave"] = np.asarray(SE.entropy_ave[: self.N]).copy()
+        self.update_data(self.data.with_columns(**cols))
 
     def cal_steinhardt_bond_orientation(self, llist, use_voronoi: bool = False, nnn: int = 0, rc: float = -1.0,
                                         average: bool = False, use_weight: bool = False, weight=None,

@@ -271,3 +271,13 @@ def cal_wcp(K, fr: Frame, rc, type_list, ntype):
     fu, v, d, n = neighbor(K, fr, rc)
     assert fu.N == fr.N
     return K.wcp(v, n, type_list, ntype)
+
+
+def cal_structure_entropy(K, fr: Frame, rc, sigma, use_local_density=False, average_rc=0.0):
+    """system.py:2480-2542: list on the (possibly replicated) frame, its volume, optional neighbour average."""
+    fu, v, d, n = neighbor(K, fr, rc)
+    vol = abs(float(np.linalg.det(fu.box)))
+    ent = K.structure_entropy(rc, sigma, use_local_density, vol, d, n)
+    if average_rc > 0:
+        return K.average_by_neighbor(average_rc, v, d, n, ent, True)[: fr.N]
+    return ent[: fr.N]

@@ -344,3 +344,14 @@ def filter_by_type(verlet, dist, nn, type_list, type1, type2, r, nt=None):
     _lib().port_filter_by_type(_i(v), C.c_int(N), C.c_int(M), _d(dist), _i(nn), _i(type_list), _i(t1), _i(t2), _d(r),
            C.c_int(t1.shape[0]), C.c_int(nt or num_threads()))
     return v
+
+
+def structure_entropy(rc, sigma, use_local_density, volume, dist, nn, nt=None):
+    """structure_entropy.cpp:11 calculate_structure_entropy."""
+    dist, nn = _f64(dist), _i32(nn)
+    N, M = dist.shape
+    out = np.zeros(N, np.float64)
+    _lib().port_structure_entropy(C.c_double(rc), C.c_double(sigma), C.c_int(int(bool(use_local_density))),
+                                    C.c_double(volume), _d(dist), C.c_int(N), C.c_int(M), _i(nn), _d(out),
+                                    C.c_int(nt or num_threads()))
+    return out

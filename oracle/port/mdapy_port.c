@@ -1085,3 +1085,54 @@ void port_filter_by_type(int *verlet, int N, int M, const double *dist, const in
                     verlet[(size_t)i * M + q] = -1;
         }
 }
+
+/* ------------------------------------------------------------------ structure entropy
+ * structure_entropy.cpp:11-103 */
+void port_structure_entropy(double rc, double sigma, int use_local_density, double volume, const double *dist, int N,
+                            int M, const int *nn, double *entropy, int num_t)
+{
+    const double MY_PI = 3.14159265358979323846;
+    const int nbins = (int)floor(rc / sigma) + 1;
+    const double global_density = N / volume;
+    const double step = rc / (nbins - 1);
+    const double factor = (4. * MY_PI * global_density * sqrt(2. * MY_PI * sigma * sigma));
+    const double sigma_sq = sigma * sigma;
+    const double local_vol = 4. / 3. * MY_PI * rc * rc * rc;
+    double *rl = (double *)malloc(sizeof(double) * (size_t)nbins);
+    double *rsq = (double *)malloc(sizeof(double) * (size_t)nbins);
+    double *pref = (double *)malloc(sizeof(double) * (size_t)nbins);
+    for (int j = 0; j < nbins; ++j) {
+        rl[j] = j * step;
+        rsq[j] = rl[j] * rl[j];
+        pref[j] = rsq[j] * factor;
+    }
+    pref[0] = pref[1];
+#pragma omp parallel for num_threads(num_t)
+    for (int i = 0; i < N; ++i) {
+        const double *di = dist + (size_t)i * M;
+        int n_neigh = 0;
+        for (int k = 0; k < nn[i]; ++k) n_neigh += di[k] <= rc;
+        double density = global_density, fac = 1.0;
+        if (use_local_density) {
+            density = n_neigh / local_vol;
+            fac = global_density / density;
+        }
+        double sum = 0.0, prev = 0.0;
+        for (int j = 0; j < nbins; ++j) {
+            double g = 0.0;
+            for (int k = 0; k < nn[i]; ++k)
+                if (di[k] <= rc) {
+                    const double delta = rl[j] - di[k];
+                    g += exp(-(delta * delta) / (2.0 * sigma_sq)) / pref[j];
+                }
+            if (use_local_density) g *= fac;
+            const double integrand = g >= 1e-10 ? (g * log(g) - g + 1.0) * rsq[j] : rsq[j];
+            if (j > 0) sum += prev + integrand;
+            prev = integrand;
+        }
+        entropy[i] = -MY_PI * density * sum * sigma;
+    }
+    free(rl);
+    free(rsq);
+    free(pref);
+}

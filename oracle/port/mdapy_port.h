@@ -50,6 +50,9 @@ int port_get_cluster(const int *verlet, int N, int M, const double *dist, const 
 void port_filter_by_type(int *verlet, int N, int M, const double *dist, const int *nn, const int *type_list,
                          const int *t1, const int *t2, const double *r, int npair, int num_t);
 
+void port_structure_entropy(double rc, double sigma, int use_local_density, double volume, const double *dist, int N,
+                            int M, const int *nn, double *entropy, int num_t);
+
 #ifdef __cplusplus
 }
 #endif

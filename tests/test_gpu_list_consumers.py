@@ -201,3 +201,52 @@ def test_system_cluster_analysis():
     t1, t2, r = type_pair_table({"1-1": 1.8, "1-2": 2.5, "2-2": 2.2})
     ref, cnt = K.cluster(K.filter_by_type(v, d, n, types, t1, t2, r), n)
     assert np.array_equal(np.asarray(system.data["cluster_id"]), ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# structure entropy (src/structure_entropy.cpp): exp / log come from the device's libm, so the bar is the
+# north star's floating-point tolerance (1e-6 relative) -- observed agreement is ~1e-14
+@pytest.mark.parametrize("uld", [False, True])
+def test_structure_entropy_device_and_host_api(uld):
+    from mdapy_b200 import _lib as L
+    from mdapy_b200.device import DeviceSystem
+
+    p, b = H.fcc(4.05, 8)
+    pos = H.rattle(p, 0.2, 17)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    o, bnd, rc, sigma = np.zeros(3), [1, 1, 1], 5.0, 0.2
+    v, d, n = K.build_neighbor_auto(x, y, z, b, o, bnd, rc)
+    vol = float(np.linalg.det(b))
+    ref = K.structure_entropy(rc, sigma, uld, vol, d, n)
+    ds = DeviceSystem(0)
+    ds.set_atoms(x, y, z, b, o, bnd)
+    ds.build_neighbor(rc)
+    ent, ave = ds.structure_entropy(rc, sigma, uld, vol, 4.0)
+    assert np.allclose(ent, ref, rtol=1e-6, atol=0) and np.abs(ent / ref - 1).max() < 1e-11
+    ref_ave = K.average_by_neighbor(4.0, v, d, n, ref, True)
+    assert np.allclose(ave, ref_ave, rtol=1e-6, atol=0)
+    out = np.zeros(x.shape[0])
+    L.check(L.lib().mdb_calculate_structure_entropy(rc, sigma, int(uld), vol, L.dptr(d), d.shape[0], d.shape[1], L.iptr(n),
+                                                    L.dptr(out), 1))
+    assert np.array_equal(out.view(np.int64), np.asarray(ent).view(np.int64))
+
+
+@pytest.mark.parametrize("name", ["rec_box_big", "rec_box_small", "tri_box_big", "tri_box_small"])
+@pytest.mark.parametrize("mode", ["default", "use_local_density", "compute_average"])
+def test_system_structure_entropy_fixture(name, mode):
+    """tests/test_structure_entropy.py:15-34."""
+    import mdapy_b200 as mp
+
+    g = np.load(GOLD / "structure_entropy.npz")
+    system = mp.System(pos=g[f"{name}__pos"], box=mp.Box(g[f"{name}__box"], [1, 1, 1], g[f"{name}__origin"]))
+    if mode == "compute_average":
+        system.cal_structure_entropy(5.0, 0.2, False, average_rc=4.0)
+        got = np.asarray(system.data["entropy_ave"])
+    elif mode == "use_local_density":
+        system.cal_structure_entropy(5.0, 0.2, True)
+        got = np.asarray(system.data["entropy"])
+    else:
+        system.cal_structure_entropy(5.0, 0.2, False)
+        got = np.asarray(system.data["entropy"])
+    exp = g[f"{name}__{mode}"]
+    assert np.allclose(got, exp, atol=1e-6), np.abs(got - exp).max()

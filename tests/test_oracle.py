@@ -246,3 +246,30 @@ def test_port_cluster_equals_reference():
     a, ca = ref.cluster(fa, n)
     b, cb = port.cluster(fb, n)
     assert ca == cb and np.array_equal(a, b)
+
+
+ENT_CONFIGS = ["rec_box_big", "rec_box_small", "tri_box_big", "tri_box_small"]
+ENT_MODES = {"default": dict(), "use_local_density": dict(use_local_density=True), "compute_average": dict(average_rc=4.0)}
+
+
+@pytest.mark.parametrize("K", BACKENDS)
+@pytest.mark.parametrize("name", ENT_CONFIGS)
+@pytest.mark.parametrize("mode", list(ENT_MODES))
+def test_golden_structure_entropy(K, name, mode):
+    """tests/test_structure_entropy.py:15-34 (rc = 5, sigma = 0.2; the small cells are replicated)."""
+    g = np.load(GOLD / "structure_entropy.npz")
+    fr = P.Frame(g[f"{name}__pos"], g[f"{name}__box"], [1, 1, 1], g[f"{name}__origin"])
+    got = P.cal_structure_entropy(K, fr, 5.0, 0.2, **ENT_MODES[mode])
+    assert np.allclose(got, g[f"{name}__{mode}"], atol=1e-6), np.abs(got - g[f"{name}__{mode}"]).max()
+
+
+@pytest.mark.skipif(not (ref.available() and port.available()), reason="needs both checkers")
+def test_port_structure_entropy_equals_reference():
+    pos, box = H.fcc(4.05, 5)
+    pos = H.rattle(pos, 0.15, 8)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    v, d, n = ref.build_neighbor_auto(x, y, z, box, np.zeros(3), [1, 1, 1], 5.0)
+    vol = float(np.linalg.det(box))
+    for uld in (False, True):
+        a, b = ref.structure_entropy(5.0, 0.2, uld, vol, d, n), port.structure_entropy(5.0, 0.2, uld, vol, d, n)
+        assert np.array_equal(a.view(np.int64), b.view(np.int64))
