@@ -249,6 +249,9 @@ int mdb_system_cluster(mdb_system *s, double rc, const int *types_host, const in
  * with include_self, structure_entropy.py:133-145).  Either host pointer may be NULL. */
 int mdb_system_structure_entropy(mdb_system *s, double rc, double sigma, int use_local_density, double volume,
                                  double average_rc, double *entropy_host, double *entropy_ave_host);
+/* self-check of the correctly rounded small-integer division used by the Legendre recurrences: counts the
+ * host values a[i] (uploaded) whose device quotient differs from a[i] / d.  Test hook. */
+int mdb_system_check_small_division(mdb_system *s, const double *a_host, int n, int d, long long *mismatches);
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 
 /* per-kernel device times (ms) of the most recent build_neighbor / fcna, measured with CUDA events */

@@ -97,6 +97,7 @@ PROTOTYPES = {
     "mdb_system_cluster": (C.c_int, [c_vp, C.c_double, c_ip, c_ip, c_ip, c_dp, C.c_int, c_ip, c_ip]),
     "mdb_system_structure_entropy": (C.c_int, [c_vp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, c_dp,
                                                c_dp]),
+    "mdb_system_check_small_division": (C.c_int, [c_vp, c_dp, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "mdb_system_result_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "mdb_system_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_last_times": (C.c_int, [c_vp, c_fp, c_fp, c_fp]),

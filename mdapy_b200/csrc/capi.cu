@@ -839,6 +839,16 @@ int mdb_system_structure_entropy(mdb_system *s, double rc, double sigma, int use
     API_END
 }
 
+int mdb_system_check_small_division(mdb_system *s, const double *a_host, int n, int d, long long *mismatches)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(a_host && n > 0 && mismatches, MDB_ERR_VALUE, "values and the output are required");
+    const double *a = h2d(*s, s->out_f64c, a_host, (size_t)n);
+    *mismatches = sbo_div_small_mismatches(*s, a, n, d);
+    API_END
+}
+
 // (n_rows, 8) = type, ordering, rmsd, interatomic distance, qw, qx, qy, qz; indices_host: (n_rows, 18).
 int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, double rmsd_threshold,
                    double *output_host, int *indices_host)

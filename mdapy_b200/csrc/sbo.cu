@@ -22,9 +22,30 @@ struct SboParams {
     int ndeg, lmax, nz, nnn, use_voronoi, use_weight;
     double rc;
     int l[8];
+    int off[9];  // compact accumulator slots: degree il owns [off[il], off[il] + 2 l + 1), off[ndeg] = total
 };
 
 __constant__ double c_norm[8][SBO_MAX_L + 1];  // sqrt((2l+1)/(4 pi prod_{i=l-m+1}^{l+m} i)) per (degree slot, m)
+
+// a / d for a small positive integer d, correctly rounded (== the IEEE quotient the reference computes)
+// without the ~35-instruction division sequence: with y = RN(1/d), q0 = RN(a y) is within an ulp of a/d and
+// each residual step q <- RN(q + RN(a - d q) y) (both FMAs exact in the residual) lands on the correctly
+// rounded quotient (Markstein); two steps leave no doubt for the rare q0 that is off by more than half an
+// ulp.  tests/test_gpu_descriptors.py::test_small_integer_division compares 2^26 quotients per divisor.
+__constant__ double c_rcp[SBO_MAX_L + 2];
+
+__device__ __noinline__ double div_small_slow(double a, double d) { return a / d; }
+
+__device__ __forceinline__ double div_small(double a, int d)
+{
+    const double y = c_rcp[d], dd = (double)d;
+    // zeros (sign!), subnormal neighbourhoods, infinities and NaN take the literal division (never on the hot path)
+    if (!(fabs(a) >= 1e-290 && fabs(a) <= 1e290)) return div_small_slow(a, dd);
+    double q = a * y;
+    q = fma(fma(-dd, q, a), y, q);
+    q = fma(fma(-dd, q, a), y, q);
+    return q;
+}
 
 // _associated_legendre, cpp:243-268
 __device__ __forceinline__ double assoc_legendre(int l, int m, double x)
@@ -37,12 +58,15 @@ __device__ __forceinline__ double assoc_legendre(int l, int m, double x)
     for (int i = m + 1; i < l + 1; ++i) {
         pm2 = pm1;
         pm1 = p;
-        p = ((2 * i - 1) * x * pm1 - (i + m - 1) * pm2) / (i - m);
+        p = div_small((2 * i - 1) * x * pm1 - (i + m - 1) * pm2, i - m);
     }
     return p;
 }
 
-template <bool LOCAL>
+// Accumulators: MODE 1 = per-thread local arrays (dense [il][m] indexing), MODE 2 = shared memory, compact slots
+// interleaved per thread (acc[slot * blockDim + tid]: conflict-free, no local-memory traffic), MODE 0 = in place
+// in global memory (very high degrees).  The operation order per accumulator is the same in all three.
+template <int MODE>
 __global__ void __launch_bounds__(128) k_qlm(const double *__restrict__ x, const double *__restrict__ y,
                                              const double *__restrict__ z, int N, DBox box,
                                              const int *__restrict__ verlet, const double *__restrict__ dist,
@@ -53,6 +77,8 @@ __global__ void __launch_bounds__(128) k_qlm(const double *__restrict__ x, const
     if (i >= N) return;
     const double EPS = 1e-15;
     const int stride = P.ndeg * P.nz;
+    constexpr bool LOCAL = MODE == 1;
+    extern __shared__ double sh_acc[];
     double *Qr = qr + (size_t)i * stride, *Qi = qi + (size_t)i * stride;
     double ar[LOCAL ? SBO_LOCAL : 1], ai[LOCAL ? SBO_LOCAL : 1];
     if (LOCAL) {
@@ -61,7 +87,16 @@ __global__ void __launch_bounds__(128) k_qlm(const double *__restrict__ x, const
             ai[t] = Qi[t];
         }
     }
-    double *R = LOCAL ? ar : Qr, *I = LOCAL ? ai : Qi;
+    // element stride and per-degree base of the accumulators
+    const int es = MODE == 2 ? (int)blockDim.x : 1;
+    double *R = LOCAL ? ar : (MODE == 2 ? sh_acc + threadIdx.x : Qr);
+    double *I = LOCAL ? ai : (MODE == 2 ? sh_acc + (size_t)P.off[P.ndeg] * blockDim.x + threadIdx.x : Qi);
+    if (MODE == 2)
+        for (int il = 0; il < P.ndeg; ++il)
+            for (int m = 0; m < 2 * P.l[il] + 1; ++m) {
+                R[(P.off[il] + m) * es] = Qr[il * P.nz + m];
+                I[(P.off[il] + m) * es] = Qi[il * P.nz + m];
+            }
     const double x1 = x[i], y1 = y[i], z1 = z[i];
     int cnt = nn[i];
     if (!P.use_voronoi && P.nnn > 0) cnt = P.nnn;
@@ -90,21 +125,21 @@ __global__ void __launch_bounds__(128) k_qlm(const double *__restrict__ x, const
         }
         for (int il = 0; il < P.ndeg; ++il) {
             const int l = P.l[il];
-            double *Rl = R + il * P.nz, *Il = I + il * P.nz;
-            Rl[l] += w * (c_norm[il][0] * assoc_legendre(l, 0, ct));
+            double *Rl = R + (MODE == 2 ? P.off[il] * es : il * P.nz), *Il = I + (MODE == 2 ? P.off[il] * es : il * P.nz);
+            Rl[l * es] += w * (c_norm[il][0] * assoc_legendre(l, 0, ct));
             double pr = er, pi = ei;
             for (int m = 1; m < l + 1; ++m) {
                 const double pf = c_norm[il][m] * assoc_legendre(l, m, ct);
                 const double cr = pf * pr, ci = pf * pi;
                 const double wr = w * cr, wi = w * ci;
-                Rl[l + m] += wr;
-                Il[l + m] += wi;
+                Rl[(l + m) * es] += wr;
+                Il[(l + m) * es] += wi;
                 if (m & 1) {
-                    Rl[l - m] -= wr;
-                    Il[l - m] += wi;
+                    Rl[(l - m) * es] -= wr;
+                    Il[(l - m) * es] += wi;
                 } else {
-                    Rl[l - m] += wr;
-                    Il[l - m] -= wi;
+                    Rl[(l - m) * es] += wr;
+                    Il[(l - m) * es] -= wi;
                 }
                 const double tr = pr * er - pi * ei;
                 const double ti = pr * ei + pi * er;
@@ -116,9 +151,10 @@ __global__ void __launch_bounds__(128) k_qlm(const double *__restrict__ x, const
     const double fac = 1.0 / wsum;
     for (int il = 0; il < P.ndeg; ++il) {
         const int mm = 2 * P.l[il] + 1;
+        const int base = MODE == 2 ? P.off[il] : il * P.nz;
         for (int m = 0; m < mm; ++m) {
-            Qr[il * P.nz + m] = R[il * P.nz + m] * fac;
-            Qi[il * P.nz + m] = I[il * P.nz + m] * fac;
+            Qr[il * P.nz + m] = R[(base + m) * es] * fac;
+            Qi[il * P.nz + m] = I[(base + m) * es] * fac;
         }
     }
 }
@@ -164,6 +200,46 @@ __global__ void __launch_bounds__(128) k_qlm_average(int N, const int *__restric
         for (int m = 0; m < mm; ++m) {
             Qr[il * P.nz + m] = R[il * P.nz + m] * inv;
             Qi[il * P.nz + m] = I[il * P.nz + m] * inv;
+        }
+    }
+}
+
+// Warp-cooperative form of the same averaging: one warp per atom, lanes over the stride = ndeg * nz
+// components of q_lm (real and imaginary rows), neighbours in list order.  Every neighbour row is then ONE
+// coalesced read instead of 32 lanes striding through 32 different rows (17 GB -> ~1 GB of DRAM reads per
+// 1.5 M atoms); the per-component summation order (own value, then neighbours in list order) is unchanged,
+// so the result is bit-identical to k_qlm_average.
+__global__ void __launch_bounds__(256) k_qlm_average_warp(int N, const int *__restrict__ verlet,
+                                                          const int *__restrict__ nn, int M, int nnn, int use_voronoi,
+                                                          int stride, const double *__restrict__ aqr,
+                                                          const double *__restrict__ aqi, double *__restrict__ qr,
+                                                          double *__restrict__ qi)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps) {
+        int cnt = nn[i];
+        if (!use_voronoi && nnn > 0) cnt = nnn;
+        const int *row = verlet + (size_t)i * M;
+        for (int c0 = 0; c0 < stride; c0 += 32) {
+            const int c = c0 + lane;
+            const bool on = c < stride;
+            double sr = on ? qr[(size_t)i * stride + c] : 0.0, si = on ? qi[(size_t)i * stride + c] : 0.0;
+            int used = 1;
+            for (int jj = 0; jj < cnt; ++jj) {
+                const int j = __ldg(row + jj);  // same address in every lane: one broadcast load
+                if (j < 0) continue;
+                if (on) {
+                    sr += __ldg(aqr + (size_t)j * stride + c);
+                    si += __ldg(aqi + (size_t)j * stride + c);
+                }
+                ++used;
+            }
+            const double inv = 1.0 / used;
+            if (on) {
+                qr[(size_t)i * stride + c] = sr * inv;
+                qi[(size_t)i * stride + c] = si * inv;
+            }
         }
     }
 }
@@ -272,7 +348,41 @@ double fact15(int n)
     return strtod(buf, nullptr);
 }
 
+__global__ void k_div_small_check(const double *__restrict__ a, int n, int d, unsigned long long *__restrict__ bad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double q = div_small(a[i], d), r = a[i] / (double)d;
+    if (__double_as_longlong(q) != __double_as_longlong(r) && !(q != q && r != r)) atomicAdd(bad, 1ull);
+}
+
+void upload_rcp_table(cudaStream_t st)
+{
+    static bool done = false;
+    if (done) return;
+    double h[SBO_MAX_L + 2];
+    h[0] = 0.0;
+    for (int d = 1; d < SBO_MAX_L + 2; ++d) h[d] = 1.0 / d;
+    CUDA_TRY(cudaMemcpyToSymbolAsync(c_rcp, h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    done = true;
+}
+
 }  // namespace
+
+// test hook: number of inputs a[i] whose div_small(a[i], d) differs from a[i] / d (device arrays)
+long long sbo_div_small_mismatches(MdbSystem &s, const double *a_dev, int n, int d)
+{
+    MDB_REQUIRE(d >= 1 && d <= SBO_MAX_L + 1, MDB_ERR_VALUE, "divisor out of range");
+    upload_rcp_table(s.stream);
+    unsigned long long *bad = s.scratch2.ensure<unsigned long long>(1);
+    CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(unsigned long long), s.stream));
+    MDB_LAUNCH(k_div_small_check, (n + 255) / 256, 256, 0, s.stream, a_dev, n, d, bad);
+    unsigned long long h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, bad, sizeof(h), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return (long long)h;
+}
 
 void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M,
                        const double *weight, const int *llist, int ndeg, int nnn, int lmax, bool wl, bool wlhat,
@@ -295,6 +405,7 @@ void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, cons
         const int l = llist[il];
         MDB_REQUIRE(l >= 0 && l <= lmax, MDB_ERR_VALUE, "degree %d outside [0, lmax=%d]", l, lmax);
         P.l[il] = l;
+        P.off[il + 1] = P.off[il] + 2 * l + 1;
         for (int m = 0; m <= l; ++m) {  // _polar_prefactor, cpp:270-286
             double pf = 1.0;
             for (int i = l - m + 1; i < l + m + 1; ++i) pf *= i;
@@ -304,13 +415,26 @@ void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, cons
         s2l1[il] = std::sqrt(2 * l + 1.0);
     }
     cudaStream_t st = s.stream;
+    upload_rcp_table(st);
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_norm, norm, sizeof(norm), 0, cudaMemcpyHostToDevice, st));
     const int N = s.n_rows;
     const int nb = (N + 127) / 128;
-    if (P.ndeg * P.nz <= SBO_LOCAL)
-        MDB_LAUNCH(k_qlm<true>, nb, 128, 0, st, s.x, s.y, s.z, N, s.box, verlet, dist, nn, weight, M, P, qr, qi);
-    else
-        MDB_LAUNCH(k_qlm<false>, nb, 128, 0, st, s.x, s.y, s.z, N, s.box, verlet, dist, nn, weight, M, P, qr, qi);
+    {
+        // accumulators in shared memory when the compact slots of a 128-thread block fit (l = {4, 6}: 45 KB)
+        const size_t smem = (size_t)2 * P.off[ndeg] * 128 * sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+            CUDA_TRY(cudaFuncSetAttribute(k_qlm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            configured = true;
+        }
+        const char *env = getenv("MDB_SBO");
+        if (smem <= 100 * 1024 && !(env && !strcmp(env, "local")))
+            MDB_LAUNCH(k_qlm<2>, nb, 128, smem, st, s.x, s.y, s.z, N, s.box, verlet, dist, nn, weight, M, P, qr, qi);
+        else if (P.ndeg * P.nz <= SBO_LOCAL)
+            MDB_LAUNCH(k_qlm<1>, nb, 128, 0, st, s.x, s.y, s.z, N, s.box, verlet, dist, nn, weight, M, P, qr, qi);
+        else
+            MDB_LAUNCH(k_qlm<0>, nb, 128, 0, st, s.x, s.y, s.z, N, s.box, verlet, dist, nn, weight, M, P, qr, qi);
+    }
     if (average) {
         // the snapshot is indexed by neighbour ids: it covers every local atom (qr/qi hold s.N rows, the
         // ghost rows of a decomposed frame are zero)
@@ -318,8 +442,15 @@ void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, cons
         double *ar = s.scratch.ensure<double>(tot), *ai = s.scratch2.ensure<double>(tot);
         CUDA_TRY(cudaMemcpyAsync(ar, qr, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ai, qi, sizeof(double) * tot, cudaMemcpyDeviceToDevice, st));
-        if (P.ndeg * P.nz <= SBO_LOCAL) MDB_LAUNCH(k_qlm_average<true>, nb, 128, 0, st, N, verlet, nn, M, P, ar, ai, qr, qi);
-        else MDB_LAUNCH(k_qlm_average<false>, nb, 128, 0, st, N, verlet, nn, M, P, ar, ai, qr, qi);
+        const char *env = getenv("MDB_SBO");
+        if (env && !strcmp(env, "local")) {
+            if (P.ndeg * P.nz <= SBO_LOCAL) MDB_LAUNCH(k_qlm_average<true>, nb, 128, 0, st, N, verlet, nn, M, P, ar, ai, qr, qi);
+            else MDB_LAUNCH(k_qlm_average<false>, nb, 128, 0, st, N, verlet, nn, M, P, ar, ai, qr, qi);
+        } else {
+            const int nbw = (N + 7) / 8 < 148 * 8 * 4 ? (N + 7) / 8 : 148 * 8 * 4;
+            MDB_LAUNCH(k_qlm_average_warp, nbw, 256, 0, st, N, verlet, nn, M, P.nnn, P.use_voronoi, P.ndeg * P.nz, ar, ai,
+                       qr, qi);
+        }
     }
     // Clebsch-Gordan table, cpp:188-224
     std::vector<double> cg(1, 0.0);

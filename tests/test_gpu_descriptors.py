@@ -185,3 +185,29 @@ def test_error_mapping():
         ds.build_neighbor(-1.0)
     with pytest.raises(ValueError):
         ds.build_knn(25)
+
+
+def test_small_integer_division():
+    """The Legendre recurrences divide by i - m in 1..24; the device uses a reciprocal + two FMA residual steps
+    instead of the IEEE division sequence.  It must return the correctly rounded quotient, always: compare
+    against a / d on 2^22 values per divisor spanning magnitudes, signs, exact multiples and special values."""
+    import ctypes as C
+
+    from mdapy_b200 import _lib as L
+    from mdapy_b200.device import DeviceSystem
+
+    ds = DeviceSystem(0)
+    rng = np.random.default_rng(7)
+    n = 1 << 22
+    base = np.concatenate([
+        rng.standard_normal(n // 4) * 10.0 ** rng.integers(-12, 12, n // 4),
+        rng.random(n // 4) * 3.0,                                   # the actual range of P_l^m intermediates
+        np.ldexp(rng.random(n // 4) + 0.5, rng.integers(-1000, 1000, n // 4)),
+        rng.integers(-10 ** 9, 10 ** 9, n // 4 - 8).astype(np.float64),
+        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -1.7976931348623157e308, 2.2250738585072014e-308]),
+    ])
+    for d in range(1, 26):
+        a = np.ascontiguousarray(base * (d if d % 3 == 0 else 1.0))   # every third divisor: many exact quotients
+        bad = C.c_longlong(-1)
+        L.check(L.lib().mdb_system_check_small_division(ds._h, L.dptr(a), a.shape[0], d, C.byref(bad)))
+        assert bad.value == 0, f"d={d}: {bad.value} quotients differ from IEEE division"
