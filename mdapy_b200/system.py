@@ -39,9 +39,13 @@ _LIST_ATTRS = ("verlet_list", "distance_list", "neighbor_number")
 
 class System:
     def __init__(self, filename=None, data=None, pos=None, box=None, device: int = 0, **_unused):
+        self.global_info = {}
         if filename is not None:
-            raise NotImplementedError("file readers are outside the hot path (SURVEY.md 2.2); pass pos/data + box")
-        if data is not None and box is not None:
+            # text readers of SURVEY.md 8f.3 (LAMMPS dump, XYZ, optionally .gz); system.py:186-198
+            from .load_save import from_file
+
+            self._data, box, self.global_info = from_file(filename)
+        elif data is not None and box is not None:
             self._data = Frame.from_any(data)
         elif pos is not None and box is not None:
             pos = np.asarray(pos, np.float64)
@@ -58,6 +62,16 @@ class System:
         self._host_list = {}                         # lazily fetched / user supplied NumPy arrays
         self._host_dirty = False                     # user assigned a list on the host side
         self._has_list = False
+
+    def write_dump(self, filename: str, timestep: int = 0) -> None:
+        from .load_save import write_dump
+
+        write_dump(filename, self.box, self.data, timestep)
+
+    def write_xyz(self, filename: str) -> None:
+        from .load_save import write_xyz
+
+        write_xyz(filename, self.box, self.data)
 
     # ------------------------------------------------------------------ data / box
     @property
