@@ -67,6 +67,10 @@ def main():
     ap.add_argument("--c4-cells", type=int, default=171)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--skip", default="")
+    ap.add_argument("--c4-input", default="thermal", choices=["thermal", "polycrystal"],
+                    help="polycrystal: 200-grain periodic Voronoi polycrystal (tools/polycrystal.py), L = 692.5 A")
+    ap.add_argument("--poly-L", type=float, default=692.5)
+    ap.add_argument("--poly-grains", type=int, default=200)
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -156,18 +160,35 @@ def main():
     # ------------------------------------------------------------------ C4: Steinhardt q4/q6 + RDF 500 bins
     if "c4" not in args.skip:
         a, n = 4.05, args.c4_cells
-        box = np.diag([n * a] * 3).astype(float)
-        N = 4 * n ** 3
+        poly = args.c4_input == "polycrystal"
+        cfg = "C4 FCC Al thermal"
+        if poly:
+            # every rank generates the same frame (deterministic) and selects its slab locally (replicated input)
+            sys.path.insert(0, str(ROOT / "tools"))
+            from polycrystal import make_polycrystal
+
+            Lp = args.poly_L
+            box = np.diag([Lp] * 3).astype(float)
+            px, py, pz, _ = make_polycrystal(Lp, args.poly_grains, a, 7, dev)
+            pgid = torch.arange(px.numel(), dtype=torch.int32, device=dev)
+            N = int(px.numel())
+            cfg = f"C4 {args.poly_grains}-grain FCC Al polycrystal L={Lp}"
+        else:
+            box = np.diag([n * a] * 3).astype(float)
+            N = 4 * n ** 3
         rc_q, rc_g, nbin = 0.85 * a, 6.0, 500
         for name, rc, halo in (("steinhardt", rc_q, 1), ("steinhardt_average", rc_q, 2), ("rdf", rc_g, 1)):
             dec = SlabDecomposition(box, o, bnd, rc, rank, world, dev, halo=halo)
-            ix0, ix1 = own_planes(dec, n, a)
-            x, y, z, gid = lattice_planes_dev(torch, FCC, a, n, ix0 - 1, ix1 + 1, 0.12, 4, dev)
-            x, y, z, gid = keep_owned(dec, x, y, z, gid)
+            if poly:
+                x, y, z, gid = px, py, pz, pgid
+            else:
+                ix0, ix1 = own_planes(dec, n, a)
+                x, y, z, gid = lattice_planes_dev(torch, FCC, a, n, ix0 - 1, ix1 + 1, 0.12, 4, dev)
+                x, y, z, gid = keep_owned(dec, x, y, z, gid)
             state = {}
 
             def build():
-                state["ds"] = dec.build(x, y, z, gid, sync_width=True)
+                state["ds"] = dec.build(x, y, z, gid, sync_width=True, replicated=poly)
 
             t_b = timed(build)
             ds = state["ds"]
@@ -179,15 +200,21 @@ def main():
                     res["g"] = dec.all_reduce_sum(ds.rdf_counts(rc, nbin, type_list=types, ntype=1))
 
                 t_k = timed(rdf)
-                report("C4 FCC Al thermal", f"neighbour build rc={rc}", N, t_b, M=ds.M)
-                report("C4 FCC Al thermal", "RDF 500 bins from the list + all-reduce", N, t_k,
-                       pairs=float(res["g"].sum()))
+                report(cfg, f"neighbour build rc={rc}", N, t_b, M=ds.M)
+                report(cfg, "RDF 500 bins from the list + all-reduce", N, t_k, pairs=float(res["g"].sum()))
             else:
                 avg = name.endswith("average")
                 t_k = timed(lambda: ds.steinhardt([4, 6], rc=rc, average=avg, fetch=False))
-                report("C4 FCC Al thermal", f"neighbour build rc={rc:.4f} halo={halo}", N, t_b, M=ds.M)
-                report("C4 FCC Al thermal", "Steinhardt q4,q6" + (" averaged" if avg else ""), N, t_k)
-            del ds, state, x, y, z, gid, dec
+                extra = {}
+                if poly and not avg:
+                    q, _, _ = ds.steinhardt([4, 6], rc=rc, average=False)
+                    q6 = q[: dec.n_owned, 1]
+                    extra = {"q6_mean_rank0": float(np.nanmean(q6)), "fcc_like_fraction_rank0": float((q6 > 0.5).mean())}
+                report(cfg, f"neighbour build rc={rc:.4f} halo={halo}", N, t_b, M=ds.M)
+                report(cfg, "Steinhardt q4,q6" + (" averaged" if avg else ""), N, t_k, **extra)
+            del ds, state, dec
+            if not poly:
+                del x, y, z, gid
             torch.cuda.empty_cache()
 
     if rank == 0:
