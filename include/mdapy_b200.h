@@ -161,6 +161,11 @@ int mdb_filter_by_type(int *verlet, int N, int M, const double *dist, const int 
 int mdb_calculate_structure_entropy(double rc, double sigma, int use_local_density, double volume, const double *dist,
                                     int N, int M, const int *nn, double *entropy, int num_t);
 
+/* _atomtemp.compute_temp(verlet_list, distance_list, vx, vy, vz, mass_list, T, rc, num_t)
+ * -- src/atomic_temperature.cpp:7 (velocities in A/ps, masses in g/mol, T in K) */
+int mdb_compute_temp(const int *verlet, int N, int M, const double *dist, const double *vx, const double *vy,
+                     const double *vz, const double *mass, double *T, double rc, int num_t);
+
 /* ------------------------------------------------------------------------
  * Section B: device-resident system handle
  * ---------------------------------------------------------------------- */
@@ -252,6 +257,9 @@ int mdb_system_structure_entropy(mdb_system *s, double rc, double sigma, int use
 /* self-check of the correctly rounded small-integer division used by the Legendre recurrences: counts the
  * host values a[i] (uploaded) whose device quotient differs from a[i] / d.  Test hook. */
 int mdb_system_check_small_division(mdb_system *s, const double *a_host, int n, int d, long long *mismatches);
+/* atomic temperature on the cached list; vx, vy, vz, mass: n_local host doubles */
+int mdb_system_atomic_temperature(mdb_system *s, const double *vx, const double *vy, const double *vz,
+                                  const double *mass, double rc, double *T_host);
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 
 /* per-kernel device times (ms) of the most recent build_neighbor / fcna, measured with CUDA events */

@@ -23,6 +23,7 @@ def __getattr__(name):
         "WarrenCowleyParameter": ("warren_cowley_parameter", "WarrenCowleyParameter"),
         "ClusterAnalysis": ("cluster_analysis", "ClusterAnalysis"),
         "StructureEntropy": ("structure_entropy", "StructureEntropy"),
+        "AtomicTemperature": ("atomic_temperature", "AtomicTemperature"),
         "build_crystal": ("lattice", "build_crystal"),
     }
     if name == "empty_cache":

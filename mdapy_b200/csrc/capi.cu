@@ -849,6 +849,27 @@ int mdb_system_check_small_division(mdb_system *s, const double *a_host, int n, 
     API_END
 }
 
+int mdb_system_atomic_temperature(mdb_system *s, const double *vx, const double *vy, const double *vz,
+                                  const double *mass, double rc, double *T_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(vx && vy && vz && mass, MDB_ERR_VALUE, "No velocity information.");
+    const size_t NA = (size_t)s->N;
+    double *buf = s->out_f64b.ensure<double>(4 * NA);
+    CUDA_TRY(cudaMemcpyAsync(buf, vx, sizeof(double) * NA, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(buf + NA, vy, sizeof(double) * NA, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(buf + 2 * NA, vz, sizeof(double) * NA, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(buf + 3 * NA, mass, sizeof(double) * NA, cudaMemcpyHostToDevice, s->stream));
+    double *T = s->out_f64.ensure<double>(s->n_rows);
+    launch_atomic_temperature(*s, s->verlet.as<int>(), s->dist.as<double>(), s->M, buf, buf + NA, buf + 2 * NA, buf + 3 * NA,
+                              rc, T);
+    d2h(*s, T_host, T, (size_t)s->n_rows);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 // (n_rows, 8) = type, ordering, rmsd, interatomic distance, qw, qx, qy, qz; indices_host: (n_rows, 18).
 int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, double rmsd_threshold,
                    double *output_host, int *indices_host)
@@ -1163,6 +1184,20 @@ int mdb_calculate_structure_entropy(double rc, double sigma, int use_local_densi
     launch_structure_entropy(*s, dd, dn, M, rc, sigma, use_local_density != 0, volume, ent);
     d2h(*s, entropy, ent, (size_t)N);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_compute_temp(const int *verlet, int N, int M, const double *dist, const double *vx, const double *vy,
+                     const double *vz, const double *mass, double *T, double rc, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(dist && T, MDB_ERR_VALUE, "distance_list and T are required");
+    ScopedSystem s;
+    s->N = s->n_rows = N;
+    int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nullptr, M, rc, LIST_CUTOFF);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_atomic_temperature(s.s, vx, vy, vz, mass, rc, T);
+    if (rcode != MDB_OK) return rcode;
     API_END
 }
 

@@ -296,6 +296,59 @@ __global__ void __launch_bounds__(128) k_structure_entropy(const double *__restr
     entropy[i] = -MY_PI * density * sum * sigma;
 }
 
+
+// Local atomic temperature, src/atomic_temperature.cpp:7-112: mass-weighted mean velocity of the atom and its
+// listed neighbours within rc, kinetic energy of the fluctuations about it, T = 2 KE / (3 n k_B).  Velocities
+// arrive in A/ps (the host multiplies A/fs by 1e3 * factor like the reference's wrapper).  Same operation order.
+__global__ void __launch_bounds__(128) k_atomic_temperature(const int *__restrict__ verlet, const double *__restrict__ dist,
+                                                            int N, int M, const double *__restrict__ vx,
+                                                            const double *__restrict__ vy, const double *__restrict__ vz,
+                                                            const double *__restrict__ mass, double rc,
+                                                            double *__restrict__ T)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double kb = 1.380649e-23, dim = 3.0, afu = 6.022140857e23;
+    const double mass_factor = 1.0 / afu / 1000.0;
+    const double vel_conv = 1e4;
+    const int *vi = verlet + (size_t)i * M;
+    const double *di = dist + (size_t)i * M;
+    const double mass_i = mass[i];
+    double sx = vx[i] * mass_i, sy = vy[i] * mass_i, sz = vz[i] * mass_i;
+    int n_neigh = 1;
+    double mass_neigh = mass_i;
+    for (int q = 0; q < M; ++q) {
+        const int j = vi[q];
+        if (j < 0) break;
+        if (j != i && di[q] <= rc) {
+            const double mj = mass[j];
+            sx += vx[j] * mj;
+            sy += vy[j] * mj;
+            sz += vz[j] * mj;
+            ++n_neigh;
+            mass_neigh += mj;
+        }
+    }
+    const double mx = sx / mass_neigh, my = sy / mass_neigh, mz = sz / mass_neigh;
+    double ke = 0.0;
+    double dx = vx[i] - mx, dy = vy[i] - my, dz = vz[i] - mz;
+    double vsq = dx * dx + dy * dy + dz * dz;
+    ke += 0.5 * mass_i * mass_factor * vsq * vel_conv;
+    for (int q = 0; q < M; ++q) {
+        const int j = vi[q];
+        if (j < 0) break;
+        if (j != i && di[q] <= rc) {
+            const double mj = mass[j];
+            dx = vx[j] - mx;
+            dy = vy[j] - my;
+            dz = vz[j] - mz;
+            vsq = dx * dx + dy * dy + dz * dz;
+            ke += 0.5 * mj * mass_factor * vsq * vel_conv;
+        }
+    }
+    T[i] = ke * 2.0 / (dim * n_neigh * kb);
+}
+
 }  // namespace
 
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k)
@@ -362,5 +415,13 @@ void launch_structure_entropy(MdbSystem &s, const double *dist, const int *nn, i
     const double global_density = N / volume;
     MDB_LAUNCH(k_structure_entropy, (N + 127) / 128, 128, 0, s.stream, dist, nn, N, M, rc, sigma,
                use_local_density ? 1 : 0, global_density, nbins, entropy);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_atomic_temperature(MdbSystem &s, const int *verlet, const double *dist, int M, const double *vx,
+                               const double *vy, const double *vz, const double *mass, double rc, double *T)
+{
+    const int N = s.n_rows;
+    MDB_LAUNCH(k_atomic_temperature, (N + 127) / 128, 128, 0, s.stream, verlet, dist, N, M, vx, vy, vz, mass, rc, T);
     CUDA_TRY(cudaGetLastError());
 }

@@ -182,6 +182,8 @@ int launch_cluster(MdbSystem &s, const int *verlet, const double *dist, const in
 void launch_structure_entropy(MdbSystem &s, const double *dist, const int *nn, int M, double rc, double sigma,
                               bool use_local_density, double volume, double *entropy);
 long long sbo_div_small_mismatches(MdbSystem &s, const double *a_dev, int n, int d);
+void launch_atomic_temperature(MdbSystem &s, const int *verlet, const double *dist, int M, const double *vx,
+                               const double *vy, const double *vz, const double *mass, double rc, double *T);
 int ptm_parse_flags(const char *structure);
 void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
                 double *output, int ocols, int *indices, int icols);

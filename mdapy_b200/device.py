@@ -242,6 +242,15 @@ class DeviceSystem:
                                                        L.dptr(ave) if ave is not None else None))
         return ent, ave
 
+    def atomic_temperature(self, vx, vy, vz, mass, rc):
+        """Local atomic temperature [K] (velocities A/ps, masses g/mol; atomic_temperature.cpp:7)."""
+        a, b, c, m = L.f64(vx), L.f64(vy), L.f64(vz), L.f64(mass)
+        assert a.shape[0] == self.N and m.shape[0] == self.N
+        out = L.result_empty(self.n_rows, np.float64)
+        L.check(self._lib.mdb_system_atomic_temperature(self._h, L.dptr(a), L.dptr(b), L.dptr(c), L.dptr(m), float(rc),
+                                                        L.dptr(out)))
+        return out
+
     def result_device(self):
         """Raw device pointers (int) of the latest int32 / f64 per-atom result."""
         a, b = C.c_void_p(), C.c_void_p()

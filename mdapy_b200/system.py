@@ -18,6 +18,7 @@ import numpy as np
 
 from . import tool_function as tool
 from .ackland_jones_analysis import AcklandJonesAnalysis
+from .atomic_temperature import AtomicTemperature
 from .box import Box
 from .centro_symmetry_parameter import CentroSymmetryParameter
 from .cluster_analysis import ClusterAnalysis
@@ -378,6 +379,14 @@ class System:
         if average_rc > 0:
             cols["entropy_ave"] = np.asarray(SE.entropy_ave[: self.N]).copy()
         self.update_data(self.data.with_columns(**cols))
+
+    def cal_atomic_temperature(self, rc: float, factor: float = 1.0, max_neigh: Optional[int] = None) -> None:
+        """system.py:1678-1714 -> data['atomic_temp'] in K (velocities in A/fs times ``factor``)."""
+        self._ensure_cutoff_list(rc, max_neigh)
+        _, data = self._get_compute_view()
+        at = AtomicTemperature(data, rc=rc, factor=factor, dev=self._device_list())
+        at.compute()
+        self.update_data(self.data.with_columns(atomic_temp=np.asarray(at.T[: self.N]).copy()))
 
     def cal_steinhardt_bond_orientation(self, llist, use_voronoi: bool = False, nnn: int = 0, rc: float = -1.0,
                                         average: bool = False, use_weight: bool = False, weight=None,

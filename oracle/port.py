@@ -355,3 +355,14 @@ def structure_entropy(rc, sigma, use_local_density, volume, dist, nn, nt=None):
                                     C.c_double(volume), _d(dist), C.c_int(N), C.c_int(M), _i(nn), _d(out),
                                     C.c_int(nt or num_threads()))
     return out
+
+
+def compute_temp(verlet, dist, vx, vy, vz, mass, rc, nt=None):
+    """atomic_temperature.cpp:7 compute_temp (velocities A/ps, masses g/mol) -> T [K]."""
+    verlet, dist = _i32(verlet), _f64(dist)
+    vx, vy, vz, mass = _f64(vx), _f64(vy), _f64(vz), _f64(mass)
+    N, M = verlet.shape
+    out = np.zeros(N, np.float64)
+    _lib().port_compute_temp(_i(verlet), C.c_int(N), C.c_int(M), _d(dist), _d(vx), _d(vy), _d(vz), _d(mass), _d(out),
+                             C.c_double(rc), C.c_int(nt or num_threads()))
+    return out

@@ -1136,3 +1136,48 @@ void port_structure_entropy(double rc, double sigma, int use_local_density, doub
     free(rsq);
     free(pref);
 }
+
+/* ------------------------------------------------------------------ atomic temperature
+ * atomic_temperature.cpp:7-112 */
+void port_compute_temp(const int *verlet, int N, int M, const double *dist, const double *vx, const double *vy,
+                       const double *vz, const double *mass, double *T, double rc, int num_t)
+{
+    const double kb = 1.380649e-23, dim = 3.0, afu = 6.022140857e23;
+    const double mass_factor = 1.0 / afu / 1000.0, vel_conv = 1e4;
+#pragma omp parallel for num_threads(num_t)
+    for (int i = 0; i < N; ++i) {
+        const int *vi = verlet + (size_t)i * M;
+        const double *di = dist + (size_t)i * M;
+        const double mi = mass[i];
+        double sx = vx[i] * mi, sy = vy[i] * mi, sz = vz[i] * mi, mn = mi;
+        int n = 1;
+        for (int q = 0; q < M; ++q) {
+            const int j = vi[q];
+            if (j < 0) break;
+            if (j != i && di[q] <= rc) {
+                sx += vx[j] * mass[j];
+                sy += vy[j] * mass[j];
+                sz += vz[j] * mass[j];
+                ++n;
+                mn += mass[j];
+            }
+        }
+        const double mx = sx / mn, my = sy / mn, mz = sz / mn;
+        double dx = vx[i] - mx, dy = vy[i] - my, dz = vz[i] - mz;
+        double vsq = dx * dx + dy * dy + dz * dz;
+        double ke = 0.0;
+        ke += 0.5 * mi * mass_factor * vsq * vel_conv;
+        for (int q = 0; q < M; ++q) {
+            const int j = vi[q];
+            if (j < 0) break;
+            if (j != i && di[q] <= rc) {
+                dx = vx[j] - mx;
+                dy = vy[j] - my;
+                dz = vz[j] - mz;
+                vsq = dx * dx + dy * dy + dz * dz;
+                ke += 0.5 * mass[j] * mass_factor * vsq * vel_conv;
+            }
+        }
+        T[i] = ke * 2.0 / (dim * n * kb);
+    }
+}

@@ -53,6 +53,9 @@ void port_filter_by_type(int *verlet, int N, int M, const double *dist, const in
 void port_structure_entropy(double rc, double sigma, int use_local_density, double volume, const double *dist, int N,
                             int M, const int *nn, double *entropy, int num_t);
 
+void port_compute_temp(const int *verlet, int N, int M, const double *dist, const double *vx, const double *vy,
+                       const double *vz, const double *mass, double *T, double rc, int num_t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -250,3 +250,38 @@ def test_system_structure_entropy_fixture(name, mode):
         got = np.asarray(system.data["entropy"])
     exp = g[f"{name}__{mode}"]
     assert np.allclose(got, exp, atol=1e-6), np.abs(got - exp).max()
+
+
+# ---------------------------------------------------------------------------------------------
+# atomic temperature (src/atomic_temperature.cpp)
+def test_atomic_temperature_bit_exact():
+    import mdapy_b200 as mp
+    from mdapy_b200 import _lib as L
+    from mdapy_b200.device import DeviceSystem
+
+    p, b = H.fcc(3.615, 8)
+    pos = H.rattle(p, 0.1, 19)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    o, bnd, rc = np.zeros(3), [1, 1, 1], 4.0
+    v, d, n = K.build_neighbor_auto(x, y, z, b, o, bnd, rc)
+    rng = np.random.default_rng(5)
+    vel = rng.standard_normal((3, x.shape[0])) * 2.5           # A/ps
+    mass = rng.choice([26.98, 63.546], x.shape[0])
+    ds = DeviceSystem(0)
+    ds.set_atoms(x, y, z, b, o, bnd)
+    ds.build_neighbor(rc)
+    for r in (rc, 3.0):
+        ref = K.compute_temp(v, d, vel[0], vel[1], vel[2], mass, r)
+        got = ds.atomic_temperature(vel[0], vel[1], vel[2], mass, r)
+        assert np.array_equal(got.view(np.int64), ref.view(np.int64))
+    out = np.zeros(x.shape[0])
+    L.check(L.lib().mdb_compute_temp(L.iptr(v), v.shape[0], v.shape[1], L.dptr(d), L.dptr(np.ascontiguousarray(vel[0])),
+                                     L.dptr(np.ascontiguousarray(vel[1])), L.dptr(np.ascontiguousarray(vel[2])),
+                                     L.dptr(mass), L.dptr(out), rc, 1))
+    assert np.array_equal(out.view(np.int64), K.compute_temp(v, d, vel[0], vel[1], vel[2], mass, rc).view(np.int64))
+    # System method: velocities in A/fs, scaled by 1e3 * factor like the reference's wrapper
+    system = mp.System(data={"x": x, "y": y, "z": z, "vx": vel[0] * 1e-3, "vy": vel[1] * 1e-3, "vz": vel[2] * 1e-3,
+                             "amass": mass}, box=mp.Box(b))
+    system.cal_atomic_temperature(rc)
+    ref = K.compute_temp(v, d, vel[0] * 1e-3 * 1e3 * 1.0, vel[1] * 1e-3 * 1e3 * 1.0, vel[2] * 1e-3 * 1e3 * 1.0, mass, rc)
+    assert np.array_equal(np.asarray(system.data["atomic_temp"]).view(np.int64), ref.view(np.int64))

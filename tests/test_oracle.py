@@ -273,3 +273,18 @@ def test_port_structure_entropy_equals_reference():
     for uld in (False, True):
         a, b = ref.structure_entropy(5.0, 0.2, uld, vol, d, n), port.structure_entropy(5.0, 0.2, uld, vol, d, n)
         assert np.array_equal(a.view(np.int64), b.view(np.int64))
+
+
+@pytest.mark.skipif(not (ref.available() and port.available()), reason="needs both checkers")
+def test_port_atomic_temperature_equals_reference():
+    pos, box = H.fcc(3.615, 6)
+    pos = H.rattle(pos, 0.1, 9)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    v, d, n = ref.build_neighbor_auto(x, y, z, box, np.zeros(3), [1, 1, 1], 4.0)
+    rng = np.random.default_rng(4)
+    vel = rng.standard_normal((3, x.shape[0])) * 3.0
+    mass = rng.choice([26.98, 63.546, 58.69], x.shape[0])
+    for rc in (4.0, 3.0):
+        a = ref.compute_temp(v, d, vel[0], vel[1], vel[2], mass, rc)
+        b = port.compute_temp(v, d, vel[0], vel[1], vel[2], mass, rc)
+        assert np.array_equal(a.view(np.int64), b.view(np.int64)) and a.min() > 0
