@@ -166,6 +166,19 @@ int mdb_calculate_structure_entropy(double rc, double sigma, int use_local_densi
 int mdb_compute_temp(const int *verlet, int N, int M, const double *dist, const double *vx, const double *vy,
                      const double *vz, const double *mass, double *T, double rc, int num_t);
 
+/* _bond_analysis.compute_bond(x,y,z,box,origin,boundary,verlet,dist,nn,bond_length_distribution I[nbins] (+=),
+ * bond_angle_distribution I[nbins] (+=), delta_r, delta_theta, rc, nbins, num_t) -- src/bond_analysis.cpp:7 */
+int mdb_compute_bond(const double *x, const double *y, const double *z, int N, const double *box9,
+                     const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                     const int *nn, int *bond_length_distribution, int *bond_angle_distribution, double delta_r,
+                     double delta_theta, double rc, int nbins, int num_t);
+/* _bond_analysis.compute_adf(x,y,z,box,origin,boundary,verlet,dist,nn,delta_theta,rc_list D[Npair,4],
+ * pair_list I[Npair,3], type_list, nbins, bond_angle_distribution I[Npair,nbins] (+=), num_t) -- :120 */
+int mdb_compute_adf(const double *x, const double *y, const double *z, int N, const double *box9,
+                    const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                    const int *nn, double delta_theta, const double *rc_list, const int *pair_list, int npair,
+                    const int *type_list, int nbins, int *bond_angle_distribution, int num_t);
+
 /* ------------------------------------------------------------------------
  * Section B: device-resident system handle
  * ---------------------------------------------------------------------- */
@@ -260,6 +273,12 @@ int mdb_system_check_small_division(mdb_system *s, const double *a_host, int n, 
 /* atomic temperature on the cached list; vx, vy, vz, mass: n_local host doubles */
 int mdb_system_atomic_temperature(mdb_system *s, const double *vx, const double *vy, const double *vz,
                                   const double *mass, double rc, double *T_host);
+/* bond-length / bond-angle histograms and the per-triplet angular distribution on the cached list; the int32
+ * host histograms are ACCUMULATED into, like the reference */
+int mdb_system_bond_analysis(mdb_system *s, double delta_r, double delta_theta, double rc, int nbins,
+                             int *bond_length_host, int *bond_angle_host);
+int mdb_system_adf(mdb_system *s, double delta_theta, const double *rc_list, const int *pair_list, int npair,
+                   const int *types_host, int nbins, int *bond_angle_host);
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 
 /* per-kernel device times (ms) of the most recent build_neighbor / fcna, measured with CUDA events */

@@ -24,6 +24,8 @@ def __getattr__(name):
         "ClusterAnalysis": ("cluster_analysis", "ClusterAnalysis"),
         "StructureEntropy": ("structure_entropy", "StructureEntropy"),
         "AtomicTemperature": ("atomic_temperature", "AtomicTemperature"),
+        "BondAnalysis": ("bond_analysis", "BondAnalysis"),
+        "AngularDistributionFunction": ("bond_analysis", "AngularDistributionFunction"),
         "build_crystal": ("lattice", "build_crystal"),
     }
     if name == "empty_cache":

@@ -64,6 +64,10 @@ PROTOTYPES = {
     "mdb_calculate_structure_entropy": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_double, c_dp, C.c_int, C.c_int,
                                                   c_ip, c_dp, C.c_int]),
     "mdb_compute_temp": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_int]),
+    "mdb_compute_bond": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, c_ip, c_ip, c_ip, C.c_double, C.c_double, C.c_double,
+                                                  C.c_int, C.c_int]),
+    "mdb_compute_adf": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, c_ip, C.c_double, c_dp, c_ip, C.c_int, c_ip, C.c_int,
+                                                 c_ip, C.c_int]),
     "mdb_system_create": (C.c_int, [C.c_int, C.POINTER(c_vp)]),
     "mdb_system_destroy": (None, [c_vp]),
     "mdb_system_set_stream": (C.c_int, [c_vp, c_vp]),
@@ -100,6 +104,8 @@ PROTOTYPES = {
                                                c_dp]),
     "mdb_system_check_small_division": (C.c_int, [c_vp, c_dp, C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "mdb_system_atomic_temperature": (C.c_int, [c_vp, c_dp, c_dp, c_dp, c_dp, C.c_double, c_dp]),
+    "mdb_system_bond_analysis": (C.c_int, [c_vp, C.c_double, C.c_double, C.c_double, C.c_int, c_ip, c_ip]),
+    "mdb_system_adf": (C.c_int, [c_vp, C.c_double, c_dp, c_ip, C.c_int, c_ip, C.c_int, c_ip]),
     "mdb_system_result_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "mdb_system_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_last_times": (C.c_int, [c_vp, c_fp, c_fp, c_fp]),

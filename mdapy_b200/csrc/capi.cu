@@ -870,6 +870,49 @@ int mdb_system_atomic_temperature(mdb_system *s, const double *vx, const double 
     API_END
 }
 
+int mdb_system_bond_analysis(mdb_system *s, double delta_r, double delta_theta, double rc, int nbins,
+                             int *bond_length_host, int *bond_angle_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(bond_length_host && bond_angle_host && nbins > 0, MDB_ERR_VALUE, "both histograms and nbins are required");
+    unsigned long long *hist = s->scratch2.ensure<unsigned long long>((size_t)2 * nbins);
+    launch_bond_hist(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, delta_r, delta_theta, rc, nbins,
+                     hist);
+    std::vector<unsigned long long> h((size_t)2 * nbins);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for (int t = 0; t < nbins; ++t) {
+        bond_length_host[t] += (int)h[t];
+        bond_angle_host[t] += (int)h[nbins + t];
+    }
+    API_END
+}
+
+int mdb_system_adf(mdb_system *s, double delta_theta, const double *rc_list, const int *pair_list, int npair,
+                   const int *types_host, int nbins, int *bond_angle_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(rc_list && pair_list && types_host && bond_angle_host && npair > 0 && nbins > 0, MDB_ERR_VALUE,
+                "rc_list, pair_list, type_list and the histogram are required");
+    const int *types = h2d(*s, s->types, types_host, (size_t)s->N);
+    double *rcs = s->out_f64c.ensure<double>((size_t)4 * npair);
+    int *pairs = s->perm_tmp.ensure<int>((size_t)3 * npair);
+    CUDA_TRY(cudaMemcpyAsync(rcs, rc_list, sizeof(double) * 4 * npair, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(pairs, pair_list, sizeof(int) * 3 * npair, cudaMemcpyHostToDevice, s->stream));
+    unsigned long long *hist = s->scratch2.ensure<unsigned long long>((size_t)npair * nbins);
+    launch_adf_hist(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, delta_theta, rcs, pairs, npair,
+                    types, nbins, hist);
+    std::vector<unsigned long long> h((size_t)npair * nbins);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for (size_t t = 0; t < h.size(); ++t) bond_angle_host[t] += (int)h[t];
+    API_END
+}
+
 // (n_rows, 8) = type, ordering, rmsd, interatomic distance, qw, qx, qy, qz; indices_host: (n_rows, 18).
 int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, double rmsd_threshold,
                    double *output_host, int *indices_host)
@@ -1197,6 +1240,38 @@ int mdb_compute_temp(const int *verlet, int N, int M, const double *dist, const 
     int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nullptr, M, rc, LIST_CUTOFF);
     if (rcode != MDB_OK) return rcode;
     rcode = mdb_system_atomic_temperature(s.s, vx, vy, vz, mass, rc, T);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_compute_bond(const double *x, const double *y, const double *z, int N, const double *box9,
+                     const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                     const int *nn, int *bond_length_distribution, int *bond_angle_distribution, double delta_r,
+                     double delta_theta, double rc, int nbins, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nn, M, rc, LIST_CUTOFF);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_bond_analysis(s.s, delta_r, delta_theta, rc, nbins, bond_length_distribution, bond_angle_distribution);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_compute_adf(const double *x, const double *y, const double *z, int N, const double *box9,
+                    const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                    const int *nn, double delta_theta, const double *rc_list, const int *pair_list, int npair,
+                    const int *type_list, int nbins, int *bond_angle_distribution, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nn, M, -1.0, LIST_CUTOFF);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_adf(s.s, delta_theta, rc_list, pair_list, npair, type_list, nbins, bond_angle_distribution);
     if (rcode != MDB_OK) return rcode;
     API_END
 }

@@ -349,6 +349,125 @@ __global__ void __launch_bounds__(128) k_atomic_temperature(const int *__restric
     T[i] = ke * 2.0 / (dim * n_neigh * kb);
 }
 
+
+// Bond-length / bond-angle histograms, src/bond_analysis.cpp:7-118 (compute_bond): lengths of listed pairs
+// j > i within rc, angles j-i-k over listed neighbour pairs jj < kk within rc; angle = acos(clamped cos) * 180 / PI,
+// bin = floor(theta / delta), clamped to the last bin.  hist: [nbins lengths | nbins angles] (64-bit).
+// acos is the device's (<= 1 ulp from libm): a bin can differ only for an angle within ~1e-14 degrees of an
+// edge, i.e. on perfect lattices whose angles sit exactly on bin edges.
+__global__ void __launch_bounds__(128) k_bond_hist(const double *__restrict__ x, const double *__restrict__ y,
+                                                   const double *__restrict__ z, int N, DBox box,
+                                                   const int *__restrict__ verlet, const double *__restrict__ dist,
+                                                   const int *__restrict__ nn, int M, double delta_r, double delta_theta,
+                                                   double rc, int nbins, unsigned long long *__restrict__ hist)
+{
+    extern __shared__ unsigned sh_b[];
+    const bool use_sh = 2 * nbins <= 8192;
+    if (use_sh) {
+        for (int t = threadIdx.x; t < 2 * nbins; t += blockDim.x) sh_b[t] = 0;
+        __syncthreads();
+    }
+    const double PI = 3.14159265358979323846;
+    const double dri = 1.0 / delta_r, dti = 1.0 / delta_theta;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int c = nn[i];
+        const int *vi = verlet + (size_t)i * M;
+        const double *di = dist + (size_t)i * M;
+        for (int jj = 0; jj < c; ++jj) {
+            if (vi[jj] > i) {
+                const double r = di[jj];
+                if (r <= rc) {
+                    int index = static_cast<int>(floor(r * dri));
+                    if (index > nbins - 1) index = nbins - 1;
+                    if (use_sh) atomicAdd(sh_b + index, 1u);
+                    else atomicAdd(hist + index, 1ull);
+                }
+            }
+        }
+        const double xi = x[i], yi = y[i], zi = z[i];
+        for (int jj = 0; jj < c; ++jj) {
+            const double rij = di[jj];
+            if (!(rij <= rc)) continue;
+            const int j = vi[jj];
+            double ax = x[j] - xi, ay = y[j] - yi, az = z[j] - zi;
+            min_image(box, ax, ay, az);
+            for (int kk = jj + 1; kk < c; ++kk) {
+                const double rik = di[kk];
+                if (!(rik <= rc)) continue;
+                const int k = vi[kk];
+                double bx = x[k] - xi, by = y[k] - yi, bz = z[k] - zi;
+                min_image(box, bx, by, bz);
+                const double dot = ax * bx + ay * by + az * bz;
+                double ct = dot / (rij * rik);
+                if (ct > 1.0) ct = 1.0;
+                if (ct < -1.0) ct = -1.0;
+                const double theta = acos(ct) * 180.0 / PI;
+                int index = static_cast<int>(floor(theta * dti));
+                if (index > nbins - 1) index = nbins - 1;
+                if (use_sh) atomicAdd(sh_b + nbins + index, 1u);
+                else atomicAdd(hist + nbins + index, 1ull);
+            }
+        }
+    }
+    if (use_sh) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < 2 * nbins; t += blockDim.x)
+            if (sh_b[t]) atomicAdd(hist + t, (unsigned long long)sh_b[t]);
+    }
+}
+
+// Angular distribution function per (centre, j, k) type triplet, src/bond_analysis.cpp:120-240 (compute_adf).
+// pairs: [Npair][3] types, rcs: [Npair][4] = r_ij min, max, r_ik min, max.  hist: [Npair][nbins] (64-bit).
+__global__ void __launch_bounds__(128) k_adf_hist(const double *__restrict__ x, const double *__restrict__ y,
+                                                  const double *__restrict__ z, int N, DBox box,
+                                                  const int *__restrict__ verlet, const double *__restrict__ dist,
+                                                  const int *__restrict__ nn, int M, double delta_theta,
+                                                  const double *__restrict__ rcs, const int *__restrict__ pairs,
+                                                  int npair, const int *__restrict__ types, int nbins,
+                                                  unsigned long long *__restrict__ hist)
+{
+    const double PI = 3.14159265358979323846;
+    const double dti = 1.0 / delta_theta;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int itype = types[i];
+        const int c = nn[i];
+        const int *vi = verlet + (size_t)i * M;
+        const double *di = dist + (size_t)i * M;
+        const double xi = x[i], yi = y[i], zi = z[i];
+        for (int m = 0; m < npair; ++m) {
+            if (itype != pairs[m * 3]) continue;
+            const int jt = pairs[m * 3 + 1], kt = pairs[m * 3 + 2];
+            const bool same = jt == kt;
+            for (int jj = 0; jj < c; ++jj) {
+                const int j = vi[jj];
+                if (types[j] != jt) continue;
+                const double rij = di[jj];
+                if (!(rij <= rcs[m * 4 + 1] && rij >= rcs[m * 4 + 0])) continue;
+                double ax = x[j] - xi, ay = y[j] - yi, az = z[j] - zi;
+                min_image(box, ax, ay, az);
+                for (int kk = same ? jj + 1 : 0; kk < c; ++kk) {
+                    if (kk == jj) continue;
+                    const int k = vi[kk];
+                    if (types[k] != kt) continue;
+                    const double rik = di[kk];
+                    if (!(rik <= rcs[m * 4 + 3] && rik >= rcs[m * 4 + 2])) continue;
+                    double bx = x[k] - xi, by = y[k] - yi, bz = z[k] - zi;
+                    min_image(box, bx, by, bz);
+                    const double dot = ax * bx + ay * by + az * bz;
+                    double ct = dot / (rij * rik);
+                    if (ct > 1.0) ct = 1.0;
+                    if (ct < -1.0) ct = -1.0;
+                    const double theta = acos(ct) * 180.0 / PI;
+                    int index = static_cast<int>(floor(theta * dti));
+                    if (index < 0) index = 0;
+                    if (index >= nbins) index = nbins - 1;
+                    atomicAdd(hist + (size_t)m * nbins + index, 1ull);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k)
@@ -423,5 +542,34 @@ void launch_atomic_temperature(MdbSystem &s, const int *verlet, const double *di
 {
     const int N = s.n_rows;
     MDB_LAUNCH(k_atomic_temperature, (N + 127) / 128, 128, 0, s.stream, verlet, dist, N, M, vx, vy, vz, mass, rc, T);
+    CUDA_TRY(cudaGetLastError());
+}
+
+// hist (device, 64-bit, 2 * nbins) is zeroed here
+void launch_bond_hist(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double delta_r,
+                      double delta_theta, double rc, int nbins, unsigned long long *hist)
+{
+    const int N = s.n_rows;
+    MDB_REQUIRE(nbins > 0 && delta_r > 0 && delta_theta > 0, MDB_ERR_VALUE, "nbins and the bin widths must be positive");
+    CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * 2 * nbins, s.stream));
+    int nb = (N + 127) / 128;
+    if (nb > 148 * 16) nb = 148 * 16;
+    const size_t smem = 2 * nbins <= 8192 ? sizeof(unsigned) * 2 * nbins : 0;
+    MDB_LAUNCH(k_bond_hist, nb, 128, smem, s.stream, s.x, s.y, s.z, N, s.box, verlet, dist, nn, M, delta_r, delta_theta, rc,
+               nbins, hist);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_adf_hist(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double delta_theta,
+                     const double *rcs, const int *pairs, int npair, const int *types, int nbins,
+                     unsigned long long *hist)
+{
+    const int N = s.n_rows;
+    MDB_REQUIRE(nbins > 0 && npair > 0 && delta_theta > 0, MDB_ERR_VALUE, "nbins, the triplet table and the bin width are required");
+    CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * (size_t)npair * nbins, s.stream));
+    int nb = (N + 127) / 128;
+    if (nb > 148 * 16) nb = 148 * 16;
+    MDB_LAUNCH(k_adf_hist, nb, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, dist, nn, M, delta_theta, rcs, pairs,
+               npair, types, nbins, hist);
     CUDA_TRY(cudaGetLastError());
 }

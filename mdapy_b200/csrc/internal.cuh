@@ -184,6 +184,11 @@ void launch_structure_entropy(MdbSystem &s, const double *dist, const int *nn, i
 long long sbo_div_small_mismatches(MdbSystem &s, const double *a_dev, int n, int d);
 void launch_atomic_temperature(MdbSystem &s, const int *verlet, const double *dist, int M, const double *vx,
                                const double *vy, const double *vz, const double *mass, double rc, double *T);
+void launch_bond_hist(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double delta_r,
+                      double delta_theta, double rc, int nbins, unsigned long long *hist);
+void launch_adf_hist(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double delta_theta,
+                     const double *rcs, const int *pairs, int npair, const int *types, int nbins,
+                     unsigned long long *hist);
 int ptm_parse_flags(const char *structure);
 void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
                 double *output, int ocols, int *indices, int icols);

@@ -251,6 +251,22 @@ class DeviceSystem:
                                                         L.dptr(out)))
         return out
 
+    def bond_analysis(self, rc: float, nbin: int):
+        """(bond_length_distribution, bond_angle_distribution), int32[nbin] each (bond_analysis.cpp:7)."""
+        bl, ba = np.zeros(int(nbin), np.int32), np.zeros(int(nbin), np.int32)
+        L.check(self._lib.mdb_system_bond_analysis(self._h, float(rc) / nbin, 180.0 / nbin, float(rc), int(nbin),
+                                                   L.iptr(bl), L.iptr(ba)))
+        return bl, ba
+
+    def adf(self, rc_list, pair_list, type_list, nbin: int):
+        """Angular distribution per type triplet, int32[Npair, nbin] (bond_analysis.cpp:120)."""
+        rcl, pl, t = L.f64(rc_list), L.i32(pair_list), L.i32(type_list)
+        assert rcl.shape == (pl.shape[0], 4) and pl.shape[1] == 3 and t.shape[0] == self.N
+        out = np.zeros((pl.shape[0], int(nbin)), np.int32)
+        L.check(self._lib.mdb_system_adf(self._h, 180.0 / nbin, L.dptr(rcl), L.iptr(pl), pl.shape[0], L.iptr(t), int(nbin),
+                                         L.iptr(out)))
+        return out
+
     def result_device(self):
         """Raw device pointers (int) of the latest int32 / f64 per-atom result."""
         a, b = C.c_void_p(), C.c_void_p()

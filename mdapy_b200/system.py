@@ -19,6 +19,7 @@ import numpy as np
 from . import tool_function as tool
 from .ackland_jones_analysis import AcklandJonesAnalysis
 from .atomic_temperature import AtomicTemperature
+from .bond_analysis import AngularDistributionFunction, BondAnalysis
 from .box import Box
 from .centro_symmetry_parameter import CentroSymmetryParameter
 from .cluster_analysis import ClusterAnalysis
@@ -387,6 +388,24 @@ class System:
         at = AtomicTemperature(data, rc=rc, factor=factor, dev=self._device_list())
         at.compute()
         self.update_data(self.data.with_columns(atomic_temp=np.asarray(at.T[: self.N]).copy()))
+
+    def cal_bond_analysis(self, rc: float, nbin: int, max_neigh: Optional[int] = None) -> BondAnalysis:
+        """system.py:2130-2178: bond-length and bond-angle histograms of the cut-off list."""
+        self._ensure_cutoff_list(rc, max_neigh)
+        box, data = self._get_compute_view()
+        ba = BondAnalysis(data, box, rc, nbin, dev=self._device_list(), device=self._device)
+        ba.compute()
+        return ba
+
+    def cal_angular_distribution_function(self, rc_dict, nbin: int,
+                                          max_neigh: Optional[int] = None) -> AngularDistributionFunction:
+        """system.py:2180-2233: angle histograms per 'A-B-C' element triplet, rc_dict[key] = [rij_min, rij_max, rik_min, rik_max]."""
+        rc = float(np.array(list(rc_dict.values())).max())
+        self._ensure_cutoff_list(rc, max_neigh)
+        box, data = self._get_compute_view()
+        adf = AngularDistributionFunction(data, box, rc_dict, nbin, dev=self._device_list(), device=self._device)
+        adf.compute()
+        return adf
 
     def cal_steinhardt_bond_orientation(self, llist, use_voronoi: bool = False, nnn: int = 0, rc: float = -1.0,
                                         average: bool = False, use_weight: bool = False, weight=None,

@@ -366,3 +366,30 @@ def compute_temp(verlet, dist, vx, vy, vz, mass, rc, nt=None):
     _lib().port_compute_temp(_i(verlet), C.c_int(N), C.c_int(M), _d(dist), _d(vx), _d(vy), _d(vz), _d(mass), _d(out),
                              C.c_double(rc), C.c_int(nt or num_threads()))
     return out
+
+
+def compute_bond(x, y, z, box, origin, boundary, verlet, dist, nn, rc, nbin, nt=None):
+    """bond_analysis.cpp:7 compute_bond -> (bond_length_distribution, bond_angle_distribution)."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet, dist, nn = _i32(verlet), _f64(dist), _i32(nn)
+    N, M = verlet.shape
+    bl, ba = np.zeros(nbin, np.int32), np.zeros(nbin, np.int32)
+    _lib().port_compute_bond(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _i(verlet), C.c_int(M), _d(dist),
+                             _i(nn), _i(bl), _i(ba), C.c_double(rc / nbin), C.c_double(180.0 / nbin), C.c_double(rc),
+                             C.c_int(nbin), C.c_int(nt or num_threads()))
+    return bl, ba
+
+
+def compute_adf(x, y, z, box, origin, boundary, verlet, dist, nn, rc_list, pair_list, type_list, nbin, nt=None):
+    """bond_analysis.cpp:120 compute_adf -> int32[Npair, nbin]."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet, dist, nn = _i32(verlet), _f64(dist), _i32(nn)
+    rcl, pl, t = _f64(rc_list), _i32(pair_list), _i32(type_list)
+    N, M = verlet.shape
+    out = np.zeros((pl.shape[0], nbin), np.int32)
+    _lib().port_compute_adf(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _i(verlet), C.c_int(M), _d(dist), _i(nn),
+                            C.c_double(180.0 / nbin), _d(rcl), _i(pl), C.c_int(pl.shape[0]), _i(t), C.c_int(nbin), _i(out),
+                            C.c_int(nt or num_threads()))
+    return out

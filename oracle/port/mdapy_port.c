@@ -1181,3 +1181,78 @@ void port_compute_temp(const int *verlet, int N, int M, const double *dist, cons
         T[i] = ke * 2.0 / (dim * n * kb);
     }
 }
+
+/* ------------------------------------------------------------------ bond analysis / angular distribution
+ * bond_analysis.cpp:7-118 and 120-240 */
+static int angle_bin(const cell_t *c, const double *x, const double *y, const double *z, int i, int j, int k, double rij,
+                     double rik, double dti, int nbins, int clamp_low)
+{
+    const double PI = 3.14159265358979323846;
+    double ax = x[j] - x[i], ay = y[j] - y[i], az = z[j] - z[i];
+    double bx = x[k] - x[i], by = y[k] - y[i], bz = z[k] - z[i];
+    min_image(c, &ax, &ay, &az);
+    min_image(c, &bx, &by, &bz);
+    const double dot = ax * bx + ay * by + az * bz;
+    double ct = dot / (rij * rik);
+    if (ct > 1.0) ct = 1.0;
+    if (ct < -1.0) ct = -1.0;
+    const double theta = acos(ct) * 180.0 / PI;
+    int index = (int)floor(theta * dti);
+    if (clamp_low && index < 0) index = 0;
+    if (index > nbins - 1) index = nbins - 1;
+    return index;
+}
+
+void port_compute_bond(const double *x, const double *y, const double *z, int N, const double *box9,
+                       const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                       const int *nn, int *blen, int *bang, double delta_r, double delta_theta, double rc, int nbins,
+                       int num_t)
+{
+    (void)num_t;
+    cell_t c;
+    cell_init(&c, box9, origin3, boundary3);
+    const double dri = 1.0 / delta_r, dti = 1.0 / delta_theta;
+    for (int i = 0; i < N; ++i) {
+        const int *vi = verlet + (size_t)i * M;
+        const double *di = dist + (size_t)i * M;
+        for (int jj = 0; jj < nn[i]; ++jj)
+            if (vi[jj] > i && di[jj] <= rc) {
+                int index = (int)floor(di[jj] * dri);
+                if (index > nbins - 1) index = nbins - 1;
+                blen[index] += 1;
+            }
+        for (int jj = 0; jj < nn[i]; ++jj) {
+            if (!(di[jj] <= rc)) continue;
+            for (int kk = jj + 1; kk < nn[i]; ++kk)
+                if (di[kk] <= rc) bang[angle_bin(&c, x, y, z, i, vi[jj], vi[kk], di[jj], di[kk], dti, nbins, 0)] += 1;
+        }
+    }
+}
+
+void port_compute_adf(const double *x, const double *y, const double *z, int N, const double *box9,
+                      const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                      const int *nn, double delta_theta, const double *rcs, const int *pairs, int npair,
+                      const int *types, int nbins, int *bang, int num_t)
+{
+    (void)num_t;
+    cell_t c;
+    cell_init(&c, box9, origin3, boundary3);
+    const double dti = 1.0 / delta_theta;
+    for (int i = 0; i < N; ++i) {
+        const int *vi = verlet + (size_t)i * M;
+        const double *di = dist + (size_t)i * M;
+        for (int m = 0; m < npair; ++m) {
+            if (types[i] != pairs[m * 3]) continue;
+            const int jt = pairs[m * 3 + 1], kt = pairs[m * 3 + 2], same = jt == kt;
+            for (int jj = 0; jj < nn[i]; ++jj) {
+                if (types[vi[jj]] != jt) continue;
+                if (!(di[jj] <= rcs[m * 4 + 1] && di[jj] >= rcs[m * 4 + 0])) continue;
+                for (int kk = same ? jj + 1 : 0; kk < nn[i]; ++kk) {
+                    if (kk == jj || types[vi[kk]] != kt) continue;
+                    if (!(di[kk] <= rcs[m * 4 + 3] && di[kk] >= rcs[m * 4 + 2])) continue;
+                    bang[(size_t)m * nbins + angle_bin(&c, x, y, z, i, vi[jj], vi[kk], di[jj], di[kk], dti, nbins, 1)] += 1;
+                }
+            }
+        }
+    }
+}

@@ -56,6 +56,15 @@ void port_structure_entropy(double rc, double sigma, int use_local_density, doub
 void port_compute_temp(const int *verlet, int N, int M, const double *dist, const double *vx, const double *vy,
                        const double *vz, const double *mass, double *T, double rc, int num_t);
 
+void port_compute_bond(const double *x, const double *y, const double *z, int N, const double *box9,
+                       const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                       const int *nn, int *blen, int *bang, double delta_r, double delta_theta, double rc, int nbins,
+                       int num_t);
+void port_compute_adf(const double *x, const double *y, const double *z, int N, const double *box9,
+                      const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                      const int *nn, double delta_theta, const double *rcs, const int *pairs, int npair,
+                      const int *types, int nbins, int *bang, int num_t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,3 +285,57 @@ def test_atomic_temperature_bit_exact():
     system.cal_atomic_temperature(rc)
     ref = K.compute_temp(v, d, vel[0] * 1e-3 * 1e3 * 1.0, vel[1] * 1e-3 * 1e3 * 1.0, vel[2] * 1e-3 * 1e3 * 1.0, mass, rc)
     assert np.array_equal(np.asarray(system.data["atomic_temp"]).view(np.int64), ref.view(np.int64))
+
+
+# ---------------------------------------------------------------------------------------------
+# bond-length / bond-angle histograms and the angular distribution function (src/bond_analysis.cpp).
+# Rattled inputs: no angle sits within rounding of a bin edge, so the device acos cannot move a count.
+@pytest.mark.parametrize("case", CASES[:3], ids=[c[0] for c in CASES[:3]])
+def test_bond_analysis_and_adf_exact(case):
+    from mdapy_b200 import _lib as L
+    from mdapy_b200.device import DeviceSystem
+
+    _, pos, box, bnd, rc = case
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    o = np.zeros(3)
+    v, d, n = K.build_neighbor_auto(x, y, z, box, o, bnd, rc)
+    ds = DeviceSystem(0)
+    ds.set_atoms(x, y, z, box, o, bnd)
+    ds.build_neighbor(rc)
+    for nbin in (40, 181):
+        rl, ra = K.compute_bond(x, y, z, box, o, bnd, v, d, n, rc, nbin)
+        gl, ga = ds.bond_analysis(rc, nbin)
+        assert np.array_equal(gl, rl) and np.array_equal(ga, ra) and ra.sum() > 0
+    t = (np.random.default_rng(3).integers(0, 2, x.shape[0])).astype(np.int32)
+    rcl = np.array([[0.0, 0.9 * rc, 0.0, rc], [0.5 * rc, rc, 0.5 * rc, rc], [0.0, rc, 0.0, 0.8 * rc]])
+    pl = np.array([[0, 1, 0], [1, 1, 1], [1, 0, 1]], np.int32)
+    ref = K.compute_adf(x, y, z, box, o, bnd, v, d, n, rcl, pl, t, 60)
+    assert np.array_equal(ds.adf(rcl, pl, t, 60), ref) and ref.sum() > 0
+    # host-pointer drop-ins accumulate into the caller's histograms
+    b, oo, p = L.box_args(box, o, bnd)
+    N, M = v.shape
+    bl, ba = np.ones(40, np.int32), np.zeros(40, np.int32)
+    L.check(L.lib().mdb_compute_bond(L.dptr(x), L.dptr(y), L.dptr(z), N, L.dptr(b), L.dptr(oo), L.iptr(p), L.iptr(v), M,
+                                     L.dptr(d), L.iptr(n), L.iptr(bl), L.iptr(ba), rc / 40, 180.0 / 40, rc, 40, 1))
+    rl, ra = K.compute_bond(x, y, z, box, o, bnd, v, d, n, rc, 40)
+    assert np.array_equal(bl, rl + 1) and np.array_equal(ba, ra)
+
+
+def test_system_bond_analysis_and_adf():
+    import mdapy_b200 as mp
+
+    p, b = H.fcc(3.615, 8)
+    pos = H.rattle(p, 0.1, 23)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    el = np.array(["Cu", "Ni"], dtype=object)[np.random.default_rng(6).integers(0, 2, x.shape[0])]
+    system = mp.System(data={"x": x, "y": y, "z": z, "element": el}, box=mp.Box(b))
+    ba = system.cal_bond_analysis(3.2, 64)
+    v, d, n = K.build_neighbor_auto(x, y, z, b, np.zeros(3), [1, 1, 1], 3.2)
+    rl, ra = K.compute_bond(x, y, z, b, np.zeros(3), [1, 1, 1], v, d, n, 3.2, 64)
+    assert np.array_equal(ba.bond_length_distribution, rl) and np.array_equal(ba.bond_angle_distribution, ra)
+    assert ba.r_angle.shape == (64,) and abs(ba.r_length[0] - 3.2 / 128) < 1e-12
+    adf = system.cal_angular_distribution_function({"Cu-Ni-Ni": [0.0, 3.0, 0.0, 3.2], "Ni-Cu-Ni": [0.0, 3.2, 0.0, 3.2]}, 45)
+    t = np.array([{"Cu": 0, "Ni": 1}[e] for e in el], np.int32)
+    ref = K.compute_adf(x, y, z, b, np.zeros(3), [1, 1, 1], v, d, n, np.array([[0.0, 3.0, 0.0, 3.2], [0.0, 3.2, 0.0, 3.2]]),
+                        np.array([[0, 1, 1], [1, 0, 1]], np.int32), t, 45)
+    assert np.array_equal(adf.bond_angle_distribution, ref)

@@ -288,3 +288,19 @@ def test_port_atomic_temperature_equals_reference():
         a = ref.compute_temp(v, d, vel[0], vel[1], vel[2], mass, rc)
         b = port.compute_temp(v, d, vel[0], vel[1], vel[2], mass, rc)
         assert np.array_equal(a.view(np.int64), b.view(np.int64)) and a.min() > 0
+
+
+@pytest.mark.skipif(not (ref.available() and port.available()), reason="needs both checkers")
+def test_port_bond_analysis_equals_reference():
+    pos, box = H.fcc(3.615, 6)
+    pos = H.rattle(pos, 0.12, 13)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    o, bnd = np.zeros(3), [1, 1, 0]
+    v, d, n = ref.build_neighbor_auto(x, y, z, box, o, bnd, 3.4)
+    a, b = ref.compute_bond(x, y, z, box, o, bnd, v, d, n, 3.4, 50), port.compute_bond(x, y, z, box, o, bnd, v, d, n, 3.4, 50)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[0].sum() > 0 and a[1].sum() > 0
+    t = (np.arange(x.shape[0]) % 2).astype(np.int32)
+    rcl = np.array([[0.0, 3.0, 0.0, 3.4], [2.0, 3.4, 2.0, 3.4]])
+    pl = np.array([[0, 1, 0], [1, 1, 1]], np.int32)
+    assert np.array_equal(ref.compute_adf(x, y, z, box, o, bnd, v, d, n, rcl, pl, t, 36),
+                          port.compute_adf(x, y, z, box, o, bnd, v, d, n, rcl, pl, t, 36))
