@@ -225,6 +225,86 @@ __device__ __forceinline__ CnaCounts cna_signatures_smem(const unsigned short *n
     return c;
 }
 
+// Register form of the same signature counts for the fast kernel (rows[] in registers, NN static).
+// For a bonded pair (a, b) the number of common neighbours d = popc(rows[a] & rows[b]) is at the same time the
+// degree of b inside the common-neighbour graph of a AND of a inside that of b, so one pass over the
+// NN(NN-1)/2 pairs with static indices yields, for every neighbour ni, twice the bond count and the largest
+// degree among its common neighbours -- half the popcounts of the per-neighbour loop and no shared-memory
+// traffic.  Only the (6 common, 6 bonds) case still needs the flood (BCC), done on the shared-memory copy.
+template <int NN>
+__device__ __forceinline__ CnaCounts cna_signatures_regs(const unsigned (&rows)[NN], unsigned short *nb)
+{
+    int tw[NN], mx[NN];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+        tw[a] = 0;
+        mx[a] = 0;
+    }
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+#pragma unroll
+        for (int b = a + 1; b < NN; ++b) {
+            const int d = (rows[a] >> b) & 1u ? __popc(rows[a] & rows[b]) : 0;
+            tw[a] += d;
+            tw[b] += d;
+            mx[a] = max(mx[a], d);
+            mx[b] = max(mx[b], d);
+        }
+    }
+    CnaCounts c{0, 0, 0, 0, 0};
+    bool need_flood = false;
+#pragma unroll
+    for (int ni = 0; ni < NN; ++ni) {
+        const int ncommon = __popc(rows[ni]);
+        const int nbonds = tw[ni] >> 1;
+        if (ncommon == 4) {
+            if (nbonds == 2) {
+                if (mx[ni] == 2) ++c.n422;
+                else ++c.n421;
+            } else if (nbonds == 4)
+                ++c.n444;
+        } else if (ncommon == 5) {
+            if (nbonds == 5) ++c.n555;
+        } else if (ncommon == 6 && nbonds == 6)
+            need_flood = true;
+    }
+    if (need_flood) {
+#pragma unroll
+        for (int a = 0; a < NN; ++a) nb[a * CNA_THREADS] = (unsigned short)rows[a];
+#pragma unroll 1
+        for (int ni = 0; ni < NN; ++ni) {
+            const unsigned common = nb[ni * CNA_THREADS];
+            if (__popc(common) != 6) continue;
+            int twice = 0, first_v = -1;
+            unsigned first_row = 0;
+            for (unsigned m = common; m; m &= m - 1) {
+                const int v = __ffs(m) - 1;
+                const unsigned r = nb[v * CNA_THREADS] & common;
+                const int d = __popc(r);
+                twice += d;
+                if (first_v < 0 && d > 0) {
+                    first_v = v;
+                    first_row = r;
+                }
+            }
+            if (twice != 12) continue;
+            // flood the component of the first bonded vertex; all 6 bonds must lie inside it
+            unsigned comp = (1u << first_v) | first_row, frontier = first_row;
+            while (frontier) {
+                unsigned next = 0;
+                for (unsigned m = frontier; m; m &= m - 1) next |= nb[(__ffs(m) - 1) * CNA_THREADS] & common;
+                next &= ~comp;
+                comp |= next;
+                frontier = next;
+            }
+            int e2 = 0;
+            for (unsigned m = comp; m; m &= m - 1) e2 += __popc(nb[(__ffs(m) - 1) * CNA_THREADS] & common);
+            if (e2 == 12) ++c.n666;
+        }
+    }
+    return c;
+}
+
 __device__ __forceinline__ int cna_label(const CnaCounts &c)
 {
     if (c.n421 == 12) return 1;
@@ -295,9 +375,7 @@ __device__ __forceinline__ int fcna_fast_body(const double *__restrict__ x, cons
         }
     }
     if (ambiguous) return fcna_exact_atom(x, y, z, box, row, NN, cutsq, nb);
-#pragma unroll
-    for (int a = 0; a < NN; ++a) nb[a * CNA_THREADS] = (unsigned short)rows[a];
-    return cna_label(cna_signatures_smem(nb, NN));
+    return cna_label(cna_signatures_regs<NN>(rows, nb));
 }
 
 __global__ void __launch_bounds__(CNA_THREADS) k_fcna_fast(const double *__restrict__ x, const double *__restrict__ y,
