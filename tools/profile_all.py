@@ -56,6 +56,10 @@ def main():
     ds.rdf_counts(rc, 200, type_list=types, ntype=1)
     ds.rdf_counts(rc, 200, type_list=types, ntype=1, streaming=True)
     ds.wcp(types, 1)
+    ds.bond_analysis(rc, 90)
+    ds.adf(np.array([[0.0, rc, 0.0, rc]]), np.array([[0, 0, 0]], np.int32), types, 90)
+    vel = np.random.default_rng(0).standard_normal((3, N))
+    ds.atomic_temperature(vel[0], vel[1], vel[2], np.full(N, 26.98), rc)
     ds.set_atoms_device(x, y, z, box, o, bnd)
     ds.build_neighbor(4.4)                     # >= 14 neighbours: sort + CSP + AJA from the cut-off list
     ds.sort_neighbor(14)
