@@ -426,6 +426,15 @@ __global__ void __launch_bounds__(128) k_adf_hist(const double *__restrict__ x, 
                                                   int npair, const int *__restrict__ types, int nbins,
                                                   unsigned long long *__restrict__ hist)
 {
+    // per-block 32-bit histogram in shared memory when it fits (a few type triplets x <= 8192 / npair bins):
+    // thousands of atoms hammering the same ~100 global 64-bit counters serialise otherwise
+    extern __shared__ unsigned sh_a[];
+    const int nslot = npair * nbins;
+    const bool use_sh = nslot <= 8192;
+    if (use_sh) {
+        for (int t = threadIdx.x; t < nslot; t += blockDim.x) sh_a[t] = 0;
+        __syncthreads();
+    }
     const double PI = 3.14159265358979323846;
     const double dti = 1.0 / delta_theta;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
@@ -461,10 +470,16 @@ __global__ void __launch_bounds__(128) k_adf_hist(const double *__restrict__ x, 
                     int index = static_cast<int>(floor(theta * dti));
                     if (index < 0) index = 0;
                     if (index >= nbins) index = nbins - 1;
-                    atomicAdd(hist + (size_t)m * nbins + index, 1ull);
+                    if (use_sh) atomicAdd(sh_a + m * nbins + index, 1u);
+                    else atomicAdd(hist + (size_t)m * nbins + index, 1ull);
                 }
             }
         }
+    }
+    if (use_sh) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < nslot; t += blockDim.x)
+            if (sh_a[t]) atomicAdd(hist + t, (unsigned long long)sh_a[t]);
     }
 }
 
@@ -569,7 +584,8 @@ void launch_adf_hist(MdbSystem &s, const int *verlet, const double *dist, const 
     CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * (size_t)npair * nbins, s.stream));
     int nb = (N + 127) / 128;
     if (nb > 148 * 16) nb = 148 * 16;
-    MDB_LAUNCH(k_adf_hist, nb, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, dist, nn, M, delta_theta, rcs, pairs,
+    const size_t smem = (size_t)npair * nbins <= 8192 ? sizeof(unsigned) * (size_t)npair * nbins : 0;
+    MDB_LAUNCH(k_adf_hist, nb, 128, smem, s.stream, s.x, s.y, s.z, N, s.box, verlet, dist, nn, M, delta_theta, rcs, pairs,
                npair, types, nbins, hist);
     CUDA_TRY(cudaGetLastError());
 }
