@@ -130,6 +130,10 @@ int mdb_rdf_streaming(const double *x, const double *y, const double *z, int N, 
                       const double *box9, const double *origin3, const int *boundary3, double *g, int ntype,
                       double rc, int nbin, int num_t);
 
+/* _neighbor.wrap_positions(x, y, z (in place), box, origin, boundary, num_t) -- src/neighbor.cpp:675 */
+int mdb_wrap_positions(double *x, double *y, double *z, int N, const double *box9, const double *origin3,
+                       const int *boundary3, int num_t);
+
 /* ---- further neighbour-list consumers ---- */
 /* _cnp.compute_cnp(x,y,z,box,origin,boundary,verlet_list,distance_list,neighbor_number,cnp,rc,num_t)
  * -- src/common_neighbor_parameter.cpp:10 */

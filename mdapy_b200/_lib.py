@@ -55,6 +55,7 @@ PROTOTYPES = {
     "mdb_rdf": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, c_ip, c_dp, C.c_int, C.c_double, C.c_int]),
     "mdb_rdf_single_species": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_double, C.c_int]),
     "mdb_rdf_streaming": (C.c_int, _XYZN + [c_ip] + _BOX + [c_dp, C.c_int, C.c_double, C.c_int, C.c_int]),
+    "mdb_wrap_positions": (C.c_int, [c_dp, c_dp, c_dp, C.c_int] + _BOX + [C.c_int]),
     "mdb_compute_cnp": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, c_ip, c_dp, C.c_double, C.c_int]),
     "mdb_get_wcp": (C.c_int, [c_ip, C.c_int, C.c_int, c_ip, c_ip, C.c_int, c_dp, C.c_int]),
     "mdb_average_by_neighbor": (C.c_int, [C.c_double, c_ip, C.c_int, C.c_int, c_dp, c_ip, c_dp, c_dp, C.c_int, C.c_int]),

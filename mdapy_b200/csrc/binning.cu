@@ -235,6 +235,25 @@ __global__ void __launch_bounds__(256) k_translate_ids(const int *__restrict__ i
 
 }  // namespace
 
+// wrap_positions, src/neighbor.cpp:675-702: every atom wrapped into the primary cell (box.h:131-176)
+__global__ void __launch_bounds__(256) k_wrap_positions(double *__restrict__ x, double *__restrict__ y,
+                                                        double *__restrict__ z, int N, DBox box)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double xi = x[i], yi = y[i], zi = z[i];
+    wrap_into_box(box, xi, yi, zi);
+    x[i] = xi;
+    y[i] = yi;
+    z[i] = zi;
+}
+
+void launch_wrap_positions(MdbSystem &s, double *x, double *y, double *z, int N)
+{
+    MDB_LAUNCH(k_wrap_positions, (N + 255) / 256, 256, 0, s.stream, x, y, z, N, s.box);
+    CUDA_TRY(cudaGetLastError());
+}
+
 // in -> out exclusive prefix sum over n ints on the system's stream (scratch: s.scan_tmp)
 void device_exclusive_scan(MdbSystem &s, const int *in, int *out, int n)
 {

@@ -1276,6 +1276,22 @@ int mdb_compute_adf(const double *x, const double *y, const double *z, int N, co
     API_END
 }
 
+int mdb_wrap_positions(double *x, double *y, double *z, int N, const double *box9, const double *origin3,
+                       const int *boundary3, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    double *dx = s->bx.as<double>(), *dy = s->by.as<double>(), *dz = s->bz.as<double>();
+    launch_wrap_positions(*s, dx, dy, dz, N);
+    d2h(*s, x, dx, (size_t)N);
+    d2h(*s, y, dy, (size_t)N);
+    d2h(*s, z, dz, (size_t)N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 int mdb_compute_aja(const double *x, const double *y, const double *z, int N, const double *box9,
                     const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
                     int Md, int *aja, int /*num_t*/)

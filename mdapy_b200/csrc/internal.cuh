@@ -189,6 +189,7 @@ void launch_bond_hist(MdbSystem &s, const int *verlet, const double *dist, const
 void launch_adf_hist(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double delta_theta,
                      const double *rcs, const int *pairs, int npair, const int *types, int nbins,
                      unsigned long long *hist);
+void launch_wrap_positions(MdbSystem &s, double *x, double *y, double *z, int N);
 int ptm_parse_flags(const char *structure);
 void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
                 double *output, int ocols, int *indices, int icols);

@@ -65,6 +65,10 @@ class System:
         self._host_dirty = False                     # user assigned a list on the host side
         self._has_list = False
 
+    def wrap_pos(self) -> None:
+        """system.py:854-856: wrap positions into the box for periodic boundaries (resets the neighbour list)."""
+        self.update_data(tool.wrap_pos(self.data, self.box), reset_neighbor=True)
+
     def write_dump(self, filename: str, timestep: int = 0) -> None:
         from .load_save import write_dump
 

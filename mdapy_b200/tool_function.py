@@ -67,3 +67,11 @@ def average_by_neighbor(average_rc: float, data: Frame, property_name: str, verl
                                             L.iptr(n), L.dptr(value), L.dptr(out), int(bool(include_self)), 1))
     name = output_name if output_name is not None else f"{property_name}_ave"
     return data.with_columns(**{name: out})
+
+
+def wrap_pos(data: Frame, box: Box) -> Frame:
+    """tool_function.py:122-138: wrap positions into the box along the periodic axes (neighbor.cpp:675)."""
+    x, y, z = (np.array(data[c], dtype=np.float64, copy=True) for c in ("x", "y", "z"))
+    b, o, p = L.box_args(box.box, box.origin, box.boundary)
+    L.check(L.lib().mdb_wrap_positions(L.dptr(x), L.dptr(y), L.dptr(z), x.shape[0], L.dptr(b), L.dptr(o), L.iptr(p), 1))
+    return data.with_columns(x=x, y=y, z=z)

@@ -393,3 +393,9 @@ def compute_adf(x, y, z, box, origin, boundary, verlet, dist, nn, rc_list, pair_
                             C.c_double(180.0 / nbin), _d(rcl), _i(pl), C.c_int(pl.shape[0]), _i(t), C.c_int(nbin), _i(out),
                             C.c_int(nt or num_threads()))
     return out
+
+
+def wrap_positions(x, y, z, box, origin, boundary, nt=None):
+    """neighbor.cpp:675 (in place)."""
+    b, o, p = _boxargs(box, origin, boundary)
+    _lib().port_wrap_positions(_d(x), _d(y), _d(z), C.c_int(x.shape[0]), _d(b), _d(o), _i(p), C.c_int(nt or num_threads()))

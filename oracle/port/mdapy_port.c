@@ -1256,3 +1256,13 @@ void port_compute_adf(const double *x, const double *y, const double *z, int N, 
         }
     }
 }
+
+/* ------------------------------------------------------------------ wrap_positions, neighbor.cpp:675-702 */
+void port_wrap_positions(double *x, double *y, double *z, int N, const double *box9, const double *origin3,
+                         const int *boundary3, int num_t)
+{
+    cell_t c;
+    cell_init(&c, box9, origin3, boundary3);
+#pragma omp parallel for num_threads(num_t)
+    for (int i = 0; i < N; ++i) wrap_point(&c, x + i, y + i, z + i);
+}

@@ -65,6 +65,9 @@ void port_compute_adf(const double *x, const double *y, const double *z, int N, 
                       const int *nn, double delta_theta, const double *rcs, const int *pairs, int npair,
                       const int *types, int nbins, int *bang, int num_t);
 
+void port_wrap_positions(double *x, double *y, double *z, int N, const double *box9, const double *origin3,
+                         const int *boundary3, int num_t);
+
 #ifdef __cplusplus
 }
 #endif

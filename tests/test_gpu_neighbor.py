@@ -195,3 +195,26 @@ def test_width_hint_across_frames_of_one_handle():
         v, d, n = ds.fetch_neighbor()
         assert M == rv.shape[1] and np.array_equal(n, rn) and np.array_equal(v, rv)
         assert np.array_equal(d.view(np.int64), rd.view(np.int64))
+
+
+
+def test_wrap_positions_bit_exact():
+    """_neighbor.wrap_positions (neighbor.cpp:675): orthogonal with origin, triclinic, mixed boundaries, far images."""
+    import mdapy_b200 as mp
+    from mdapy_b200 import tool_function as tool
+
+    rng = np.random.default_rng(41)
+    p, b = H.fcc(3.615, 6)
+    far = H.rattle(p, 0.3, 42) + rng.integers(-3, 4, p.shape) * np.diag(b)
+    ps, bs = H.shear(far, b, xy=0.25, xz=-0.1, yz=0.2)
+    for pos, box, origin, bnd in ((far, b, np.array([-3.0, 1.5, 0.25]), [1, 1, 1]), (far, b, np.zeros(3), [1, 0, 1]),
+                                  (ps, bs, np.array([0.5, -2.0, 4.0]), [1, 1, 1]), (ps, bs, np.zeros(3), [0, 1, 1])):
+        x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+        rx, ry, rz = x.copy(), y.copy(), z.copy()
+        K.wrap_positions(rx, ry, rz, box, origin, bnd)
+        out = tool.wrap_pos(mp.Frame({"x": x, "y": y, "z": z}), mp.Box(box, bnd, origin))
+        for got, ref in zip((out["x"], out["y"], out["z"]), (rx, ry, rz)):
+            assert np.array_equal(np.asarray(got).view(np.int64), ref.view(np.int64))
+    system = mp.System(pos=far, box=mp.Box(b))
+    system.wrap_pos()
+    assert float(np.asarray(system.data["x"]).min()) >= 0.0 and float(np.asarray(system.data["x"]).max()) < b[0, 0]

@@ -304,3 +304,18 @@ def test_port_bond_analysis_equals_reference():
     pl = np.array([[0, 1, 0], [1, 1, 1]], np.int32)
     assert np.array_equal(ref.compute_adf(x, y, z, box, o, bnd, v, d, n, rcl, pl, t, 36),
                           port.compute_adf(x, y, z, box, o, bnd, v, d, n, rcl, pl, t, 36))
+
+
+@pytest.mark.skipif(not (ref.available() and port.available()), reason="needs both checkers")
+def test_port_wrap_positions_equals_reference():
+    rng = np.random.default_rng(2)
+    p, b = H.fcc(3.615, 4)
+    far = H.rattle(p, 0.3, 3) + rng.integers(-3, 4, p.shape) * np.diag(b)
+    ps, bs = H.shear(far, b, xy=0.25, xz=-0.1, yz=0.2)
+    for pos, box, origin, bnd in ((far, b, np.array([-3.0, 1.5, 0.25]), [1, 1, 1]), (ps, bs, np.zeros(3), [1, 0, 1])):
+        a = [np.ascontiguousarray(pos[:, k]) for k in range(3)]
+        c = [v.copy() for v in a]
+        ref.wrap_positions(*a, box, origin, bnd)
+        port.wrap_positions(*c, box, origin, bnd)
+        for u, w in zip(a, c):
+            assert np.array_equal(u.view(np.int64), w.view(np.int64))
