@@ -6,7 +6,8 @@ id/type/ix/iy/iz, float64 otherwise, str for element), box conventions (rows = c
 restricted-triclinic ``xy xz yz`` bounds converted like 109-126) and boundary flags (``pp`` = periodic).
 
 Host-side text parsing only: the arrays land in pinned-friendly contiguous NumPy columns that ``System``
-uploads once.  Binary ``.mp`` (parquet), LAMMPS data files and POSCAR are not on the hot path.
+uploads once.  mdapy's binary ``.mp`` (parquet + key-value metadata, 610-650 / 1534-1564) goes through pyarrow.
+LAMMPS data files and POSCAR are not on the hot path.
 """
 from __future__ import annotations
 
@@ -260,6 +261,54 @@ def write_xyz(filename: str, box: Box, data: Frame) -> None:
                              for v in row) + "\n")
 
 
+# --------------------------------------------------------------------------- .mp (parquet)
+def read_mp(filename: str) -> Tuple[Frame, Box, Dict[str, Any]]:
+    """mdapy's native ``.mp`` file: a parquet table whose key-value metadata carries ``box`` (9 numbers),
+    ``origin`` and ``boundary`` as strings (load_save.py:610-650).  Read with pyarrow (polars is not needed)."""
+    import pyarrow.parquet as pq
+
+    table = pq.read_table(filename)
+    meta = {k.decode(): v.decode() for k, v in (table.schema.metadata or {}).items()}
+    cols: Dict[str, np.ndarray] = {}
+    for name in table.column_names:
+        col = table.column(name).combine_chunks()
+        a = col.to_numpy(zero_copy_only=False)
+        if a.dtype.kind in "OUS":
+            a = np.asarray(a, dtype=object)
+        cols[name] = np.ascontiguousarray(a) if a.dtype != object else a
+    if "box" in meta:
+        cell = np.array(meta["box"].split(), float).reshape(3, 3)
+    else:   # no stored cell: bounding box of the atom cloud, zero extents padded (610-637)
+        ext = np.array([cols[c].max() - cols[c].min() for c in ("x", "y", "z")], float)
+        cell = np.diag(np.where(ext > 0, ext, 1e-9))
+    origin = np.array(meta["origin"].split(), float) if "origin" in meta else None
+    boundary = np.array(meta["boundary"].split(), np.int32) if "boundary" in meta else None
+    info = {k: v for k, v in meta.items() if k not in ("box", "origin", "boundary") and not k.startswith("ARROW")
+            and k != "pandas"}
+    return Frame(cols), Box(cell, boundary, origin), info
+
+
+def write_mp(filename: str, box: Box, data: Frame, global_info: Optional[Dict[str, Any]] = None) -> None:
+    """Write ``.mp`` (load_save.py:1534-1564): parquet + box / origin / boundary (+ energy, stress, virial,
+    timestep) in the key-value metadata."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    arrays, names = [], []
+    for c in data.columns:
+        a = np.asarray(data[c])
+        arrays.append(pa.array(a.tolist() if a.dtype == object else a))
+        names.append(c)
+    meta = {"box": " ".join(np.asarray(box.box, float).astype(str).flatten().tolist()),
+            "origin": " ".join(np.asarray(box.origin, float).astype(str).tolist()),
+            "boundary": " ".join(np.asarray(box.boundary).astype(str).tolist())}
+    for k, v in (global_info or {}).items():
+        if k in ("energy", "stress", "virial", "timestep"):
+            meta[str(k)] = str(v)
+    table = pa.Table.from_arrays(arrays, names=names).replace_schema_metadata(meta)
+    pq.write_table(table, filename)
+
+
 def from_file(filename: str) -> Tuple[Frame, Box, Dict[str, Any]]:
     """Dispatch on the extension like BuildSystem.from_file (load_save.py:358-411)."""
     name = str(filename)
@@ -269,6 +318,8 @@ def from_file(filename: str) -> Tuple[Frame, Box, Dict[str, Any]]:
         return read_dump(name)
     if ext == "xyz":
         return read_xyz(name)
+    if ext == "mp":
+        return read_mp(name)
     raise NotImplementedError(
-        f"{filename}: only LAMMPS dump (.dump) and XYZ (.xyz), optionally .gz, are read here; "
+        f"{filename}: LAMMPS dump (.dump), XYZ (.xyz) -- optionally .gz -- and mdapy's .mp (parquet) are read here; "
         "other formats are outside the hot path (SURVEY.md 2.2)")

@@ -79,6 +79,17 @@ class System:
 
         write_xyz(filename, self.box, self.data)
 
+    def write_mp(self, filename: str) -> None:
+        from .load_save import write_mp
+
+        write_mp(filename, self.box, self.data, self.global_info)
+
+    def replicate(self, nx: int, ny: int, nz: int) -> None:
+        """system.py:858-890: replace the frame by its nx x ny x nz supercell (resets the neighbour list)."""
+        data, box = tool.replicate(self.data, self.box, nx, ny, nz)
+        self._box = box
+        self.update_data(data, reset_neighbor=True)
+
     # ------------------------------------------------------------------ data / box
     @property
     def data(self) -> Frame:

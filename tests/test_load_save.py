@@ -106,3 +106,27 @@ def test_classical_xyz_and_errors(tmp_path):
         LS.parse_dump_frame(["ITEM: TIMESTEP\n", "0\n"], "short")
     with pytest.raises(NotImplementedError):
         LS.from_file(str(tmp_path / "x.poscar"))
+
+
+def test_mp_roundtrip_and_system_helpers(tmp_path):
+    pytest.importorskip("pyarrow")
+    rng = np.random.default_rng(3)
+    pos = rng.random((40, 3)) * 7.0
+    box = mp.Box(np.array([[7.0, 0, 0], [0.5, 7.0, 0], [0, 0, 8.0]]), [1, 1, 0], [0.5, -1.0, 2.0])
+    frame = mp.Frame({"id": np.arange(1, 41, dtype=np.int32), "type": (np.arange(40) % 3 + 1).astype(np.int32),
+                      "x": pos[:, 0], "y": pos[:, 1], "z": pos[:, 2], "element": np.array(["Fe", "Ni"] * 20, dtype=object)})
+    p = tmp_path / "model.mp"
+    LS.write_mp(str(p), box, frame, {"timestep": 7, "ignored": "x"})
+    d, b, info = LS.read_mp(str(p))
+    assert info == {"timestep": "7"}
+    for c in ("x", "y", "z"):
+        assert np.array_equal(np.asarray(d[c]), np.asarray(frame[c]))
+    assert np.asarray(d["type"]).dtype == np.int32 and list(d["element"]) == list(frame["element"])
+    assert np.array_equal(b.box, box.box) and np.array_equal(b.origin, box.origin) and list(b.boundary) == [1, 1, 0]
+    system = mp.System(str(p))
+    assert system.N == 40 and system.global_info == {"timestep": "7"}
+    system.replicate(2, 1, 3)
+    assert system.N == 240 and np.allclose(system.box.box, box.box * np.array([2, 1, 3]).reshape(3, 1))
+    # the replicas are the original shifted by whole cell vectors (repeat_cell.cpp:41-59)
+    x = np.asarray(system.data["x"])
+    assert np.array_equal(x[:40], pos[:, 0])
