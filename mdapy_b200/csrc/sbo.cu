@@ -63,6 +63,31 @@ __device__ __forceinline__ double assoc_legendre(int l, int m, double x)
     return p;
 }
 
+// Two independent P_l^m chains in one loop (same l, m; arguments xa, xb): the serial FP64 recurrence of one
+// neighbour leaves the pipe mostly idle, two interleaved chains hide each other's latency.  Every value is
+// computed by exactly the operations of assoc_legendre().
+__device__ __forceinline__ void assoc_legendre2(int l, int m, double xa, double xb, double &pa_out, double &pb_out)
+{
+    double pa = 1.0, pa1 = 0.0, pa2 = 0.0, pb = 1.0, pb1 = 0.0, pb2 = 0.0;
+    if (m != 0) {
+        const double sa = sqrt(1.0 - xa * xa), sb = sqrt(1.0 - xb * xb);
+        for (int i = 1; i < m + 1; ++i) {
+            pa *= (2 * i - 1) * sa;
+            pb *= (2 * i - 1) * sb;
+        }
+    }
+    for (int i = m + 1; i < l + 1; ++i) {
+        pa2 = pa1;
+        pa1 = pa;
+        pb2 = pb1;
+        pb1 = pb;
+        pa = div_small((2 * i - 1) * xa * pa1 - (i + m - 1) * pa2, i - m);
+        pb = div_small((2 * i - 1) * xb * pb1 - (i + m - 1) * pb2, i - m);
+    }
+    pa_out = pa;
+    pb_out = pb;
+}
+
 // Accumulators: MODE 1 = per-thread local arrays (dense [il][m] indexing), MODE 2 = shared memory, compact slots
 // interleaved per thread (acc[slot * blockDim + tid]: conflict-free, no local-memory traffic), MODE 0 = in place
 // in global memory (very high degrees).  The operation order per accumulator is the same in all three.
@@ -101,50 +126,91 @@ __global__ void __launch_bounds__(128) k_qlm(const double *__restrict__ x, const
     int cnt = nn[i];
     if (!P.use_voronoi && P.nnn > 0) cnt = P.nnn;
     double wsum = 0.0;
-    for (int jj = 0; jj < cnt; ++jj) {
-        const size_t at = (size_t)i * M + jj;
-        const int j = verlet[at];
-        if (j < 0) continue;
-        double dx = x[j] - x1, dy = y[j] - y1, dz = z[j] - z1;
-        min_image(box, dx, dy, dz);
-        const double rmag = dist[at];
-        if (!((rmag > EPS) && (rmag <= P.rc))) continue;
-        const double w = P.use_weight ? weight[at] : 1.0;
-        wsum += w;
-        const double rinv = 1.0 / rmag;
-        const double ct = dz * rinv;
-        double er = dx, ei = dy;
-        const double rxy2 = er * er + ei * ei;
-        if (rxy2 < EPS * EPS) {
-            er = 1.0;
-            ei = 0.0;
-        } else {
-            const double inv = 1.0 / sqrt(rxy2);
-            er *= inv;
-            ei *= inv;
+    // Neighbours are taken two at a time (A, then B): their Legendre chains run interleaved, and every
+    // accumulator still receives A's term before B's, i.e. the reference's neighbour order.
+    struct Prepared {
+        double w, ct, er, ei;
+    };
+    int jj = 0;
+    auto next_valid = [&](Prepared &nb) -> bool {
+        for (; jj < cnt; ++jj) {
+            const size_t at = (size_t)i * M + jj;
+            const int j = verlet[at];
+            if (j < 0) continue;
+            double dx = x[j] - x1, dy = y[j] - y1, dz = z[j] - z1;
+            min_image(box, dx, dy, dz);
+            const double rmag = dist[at];
+            if (!((rmag > EPS) && (rmag <= P.rc))) continue;
+            nb.w = P.use_weight ? weight[at] : 1.0;
+            const double rinv = 1.0 / rmag;
+            nb.ct = dz * rinv;
+            double er = dx, ei = dy;
+            const double rxy2 = er * er + ei * ei;
+            if (rxy2 < EPS * EPS) {
+                er = 1.0;
+                ei = 0.0;
+            } else {
+                const double inv = 1.0 / sqrt(rxy2);
+                er *= inv;
+                ei *= inv;
+            }
+            nb.er = er;
+            nb.ei = ei;
+            ++jj;
+            return true;
         }
+        return false;
+    };
+    for (;;) {
+        Prepared A, B;
+        if (!next_valid(A)) break;
+        const bool hasB = next_valid(B);
+        if (!hasB) B = Prepared{0.0, 0.0, 1.0, 0.0};
+        wsum += A.w;
+        if (hasB) wsum += B.w;
         for (int il = 0; il < P.ndeg; ++il) {
             const int l = P.l[il];
             double *Rl = R + (MODE == 2 ? P.off[il] * es : il * P.nz), *Il = I + (MODE == 2 ? P.off[il] * es : il * P.nz);
-            Rl[l * es] += w * (c_norm[il][0] * assoc_legendre(l, 0, ct));
-            double pr = er, pi = ei;
+            double pa, pb;
+            assoc_legendre2(l, 0, A.ct, B.ct, pa, pb);
+            Rl[l * es] += A.w * (c_norm[il][0] * pa);
+            if (hasB) Rl[l * es] += B.w * (c_norm[il][0] * pb);
+            double pra = A.er, pia = A.ei, prb = B.er, pib = B.ei;
             for (int m = 1; m < l + 1; ++m) {
-                const double pf = c_norm[il][m] * assoc_legendre(l, m, ct);
-                const double cr = pf * pr, ci = pf * pi;
-                const double wr = w * cr, wi = w * ci;
-                Rl[(l + m) * es] += wr;
-                Il[(l + m) * es] += wi;
-                if (m & 1) {
-                    Rl[(l - m) * es] -= wr;
-                    Il[(l - m) * es] += wi;
-                } else {
-                    Rl[(l - m) * es] += wr;
-                    Il[(l - m) * es] -= wi;
+                assoc_legendre2(l, m, A.ct, B.ct, pa, pb);
+                const double pfa = c_norm[il][m] * pa, pfb = c_norm[il][m] * pb;
+                const double wra = A.w * (pfa * pra), wia = A.w * (pfa * pia);
+                const double wrb = B.w * (pfb * prb), wib = B.w * (pfb * pib);
+                const bool sgn_is_odd = (m & 1) != 0;
+                // slot l + m
+                Rl[(l + m) * es] += wra;
+                Il[(l + m) * es] += wia;
+                if (hasB) {
+                    Rl[(l + m) * es] += wrb;
+                    Il[(l + m) * es] += wib;
                 }
-                const double tr = pr * er - pi * ei;
-                const double ti = pr * ei + pi * er;
-                pr = tr;
-                pi = ti;
+                // slot l - m: (-1)^m conj
+                if (sgn_is_odd) {
+                    Rl[(l - m) * es] -= wra;
+                    Il[(l - m) * es] += wia;
+                    if (hasB) {
+                        Rl[(l - m) * es] -= wrb;
+                        Il[(l - m) * es] += wib;
+                    }
+                } else {
+                    Rl[(l - m) * es] += wra;
+                    Il[(l - m) * es] -= wia;
+                    if (hasB) {
+                        Rl[(l - m) * es] += wrb;
+                        Il[(l - m) * es] -= wib;
+                    }
+                }
+                const double tra = pra * A.er - pia * A.ei, tia = pra * A.ei + pia * A.er;
+                const double trb = prb * B.er - pib * B.ei, tib = prb * B.ei + pib * B.er;
+                pra = tra;
+                pia = tia;
+                prb = trb;
+                pib = tib;
             }
         }
     }
