@@ -10,7 +10,9 @@ configs[4], FCC Al a=4.05, n^3*4 atoms (n=292 -> 99,588,352), rc = 0.8536*a, gen
 exactly like the reference's build_crystal.  `value` is device-resident
 throughput (inputs already in HBM), `e2e` goes through the public API (`System(...)` +
 `cal_common_neighbor_analysis`) from pinned HOST arrays with the label read-back inside
-the timed region.  N > 1: the frame is split into x-slabs of the global cell grid, one rank
+the timed region (the labels leave in chunks on a copy stream while the next chunk is classified;
+`e2e.two_host_threads` is extra information: the same call from two host threads, not the headline).
+N > 1: the frame is split into x-slabs of the global cell grid, one rank
 per GPU, ghost cell planes exchanged over NCCL (mdapy_b200/distributed.py), strong scaling.
 Prints ONE JSON line on rank 0.
 """
