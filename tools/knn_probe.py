@@ -1,5 +1,8 @@
+"""k-nearest build time vs the cell-width factor (MDB_KNN_CELL) on rattled BCC / FCC frames."""
 import sys, os, time
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tools")
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tools"))
 import numpy as np, torch
 from profile_all import lattice, FCC, BCC
 from mdapy_b200.device import DeviceSystem

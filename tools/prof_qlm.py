@@ -1,5 +1,8 @@
+"""One Steinhardt q4,q6 call on a 2 M-atom thermal FCC frame, meant to run under ncu (kernel filter k_qlm)."""
 import sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tools")
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tools"))
 import numpy as np, torch
 from profile_all import lattice, FCC
 from mdapy_b200.device import DeviceSystem
