@@ -130,3 +130,24 @@ def test_mp_roundtrip_and_system_helpers(tmp_path):
     # the replicas are the original shifted by whole cell vectors (repeat_cell.cpp:41-59)
     x = np.asarray(system.data["x"])
     assert np.array_equal(x[:40], pos[:, 0])
+
+
+def test_dump_general_triclinic_and_unwrapped(tmp_path):
+    """'abc origin' bounds (general triclinic) round-trip through the writer; xu/yu/zu are promoted to x/y/z
+    when no wrapped coordinates are present (load_save.py:96-106, 186-197)."""
+    rng = np.random.default_rng(5)
+    cell = np.array([[8.0, 0.3, -0.2], [1.0, 7.5, 0.4], [0.2, -0.6, 9.0]])
+    box = mp.Box(cell, [1, 1, 1], [1.0, 2.0, 3.0])
+    pos = rng.random((10, 3)) @ cell + np.array([1.0, 2.0, 3.0])
+    frame = mp.Frame({"id": np.arange(1, 11, dtype=np.int32), "x": pos[:, 0], "y": pos[:, 1], "z": pos[:, 2]})
+    p = tmp_path / "g.dump"
+    LS.write_dump(str(p), box, frame, timestep=3)
+    assert "abc origin" in p.read_text().splitlines()[4]
+    d, b, info = LS.read_dump(str(p))
+    assert info["timestep"] == 3 and np.array_equal(b.box, cell) and np.array_equal(b.origin, [1.0, 2.0, 3.0])
+    assert np.array_equal(np.asarray(d["y"]), pos[:, 1])
+    q = tmp_path / "u.dump"
+    q.write_text("ITEM: TIMESTEP\n0\nITEM: NUMBER OF ATOMS\n2\nITEM: BOX BOUNDS pp pp pp\n0 5\n0 5\n0 5\n"
+                 "ITEM: ATOMS id xu yu zu\n1 6.5 -1.0 2.0\n2 1.0 1.0 1.0\n")
+    d, b, _ = LS.read_dump(str(q))
+    assert d.columns == ["id", "x", "y", "z"] and np.asarray(d["x"])[0] == 6.5
