@@ -48,6 +48,9 @@ struct TileArgs {
     int tile_stride, tile_offset, n_tiles;  // sampling of the tile list (count-only estimate)
     int count_only;
     int use_tma;
+    int tiles_x;     // tiles along x (warp-per-cell kernel: strip order of the tile list)
+    int ocap;        // owned-atom capacity of the per-tile wrapped-position table
+    int ltot;        // pooled capacity of the per-cell candidate lists (entries)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -567,6 +570,708 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
     if (lane == 0 && local_min != INT_MAX) atomicMin(A.min_count, local_min);
 }
 
+
+// =====================================================================================================
+// Warp-per-cell kernel (round 2).  Same tile staging as above; the search itself is split into stages
+// that each run with (nearly) all lanes busy:
+//
+//   lists    a pre-pass (one THREAD per owned cell / per (cell, pencil), overlapped with the TMA copies)
+//            writes every owned cell's candidate list -- the 27-cell stencil = 9 pencils x one contiguous
+//            3-cell run walked backwards, i.e. the reference's order -- as staged indices into shared
+//            memory, padded to whole rounds of 32 with a sentinel whose fp32 record can never pass;
+//   stage 1  a WARP takes one owned cell at a time.  Its lanes hold the cell's ~67 candidates in registers
+//            (up to four rounds of 32).  Every atom of the cell is broadcast to the lanes (one uniform
+//            LDS.128 of its pre-computed constants): three FFMA + one compare per round, one ballot per
+//            round.  The ballot masks ARE the survivors in reference order; lane 0 parks them in shared
+//            memory (one STS.128 per atom);
+//   stage 2  one THREAD per atom: clears its own bit, counts (popc), writes neighbor_number, pads the row
+//            tail, and -- after a warp scan of the counts -- expands its masks into a flat per-warp ring
+//            of (candidate | owner | row slot) words, atom-major;
+//   stage 3  the ring is consumed 32 survivors at a time, one per LANE: exact f64 test of the reference
+//            (xi wrapped, x[j] raw, left-to-right sum, <= rc^2), sqrt, and the rows leave as contiguous
+//            4-byte / 8-byte segments.
+//   The row slot is optimistic (pre-filter rank).  A survivor the exact test rejects (d^2 inside the 4e-4
+//   guard band above rc^2: ~1e-3 of the atoms of a hot crystal, none of a cold one) marks its atom, and
+//   marked atoms are redone by the exact per-thread walk after the tile (direct_atom).  Cells with more
+//   than 128 candidates (dense frames) loop over their list in shared memory and feed the ring directly.
+// Row order, distances and counts are bit-identical to k_neighbor_tiled / k_neighbor_direct / the reference.
+struct __align__(32) OwnAtom {
+    double x, y, z;  // wrapped position (box.h:131-176), what the reference uses as atom i
+    int idx;         // original index (row)
+    int flags;       // bit 0: outside the box -> the minimum-image step is needed; bit 1: finished in stage 1
+};
+struct __align__(16) CellRec {
+    int s0n;   // first staged index | atoms << 16
+    int t0;    // ordinal of the first atom among the tile's owned atoms
+    int loff;  // offset of the candidate list (entries)
+    int misc;  // rounds (list length / 32) | position of atom 0 in the list << 8 | list overflow << 31
+};
+
+constexpr int CELL_RCAP = 512;   // survivor ring per warp (entries, power of two)
+
+__device__ __forceinline__ unsigned lds_u32(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned addr, unsigned v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ bool pre_pass(const float4 &me, const float4 &c)
+{   // |rj|^2 - 2 ri.rj <= rc^2 (1 + guard) - |ri|^2 with me = (-2 xi, -2 yi, -2 zi, threshold)
+    return __fmaf_rn(me.x, c.x, __fmaf_rn(me.y, c.y, __fmaf_rn(me.z, c.z, c.w))) <= me.w;
+}
+
+template <int T, int TZ, int NT, bool COUNT_ONLY>
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const __grid_constant__ TileArgs A)
+{
+    constexpr int P = T + 2;
+    constexpr int PZ = TZ + 2;
+    constexpr int NPEN = P * P;
+    constexpr int NCELL = NPEN * PZ;
+    constexpr int CSW = PZ + 1;
+    constexpr int NW = NT / 32;
+    constexpr int NOWN = T * T * TZ;            // owned cells of a full tile
+    constexpr int CPW = (NOWN + NW - 1) / NW;   // cells per warp (contiguous: a warp walks along z)
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    // every array is addressed as smem + offset (no pointer -> integer -> pointer round trip, so the compiler
+    // keeps all accesses in the shared window: LDS / STS instead of generic loads)
+    const unsigned o_f4 = (unsigned)A.cap * 32u;                       // [cap + 2], f4[cap] = sentinel
+    const unsigned o_own = o_f4 + ((unsigned)A.cap + 2u) * 16u;        // [ocap] 32 B
+    const unsigned o_pm = o_own + (unsigned)A.ocap * 32u;              // [ocap] 16 B: pre-filter constants, then ballot masks
+    const unsigned o_ring = o_pm + (unsigned)A.ocap * 16u;             // [NW][CELL_RCAP] u32
+    const unsigned o_crec = o_ring + NW * CELL_RCAP * 4u;              // [NOWN] 16 B
+    const unsigned o_bar = o_crec + NOWN * 16u;                        // mbarrier (8 B, 16-byte slot)
+    const unsigned o_cs = o_bar + 16u;                                 // [NPEN][CSW] int
+    const unsigned o_gstart = o_cs + NPEN * CSW * 4u;                  // [NCELL]
+    const unsigned o_ptot = o_gstart + NCELL * 4u;                     // [NPEN + 1]
+    const unsigned o_opref = o_ptot + (NPEN + 1) * 4u;                 // [T*T + 1]
+    const unsigned o_cpad = o_opref + (T * T + 1) * 4u;                // [NOWN + 1] padded list lengths -> offsets
+    const unsigned o_flag = o_cpad + (NOWN + 1) * 4u;                  // [4]
+    const unsigned o_pp = o_flag + 16u;                                // [NOWN][10] u16 per-pencil list offsets
+    const unsigned o_tcell = o_pp + NOWN * 20u;                        // [ocap] u16 owned cell of every owned atom
+    const unsigned o_clist = (o_tcell + (unsigned)A.ocap * 2u + 15u) & ~15u;   // [ltot] u16 candidate lists
+    const unsigned o_redo = o_clist + (unsigned)A.ltot * 2u;           // [ocap] u8
+    SortedAtom *raw = reinterpret_cast<SortedAtom *>(smem);
+    float4 *f4 = reinterpret_cast<float4 *>(smem + o_f4);
+    OwnAtom *own = reinterpret_cast<OwnAtom *>(smem + o_own);
+    float4 *pm = reinterpret_cast<float4 *>(smem + o_pm);
+    unsigned *ring = reinterpret_cast<unsigned *>(smem + o_ring);
+    CellRec *crec = reinterpret_cast<CellRec *>(smem + o_crec);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + o_bar);
+    int *cs = reinterpret_cast<int *>(smem + o_cs);
+    int *gstart = reinterpret_cast<int *>(smem + o_gstart);
+    int *ptot = reinterpret_cast<int *>(smem + o_ptot);
+    int *opref = reinterpret_cast<int *>(smem + o_opref);
+    int *cpad = reinterpret_cast<int *>(smem + o_cpad);
+    int *far_flag = reinterpret_cast<int *>(smem + o_flag);   // [0] beyond the fp32 radius, [1] periodic shift used, [2] atoms to redo
+    unsigned short *pp = reinterpret_cast<unsigned short *>(smem + o_pp);
+    unsigned short *tcell = reinterpret_cast<unsigned short *>(smem + o_tcell);
+    unsigned short *clist = reinterpret_cast<unsigned short *>(smem + o_clist);
+    unsigned char *redo = smem + o_redo;
+
+    const int tid = threadIdx.x;
+    const CellGrid &g = A.g;
+    int tx, ty, tz;
+    if (A.tile_stride != 1) {   // sampled estimate pass (stride > 1) or a grid too large for 3-D launch (stride 0): linear list of tiles
+        int tl = blockIdx.x * max(A.tile_stride, 1) + A.tile_offset;
+        if (tl >= A.n_tiles) return;
+        tz = tl % A.tiles_z;
+        tl /= A.tiles_z;
+        ty = tl % A.tiles_y;
+        tx = tl / A.tiles_y;
+    } else {
+        // strip order: grid = (tiles_z, 8 rows of tiles in y, strips * tiles_x).  x- and y-neighbouring tiles
+        // run within a few hundred CTAs of each other, so their shared halo planes are still in L2 when
+        // they are staged again
+        tz = blockIdx.x;
+        const int strip = blockIdx.z / A.tiles_x;
+        tx = blockIdx.z - strip * A.tiles_x;
+        ty = strip * 8 + blockIdx.y;
+        if (ty >= A.tiles_y) return;
+    }
+    const int u0x = A.p_lo + tx * T - 1, u0y = ty * T - 1, u0z = tz * TZ - 1;
+    const int amax = min(T, A.p_hi - (u0x + 1)), bmax = min(T, g.n[1] - (u0y + 1)), kmax = min(TZ, g.n[2] - (u0z + 1));
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        far_flag[0] = 0;
+        far_flag[1] = 0;
+        far_flag[2] = 0;
+    }
+
+    // ---- A. population and global start of every cell of the block (z slots in memory order)
+    for (int c = tid; c < NCELL; c += NT) {
+        const int ks = c % PZ, b = (c / PZ) % P, a = c / (PZ * P);
+        const int kk = PZ - 1 - ks;
+        int px;
+        const int ux = u0x + a;
+        if (A.wrap_x) px = (ux >= A.p_lo - 1 && ux <= A.p_hi) ? map_axis(ux, g.n[0]) : -1;
+        else px = (ux >= A.p_lo - 1 && ux <= A.p_hi && ux >= 0 && ux < g.nxl) ? ux : -1;
+        const int py = map_axis(u0y + b, g.n[1]);
+        const int pz = map_axis(u0z + kk, g.n[2]);
+        int beg = -1, cnt = 0;
+        if (px >= 0 && py >= 0 && pz >= 0) {
+            const int cell = (px * g.n[1] + py) * g.n[2] + (g.n[2] - 1 - pz);
+            beg = __ldg(A.cell_start + cell);
+            cnt = __ldg(A.cell_start + cell + 1) - beg;
+        }
+        gstart[c] = beg;
+        cs[(a * P + b) * CSW + ks + 1] = cnt;
+    }
+    __syncthreads();
+    for (int p = tid; p < NPEN; p += NT) {
+        int s = 0;
+        for (int kk = 0; kk < PZ; ++kk) s += cs[p * CSW + kk + 1];
+        ptot[p] = s;
+    }
+    __syncthreads();
+    warp0_exclusive_scan(ptot, NPEN);
+    __syncthreads();
+    for (int p = tid; p < NPEN; p += NT) {
+        int off = ptot[p];
+        cs[p * CSW] = off;
+        for (int kk = 0; kk < PZ; ++kk) {
+            off += cs[p * CSW + kk + 1];
+            cs[p * CSW + kk + 1] = off;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < T * T; i += NT) {
+        const int a = i / T + 1, b = i % T + 1;
+        const int p = a * P + b;
+        opref[i] = (a <= amax && b <= bmax) ? cs[p * CSW + PZ - 1] - cs[p * CSW + PZ - 1 - kmax] : 0;
+    }
+    __syncthreads();
+    warp0_exclusive_scan(opref, T * T);
+    __syncthreads();
+    const int n_staged = ptot[NPEN];
+    const int n_owned = opref[T * T];
+    if (n_owned == 0) return;
+    const bool fits = n_staged <= A.cap && n_owned <= A.ocap;
+
+    const DBox &box = A.box;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (fits) {
+        // ---- B. stage the records: one bulk copy per run of consecutive global cells of a pencil
+        if (A.use_tma) {
+            if (tid == 0) mbar_expect_tx(bar, (unsigned)n_staged * (unsigned)sizeof(SortedAtom));
+            __syncthreads();
+            for (int p = tid; p < NPEN; p += NT) {
+                int kk = 0;
+                while (kk < PZ) {
+                    const int beg = gstart[p * PZ + kk];
+                    const int dst0 = cs[p * CSW + kk];
+                    int total = cs[p * CSW + kk + 1] - dst0;
+                    int k2 = kk + 1;
+                    if (beg >= 0) {
+                        while (k2 < PZ && gstart[p * PZ + k2] == beg + total) {
+                            total += cs[p * CSW + k2 + 1] - cs[p * CSW + k2];
+                            ++k2;
+                        }
+                        if (total > 0)
+                            bulk_g2s(raw + dst0, A.sorted + beg, (unsigned)total * (unsigned)sizeof(SortedAtom), bar);
+                    }
+                    kk = k2;
+                }
+            }
+        } else {
+            for (int c = warp; c < NCELL; c += NW) {
+                const int beg = gstart[c];
+                if (beg < 0) continue;
+                const int p = c / PZ, kk = c % PZ;
+                const int dst0 = cs[p * CSW + kk];
+                const int chunks = (cs[p * CSW + kk + 1] - dst0) * 2;
+                const double2 *src = reinterpret_cast<const double2 *>(A.sorted + beg);
+                double2 *dst = reinterpret_cast<double2 *>(raw + dst0);
+                for (int t = lane; t < chunks; t += 32) dst[t] = __ldg(src + t);
+            }
+        }
+
+        // ---- lists, part 1 (needs only the offset tables: runs while the copies fly): one thread per
+        // owned cell -- atoms, candidates per pencil, padded list length
+        for (int t = tid; t < n_owned; t += NT) redo[t] = 0;
+        if (tid == 0) f4[A.cap] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));  // the sentinel never passes
+        {   // the whole list pool starts as sentinels: lists are padded to whole rounds for free
+            const unsigned sv = (unsigned)A.cap | ((unsigned)A.cap << 16);
+            uint4 *pool = reinterpret_cast<uint4 *>(clist);
+            for (int i = tid; i < A.ltot / 8; i += NT) pool[i] = make_uint4(sv, sv, sv, sv);
+        }
+        for (int c = tid; c < NOWN; c += NT) {
+            const int pi = c / TZ, kz = c % TZ;
+            const int a = pi / T + 1, b = pi % T + 1;
+            CellRec r;
+            r.s0n = 0;
+            r.t0 = 0;
+            r.loff = 0;
+            r.misc = 0;
+            int padded = 0;
+            if (a <= amax && b <= bmax && kz < kmax) {
+                const int p = a * P + b, ks = PZ - 1 - kmax + kz;
+                const int s0 = cs[p * CSW + ks], n_i = cs[p * CSW + ks + 1] - s0;
+                if (n_i > 0) {
+                    const int t0 = opref[pi] + s0 - cs[p * CSW + PZ - 1 - kmax];
+                    int C = 0, selfpos = 0;
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int *row = cs + (p + (q / 3 - 1) * P + (q % 3 - 1)) * CSW + ks;
+                        pp[c * 10 + q] = (unsigned short)min(C, 65535);
+                        if (q == 4) selfpos = C + row[2] - 1 - s0;   // list position of the cell's first atom
+                        C += row[2] - row[-1];
+                    }
+                    pp[c * 10 + 9] = (unsigned short)min(C, 65535);
+                    padded = (C + 31) & ~31;
+                    if (padded == 0) padded = 32;
+                    const int ovf = padded > 1024 ? 1 : 0;   // rounds field: 5 bits; such a cell is redone exactly
+                    if (ovf) padded = 0;
+                    r.s0n = s0 | (n_i << 16);
+                    r.t0 = t0;
+                    r.misc = (padded >> 5) | (selfpos << 8) | (ovf << 31);
+                    for (int ii = 0; ii < n_i; ++ii) tcell[t0 + ii] = (unsigned short)c;
+                }
+            }
+            crec[c] = r;
+            cpad[c] = padded;
+        }
+        __syncthreads();
+        warp0_exclusive_scan(cpad, NOWN);
+        __syncthreads();
+        // ---- lists, part 2: one thread per (owned cell, pencil)
+        for (int it = tid; it < NOWN * 9; it += NT) {
+            const int c = it / 9, q = it - c * 9;
+            const int misc = crec[c].misc;
+            const int rounds = misc & 0xff;
+            if (rounds == 0) continue;
+            const int loff = cpad[c];
+            int over = 0;
+            if (loff + rounds * 32 > A.ltot) over = 1;   // the pooled list space is exhausted: exact walk for this cell
+            if (q == 0) {
+                crec[c].loff = loff;
+                if (over) crec[c].misc = misc | (1 << 31);
+            }
+            if (over) continue;
+            const int pi = c / TZ, kz = c % TZ;
+            const int p = (pi / T + 1) * P + (pi % T + 1), ks = PZ - 1 - kmax + kz;
+            const int *row = cs + (p + (q / 3 - 1) * P + (q % 3 - 1)) * CSW + ks;
+            unsigned short *L = clist + loff + pp[c * 10 + q];
+            const int beg = row[-1], len = row[2] - beg, top = row[2] - 1;
+            for (int o = 0; o < len; ++o) L[o] = (unsigned short)(top - o);
+        }
+        if (A.use_tma) mbar_wait(bar, 0);
+        else __syncthreads();
+
+        // ---- C. fp32 positions relative to the tile centre (nearest periodic image), flat over the staged atoms
+        const double rcw = 1.0 / g.rc_inv;
+        const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0);
+        const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
+                     ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
+        auto rel32 = [&](const double2 lo, const double z, bool &shifted) {
+            double d0 = lo.x - ctr0, d1 = lo.y - ctr1, d2 = z - ctr2;
+            double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+            if (box.pbc[0]) n0 = rint(d0 * box.hinv[0]);
+            if (box.pbc[1]) n1 = rint(d1 * box.hinv[4]);
+            if (box.pbc[2]) n2 = rint(d2 * box.hinv[8]);
+            d0 -= box.h[0] * n0;
+            d1 -= box.h[4] * n1;
+            d2 -= box.h[8] * n2;
+            shifted = (n0 != 0.0) | (n1 != 0.0) | (n2 != 0.0);
+            const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
+            return make_float4(f0, f1, f2, __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0)));
+        };
+        for (int s = tid; s < n_staged; s += NT) {
+            const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
+            const double z = reinterpret_cast<const double *>(raw + s)[2];
+            bool sh;
+            const float4 v = rel32(lo, z, sh);
+            if (sh) far_flag[1] = 1;                    // some staged atom is a periodic image
+            if (!(v.w <= A.w_limit)) far_flag[0] = 1;   // outside the radius the fp32 bound covers (or NaN)
+            f4[s] = v;
+        }
+        // owned atoms: wrapped f64 position (atom i of the reference's loop) and pre-filter constants
+        for (int t = tid; t < n_owned; t += NT) {
+            const int c = tcell[t];
+            const CellRec r = crec[c];
+            const int s = (r.s0n & 0xffff) + (t - r.t0);
+            const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
+            const double2 hi = reinterpret_cast<const double2 *>(raw + s)[1];
+            bool sh;
+            const float4 v = rel32(lo, hi.x, sh);
+            pm[t] = make_float4(-2.0f * v.x, -2.0f * v.y, -2.0f * v.z, A.rcsq_hi - v.w);
+            double xi = lo.x, yi = lo.y, zi = hi.x;
+            int fl = 0;
+            if (box.pbc[0]) { const double d = xi - box.origin[0]; fl |= !(d >= box.wrap_t[0][1] && d < box.wrap_t[0][2]); }
+            if (box.pbc[1]) { const double d = yi - box.origin[1]; fl |= !(d >= box.wrap_t[1][1] && d < box.wrap_t[1][2]); }
+            if (box.pbc[2]) { const double d = zi - box.origin[2]; fl |= !(d >= box.wrap_t[2][1] && d < box.wrap_t[2][2]); }
+            wrap_ortho(box, xi, yi, zi);
+            OwnAtom o;
+            o.x = xi;
+            o.y = yi;
+            o.z = zi;
+            o.idx = __double2loint(hi.y);
+            o.flags = fl;
+            own[t] = o;
+        }
+        __syncthreads();
+    }
+    const bool staged_ok = fits && far_flag[0] == 0;
+    const bool tile_shifted = far_flag[1] != 0;
+
+    int local_max = 0, local_min = INT_MAX;
+    if (!staged_ok) {
+        // overflow tile / atoms beyond the fp32 radius: exact per-thread walk through global memory
+#pragma unroll 1
+        for (int t = tid; t < n_owned; t += NT) {
+            int lo = 0, hi = T * T;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (opref[mid] <= t) lo = mid;
+                else hi = mid;
+            }
+            const int p = (lo / T + 1) * P + (lo % T + 1);
+            const int sg = gstart[p * PZ + PZ - 1 - kmax] + (t - opref[lo]);
+            const int c = direct_atom<COUNT_ONLY>(A, sg);
+            local_max = max(local_max, c);
+            if (c >= 0) local_min = min(local_min, c);
+        }
+    } else {
+        const unsigned raw_base = smem_u32(raw), own_base = smem_u32(own);
+        const unsigned ring_base = smem_u32(ring + warp * CELL_RCAP);
+        const double rcsq = A.rcsq;
+        const double Lx = box.h[0], Ly = box.h[4], Lz = box.h[8];
+        const double iLx = box.hinv[0], iLy = box.hinv[4], iLz = box.hinv[8];
+        const bool px = box.pbc[0] != 0, py = box.pbc[1] != 0, pz = box.pbc[2] != 0;
+        const int M = A.M;
+        const unsigned lt = lanemask_lt();
+        unsigned head = 0, tail = 0;             // ring positions (monotonic)
+        const float4 SENT = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+
+        // ---- stage 3: 32 survivors per call, one per lane
+        auto consume = [&](int nvalid) {
+            const bool valid = lane < nvalid;
+            unsigned e = lds_u32(ring_base + (((head + (unsigned)lane) & (CELL_RCAP - 1)) << 2));
+            if (!valid) e = 0;
+            const unsigned cand = e & 0xfffu, t = (e >> 12) & 0x3ffu, slot = e >> 22;
+            const unsigned ra = raw_base + 32u * cand, oa = own_base + 32u * t;
+            double xj, yj, zj, wj, xi, yi, zi, wi;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj), "=d"(yj) : "r"(ra));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(zj), "=d"(wj) : "r"(ra + 16u));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi), "=d"(yi) : "r"(oa));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(zi), "=d"(wi) : "r"(oa + 16u));
+            const int jdx = __double2loint(wj);
+            const int idx = __double2loint(wi), fl = __double2hiint(wi);
+            double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+            if (tile_shifted || __any_sync(0xffffffffu, valid && (fl & 1))) {
+                if (px) dx = near_image(dx, Lx, iLx);
+                if (py) dy = near_image(dy, Ly, iLy);
+                if (pz) dz = near_image(dz, Lz, iLz);
+            }
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (valid) {
+                if (d2 <= rcsq) {
+                    if ((int)slot < M) {
+                        const size_t off = (size_t)idx * M + slot;
+                        A.verlet[off] = jdx;
+                        A.dist[off] = sqrt(d2);
+                    }
+                } else {
+                    redo[t] = 1;       // the optimistic slots of this atom are wrong: exact walk after the tile
+                    far_flag[2] = 1;
+                }
+            }
+            head += (unsigned)nvalid;
+            __syncwarp();
+        };
+        auto pad_row = [&](int idx, int n) {   // lanes over the free slots of one row
+            int *vrow = A.verlet + (size_t)idx * M;
+            double *drow = A.dist + (size_t)idx * M;
+            for (int u = n + lane; u < M; u += 32) {
+                vrow[u] = -1;
+                drow[u] = A.pad;
+            }
+        };
+
+        // ---- stage 1: ballot masks of every atom, one cell at a time
+        int t_first = -1, t_end = 0;
+#pragma unroll 1
+        for (int ci = 0; ci < CPW; ++ci) {
+            const int c = warp * CPW + ci;
+            if (c >= NOWN) break;
+            const CellRec rec = crec[c];
+            const int n_i = rec.s0n >> 16;
+            if (n_i == 0) continue;
+            const int s0 = rec.s0n & 0xffff, t0 = rec.t0;
+            if (t_first < 0) t_first = t0;
+            t_end = t0 + n_i;
+            if (rec.misc < 0) {   // list overflow: exact walk after the tile; stage 2 skips these atoms
+                for (int ii = lane; ii < n_i; ii += 32) {
+                    redo[t0 + ii] = 1;
+                    own[t0 + ii].flags |= 2;
+                    far_flag[2] = 1;
+                }
+                continue;
+            }
+            const int rounds = rec.misc & 0xff;
+            const int loff = rec.loff;
+            if (rounds <= 4) {
+                // the whole stencil in registers: up to four rounds of 32 candidates in reference order
+                auto cell_masks = [&](auto RT) {
+                    constexpr int R = decltype(RT)::value;
+                    const float4 c0 = f4[clist[loff + lane]];
+                    const float4 c1 = R > 1 ? f4[clist[loff + 32 + lane]] : SENT;
+                    const float4 c2 = R > 2 ? f4[clist[loff + 64 + lane]] : SENT;
+                    const float4 c3 = R > 3 ? f4[clist[loff + 96 + lane]] : SENT;
+#pragma unroll 1
+                    for (int ii = 0; ii < n_i; ++ii) {
+                        const float4 me = pm[t0 + ii];
+                        const unsigned m0 = __ballot_sync(0xffffffffu, pre_pass(me, c0));
+                        const unsigned m1 = R > 1 ? __ballot_sync(0xffffffffu, pre_pass(me, c1)) : 0u;
+                        const unsigned m2 = R > 2 ? __ballot_sync(0xffffffffu, pre_pass(me, c2)) : 0u;
+                        const unsigned m3 = R > 3 ? __ballot_sync(0xffffffffu, pre_pass(me, c3)) : 0u;
+                        if (lane == 0) reinterpret_cast<uint4 *>(pm)[t0 + ii] = make_uint4(m0, m1, m2, m3);
+                    }
+                };
+                if (rounds == 3) cell_masks(std::integral_constant<int, 3>{});
+                else if (rounds == 2) cell_masks(std::integral_constant<int, 2>{});
+                else if (rounds == 4) cell_masks(std::integral_constant<int, 4>{});
+                else cell_masks(std::integral_constant<int, 1>{});
+            } else {
+                // dense cell: any number of rounds, candidates re-read per atom, survivors straight into the ring
+#pragma unroll 1
+                for (int ii = 0; ii < n_i; ++ii) {
+                    const int s_i = s0 + ii, t = t0 + ii;
+                    const int idx = own[t].idx;
+                    __syncwarp();
+                    if (lane == 0) own[t].flags |= 2;
+                    if (idx >= A.n_rows) continue;
+                    const float4 me = pm[t];
+                    const unsigned tb = (unsigned)t << 12;
+                    int n = 0;
+                    bool over = false;
+#pragma unroll 1
+                    for (int r0 = 0; r0 < rounds * 32; r0 += 32) {
+                        const int k = clist[loff + r0 + lane];
+                        const bool qq = (k != s_i) && pre_pass(me, f4[k]);
+                        const unsigned m = __ballot_sync(0xffffffffu, qq);
+                        const unsigned rr = __popc(m & lt);
+                        const unsigned r = (unsigned)n + rr;
+                        const bool room = r < 1024u;
+                        over |= qq && !room;
+                        n += __popc(m);
+                        if (!COUNT_ONLY) {
+                            if (qq && room) sts_u32(ring_base + (((tail + rr) & (CELL_RCAP - 1)) << 2), (unsigned)k | tb | (r << 22));
+                            // entries beyond slot 1023 were not stored: the ring only advances by what was
+                            tail += (unsigned)__popc(__ballot_sync(0xffffffffu, qq && room));
+                            __syncwarp();
+                            while (tail - head >= 32u) consume(32);
+                        }
+                    }
+                    local_max = max(local_max, n);
+                    local_min = min(local_min, n);
+                    if (lane == 0) A.nn[idx] = n;
+                    if (COUNT_ONLY) continue;
+                    if (__any_sync(0xffffffffu, over)) {
+                        if (lane == 0) {
+                            redo[t] = 1;
+                            far_flag[2] = 1;
+                        }
+                    }
+                    if (n < M) pad_row(idx, n);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- stage 2: one thread per atom -- count, neighbor_number, row tail, masks -> ring; stage 3 as it fills
+        if (t_first >= 0) {
+#pragma unroll 1
+            for (int tb0 = t_first; tb0 < t_end; tb0 += 32) {
+                const int t = tb0 + lane;
+                unsigned m[4] = {0u, 0u, 0u, 0u};
+                int idx = 0, loff = 0;
+                bool live = false;
+                if (t < t_end) {
+                    const OwnAtom *o = own + t;
+                    idx = o->idx;
+                    live = idx < A.n_rows && !(o->flags & 2);
+                    if (live) {
+                        const uint4 mm = reinterpret_cast<const uint4 *>(pm)[t];
+                        const CellRec rec = crec[tcell[t]];
+                        loff = rec.loff;
+                        const int sp = ((rec.misc >> 8) & 0x7fffff) - (t - rec.t0);   // my own position in the list
+                        m[0] = mm.x;
+                        m[1] = mm.y;
+                        m[2] = mm.z;
+                        m[3] = mm.w;
+                        const unsigned bit = ~(1u << (sp & 31));
+                        const int w = sp >> 5;
+                        m[0] &= w == 0 ? bit : ~0u;
+                        m[1] &= w == 1 ? bit : ~0u;
+                        m[2] &= w == 2 ? bit : ~0u;
+                        m[3] &= w == 3 ? bit : ~0u;
+                    }
+                }
+                const int n = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+                if (live) {
+                    A.nn[idx] = n;
+                    local_max = max(local_max, n);
+                    local_min = min(local_min, n);
+                }
+                if (COUNT_ONLY) continue;
+                if (live && n < M) {   // row tail (-1 / rc+1)
+                    int *vrow = A.verlet + (size_t)idx * M;
+                    double *drow = A.dist + (size_t)idx * M;
+                    for (int u = n; u < M; ++u) {
+                        vrow[u] = -1;
+                        drow[u] = A.pad;
+                    }
+                }
+                // atoms go to the ring in sub-batches that fit (one batch unless the frame is dense)
+                bool pending = live && n > 0;
+#pragma unroll 1
+                while (__any_sync(0xffffffffu, pending)) {
+                    int incl = pending ? n : 0;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    const int space = CELL_RCAP - (int)(tail - head);
+                    const bool go = pending && incl <= space;
+                    const unsigned gom = __ballot_sync(0xffffffffu, go);
+                    if (gom == 0u) {
+                        // the first pending atom alone exceeds the ring: exact walk after the tile
+                        const unsigned pend = __ballot_sync(0xffffffffu, pending);
+                        if (lane == __ffs(pend) - 1) {
+                            redo[t] = 1;
+                            far_flag[2] = 1;
+                            pending = false;
+                        }
+                        continue;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31 - __clz(gom));
+                    unsigned pos = tail + (unsigned)(incl - n);   // first ring position / row slot of this word
+                    const unsigned tbits = (unsigned)t << 12;
+                    unsigned slot = 0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        unsigned mw = go ? m[w] : 0u;
+                        const int cw = __popc(mw);
+                        const int maxc = __reduce_max_sync(0xffffffffu, cw);
+                        // bits from the top down (one FLO per survivor): the j-th from the top is entry cw-1-j
+                        unsigned pw = pos + (unsigned)cw, sw = slot + (unsigned)cw;
+#pragma unroll 1
+                        for (int j = 0; j < maxc; ++j) {
+                            if (mw) {
+                                const int b = 31 - __clz(mw);
+                                mw ^= 1u << b;
+                                --pw;
+                                --sw;
+                                const unsigned k = clist[loff + w * 32 + b];
+                                sts_u32(ring_base + ((pw & (CELL_RCAP - 1)) << 2), k | tbits | (sw << 22));
+                            }
+                        }
+                        pos += (unsigned)cw;
+                        slot += (unsigned)cw;
+                    }
+                    if (go) pending = false;
+                    tail += (unsigned)total;
+                    __syncwarp();
+                    while (tail - head >= 32u) consume(32);
+                }
+            }
+        }
+        if (!COUNT_ONLY) {
+            while (tail != head) consume(min(32, (int)(tail - head)));
+            __syncthreads();
+            if (far_flag[2]) {   // atoms whose optimistic slots were wrong (or that overflowed): exact walk
+#pragma unroll 1
+                for (int t = tid; t < n_owned; t += NT) {
+                    if (!redo[t]) continue;
+                    int lo = 0, hi = T * T;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (opref[mid] <= t) lo = mid;
+                        else hi = mid;
+                    }
+                    const int p = (lo / T + 1) * P + (lo % T + 1);
+                    const int sg = gstart[p * PZ + PZ - 1 - kmax] + (t - opref[lo]);
+                    direct_atom<false>(A, sg);
+                }
+            }
+        }
+    }
+    if (COUNT_ONLY || !staged_ok) {
+        // estimate pass (pre-filter counts are upper bounds) and overflow tiles; the fill pass takes the
+        // exact extremes from nn[] afterwards (k_nn_minmax)
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, d));
+            local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, d));
+        }
+        if (lane == 0 && local_max > 0) atomicMax(A.max_count, local_max);
+        if (lane == 0 && local_min != INT_MAX) atomicMin(A.min_count, local_min);
+    }
+}
+
+// exact extremes of the counts after a fill pass
+__global__ void __launch_bounds__(256) k_nn_minmax(const int *__restrict__ nn, int n, int *__restrict__ mx, int *__restrict__ mn)
+{
+    int a = 0, b = INT_MAX;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int v = nn[i];
+        a = max(a, v);
+        b = min(b, v);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        a = max(a, __shfl_xor_sync(0xffffffffu, a, d));
+        b = min(b, __shfl_xor_sync(0xffffffffu, b, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(mx, a);
+        atomicMin(mn, b);
+    }
+}
+
+template <int T, int TZ, int NT> size_t cells_smem_bytes(int cap, int ocap, int ltot)
+{
+    constexpr int P = T + 2, PZ = TZ + 2, NPEN = P * P, NCELL = NPEN * PZ, NW = NT / 32, NOWN = T * T * TZ;
+    return (size_t)cap * (sizeof(SortedAtom) + sizeof(float4)) + 2 * sizeof(float4) +
+           (size_t)ocap * (sizeof(OwnAtom) + sizeof(float4) + 2 + 1) + sizeof(unsigned) * NW * CELL_RCAP +
+           sizeof(CellRec) * NOWN + sizeof(unsigned short) * ((size_t)NOWN * 10 + ltot) +
+           sizeof(int) * (NPEN * (PZ + 1) + NCELL + NPEN + 1 + T * T + 1 + NOWN + 1 + 4) + 16 + 16 + 64;
+}
+
+template <int T, int TZ, int NT> void launch_cells_T(const TileArgs &A, int nblocks, cudaStream_t st)
+{
+    const size_t smem = cells_smem_bytes<T, TZ, NT>(A.cap, A.ocap, A.ltot);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_cells<T, TZ, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_cells<T, TZ, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+        configured = true;
+    }
+    dim3 grid(nblocks, 1, 1);
+    if (A.tile_stride == 1) {   // strip order (see the kernel)
+        const int strips = (A.tiles_y + 7) / 8;
+        grid = dim3(A.tiles_z, A.tiles_y < 8 ? A.tiles_y : 8, strips * A.tiles_x);
+    }
+    if (A.count_only) MDB_LAUNCH((k_neighbor_cells<T, TZ, NT, true>), grid, NT, smem, st, A);
+    else MDB_LAUNCH((k_neighbor_cells<T, TZ, NT, false>), grid, NT, smem, st, A);
+}
+
 template <int T, int TZ> size_t tile_smem_bytes(int cap)
 {
     constexpr int P = T + 2, PZ = TZ + 2, NPEN = P * P, NCELL = NPEN * PZ;
@@ -614,6 +1319,10 @@ bool tiled_neighbor_plan(const MdbSystem &s, int &T)
     }
     const char *env = getenv("MDB_NEIGHBOR");
     if (env && !strcmp(env, "direct")) return false;
+    if (const char *tenv = getenv("MDB_TILE")) {   // experiments: force a tile shape (T*16 + TZ)
+        const int want = atoi(tenv);
+        if (want == 8 * 16 + 8 || want == 4 * 16 + 8 || want == 4 * 16 + 6 || want == 2 * 16 + 4 || want == 2 * 16 + 2 || want == 17) code = want;
+    }
     T = code;
     return true;
 }
@@ -668,6 +1377,47 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     }
     const int nblocks = (A.n_tiles + A.tile_stride - 1) / A.tile_stride;
     if (nblocks <= 0) return;
+    A.tiles_x = tiles_x;
+    {   // owned-atom capacity of the warp-per-cell kernel's wrapped-position table (slot field: 10 bits)
+        const double rho = (double)s.N / ((double)g.nxl * g.n[1] * g.n[2]);
+        int ocap = (int)(rho * TT * TT * TZ * 1.25) + 48;
+        ocap = (ocap + 31) / 32 * 32;
+        A.ocap = ocap > 1024 ? 1024 : ocap;
+        // pooled candidate-list space: 27 cells of mean population per owned cell, padded to whole rounds
+        // of 32 (+16 on average), + 25 %
+        const int ncell_own = TT * TT * TZ;
+        int ltot = (int)(ncell_own * (rho * 27 + 16) * 1.25) + 256;
+        A.ltot = (ltot + 31) / 32 * 32;
+    }
+    const char *kenv = getenv("MDB_NEIGHBOR");
+    const bool v1 = (kenv && !strcmp(kenv, "tiled_v1")) || M > 1023;
+    if (!v1) {
+        if (A.tile_stride == 1 && ((long long)((A.tiles_y + 7) / 8) * tiles_x > 65535 || A.tiles_z > 65535))
+            A.tile_stride = 0;   // linear tile list
+        static const int nt = getenv("MDB_CELLS_NT") ? atoi(getenv("MDB_CELLS_NT")) : 384;
+        switch (T) {
+            case 8 * 16 + 8: launch_cells_T<8, 8, 256>(A, nblocks, s.stream); break;
+            case 4 * 16 + 8:
+                if (nt == 384) launch_cells_T<4, 8, 384>(A, nblocks, s.stream);
+                else launch_cells_T<4, 8, 256>(A, nblocks, s.stream);
+                break;
+            case 4 * 16 + 6:
+                if (nt == 384) launch_cells_T<4, 6, 384>(A, nblocks, s.stream);
+                else launch_cells_T<4, 6, 256>(A, nblocks, s.stream);
+                break;
+            case 2 * 16 + 4: launch_cells_T<2, 4, 256>(A, nblocks, s.stream); break;
+            case 2 * 16 + 2: launch_cells_T<2, 2, 256>(A, nblocks, s.stream); break;
+            default: launch_cells_T<1, 1, 256>(A, nblocks, s.stream); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        if (!count_only) {   // exact extremes of the counts (the kernel's own are pre-filter estimates)
+            const int blocks = (s.n_rows + 256 * 8 - 1) / (256 * 8);
+            MDB_LAUNCH(k_nn_minmax, blocks < 1 ? 1 : (blocks > 2048 ? 2048 : blocks), 256, 0, s.stream, A.nn, s.n_rows,
+                       A.max_count, A.min_count);
+            CUDA_TRY(cudaGetLastError());
+        }
+        return;
+    }
     switch (T) {
         case 8 * 16 + 8: launch_T<8, 8>(A, nblocks, s.stream); break;
         case 4 * 16 + 8: launch_T<4, 8>(A, nblocks, s.stream); break;
