@@ -572,42 +572,32 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
 
 
 // =====================================================================================================
-// Warp-per-cell kernel (round 2).  Same tile staging as above; the search itself is split into stages
-// that each run with (nearly) all lanes busy:
+// Cooperative kernel (round 2).  Same tile staging as k_neighbor_tiled; the two phases are mapped the way
+// each of them is cheap (measured: profiles/r2_*):
 //
-//   lists    a pre-pass (one THREAD per owned cell / per (cell, pencil), overlapped with the TMA copies)
-//            writes every owned cell's candidate list -- the 27-cell stencil = 9 pencils x one contiguous
-//            3-cell run walked backwards, i.e. the reference's order -- as staged indices into shared
-//            memory, padded to whole rounds of 32 with a sentinel whose fp32 record can never pass;
-//   stage 1  a WARP takes one owned cell at a time.  Its lanes hold the cell's ~67 candidates in registers
-//            (up to four rounds of 32).  Every atom of the cell is broadcast to the lanes (one uniform
-//            LDS.128 of its pre-computed constants): three FFMA + one compare per round, one ballot per
-//            round.  The ballot masks ARE the survivors in reference order; lane 0 parks them in shared
-//            memory (one STS.128 per atom);
-//   stage 2  one THREAD per atom: clears its own bit, counts (popc), writes neighbor_number, pads the row
-//            tail, and -- after a warp scan of the counts -- expands its masks into a flat per-warp ring
-//            of (candidate | owner | row slot) words, atom-major;
-//   stage 3  the ring is consumed 32 survivors at a time, one per LANE: exact f64 test of the reference
-//            (xi wrapped, x[j] raw, left-to-right sum, <= rc^2), sqrt, and the rows leave as contiguous
-//            4-byte / 8-byte segments.
-//   The row slot is optimistic (pre-filter rank).  A survivor the exact test rejects (d^2 inside the 4e-4
-//   guard band above rc^2: ~1e-3 of the atoms of a hot crystal, none of a cold one) marks its atom, and
-//   marked atoms are redone by the exact per-thread walk after the tile (direct_atom).  Cells with more
-//   than 128 candidates (dense frames) loop over their list in shared memory and feed the ring directly.
+//   phase 1  one THREAD per owned atom walks its 27-cell stencil (9 pencils x one contiguous 3-cell run,
+//            backwards = the reference's order) with the fp32 pre-filter and pushes survivors onto its
+//            own queue in shared memory -- compaction is free when every thread owns its queue;
+//   flatten  a warp scan of the queue lengths turns the 32 queues into one atom-major ring of
+//            (candidate | owner | row slot) words;
+//   phase 2  the ring is consumed 32 survivors at a time, one per LANE, all lanes busy: exact f64 test of
+//            the reference (xi wrapped, x[j] raw, left-to-right sum, <= rc^2), sqrt, and the rows leave as
+//            contiguous 4-byte / 8-byte segments of consecutive lanes.
+//            The row slot of a survivor is its rank among the ACCEPTED survivors of its atom: entries of one
+//            atom are consecutive in the ring, so a ballot of the accept flags, a ballot of the "first
+//            entry of an atom" flags and one popc give it (plus a carry for an atom that straddles two
+//            calls).  The exact count of every atom is left in shared memory for its thread, which writes
+//            neighbor_number and the row tail.
 // Row order, distances and counts are bit-identical to k_neighbor_tiled / k_neighbor_direct / the reference.
 struct __align__(32) OwnAtom {
     double x, y, z;  // wrapped position (box.h:131-176), what the reference uses as atom i
     int idx;         // original index (row)
-    int flags;       // bit 0: outside the box -> the minimum-image step is needed; bit 1: finished in stage 1
-};
-struct __align__(16) CellRec {
-    int s0n;   // first staged index | atoms << 16
-    int t0;    // ordinal of the first atom among the tile's owned atoms
-    int loff;  // offset of the candidate list (entries)
-    int misc;  // rounds (list length / 32) | position of atom 0 in the list << 8 | list overflow << 31
+    int flags;       // bit 0: outside the box -> the minimum-image step is needed
 };
 
-constexpr int CELL_RCAP = 512;   // survivor ring per warp (entries, power of two)
+constexpr int COOP_RCAP = 256;   // survivor ring per warp (entries, power of two)
+constexpr int COOP_QCAP = 26;    // per-thread queue (uint16 entries)
+constexpr int COOP_CHUNK = 12;   // a thread enters a run with at least this much room in its queue
 
 __device__ __forceinline__ unsigned lds_u32(unsigned addr)
 {
@@ -625,13 +615,9 @@ __device__ __forceinline__ unsigned lanemask_lt()
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
-__device__ __forceinline__ bool pre_pass(const float4 &me, const float4 &c)
-{   // |rj|^2 - 2 ri.rj <= rc^2 (1 + guard) - |ri|^2 with me = (-2 xi, -2 yi, -2 zi, threshold)
-    return __fmaf_rn(me.x, c.x, __fmaf_rn(me.y, c.y, __fmaf_rn(me.z, c.z, c.w))) <= me.w;
-}
 
 template <int T, int TZ, int NT, bool COUNT_ONLY>
-__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const __grid_constant__ TileArgs A)
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_coop(const __grid_constant__ TileArgs A)
 {
     constexpr int P = T + 2;
     constexpr int PZ = TZ + 2;
@@ -639,50 +625,38 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
     constexpr int NCELL = NPEN * PZ;
     constexpr int CSW = PZ + 1;
     constexpr int NW = NT / 32;
-    constexpr int NOWN = T * T * TZ;            // owned cells of a full tile
-    constexpr int CPW = (NOWN + NW - 1) / NW;   // cells per warp (contiguous: a warp walks along z)
 
     extern __shared__ __align__(128) unsigned char smem[];
     // every array is addressed as smem + offset (no pointer -> integer -> pointer round trip, so the compiler
     // keeps all accesses in the shared window: LDS / STS instead of generic loads)
-    const unsigned o_f4 = (unsigned)A.cap * 32u;                       // [cap + 2], f4[cap] = sentinel
-    const unsigned o_own = o_f4 + ((unsigned)A.cap + 2u) * 16u;        // [ocap] 32 B
-    const unsigned o_pm = o_own + (unsigned)A.ocap * 32u;              // [ocap] 16 B: pre-filter constants, then ballot masks
-    const unsigned o_ring = o_pm + (unsigned)A.ocap * 16u;             // [NW][CELL_RCAP] u32
-    const unsigned o_crec = o_ring + NW * CELL_RCAP * 4u;              // [NOWN] 16 B
-    const unsigned o_bar = o_crec + NOWN * 16u;                        // mbarrier (8 B, 16-byte slot)
+    const unsigned o_f4 = (unsigned)A.cap * 32u;                       // [cap] 16 B
+    const unsigned o_own = o_f4 + (unsigned)A.cap * 16u;               // [ocap] 32 B
+    const unsigned o_ring = o_own + (unsigned)A.ocap * 32u;            // [NW][COOP_RCAP] u32
+    const unsigned o_queue = o_ring + NW * COOP_RCAP * 4u;             // [COOP_QCAP][NT] u16, interleaved
+    const unsigned o_bar = o_queue + COOP_QCAP * NT * 2u;              // mbarrier (8 B, 16-byte slot)
     const unsigned o_cs = o_bar + 16u;                                 // [NPEN][CSW] int
     const unsigned o_gstart = o_cs + NPEN * CSW * 4u;                  // [NCELL]
     const unsigned o_ptot = o_gstart + NCELL * 4u;                     // [NPEN + 1]
     const unsigned o_opref = o_ptot + (NPEN + 1) * 4u;                 // [T*T + 1]
-    const unsigned o_cpad = o_opref + (T * T + 1) * 4u;                // [NOWN + 1] padded list lengths -> offsets
-    const unsigned o_flag = o_cpad + (NOWN + 1) * 4u;                  // [4]
-    const unsigned o_pp = o_flag + 16u;                                // [NOWN][10] u16 per-pencil list offsets
-    const unsigned o_tcell = o_pp + NOWN * 20u;                        // [ocap] u16 owned cell of every owned atom
-    const unsigned o_clist = (o_tcell + (unsigned)A.ocap * 2u + 15u) & ~15u;   // [ltot] u16 candidate lists
-    const unsigned o_redo = o_clist + (unsigned)A.ltot * 2u;           // [ocap] u8
+    const unsigned o_flag = o_opref + (T * T + 1) * 4u;                // [4]
+    const unsigned o_acnt = o_flag + 16u;                              // [ocap] u16 accepted neighbours per owned atom
     SortedAtom *raw = reinterpret_cast<SortedAtom *>(smem);
     float4 *f4 = reinterpret_cast<float4 *>(smem + o_f4);
     OwnAtom *own = reinterpret_cast<OwnAtom *>(smem + o_own);
-    float4 *pm = reinterpret_cast<float4 *>(smem + o_pm);
     unsigned *ring = reinterpret_cast<unsigned *>(smem + o_ring);
-    CellRec *crec = reinterpret_cast<CellRec *>(smem + o_crec);
+    unsigned short *queue = reinterpret_cast<unsigned short *>(smem + o_queue);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + o_bar);
     int *cs = reinterpret_cast<int *>(smem + o_cs);
     int *gstart = reinterpret_cast<int *>(smem + o_gstart);
     int *ptot = reinterpret_cast<int *>(smem + o_ptot);
     int *opref = reinterpret_cast<int *>(smem + o_opref);
-    int *cpad = reinterpret_cast<int *>(smem + o_cpad);
     int *far_flag = reinterpret_cast<int *>(smem + o_flag);   // [0] beyond the fp32 radius, [1] periodic shift used, [2] atoms to redo
-    unsigned short *pp = reinterpret_cast<unsigned short *>(smem + o_pp);
-    unsigned short *tcell = reinterpret_cast<unsigned short *>(smem + o_tcell);
-    unsigned short *clist = reinterpret_cast<unsigned short *>(smem + o_clist);
-    unsigned char *redo = smem + o_redo;
+    unsigned short *acnt = reinterpret_cast<unsigned short *>(smem + o_acnt);
 
     const int tid = threadIdx.x;
     const CellGrid &g = A.g;
     int tx, ty, tz;
-    if (A.tile_stride != 1) {   // sampled estimate pass (stride > 1) or a grid too large for 3-D launch (stride 0): linear list of tiles
+    if (A.tile_stride != 1) {   // sampled estimate pass (stride > 1) or a grid too large for a 3-D launch (stride 0): linear list of tiles
         int tl = blockIdx.x * max(A.tile_stride, 1) + A.tile_offset;
         if (tl >= A.n_tiles) return;
         tz = tl % A.tiles_z;
@@ -762,6 +736,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
     const DBox &box = A.box;
     const int warp = tid >> 5, lane = tid & 31;
 
+    // owned atom t of the tile -> its pencil (index into the T x T owned pencils) by bisection over opref
+    auto pencil_of = [&](int t) {
+        int lo = 0, hi = T * T;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (opref[mid] <= t) lo = mid;
+            else hi = mid;
+        }
+        return lo;
+    };
+
     if (fits) {
         // ---- B. stage the records: one bulk copy per run of consecutive global cells of a pencil
         if (A.use_tma) {
@@ -785,6 +770,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
                     kk = k2;
                 }
             }
+            if (warp == 0) mbar_wait(bar, 0);   // one warp polls; the others sleep on the CTA barrier
+            __syncthreads();
         } else {
             for (int c = warp; c < NCELL; c += NW) {
                 const int beg = gstart[c];
@@ -796,86 +783,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
                 double2 *dst = reinterpret_cast<double2 *>(raw + dst0);
                 for (int t = lane; t < chunks; t += 32) dst[t] = __ldg(src + t);
             }
+            __syncthreads();
         }
-
-        // ---- lists, part 1 (needs only the offset tables: runs while the copies fly): one thread per
-        // owned cell -- atoms, candidates per pencil, padded list length
-        for (int t = tid; t < n_owned; t += NT) redo[t] = 0;
-        if (tid == 0) f4[A.cap] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));  // the sentinel never passes
-        {   // the whole list pool starts as sentinels: lists are padded to whole rounds for free
-            const unsigned sv = (unsigned)A.cap | ((unsigned)A.cap << 16);
-            uint4 *pool = reinterpret_cast<uint4 *>(clist);
-            for (int i = tid; i < A.ltot / 8; i += NT) pool[i] = make_uint4(sv, sv, sv, sv);
-        }
-        for (int c = tid; c < NOWN; c += NT) {
-            const int pi = c / TZ, kz = c % TZ;
-            const int a = pi / T + 1, b = pi % T + 1;
-            CellRec r;
-            r.s0n = 0;
-            r.t0 = 0;
-            r.loff = 0;
-            r.misc = 0;
-            int padded = 0;
-            if (a <= amax && b <= bmax && kz < kmax) {
-                const int p = a * P + b, ks = PZ - 1 - kmax + kz;
-                const int s0 = cs[p * CSW + ks], n_i = cs[p * CSW + ks + 1] - s0;
-                if (n_i > 0) {
-                    const int t0 = opref[pi] + s0 - cs[p * CSW + PZ - 1 - kmax];
-                    int C = 0, selfpos = 0;
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) {
-                        const int *row = cs + (p + (q / 3 - 1) * P + (q % 3 - 1)) * CSW + ks;
-                        pp[c * 10 + q] = (unsigned short)min(C, 65535);
-                        if (q == 4) selfpos = C + row[2] - 1 - s0;   // list position of the cell's first atom
-                        C += row[2] - row[-1];
-                    }
-                    pp[c * 10 + 9] = (unsigned short)min(C, 65535);
-                    padded = (C + 31) & ~31;
-                    if (padded == 0) padded = 32;
-                    const int ovf = padded > 1024 ? 1 : 0;   // rounds field: 5 bits; such a cell is redone exactly
-                    if (ovf) padded = 0;
-                    r.s0n = s0 | (n_i << 16);
-                    r.t0 = t0;
-                    r.misc = (padded >> 5) | (selfpos << 8) | (ovf << 31);
-                    for (int ii = 0; ii < n_i; ++ii) tcell[t0 + ii] = (unsigned short)c;
-                }
-            }
-            crec[c] = r;
-            cpad[c] = padded;
-        }
-        __syncthreads();
-        warp0_exclusive_scan(cpad, NOWN);
-        __syncthreads();
-        // ---- lists, part 2: one thread per (owned cell, pencil)
-        for (int it = tid; it < NOWN * 9; it += NT) {
-            const int c = it / 9, q = it - c * 9;
-            const int misc = crec[c].misc;
-            const int rounds = misc & 0xff;
-            if (rounds == 0) continue;
-            const int loff = cpad[c];
-            int over = 0;
-            if (loff + rounds * 32 > A.ltot) over = 1;   // the pooled list space is exhausted: exact walk for this cell
-            if (q == 0) {
-                crec[c].loff = loff;
-                if (over) crec[c].misc = misc | (1 << 31);
-            }
-            if (over) continue;
-            const int pi = c / TZ, kz = c % TZ;
-            const int p = (pi / T + 1) * P + (pi % T + 1), ks = PZ - 1 - kmax + kz;
-            const int *row = cs + (p + (q / 3 - 1) * P + (q % 3 - 1)) * CSW + ks;
-            unsigned short *L = clist + loff + pp[c * 10 + q];
-            const int beg = row[-1], len = row[2] - beg, top = row[2] - 1;
-            for (int o = 0; o < len; ++o) L[o] = (unsigned short)(top - o);
-        }
-        if (A.use_tma) mbar_wait(bar, 0);
-        else __syncthreads();
 
         // ---- C. fp32 positions relative to the tile centre (nearest periodic image), flat over the staged atoms
         const double rcw = 1.0 / g.rc_inv;
         const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0);
         const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
                      ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
-        auto rel32 = [&](const double2 lo, const double z, bool &shifted) {
+        for (int s = tid; s < n_staged; s += NT) {
+            const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
+            const double z = reinterpret_cast<const double *>(raw + s)[2];
             double d0 = lo.x - ctr0, d1 = lo.y - ctr1, d2 = z - ctr2;
             double n0 = 0.0, n1 = 0.0, n2 = 0.0;
             if (box.pbc[0]) n0 = rint(d0 * box.hinv[0]);
@@ -884,42 +802,11 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
             d0 -= box.h[0] * n0;
             d1 -= box.h[4] * n1;
             d2 -= box.h[8] * n2;
-            shifted = (n0 != 0.0) | (n1 != 0.0) | (n2 != 0.0);
+            if ((n0 != 0.0) | (n1 != 0.0) | (n2 != 0.0)) far_flag[1] = 1;   // some staged atom is a periodic image
             const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
-            return make_float4(f0, f1, f2, __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0)));
-        };
-        for (int s = tid; s < n_staged; s += NT) {
-            const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
-            const double z = reinterpret_cast<const double *>(raw + s)[2];
-            bool sh;
-            const float4 v = rel32(lo, z, sh);
-            if (sh) far_flag[1] = 1;                    // some staged atom is a periodic image
-            if (!(v.w <= A.w_limit)) far_flag[0] = 1;   // outside the radius the fp32 bound covers (or NaN)
-            f4[s] = v;
-        }
-        // owned atoms: wrapped f64 position (atom i of the reference's loop) and pre-filter constants
-        for (int t = tid; t < n_owned; t += NT) {
-            const int c = tcell[t];
-            const CellRec r = crec[c];
-            const int s = (r.s0n & 0xffff) + (t - r.t0);
-            const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
-            const double2 hi = reinterpret_cast<const double2 *>(raw + s)[1];
-            bool sh;
-            const float4 v = rel32(lo, hi.x, sh);
-            pm[t] = make_float4(-2.0f * v.x, -2.0f * v.y, -2.0f * v.z, A.rcsq_hi - v.w);
-            double xi = lo.x, yi = lo.y, zi = hi.x;
-            int fl = 0;
-            if (box.pbc[0]) { const double d = xi - box.origin[0]; fl |= !(d >= box.wrap_t[0][1] && d < box.wrap_t[0][2]); }
-            if (box.pbc[1]) { const double d = yi - box.origin[1]; fl |= !(d >= box.wrap_t[1][1] && d < box.wrap_t[1][2]); }
-            if (box.pbc[2]) { const double d = zi - box.origin[2]; fl |= !(d >= box.wrap_t[2][1] && d < box.wrap_t[2][2]); }
-            wrap_ortho(box, xi, yi, zi);
-            OwnAtom o;
-            o.x = xi;
-            o.y = yi;
-            o.z = zi;
-            o.idx = __double2loint(hi.y);
-            o.flags = fl;
-            own[t] = o;
+            const float w = __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0));
+            if (!(w <= A.w_limit)) far_flag[0] = 1;   // outside the radius the fp32 bound covers (or NaN)
+            f4[s] = make_float4(f0, f1, f2, w);
         }
         __syncthreads();
     }
@@ -931,12 +818,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
         // overflow tile / atoms beyond the fp32 radius: exact per-thread walk through global memory
 #pragma unroll 1
         for (int t = tid; t < n_owned; t += NT) {
-            int lo = 0, hi = T * T;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (opref[mid] <= t) lo = mid;
-                else hi = mid;
-            }
+            const int lo = pencil_of(t);
             const int p = (lo / T + 1) * P + (lo % T + 1);
             const int sg = gstart[p * PZ + PZ - 1 - kmax] + (t - opref[lo]);
             const int c = direct_atom<COUNT_ONLY>(A, sg);
@@ -944,29 +826,34 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
             if (c >= 0) local_min = min(local_min, c);
         }
     } else {
-        const unsigned raw_base = smem_u32(raw), own_base = smem_u32(own);
-        const unsigned ring_base = smem_u32(ring + warp * CELL_RCAP);
+        const unsigned f4_base = smem_u32(f4), raw_base = smem_u32(raw), own_base = smem_u32(own);
+        const unsigned ring_base = smem_u32(ring + warp * COOP_RCAP);
+        const unsigned q_base = smem_u32(queue) + 2u * tid;   // entry u of this thread at q_base + u * 2 * NT
+        constexpr unsigned QS = 2u * NT;
+        const float rc2hi = A.rcsq_hi;
         const double rcsq = A.rcsq;
         const double Lx = box.h[0], Ly = box.h[4], Lz = box.h[8];
         const double iLx = box.hinv[0], iLy = box.hinv[4], iLz = box.hinv[8];
         const bool px = box.pbc[0] != 0, py = box.pbc[1] != 0, pz = box.pbc[2] != 0;
         const int M = A.M;
-        const unsigned lt = lanemask_lt();
-        unsigned head = 0, tail = 0;             // ring positions (monotonic)
-        const float4 SENT = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+        unsigned head = 0, tail = 0;   // ring positions (monotonic, warp-uniform)
 
-        // ---- stage 3: 32 survivors per call, one per lane
+        // ---- phase 2: 32 survivors per call, one per lane
+        const unsigned lt = lanemask_lt();
+        const unsigned acnt_base = smem_u32(acnt);
         auto consume = [&](int nvalid) {
             const bool valid = lane < nvalid;
-            unsigned e = lds_u32(ring_base + (((head + (unsigned)lane) & (CELL_RCAP - 1)) << 2));
-            if (!valid) e = 0;
-            const unsigned cand = e & 0xfffu, t = (e >> 12) & 0x3ffu, slot = e >> 22;
-            const unsigned ra = raw_base + 32u * cand, oa = own_base + 32u * t;
+            unsigned e = lds_u32(ring_base + (((head + (unsigned)lane) & (COOP_RCAP - 1)) << 2));
+            if (!valid) e = 0xffffu << 12;   // owner no real atom has: a segment of its own
+            const unsigned cand = e & 0xfffu, t = e >> 12;
+            const unsigned tt = valid ? t : 0u;
+            const unsigned ra = raw_base + 32u * cand, oa = own_base + 32u * tt;
             double xj, yj, zj, wj, xi, yi, zi, wi;
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj), "=d"(yj) : "r"(ra));
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(zj), "=d"(wj) : "r"(ra + 16u));
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi), "=d"(yi) : "r"(oa));
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(zi), "=d"(wi) : "r"(oa + 16u));
+            const unsigned have = lds_u16(acnt_base + 2u * tt);   // accepted in earlier calls
             const int jdx = __double2loint(wj);
             const int idx = __double2loint(wi), fl = __double2hiint(wi);
             double dx = xj - xi, dy = yj - yi, dz = zj - zi;
@@ -976,167 +863,72 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
                 if (pz) dz = near_image(dz, Lz, iLz);
             }
             const double d2 = dx * dx + dy * dy + dz * dz;
-            if (valid) {
-                if (d2 <= rcsq) {
-                    if ((int)slot < M) {
-                        const size_t off = (size_t)idx * M + slot;
-                        A.verlet[off] = jdx;
-                        A.dist[off] = sqrt(d2);
-                    }
-                } else {
-                    redo[t] = 1;       // the optimistic slots of this atom are wrong: exact walk after the tile
-                    far_flag[2] = 1;
-                }
+            const bool acc = valid && d2 <= rcsq;
+            // entries of one atom are consecutive: a new atom starts where the owner changes
+            const unsigned tprev = __shfl_up_sync(0xffffffffu, t, 1);
+            const bool first = lane == 0 || t != tprev;
+            const unsigned mfirst = __ballot_sync(0xffffffffu, first), macc = __ballot_sync(0xffffffffu, acc);
+            const int start = 31 - __clz(mfirst & (lt | (1u << lane)));   // lane 0 always starts a run
+            const unsigned slot = have + __popc(macc & lt & ~((1u << start) - 1u));
+            if (acc && (int)slot < M) {
+                const size_t off = (size_t)idx * M + slot;
+                A.verlet[off] = jdx;
+                A.dist[off] = sqrt(d2);
             }
+            // the last entry of every run leaves the atom's running count behind
+            if (valid && (lane == 31 || ((mfirst >> (lane + 1)) & 1u)))
+                sts_u16(acnt_base + 2u * tt, min(slot + (acc ? 1u : 0u), 65535u));
             head += (unsigned)nvalid;
             __syncwarp();
         };
-        auto pad_row = [&](int idx, int n) {   // lanes over the free slots of one row
-            int *vrow = A.verlet + (size_t)idx * M;
-            double *drow = A.dist + (size_t)idx * M;
-            for (int u = n + lane; u < M; u += 32) {
-                vrow[u] = -1;
-                drow[u] = A.pad;
-            }
-        };
 
-        // ---- stage 1: ballot masks of every atom, one cell at a time
-        int t_first = -1, t_end = 0;
 #pragma unroll 1
-        for (int ci = 0; ci < CPW; ++ci) {
-            const int c = warp * CPW + ci;
-            if (c >= NOWN) break;
-            const CellRec rec = crec[c];
-            const int n_i = rec.s0n >> 16;
-            if (n_i == 0) continue;
-            const int s0 = rec.s0n & 0xffff, t0 = rec.t0;
-            if (t_first < 0) t_first = t0;
-            t_end = t0 + n_i;
-            if (rec.misc < 0) {   // list overflow: exact walk after the tile; stage 2 skips these atoms
-                for (int ii = lane; ii < n_i; ii += 32) {
-                    redo[t0 + ii] = 1;
-                    own[t0 + ii].flags |= 2;
-                    far_flag[2] = 1;
-                }
-                continue;
+        for (int base = warp * 32; base < n_owned; base += NT) {
+            const int t = base + lane;
+            const bool active = t < n_owned;
+            int idx = 0, s_i = 0, kk = 1, p = P + 1;
+            bool live = false;
+            float fx = 0.f, fy = 0.f, fz = 0.f, thr = 0.f;
+            if (active) {
+                const int pi = pencil_of(t);
+                p = (pi / T + 1) * P + (pi % T + 1);
+                const int *prow = cs + p * CSW;
+                s_i = prow[PZ - 1 - kmax] + (t - opref[pi]);
+                kk = PZ - 1 - kmax;   // my memory slot along z: owned slots are PZ-1-kmax .. PZ-2
+                while (kk < PZ - 2 && prow[kk + 1] <= s_i) ++kk;
+                const double2 lo = reinterpret_cast<const double2 *>(raw + s_i)[0];
+                const double2 hi = reinterpret_cast<const double2 *>(raw + s_i)[1];
+                idx = __double2loint(hi.y);
+                live = idx < A.n_rows;
+                double xi = lo.x, yi = lo.y, zi = hi.x;
+                int fl = 0;
+                if (box.pbc[0]) { const double d = xi - box.origin[0]; fl |= !(d >= box.wrap_t[0][1] && d < box.wrap_t[0][2]); }
+                if (box.pbc[1]) { const double d = yi - box.origin[1]; fl |= !(d >= box.wrap_t[1][1] && d < box.wrap_t[1][2]); }
+                if (box.pbc[2]) { const double d = zi - box.origin[2]; fl |= !(d >= box.wrap_t[2][1] && d < box.wrap_t[2][2]); }
+                wrap_ortho(box, xi, yi, zi);
+                OwnAtom o;
+                o.x = xi;
+                o.y = yi;
+                o.z = zi;
+                o.idx = idx;
+                o.flags = fl;
+                own[t] = o;
+                acnt[t] = 0;
+                const float4 me = f4[s_i];
+                fx = -2.0f * me.x;
+                fy = -2.0f * me.y;
+                fz = -2.0f * me.z;
+                thr = rc2hi - me.w;
             }
-            const int rounds = rec.misc & 0xff;
-            const int loff = rec.loff;
-            if (rounds <= 4) {
-                // the whole stencil in registers: up to four rounds of 32 candidates in reference order
-                auto cell_masks = [&](auto RT) {
-                    constexpr int R = decltype(RT)::value;
-                    const float4 c0 = f4[clist[loff + lane]];
-                    const float4 c1 = R > 1 ? f4[clist[loff + 32 + lane]] : SENT;
-                    const float4 c2 = R > 2 ? f4[clist[loff + 64 + lane]] : SENT;
-                    const float4 c3 = R > 3 ? f4[clist[loff + 96 + lane]] : SENT;
-#pragma unroll 1
-                    for (int ii = 0; ii < n_i; ++ii) {
-                        const float4 me = pm[t0 + ii];
-                        const unsigned m0 = __ballot_sync(0xffffffffu, pre_pass(me, c0));
-                        const unsigned m1 = R > 1 ? __ballot_sync(0xffffffffu, pre_pass(me, c1)) : 0u;
-                        const unsigned m2 = R > 2 ? __ballot_sync(0xffffffffu, pre_pass(me, c2)) : 0u;
-                        const unsigned m3 = R > 3 ? __ballot_sync(0xffffffffu, pre_pass(me, c3)) : 0u;
-                        if (lane == 0) reinterpret_cast<uint4 *>(pm)[t0 + ii] = make_uint4(m0, m1, m2, m3);
-                    }
-                };
-                if (rounds == 3) cell_masks(std::integral_constant<int, 3>{});
-                else if (rounds == 2) cell_masks(std::integral_constant<int, 2>{});
-                else if (rounds == 4) cell_masks(std::integral_constant<int, 4>{});
-                else cell_masks(std::integral_constant<int, 1>{});
-            } else {
-                // dense cell: any number of rounds, candidates re-read per atom, survivors straight into the ring
-#pragma unroll 1
-                for (int ii = 0; ii < n_i; ++ii) {
-                    const int s_i = s0 + ii, t = t0 + ii;
-                    const int idx = own[t].idx;
-                    __syncwarp();
-                    if (lane == 0) own[t].flags |= 2;
-                    if (idx >= A.n_rows) continue;
-                    const float4 me = pm[t];
-                    const unsigned tb = (unsigned)t << 12;
-                    int n = 0;
-                    bool over = false;
-#pragma unroll 1
-                    for (int r0 = 0; r0 < rounds * 32; r0 += 32) {
-                        const int k = clist[loff + r0 + lane];
-                        const bool qq = (k != s_i) && pre_pass(me, f4[k]);
-                        const unsigned m = __ballot_sync(0xffffffffu, qq);
-                        const unsigned rr = __popc(m & lt);
-                        const unsigned r = (unsigned)n + rr;
-                        const bool room = r < 1024u;
-                        over |= qq && !room;
-                        n += __popc(m);
-                        if (!COUNT_ONLY) {
-                            if (qq && room) sts_u32(ring_base + (((tail + rr) & (CELL_RCAP - 1)) << 2), (unsigned)k | tb | (r << 22));
-                            // entries beyond slot 1023 were not stored: the ring only advances by what was
-                            tail += (unsigned)__popc(__ballot_sync(0xffffffffu, qq && room));
-                            __syncwarp();
-                            while (tail - head >= 32u) consume(32);
-                        }
-                    }
-                    local_max = max(local_max, n);
-                    local_min = min(local_min, n);
-                    if (lane == 0) A.nn[idx] = n;
-                    if (COUNT_ONLY) continue;
-                    if (__any_sync(0xffffffffu, over)) {
-                        if (lane == 0) {
-                            redo[t] = 1;
-                            far_flag[2] = 1;
-                        }
-                    }
-                    if (n < M) pad_row(idx, n);
-                }
-            }
-        }
-        __syncwarp();
+            unsigned q_top = q_base;   // queue write pointer
+            const unsigned q_full = q_base + QS * COOP_QCAP, q_warn = q_base + QS * (COOP_QCAP - COOP_CHUNK);
+            unsigned cnt = 0;          // pre-filter count so far (the estimate pass reports it)
+            const unsigned tbits = (unsigned)t << 12;
 
-        // ---- stage 2: one thread per atom -- count, neighbor_number, row tail, masks -> ring; stage 3 as it fills
-        if (t_first >= 0) {
-#pragma unroll 1
-            for (int tb0 = t_first; tb0 < t_end; tb0 += 32) {
-                const int t = tb0 + lane;
-                unsigned m[4] = {0u, 0u, 0u, 0u};
-                int idx = 0, loff = 0;
-                bool live = false;
-                if (t < t_end) {
-                    const OwnAtom *o = own + t;
-                    idx = o->idx;
-                    live = idx < A.n_rows && !(o->flags & 2);
-                    if (live) {
-                        const uint4 mm = reinterpret_cast<const uint4 *>(pm)[t];
-                        const CellRec rec = crec[tcell[t]];
-                        loff = rec.loff;
-                        const int sp = ((rec.misc >> 8) & 0x7fffff) - (t - rec.t0);   // my own position in the list
-                        m[0] = mm.x;
-                        m[1] = mm.y;
-                        m[2] = mm.z;
-                        m[3] = mm.w;
-                        const unsigned bit = ~(1u << (sp & 31));
-                        const int w = sp >> 5;
-                        m[0] &= w == 0 ? bit : ~0u;
-                        m[1] &= w == 1 ? bit : ~0u;
-                        m[2] &= w == 2 ? bit : ~0u;
-                        m[3] &= w == 3 ? bit : ~0u;
-                    }
-                }
-                const int n = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-                if (live) {
-                    A.nn[idx] = n;
-                    local_max = max(local_max, n);
-                    local_min = min(local_min, n);
-                }
-                if (COUNT_ONLY) continue;
-                if (live && n < M) {   // row tail (-1 / rc+1)
-                    int *vrow = A.verlet + (size_t)idx * M;
-                    double *drow = A.dist + (size_t)idx * M;
-                    for (int u = n; u < M; ++u) {
-                        vrow[u] = -1;
-                        drow[u] = A.pad;
-                    }
-                }
-                // atoms go to the ring in sub-batches that fit (one batch unless the frame is dense)
-                bool pending = live && n > 0;
+            // queues -> ring (atom-major), phase 2 as the ring fills
+            auto flush = [&]() {
+                const int n = (int)((q_top - q_base) / QS);
+                bool pending = n > 0;
 #pragma unroll 1
                 while (__any_sync(0xffffffffu, pending)) {
                     int incl = pending ? n : 0;
@@ -1145,74 +937,108 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
                         const int v = __shfl_up_sync(0xffffffffu, incl, d);
                         if (lane >= d) incl += v;
                     }
-                    const int space = CELL_RCAP - (int)(tail - head);
-                    const bool go = pending && incl <= space;
+                    const int space = COOP_RCAP - (int)(tail - head);
+                    const bool go = pending && incl <= space;   // a prefix of the pending lanes
                     const unsigned gom = __ballot_sync(0xffffffffu, go);
-                    if (gom == 0u) {
-                        // the first pending atom alone exceeds the ring: exact walk after the tile
-                        const unsigned pend = __ballot_sync(0xffffffffu, pending);
-                        if (lane == __ffs(pend) - 1) {
-                            redo[t] = 1;
-                            far_flag[2] = 1;
-                            pending = false;
-                        }
-                        continue;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, incl, 31 - __clz(gom));
-                    unsigned pos = tail + (unsigned)(incl - n);   // first ring position / row slot of this word
-                    const unsigned tbits = (unsigned)t << 12;
-                    unsigned slot = 0;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        unsigned mw = go ? m[w] : 0u;
-                        const int cw = __popc(mw);
-                        const int maxc = __reduce_max_sync(0xffffffffu, cw);
-                        // bits from the top down (one FLO per survivor): the j-th from the top is entry cw-1-j
-                        unsigned pw = pos + (unsigned)cw, sw = slot + (unsigned)cw;
+                    const int total = __shfl_sync(0xffffffffu, incl, 31 - __clz(gom | 1u));
+                    const int maxn = __reduce_max_sync(0xffffffffu, go ? n : 0);
+                    unsigned ra = ring_base + (((tail + (unsigned)(incl - n)) & (COOP_RCAP - 1)) << 2);
+                    unsigned qa = q_base;
 #pragma unroll 1
-                        for (int j = 0; j < maxc; ++j) {
-                            if (mw) {
-                                const int b = 31 - __clz(mw);
-                                mw ^= 1u << b;
-                                --pw;
-                                --sw;
-                                const unsigned k = clist[loff + w * 32 + b];
-                                sts_u32(ring_base + ((pw & (CELL_RCAP - 1)) << 2), k | tbits | (sw << 22));
+                    for (int i = 0; i < maxn; ++i) {
+                        if (go && i < n) {
+                            const unsigned k = ((lds_u16(qa) - f4_base) & 0xffffu) >> 4;
+                            sts_u32(ra, k | tbits);
+                            qa += QS;
+                            ra += 4u;
+                            if (ra == ring_base + COOP_RCAP * 4u) ra = ring_base;
+                        }
+                    }
+                    if (go) {
+                        pending = false;
+                        cnt += (unsigned)n;
+                        q_top = q_base;
+                    }
+                    tail += gom ? (unsigned)total : 0u;
+                    __syncwarp();
+                    // everything that was copied is consumed before the next copy: a call never sees two
+                    // separate runs of one atom (its running count is read once per call)
+                    while (tail != head) consume(min(32, (int)(tail - head)));
+                }
+            };
+
+            // phase 1: the 9 pencils of the stencil in (x, y) order.  The three z cells of a pencil are one
+            // contiguous staged run stored in descending z, so a single backward walk yields cell z-1, z,
+            // z+1, each in descending original index: the reference's order.  The centre pencil is walked in
+            // two pieces that leave the atom itself out.
+            int pen_off = -P - 1, pen_y = 0;
+            const unsigned self = f4_base + 16u * (unsigned)s_i;
+#pragma unroll 1
+            for (int pen = 0; pen < 9; ++pen) {
+                unsigned abeg = f4_base, aend = f4_base;
+                if (live) {
+                    const int *row = cs + (p + pen_off) * CSW + kk;
+                    abeg = f4_base + 16u * (unsigned)row[-1];
+                    aend = f4_base + 16u * (unsigned)row[2];   // one past the last candidate
+                }
+#pragma unroll 1
+                for (int piece = 0; piece < (pen == 4 ? 2 : 1); ++piece) {
+                    unsigned lo_a = abeg, aq = aend;
+                    if (pen == 4 && live) {
+                        if (piece == 0) lo_a = self + 16u;   // candidates above me
+                        else aq = self;                      // candidates below me
+                    }
+#pragma unroll 1
+                    while (__any_sync(0xffffffffu, aq > lo_a)) {
+                        // scan at most as many candidates as the queue has room for (all of the run unless the
+                        // frame is dense); the next candidate is loaded while the current one is tested
+                        const unsigned room = (q_full - q_top) / QS;
+                        const unsigned astop = (aq - lo_a > 16u * room && aq > lo_a) ? aq - 16u * room : lo_a;
+                        float4 o = lds_f4(aq - 16u);   // (a read below the run is harmless: it stays inside the staged arrays)
+#pragma unroll 2
+                        while (aq > astop) {
+                            aq -= 16u;
+                            const float4 c = o;
+                            o = lds_f4(aq - 16u);
+                            // |rj|^2 - 2 ri.rj  <=  rc^2 (1 + guard) - |ri|^2
+                            if (__fmaf_rn(fx, c.x, __fmaf_rn(fy, c.y, __fmaf_rn(fz, c.z, c.w))) <= thr) {
+                                if (COUNT_ONLY) ++cnt;
+                                else {
+                                    sts_u16(q_top, aq);
+                                    q_top += QS;
+                                }
                             }
                         }
-                        pos += (unsigned)cw;
-                        slot += (unsigned)cw;
+                        if (!COUNT_ONLY && __any_sync(0xffffffffu, q_top > q_warn || aq > lo_a)) flush();
                     }
-                    if (go) pending = false;
-                    tail += (unsigned)total;
-                    __syncwarp();
-                    while (tail - head >= 32u) consume(32);
                 }
+                if (++pen_y == 3) {
+                    pen_y = 0;
+                    pen_off += P - 2;
+                } else ++pen_off;
             }
-        }
-        if (!COUNT_ONLY) {
-            while (tail != head) consume(min(32, (int)(tail - head)));
-            __syncthreads();
-            if (far_flag[2]) {   // atoms whose optimistic slots were wrong (or that overflowed): exact walk
-#pragma unroll 1
-                for (int t = tid; t < n_owned; t += NT) {
-                    if (!redo[t]) continue;
-                    int lo = 0, hi = T * T;
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (opref[mid] <= t) lo = mid;
-                        else hi = mid;
+            if (!COUNT_ONLY) {
+                flush();
+                while (tail != head) consume(min(32, (int)(tail - head)));   // the batch's last (partial) call
+                cnt = active ? acnt[t] : 0u;                                  // exact count
+            }
+            if (live) {
+                A.nn[idx] = (int)cnt;
+                local_max = max(local_max, (int)cnt);
+                local_min = min(local_min, (int)cnt);
+                if (!COUNT_ONLY && (int)cnt < M) {   // row tail (-1 / rc+1)
+                    int *vrow = A.verlet + (size_t)idx * M;
+                    double *drow = A.dist + (size_t)idx * M;
+                    for (int u = (int)cnt; u < M; ++u) {
+                        vrow[u] = -1;
+                        drow[u] = A.pad;
                     }
-                    const int p = (lo / T + 1) * P + (lo % T + 1);
-                    const int sg = gstart[p * PZ + PZ - 1 - kmax] + (t - opref[lo]);
-                    direct_atom<false>(A, sg);
                 }
             }
         }
     }
-    if (COUNT_ONLY || !staged_ok) {
-        // estimate pass (pre-filter counts are upper bounds) and overflow tiles; the fill pass takes the
-        // exact extremes from nn[] afterwards (k_nn_minmax)
+    {
+        // (estimate pass: pre-filter counts, i.e. upper bounds; fill pass: exact counts)
 #pragma unroll
         for (int d = 16; d; d >>= 1) {
             local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, d));
@@ -1223,43 +1049,22 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_cells(const 
     }
 }
 
-// exact extremes of the counts after a fill pass
-__global__ void __launch_bounds__(256) k_nn_minmax(const int *__restrict__ nn, int n, int *__restrict__ mx, int *__restrict__ mn)
+template <int T, int TZ, int NT> size_t coop_smem_bytes(int cap, int ocap)
 {
-    int a = 0, b = INT_MAX;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int v = nn[i];
-        a = max(a, v);
-        b = min(b, v);
-    }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        a = max(a, __shfl_xor_sync(0xffffffffu, a, d));
-        b = min(b, __shfl_xor_sync(0xffffffffu, b, d));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(mx, a);
-        atomicMin(mn, b);
-    }
-}
-
-template <int T, int TZ, int NT> size_t cells_smem_bytes(int cap, int ocap, int ltot)
-{
-    constexpr int P = T + 2, PZ = TZ + 2, NPEN = P * P, NCELL = NPEN * PZ, NW = NT / 32, NOWN = T * T * TZ;
-    return (size_t)cap * (sizeof(SortedAtom) + sizeof(float4)) + 2 * sizeof(float4) +
-           (size_t)ocap * (sizeof(OwnAtom) + sizeof(float4) + 2 + 1) + sizeof(unsigned) * NW * CELL_RCAP +
-           sizeof(CellRec) * NOWN + sizeof(unsigned short) * ((size_t)NOWN * 10 + ltot) +
-           sizeof(int) * (NPEN * (PZ + 1) + NCELL + NPEN + 1 + T * T + 1 + NOWN + 1 + 4) + 16 + 16 + 64;
+    constexpr int P = T + 2, PZ = TZ + 2, NPEN = P * P, NCELL = NPEN * PZ, NW = NT / 32;
+    return (size_t)cap * (sizeof(SortedAtom) + sizeof(float4)) + (size_t)ocap * (sizeof(OwnAtom) + 2) +
+           sizeof(unsigned) * NW * COOP_RCAP + sizeof(unsigned short) * COOP_QCAP * NT +
+           sizeof(int) * (NPEN * (PZ + 1) + NCELL + NPEN + 1 + T * T + 1 + 4) + 16 + 64;
 }
 
 template <int T, int TZ, int NT> void launch_cells_T(const TileArgs &A, int nblocks, cudaStream_t st)
 {
-    const size_t smem = cells_smem_bytes<T, TZ, NT>(A.cap, A.ocap, A.ltot);
+    const size_t smem = coop_smem_bytes<T, TZ, NT>(A.cap, A.ocap);
     static bool configured = false;
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_cells<T, TZ, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_coop<T, TZ, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       200 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_cells<T, TZ, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_coop<T, TZ, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       200 * 1024));
         configured = true;
     }
@@ -1268,8 +1073,8 @@ template <int T, int TZ, int NT> void launch_cells_T(const TileArgs &A, int nblo
         const int strips = (A.tiles_y + 7) / 8;
         grid = dim3(A.tiles_z, A.tiles_y < 8 ? A.tiles_y : 8, strips * A.tiles_x);
     }
-    if (A.count_only) MDB_LAUNCH((k_neighbor_cells<T, TZ, NT, true>), grid, NT, smem, st, A);
-    else MDB_LAUNCH((k_neighbor_cells<T, TZ, NT, false>), grid, NT, smem, st, A);
+    if (A.count_only) MDB_LAUNCH((k_neighbor_coop<T, TZ, NT, true>), grid, NT, smem, st, A);
+    else MDB_LAUNCH((k_neighbor_coop<T, TZ, NT, false>), grid, NT, smem, st, A);
 }
 
 template <int T, int TZ> size_t tile_smem_bytes(int cap)
@@ -1371,8 +1176,8 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     A.use_tma = !(env && !strcmp(env, "ldg"));
     {   // staged-atom capacity from the mean cell population (tiles above it take the in-kernel direct path)
         const double rho = (double)s.N / ((double)g.nxl * g.n[1] * g.n[2]);
-        int cap = (int)(rho * (TT + 2) * (TT + 2) * (TZ + 2) * 1.15) + 64;
-        cap = (cap + 31) / 32 * 32;
+        int cap = (int)(rho * (TT + 2) * (TT + 2) * (TZ + 2) * 1.12) + 32;
+        cap = (cap + 15) / 16 * 16;
         A.cap = cap < 256 ? 256 : (cap > 2048 ? 2048 : cap);
     }
     const int nblocks = (A.n_tiles + A.tile_stride - 1) / A.tile_stride;
@@ -1380,7 +1185,7 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     A.tiles_x = tiles_x;
     {   // owned-atom capacity of the warp-per-cell kernel's wrapped-position table (slot field: 10 bits)
         const double rho = (double)s.N / ((double)g.nxl * g.n[1] * g.n[2]);
-        int ocap = (int)(rho * TT * TT * TZ * 1.25) + 48;
+        int ocap = (int)(rho * TT * TT * TZ * 1.15) + 32;
         ocap = (ocap + 31) / 32 * 32;
         A.ocap = ocap > 1024 ? 1024 : ocap;
         // pooled candidate-list space: 27 cells of mean population per owned cell, padded to whole rounds
@@ -1389,12 +1194,16 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
         int ltot = (int)(ncell_own * (rho * 27 + 16) * 1.25) + 256;
         A.ltot = (ltot + 31) / 32 * 32;
     }
+    // Kernel choice (measured, profiles/r2_neighbor_kernel_study.md): the thread-per-atom kernel above is the
+    // faster one while rows are short (FCC / BCC first shells: 20.5 vs 21.9 ms per 99.6 M atoms), the
+    // cooperative kernel wins as rows grow (M = 64: 20.9 vs 31.0 ms per 16.4 M atoms) -- dense frames use the
+    // small tile shapes.  MDB_NEIGHBOR=tiled_v1 / coop forces one of them.
     const char *kenv = getenv("MDB_NEIGHBOR");
-    const bool v1 = (kenv && !strcmp(kenv, "tiled_v1")) || M > 1023;
+    const bool v1 = kenv ? !strcmp(kenv, "tiled_v1") : TT >= 4;
     if (!v1) {
         if (A.tile_stride == 1 && ((long long)((A.tiles_y + 7) / 8) * tiles_x > 65535 || A.tiles_z > 65535))
             A.tile_stride = 0;   // linear tile list
-        static const int nt = getenv("MDB_CELLS_NT") ? atoi(getenv("MDB_CELLS_NT")) : 384;
+        static const int nt = getenv("MDB_CELLS_NT") ? atoi(getenv("MDB_CELLS_NT")) : 256;
         switch (T) {
             case 8 * 16 + 8: launch_cells_T<8, 8, 256>(A, nblocks, s.stream); break;
             case 4 * 16 + 8:
@@ -1410,12 +1219,6 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
             default: launch_cells_T<1, 1, 256>(A, nblocks, s.stream); break;
         }
         CUDA_TRY(cudaGetLastError());
-        if (!count_only) {   // exact extremes of the counts (the kernel's own are pre-filter estimates)
-            const int blocks = (s.n_rows + 256 * 8 - 1) / (256 * 8);
-            MDB_LAUNCH(k_nn_minmax, blocks < 1 ? 1 : (blocks > 2048 ? 2048 : blocks), 256, 0, s.stream, A.nn, s.n_rows,
-                       A.max_count, A.min_count);
-            CUDA_TRY(cudaGetLastError());
-        }
         return;
     }
     switch (T) {
