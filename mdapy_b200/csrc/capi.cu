@@ -131,6 +131,7 @@ static void build_neighbor(MdbSystem &s, double rc, int max_neigh)
     }
     s.list_kind = LIST_CUTOFF;
     s.list_rc = rc;
+    s.has_dist = true;
     if (s.profile) {
         CUDA_TRY(cudaStreamSynchronize(s.stream));
         CUDA_TRY(cudaEventElapsedTime(&s.t_bin, s.ev[0], s.ev[1]));
@@ -150,6 +151,56 @@ template <class T> static T *h2d(MdbSystem &s, DevBuf &buf, const T *host, size_
     return d;
 }
 
+// ---- lists handed in by the caller (mdb_system_put_neighbor) may come without counts or distances
+// (the reference's L3 classes accept a bare verlet_list): counts follow from the -1 padding, distances are
+// recomputed on first use with the list builder's arithmetic (xi wrapped, x[j] raw, minimum image;
+// neighbor.cpp:130-186).
+__global__ void __launch_bounds__(256) k_counts_from_padding(const int *__restrict__ verlet, int rows, int M,
+                                                             int *__restrict__ nn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const int *row = verlet + (size_t)i * M;
+    int c = 0;
+    while (c < M && row[c] >= 0) ++c;
+    nn[i] = c;
+}
+
+__global__ void __launch_bounds__(256) k_dist_from_verlet(const double *__restrict__ x, const double *__restrict__ y,
+                                                          const double *__restrict__ z, DBox box,
+                                                          const int *__restrict__ verlet, int rows, int M, double pad,
+                                                          double *__restrict__ dist)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)rows * M) return;
+    const int i = (int)(e / M), j = verlet[e];
+    if (j < 0) {
+        dist[e] = pad;
+        return;
+    }
+    double xi = x[i], yi = y[i], zi = z[i];
+    if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
+    double dx = x[j] - xi, dy = y[j] - yi, dz = z[j] - zi;
+    min_image(box, dx, dy, dz);
+    dist[e] = sqrt(dx * dx + dy * dy + dz * dz);
+}
+
+static double *list_dist(MdbSystem &s)
+{
+    if (!s.has_dist && s.list_kind != LIST_NONE) {
+        const size_t n = (size_t)s.n_rows * s.M;
+        double *d = s.dist.ensure<double>(n ? n : 1);
+        if (n) {
+            const double pad = s.list_rc > 0 ? s.list_rc + 1.0 : 1.0e300;
+            MDB_LAUNCH(k_dist_from_verlet, (unsigned)((n + 255) / 256), 256, 0, s.stream, s.x, s.y, s.z, s.box,
+                       s.verlet.as<int>(), s.n_rows, s.M, pad, d);
+            CUDA_TRY(cudaGetLastError());
+        }
+        s.has_dist = true;
+    }
+    return s.dist.as<double>();
+}
+
 static void require_list(MdbSystem &s)
 {
     MDB_REQUIRE(s.list_kind != LIST_NONE, MDB_ERR_STATE, "no neighbour list on the device; build one first");
@@ -158,7 +209,11 @@ static void require_list(MdbSystem &s)
 // ---------------------------------------------------------------- block caches
 namespace {
 std::mutex g_pool_mu;
-std::map<std::pair<int, size_t>, std::vector<void *>> g_dev_free;  // (device, bytes) -> blocks
+struct CachedBlock {
+    void *p;
+    cudaEvent_t ready;  // recorded on the last user's stream at release (nullptr: released after a host sync)
+};
+std::map<std::pair<int, size_t>, std::vector<CachedBlock>> g_dev_free;  // (device, bytes) -> blocks
 size_t g_dev_cached = 0;
 std::multimap<size_t, void *> g_host_free;                         // bytes -> pinned block
 std::unordered_map<void *, size_t> g_host_live;
@@ -178,8 +233,12 @@ void trim_device_locked(int device)
             int cur = 0;
             cudaGetDevice(&cur);
             cudaSetDevice(it->first.first);
-            for (void *q : it->second) {
-                cudaFree(q);
+            for (CachedBlock &q : it->second) {
+                if (q.ready) {
+                    cudaEventSynchronize(q.ready);
+                    cudaEventDestroy(q.ready);
+                }
+                cudaFree(q.p);
                 g_dev_cached -= it->first.second;
             }
             cudaSetDevice(cur);
@@ -189,24 +248,35 @@ void trim_device_locked(int device)
 }
 }  // namespace
 
-void *mdb_pool_alloc(size_t bytes, size_t *got)
+void *mdb_pool_alloc(size_t bytes, size_t *got, cudaStream_t user)
 {
     int device = 0;
     CUDA_TRY(cudaGetDevice(&device));
     const size_t want = round_block(bytes);
     {
-        std::lock_guard<std::mutex> lk(g_pool_mu);
-        // smallest cached block that fits without wasting more than half of it
-        auto it = g_dev_free.lower_bound({device, want});
-        while (it != g_dev_free.end() && it->first.first == device && it->first.second <= want + want / 2 + (1 << 20)) {
-            if (!it->second.empty()) {
-                void *q = it->second.back();
-                it->second.pop_back();
-                g_dev_cached -= it->first.second;
-                *got = it->first.second;
-                return q;
+        CachedBlock hit{nullptr, nullptr};
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            // smallest cached block that fits without wasting more than half of it
+            auto it = g_dev_free.lower_bound({device, want});
+            while (it != g_dev_free.end() && it->first.first == device && it->first.second <= want + want / 2 + (1 << 20)) {
+                if (!it->second.empty()) {
+                    hit = it->second.back();
+                    it->second.pop_back();
+                    g_dev_cached -= it->first.second;
+                    *got = it->first.second;
+                    break;
+                }
+                ++it;
             }
-            ++it;
+        }
+        if (hit.p) {
+            if (hit.ready) {   // the previous owner's queued work comes first
+                if (user) CUDA_TRY(cudaStreamWaitEvent(user, hit.ready, 0));
+                else CUDA_TRY(cudaEventSynchronize(hit.ready));
+                cudaEventDestroy(hit.ready);
+            }
+            return hit.p;
         }
     }
     void *q = nullptr;
@@ -224,18 +294,29 @@ void *mdb_pool_alloc(size_t bytes, size_t *got)
     return q;
 }
 
-void mdb_pool_free(void *p, size_t bytes)
+void mdb_pool_free(void *p, size_t bytes, cudaStream_t last_user)
 {
     if (!p) return;
     int device = 0;
     cudaGetDevice(&device);
     static const bool off = getenv("MDB_NO_CACHE") != nullptr;
     if (off) {
-        cudaFree(p);
+        cudaFree(p);   // synchronises with all outstanding work by itself
         return;
     }
+    cudaEvent_t ready = nullptr;
+    if (last_user) {
+        if (cudaEventCreateWithFlags(&ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(ready, last_user) != cudaSuccess) {
+            if (ready) cudaEventDestroy(ready);
+            ready = nullptr;
+            cudaStreamSynchronize(last_user);   // no event: fall back to a host-side wait
+        }
+    } else {
+        cudaDeviceSynchronize();   // unknown owner: be safe
+    }
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    g_dev_free[{device, bytes}].push_back(p);
+    g_dev_free[{device, bytes}].push_back(CachedBlock{p, ready});
     g_dev_cached += bytes;
 }
 
@@ -317,6 +398,7 @@ int mdb_system_create(int device, mdb_system **out)
     MDB_REQUIRE(device >= 0 && device < ndev, MDB_ERR_VALUE, "device %d out of range [0,%d)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
     MdbSystem *s = new MdbSystem();
+    s->bind_buffers();
     s->device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
@@ -331,21 +413,15 @@ void mdb_system_destroy(mdb_system *s)
 {
     if (!s) return;
     cudaSetDevice(s->device);
+    // both streams drain BEFORE any block goes back to the process-wide cache
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     cudaStreamSynchronize(s->stream);
-    DevBuf *more[] = {&s->wx, &s->wy, &s->wz, &s->qlm_r, &s->qlm_i, &s->qn, &s->types, &s->weight, &s->ptm_out, &s->ptm_idx};
-    for (DevBuf *b : more) b->release();
-    DevBuf *bufs[] = {&s->bx, &s->by, &s->bz, &s->cell_count, &s->cell_start, &s->perm, &s->perm_tmp, &s->sorted,
-                      &s->scan_tmp, &s->big_cells, &s->counters, &s->verlet, &s->dist, &s->nn, &s->verlet_tmp,
-                      &s->dist_tmp, &s->out_i32, &s->out_f64, &s->out_f64b, &s->out_f64c, &s->scratch, &s->scratch2};
-    for (DevBuf *b : bufs) b->release();
+    s->for_each_buffer([](DevBuf &b) { b.release(); });
     for (int k = 0; k < 4; ++k)
         if (s->ev[k]) cudaEventDestroy(s->ev[k]);
     for (int k = 0; k < 2; ++k)
         if (s->chunk_ev[k]) cudaEventDestroy(s->chunk_ev[k]);
-    if (s->copy_stream) {
-        cudaStreamSynchronize(s->copy_stream);
-        cudaStreamDestroy(s->copy_stream);
-    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -478,7 +554,7 @@ int mdb_system_sort_neighbor(mdb_system *s, int k)
     API_BEGIN
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
-    launch_sort_rows(*s, s->verlet.as<int>(), s->dist.as<double>(), s->n_rows, s->M, k);
+    launch_sort_rows(*s, s->verlet.as<int>(), list_dist(*s), s->n_rows, s->M, k);
     API_END
 }
 
@@ -504,7 +580,7 @@ int mdb_system_fetch_neighbor(mdb_system *s, int *verlet, double *dist, int *nn)
     } else {
         d2h(*s, verlet, s->verlet.as<int>(), n);
     }
-    d2h(*s, dist, s->dist.as<double>(), n);
+    d2h(*s, dist, list_dist(*s), n);
     d2h(*s, nn, s->nn.as<int>(), (size_t)s->n_rows);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
@@ -520,9 +596,13 @@ int mdb_system_put_neighbor(mdb_system *s, const int *verlet, const double *dist
     const size_t n = (size_t)s->n_rows * M;
     h2d(*s, s->verlet, verlet, n);
     if (dist) h2d(*s, s->dist, dist, n);
-    else s->dist.ensure<double>(n);
+    s->has_dist = dist != nullptr;   // recomputed on first use otherwise (list_dist)
     if (nn) h2d(*s, s->nn, nn, (size_t)s->n_rows);
-    else s->nn.ensure<int>(s->n_rows);
+    else {
+        MDB_LAUNCH(k_counts_from_padding, (s->n_rows + 255) / 256, 256, 0, s->stream, s->verlet.as<int>(), s->n_rows, M,
+                   s->nn.ensure<int>(s->n_rows));
+        CUDA_TRY(cudaGetLastError());
+    }
     s->M = M;
     s->list_rc = rc;
     s->list_kind = kind ? kind : LIST_CUTOFF;
@@ -534,7 +614,7 @@ int mdb_system_neighbor_device(mdb_system *s, int **verlet, double **dist, int *
     API_BEGIN
     require_list(*s);
     if (verlet) *verlet = s->verlet.as<int>();
-    if (dist) *dist = s->dist.as<double>();
+    if (dist) *dist = list_dist(*s);
     if (nn) *nn = s->nn.as<int>();
     if (M) *M = s->M;
     API_END
@@ -622,7 +702,7 @@ int mdb_system_aja(mdb_system *s, int *aja_host)
     CUDA_TRY(cudaSetDevice(s->device));
     require_list(*s);
     int *out = s->out_i32.ensure<int>(s->n_rows);
-    launch_aja(*s, s->verlet.as<int>(), s->M, s->dist.as<double>(), s->M, out);
+    launch_aja(*s, s->verlet.as<int>(), s->M, list_dist(*s), s->M, out);
     d2h(*s, aja_host, out, (size_t)s->n_rows);
     if (aja_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
@@ -657,7 +737,7 @@ int mdb_system_steinhardt(mdb_system *s, const int *llist, int ndeg, int nnn, do
     if (use_voronoi) rc_eff = 10000000000.0;
     else if (nnn > 0) rc_eff = 1000000000.0;
     else MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "At least use voronoi, or set positive nnn, or positive rc.");
-    launch_steinhardt(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, w, llist, ndeg, nnn, lmax,
+    launch_steinhardt(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->M, w, llist, ndeg, nnn, lmax,
                       wl != 0, wlhat != 0, average != 0, use_voronoi != 0, rc_eff, weight_host != nullptr, qr, qi, qn);
     s->sbo_ndeg = ndeg;
     s->sbo_nz = nz;
@@ -690,7 +770,7 @@ int mdb_system_solid_liquid(mdb_system *s, int q6index, double threshold, int n_
     int *solid = s->out_i32.ensure<int>((size_t)2 * NA);
     int *nbond = solid + NA;
     CUDA_TRY(cudaMemsetAsync(solid, 0, sizeof(int) * 2 * (size_t)NA, s->stream));
-    launch_solid_liquid(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, q6index, q6,
+    launch_solid_liquid(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->M, q6index, q6,
                         s->qlm_r.as<double>(), s->qlm_i.as<double>(), s->sbo_ndeg, s->sbo_nz, threshold, n_bond,
                         use_voronoi != 0, nnn, rc_eff, solid, nbond);
     d2h(*s, solidliquid_host, solid, (size_t)R);
@@ -715,7 +795,7 @@ int mdb_system_rdf(mdb_system *s, const int *types_host, int ntype, double rc, i
         launch_rdf_streaming(*s, types, ntype, rc, nbin, g);
     } else {
         require_list(*s);
-        launch_rdf_list(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->n_rows, s->M, types, ntype,
+        launch_rdf_list(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->n_rows, s->M, types, ntype,
                         rc, nbin, g);
     }
     d2h(*s, g_host, g, (size_t)nslot);
@@ -733,7 +813,7 @@ int mdb_system_cnp(mdb_system *s, double rc, double *cnp_host)
     MDB_REQUIRE(s->n_rows == s->N, MDB_ERR_STATE, "the common neighbour parameter reads its neighbours' rows: use a halo >= 2 frame "
                                                    "through distributed.py (rows for the inner ghost layer)");
     double *out = s->out_f64.ensure<double>(s->n_rows);
-    launch_cnp(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, rc, out);
+    launch_cnp(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->M, rc, out);
     d2h(*s, cnp_host, out, (size_t)s->n_rows);
     if (cnp_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
@@ -776,7 +856,7 @@ int mdb_system_average_by_neighbor(mdb_system *s, double rc, const double *value
     MDB_REQUIRE(value_host, MDB_ERR_VALUE, "value is required");
     const double *val = h2d(*s, s->out_f64b, value_host, (size_t)s->N);
     double *out = s->out_f64.ensure<double>(s->n_rows);
-    launch_average_by_neighbor(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, rc, val,
+    launch_average_by_neighbor(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->M, rc, val,
                                include_self != 0, out);
     d2h(*s, value_ave_host, out, (size_t)s->n_rows);
     if (value_ave_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -805,11 +885,11 @@ int mdb_system_cluster(mdb_system *s, double rc, const int *types_host, const in
         CUDA_TRY(cudaMemcpyAsync(pairs, type1, sizeof(int) * npair, cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaMemcpyAsync(pairs + npair, type2, sizeof(int) * npair, cudaMemcpyHostToDevice, s->stream));
         CUDA_TRY(cudaMemcpyAsync(rr, r, sizeof(double) * npair, cudaMemcpyHostToDevice, s->stream));
-        launch_filter_by_type(*s, vcopy, s->dist.as<double>(), s->nn.as<int>(), M, types, pairs, pairs + npair, rr, npair);
+        launch_filter_by_type(*s, vcopy, list_dist(*s), s->nn.as<int>(), M, types, pairs, pairs + npair, rr, npair);
         count = launch_cluster(*s, vcopy, nullptr, s->nn.as<int>(), M, 0.0, out);
     } else {
         MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "rc should be a positive number, got %g.", rc);
-        count = launch_cluster(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), M, rc, out);
+        count = launch_cluster(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), M, rc, out);
     }
     if (cluster_number) *cluster_number = count;
     d2h(*s, cluster_host, out, (size_t)R);
@@ -826,12 +906,12 @@ int mdb_system_structure_entropy(mdb_system *s, double rc, double sigma, int use
     const int R = s->n_rows;
     MDB_REQUIRE(average_rc <= 0 || R == s->N, MDB_ERR_STATE, "the neighbour average needs rows for every listed atom");
     double *ent = s->out_f64.ensure<double>((size_t)2 * R);
-    launch_structure_entropy(*s, s->dist.as<double>(), s->nn.as<int>(), s->M, rc, sigma, use_local_density != 0, volume,
+    launch_structure_entropy(*s, list_dist(*s), s->nn.as<int>(), s->M, rc, sigma, use_local_density != 0, volume,
                              ent);
     d2h(*s, entropy_host, ent, (size_t)R);
     if (average_rc > 0) {
         MDB_REQUIRE(average_rc <= rc, MDB_ERR_VALUE, "average_rc should be smaller than rc.");
-        launch_average_by_neighbor(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, average_rc, ent,
+        launch_average_by_neighbor(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->M, average_rc, ent,
                                    true, ent + R);
         d2h(*s, entropy_ave_host, ent + R, (size_t)R);
     }
@@ -863,7 +943,7 @@ int mdb_system_atomic_temperature(mdb_system *s, const double *vx, const double 
     CUDA_TRY(cudaMemcpyAsync(buf + 2 * NA, vz, sizeof(double) * NA, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(buf + 3 * NA, mass, sizeof(double) * NA, cudaMemcpyHostToDevice, s->stream));
     double *T = s->out_f64.ensure<double>(s->n_rows);
-    launch_atomic_temperature(*s, s->verlet.as<int>(), s->dist.as<double>(), s->M, buf, buf + NA, buf + 2 * NA, buf + 3 * NA,
+    launch_atomic_temperature(*s, s->verlet.as<int>(), list_dist(*s), s->M, buf, buf + NA, buf + 2 * NA, buf + 3 * NA,
                               rc, T);
     d2h(*s, T_host, T, (size_t)s->n_rows);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -878,7 +958,7 @@ int mdb_system_bond_analysis(mdb_system *s, double delta_r, double delta_theta, 
     require_list(*s);
     MDB_REQUIRE(bond_length_host && bond_angle_host && nbins > 0, MDB_ERR_VALUE, "both histograms and nbins are required");
     unsigned long long *hist = s->scratch2.ensure<unsigned long long>((size_t)2 * nbins);
-    launch_bond_hist(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, delta_r, delta_theta, rc, nbins,
+    launch_bond_hist(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->M, delta_r, delta_theta, rc, nbins,
                      hist);
     std::vector<unsigned long long> h((size_t)2 * nbins);
     CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, s->stream));
@@ -904,7 +984,7 @@ int mdb_system_adf(mdb_system *s, double delta_theta, const double *rc_list, con
     CUDA_TRY(cudaMemcpyAsync(rcs, rc_list, sizeof(double) * 4 * npair, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(pairs, pair_list, sizeof(int) * 3 * npair, cudaMemcpyHostToDevice, s->stream));
     unsigned long long *hist = s->scratch2.ensure<unsigned long long>((size_t)npair * nbins);
-    launch_adf_hist(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), s->M, delta_theta, rcs, pairs, npair,
+    launch_adf_hist(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->M, delta_theta, rcs, pairs, npair,
                     types, nbins, hist);
     std::vector<unsigned long long> h((size_t)npair * nbins);
     CUDA_TRY(cudaMemcpyAsync(h.data(), hist, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, s->stream));
@@ -982,7 +1062,7 @@ int mdb_build_neighbor(const double *x, const double *y, const double *z, int N,
     upload_atoms(*s, x, y, z, N);
     build_neighbor(*s, rc, M);
     d2h(*s, verlet, s->verlet.as<int>(), (size_t)N * M);
-    d2h(*s, dist, s->dist.as<double>(), (size_t)N * M);
+    d2h(*s, dist, list_dist(*s), (size_t)N * M);
     d2h(*s, nn, s->nn.as<int>(), (size_t)N);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
@@ -1031,7 +1111,7 @@ int mdb_knn(const double *x, const double *y, const double *z, int N, const doub
     upload_atoms(*s, x, y, z, N);
     launch_knn(*s, k);
     d2h(*s, indices, s->verlet.as<int>(), (size_t)N * k);
-    d2h(*s, distances, s->dist.as<double>(), (size_t)N * k);
+    d2h(*s, distances, list_dist(*s), (size_t)N * k);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     API_END
 }
@@ -1207,7 +1287,7 @@ int mdb_filter_by_type(int *verlet, int N, int M, const double *dist, const int 
     CUDA_TRY(cudaMemcpyAsync(pairs, type1, sizeof(int) * npair, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(pairs + npair, type2, sizeof(int) * npair, cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(rr, r, sizeof(double) * npair, cudaMemcpyHostToDevice, s->stream));
-    launch_filter_by_type(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), M, types, pairs, pairs + npair,
+    launch_filter_by_type(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), M, types, pairs, pairs + npair,
                           rr, npair);
     d2h(*s, verlet, s->verlet.as<int>(), (size_t)N * M);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1351,7 +1431,7 @@ int mdb_get_sq(const double *x, const double *y, const double *z, int N, const d
     double *qr = h2d(*s, s->qlm_r, qlm_r, nq), *qi = h2d(*s, s->qlm_i, qlm_i, nq);
     double *qn = h2d(*s, s->qn, qnarray, (size_t)N * ncol);
     const double *w = use_weight ? h2d(*s, s->weight, weight, (size_t)N * M) : nullptr;
-    launch_steinhardt(*s, s->verlet.as<int>(), s->dist.as<double>(), s->nn.as<int>(), M, w, llist, ndeg, nnn, lmax,
+    launch_steinhardt(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), M, w, llist, ndeg, nnn, lmax,
                       wl != 0, wlhat != 0, average != 0, use_voronoi != 0, rc, use_weight != 0, qr, qi, qn);
     d2h(*s, qlm_r, qr, nq);
     d2h(*s, qlm_i, qi, nq);

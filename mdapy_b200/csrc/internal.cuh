@@ -56,26 +56,31 @@ struct MdbError {
 // (system.py mirrors the reference's one-System-per-file usage); cudaMalloc/cudaFree of ~20 GB of
 // buffers per frame would dominate the end-to-end time, so released blocks are parked per device and
 // reused by the next System.  mdb_trim_cache() returns everything to the driver.
-void *mdb_pool_alloc(size_t bytes, size_t *got);
-void mdb_pool_free(void *p, size_t bytes);
+// Frees are STREAM ORDERED: a released block carries an event recorded on the stream that last used it,
+// and whoever takes the block from the cache waits for that event on its own stream (or on the host when
+// it has none) -- work still queued on the old owner's stream can never overlap the new owner's.
+void *mdb_pool_alloc(size_t bytes, size_t *got, cudaStream_t user);
+void mdb_pool_free(void *p, size_t bytes, cudaStream_t last_user);
 
 // grow-only device buffer; allocation cost is paid once per high-water mark
 struct DevBuf {
     void *p{nullptr};
     size_t cap{0};
+    const cudaStream_t *owner{nullptr};  // the stream of the handle this buffer belongs to (MdbSystem::bind_buffers)
+    cudaStream_t stream() const { return owner ? *owner : nullptr; }
     template <class T> T *ensure(size_t count)
     {
         const size_t bytes = count * sizeof(T);
         if (bytes > cap) {
             release();
-            p = mdb_pool_alloc(bytes + bytes / 16 + 256, &cap);
+            p = mdb_pool_alloc(bytes + bytes / 16 + 256, &cap, stream());
         }
         return static_cast<T *>(p);
     }
     template <class T> T *as() const { return static_cast<T *>(p); }
     void release()
     {
-        if (p) mdb_pool_free(p, cap);
+        if (p) mdb_pool_free(p, cap, stream());
         p = nullptr;
         cap = 0;
     }
@@ -122,6 +127,7 @@ struct MdbSystem {
     double list_rc{-1.0};
     int M{0};
     int max_count{0};
+    bool has_dist{true};  // false: the caller handed in a bare verlet list; distances are recomputed on first use
     DevBuf verlet, dist, nn, verlet_tmp, dist_tmp;
     // width of the previous automatic build on this handle (frames of a trajectory reuse one handle: the
     // next frame starts from this width instead of sampling tiles again)
@@ -140,6 +146,20 @@ struct MdbSystem {
     bool profile{false};
     float t_bin{0}, t_neigh{0}, t_cna{0};
     cudaEvent_t ev[4]{};
+
+    // every device buffer of the handle (stream binding, destruction)
+    template <class F> void for_each_buffer(F f)
+    {
+        DevBuf *all[] = {&bx, &by, &bz, &cell_count, &cell_start, &perm, &perm_tmp, &sorted, &scan_tmp, &big_cells,
+                         &counters, &verlet, &dist, &nn, &verlet_tmp, &dist_tmp, &out_i32, &out_f64, &out_f64b,
+                         &out_f64c, &scratch, &scratch2, &wx, &wy, &wz, &qlm_r, &qlm_i, &qn, &types, &weight,
+                         &ptm_out, &ptm_idx};
+        for (DevBuf *b : all) f(*b);
+    }
+    void bind_buffers()
+    {
+        for_each_buffer([this](DevBuf &b) { b.owner = &stream; });
+    }
 };
 
 // ---- kernels launchers (one per .cu) ---------------------------------------

@@ -390,5 +390,6 @@ void launch_knn(MdbSystem &s, int k)
     s.M = k;
     s.max_count = k;
     s.list_kind = LIST_KNN;
+    s.has_dist = true;
     s.list_rc = -1.0;
 }

@@ -259,6 +259,11 @@ class SlabDecomposition:
         """Halo exchange (or local selection from a replicated frame), then hand owned + ghost atoms to
         this rank's DeviceSystem (no list yet)."""
         torch = self.torch
+        # the library reads x/y/z as f64 and ids as int32 device arrays: convert once, never reinterpret
+        x, y, z = (t.to(device=self.device, dtype=torch.float64).contiguous() for t in (x, y, z))
+        if gid.dtype != torch.int32:
+            assert int(gid.max()) < 2 ** 31, "global ids must fit int32"
+        gid = gid.to(device=self.device, dtype=torch.int32).contiguous()
         if replicated:
             ax, ay, az, ag, aext = self.select_replicated(x, y, z, gid, extra)
         else:

@@ -224,17 +224,20 @@ def read_xyz(filename: str) -> Tuple[Frame, Box, Dict[str, Any]]:
     int_cols = {n for n, k in kinds.items() if k == "I"}
     cols = (_table(body, names, STR_COLS | text_cols, INT_COLS | int_cols) if natom
             else {n: np.zeros(0) for n in names})
+    # pbc is honoured with or without a Lattice (load_save.py of the reference parses it first);
+    # only "T" / "1" count as periodic, like the reference
+    boundary = None
+    if "pbc" in info:
+        boundary = [1 if t in ("T", "1") else 0 for t in info["pbc"].split()]
     if "lattice" in info:
         cell = np.array(info["lattice"].split(), float).reshape(3, 3)
         origin = np.array(info["origin"].split(), float) if "origin" in info else np.zeros(3)
-        boundary = [1, 1, 1]
-        if "pbc" in info:
-            boundary = [1 if t.upper() in ("T", "TRUE", "1") else 0 for t in info["pbc"].split()]
-        box = Box(cell, boundary, origin)
+        box = Box(cell, boundary if boundary is not None else [1, 1, 1], origin)
     else:
         pos = np.stack([cols["x"], cols["y"], cols["z"]], axis=1)
         lo, hi = pos.min(axis=0), pos.max(axis=0)
-        box = Box(np.diag(np.maximum(hi - lo, 1e-3)), [0, 0, 0], lo)
+        ext = hi - lo
+        box = Box(np.diag(np.where(ext > 0, ext, 1e-9)), boundary if boundary is not None else [0, 0, 0], lo)
     for k in ("lattice", "properties", "pbc", "origin"):
         info.pop(k, None)
     return Frame(cols), box, info

@@ -176,6 +176,9 @@ class System:
         dev = self._device_view()
         if self._host_dirty:
             h = self._host_list
+            if "verlet_list" not in h:
+                # the reference's consumers read self.verlet_list: a list needs at least its index array
+                raise AttributeError("verlet_list")
             dev.put_neighbor(h["verlet_list"], h.get("distance_list"), h.get("neighbor_number"),
                              rc=float(self.__dict__.get("rc", -1.0)),
                              kind=LIST_CUTOFF if "rc" in self.__dict__ else LIST_KNN)
@@ -202,7 +205,14 @@ class System:
         dev = None
         if "_enlarge_data" not in self.__dict__ and sum(self.box.check_small_box(float(rc))) == 3:
             dev = self._device_view()
-        neigh.compute(dev=dev, fetch=False)
+        try:
+            neigh.compute(dev=dev, fetch=False)
+        except Exception:
+            # (max_neigh too small, ...) the shared device handle may already hold the truncated rows of
+            # THIS build: no cached list survives a failed build
+            if dev is not None:
+                self._reset_neighbor()
+            raise
         self.rc = rc
         if hasattr(neigh, "_enlarge_box"):
             self._enlarge_box = neigh._enlarge_box
