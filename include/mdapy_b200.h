@@ -238,6 +238,10 @@ int mdb_system_neighbor_device(mdb_system *s, int **verlet, double **dist, int *
 
 /* descriptors on the cached list; results stay on the device when out == NULL */
 int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host);
+/* Neighbour search (neighbor.cpp:130-186) and FixedCNA (cna.cpp:429-506) in ONE pass that never writes the
+ * list: what System.cal_common_neighbor_analysis(rc) needs when nothing else reads the list (it is built
+ * lazily on first access).  *used = 0: frame not eligible (triclinic / tiny box), nothing was computed. */
+int mdb_system_fused_cna(mdb_system *s, double rc, int *pattern_host, int *used);
 int mdb_system_acna(mdb_system *s, int *pattern_host);
 int mdb_system_ids(mdb_system *s, int *pattern_host);
 int mdb_system_csp(mdb_system *s, int nnei, double *csp_host);

@@ -87,6 +87,7 @@ PROTOTYPES = {
     "mdb_system_put_neighbor": (C.c_int, [c_vp, c_ip, c_dp, c_ip, C.c_int, C.c_double, C.c_int]),
     "mdb_system_neighbor_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), c_ip]),
     "mdb_system_fcna": (C.c_int, [c_vp, C.c_double, c_ip]),
+    "mdb_system_fused_cna": (C.c_int, [c_vp, C.c_double, c_ip, c_ip]),
     "mdb_system_acna": (C.c_int, [c_vp, c_ip]),
     "mdb_system_ids": (C.c_int, [c_vp, c_ip]),
     "mdb_system_csp": (C.c_int, [c_vp, C.c_int, c_dp]),

@@ -656,6 +656,37 @@ int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host)
     API_END
 }
 
+// Fused neighbour search + fixed-cutoff CNA: labels without a neighbour list in HBM (neighbor_tiled.cu,
+// k_fused_cna).  *used = 1 when the fused kernel produced the labels, 0 when the frame is not eligible
+// (triclinic / tiny box / overflow tiles) -- nothing was computed then and the caller takes the list path.
+int mdb_system_fused_cna(mdb_system *s, double rc, int *pattern_host, int *used)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->N > 0 && s->has_box, MDB_ERR_STATE, "no atoms uploaded");
+    MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "rc must be positive, got %g.", rc);
+    MDB_REQUIRE(used, MDB_ERR_VALUE, "used is required");
+    *used = 0;
+    prof_mark(*s, 0);
+    if (s->bin_rc != rc) launch_binning(*s, rc);
+    prof_mark(*s, 1);
+    int *pat = s->out_i32.ensure<int>(s->n_rows);
+    int left = 0;
+    const bool ok = launch_fused_cna(*s, rc, pat, &left);
+    prof_mark(*s, 2);
+    if (ok && left == 0) {
+        *used = 1;
+        d2h(*s, pattern_host, pat, (size_t)s->n_rows);
+        if (pattern_host || s->profile) CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if (s->profile) {
+            CUDA_TRY(cudaEventElapsedTime(&s->t_bin, s->ev[0], s->ev[1]));
+            CUDA_TRY(cudaEventElapsedTime(&s->t_neigh, s->ev[1], s->ev[2]));
+            s->t_cna = 0.f;
+        }
+    }
+    API_END
+}
+
 int mdb_system_acna(mdb_system *s, int *pattern_host)
 {
     API_BEGIN

@@ -174,6 +174,7 @@ void launch_compact_rows(MdbSystem &s, int M_from, int M_to);
 bool tiled_neighbor_plan(const MdbSystem &s, int &T);
 void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_only, int sample_stride);
 int neighbor_tiled_max(MdbSystem &s, int *min_count = nullptr);
+bool launch_fused_cna(MdbSystem &s, double rc, int *pattern, int *n_fallback);
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k);
 void launch_fcna(MdbSystem &s, const int *verlet, const int *nn, int M, double rc, int *pattern, int first = 0,
                  int count = -1);

@@ -17,6 +17,7 @@
 // Only ~20 % of the 27-cell candidates survive phase 1, so the f64 pipe sees ~13 pairs per atom
 // instead of ~67.  Rows are padded by the writing thread (-1 / rc+1), so no prefill pass is needed.
 #include "internal.cuh"
+#include "cna_core.cuh"
 #include <type_traits>
 
 namespace {
@@ -50,7 +51,9 @@ struct TileArgs {
     int use_tma;
     int tiles_x;     // tiles along x (warp-per-cell kernel: strip order of the tile list)
     int ocap;        // owned-atom capacity of the per-tile wrapped-position table
-    int ltot;        // pooled capacity of the per-cell candidate lists (entries)
+    int *pattern;    // fused neighbour + CNA kernel: labels out
+    float rcsq_lo;   // fp32 bound below which a candidate is a neighbour without the exact test
+    float cut_lo, cut_hi;   // fp32 band of the bond test among neighbours
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -853,7 +856,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_coop(const _
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(zj), "=d"(wj) : "r"(ra + 16u));
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xi), "=d"(yi) : "r"(oa));
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(zi), "=d"(wi) : "r"(oa + 16u));
-            const unsigned have = lds_u16(acnt_base + 2u * tt);   // accepted in earlier calls
+            const unsigned have = valid ? lds_u16(acnt_base + 2u * tt) : 0u;   // accepted in earlier calls
             const int jdx = __double2loint(wj);
             const int idx = __double2loint(wi), fl = __double2hiint(wi);
             double dx = xj - xi, dy = yj - yi, dz = zj - zi;
@@ -1099,6 +1102,416 @@ template <int T, int TZ> void launch_T(const TileArgs &A, int nblocks, cudaStrea
     else MDB_LAUNCH((k_neighbor_tiled<T, TZ, false>), nblocks, TILE_THREADS, smem, st, A);
 }
 
+// =====================================================================================================
+// Fused neighbour search + fixed-cutoff CNA (SURVEY.md 8d "fused neighbour+CNA (no list)", 28 B/atom).
+// Replaces build_neighbor (src/neighbor.cpp:130-186) followed by FixedCNA (src/cna.cpp:429-506) for callers
+// that only read the labels: the neighbour list never goes to HBM.  Same tile staging as the list kernels;
+// one thread per owned atom:
+//   1. the 27-cell stencil with the fp32 form of the distance test.  A candidate well inside the cut-off
+//      (fp32 d^2 <= rc^2 (1 - 4e-4)) is a neighbour, one well outside is not -- the band is > 5x the fp32
+//      error bound -- and a candidate inside the band takes the reference's exact f64 test (xi wrapped,
+//      x[j] raw, minimum image, <= rc^2).  The neighbour SET therefore equals the reference's list row;
+//      CNA does not depend on its order.
+//   2. atoms with 12 or 14 neighbours: the 66 / 91 bond tests among the neighbours on the staged fp32
+//      positions (all nearest images of one tile centre, so differences are minimum-image vectors), a pair
+//      within 1e-4 rc^2 of the threshold sends the atom to the exact f64 bond matrix (cna.cpp:149-161 on
+//      raw coordinates); signatures from the bond rows in registers (cna_core.cuh).
+// Labels are identical to FixedCNA on the reference's list (tests/test_gpu_fused.py, at-scale parity tool).
+constexpr int FUSED_QCAP = 16;   // neighbour slots per thread (more than 14 neighbours -> label 0)
+
+// exact membership test of the list build for one pair (cold)
+__device__ __noinline__ bool fused_exact_neighbor(const DBox &box, const SortedAtom *raw, int s_i, int k, double rcsq)
+{
+    double xi = raw[s_i].x, yi = raw[s_i].y, zi = raw[s_i].z;
+    wrap_ortho(box, xi, yi, zi);
+    double dx = raw[k].x - xi, dy = raw[k].y - yi, dz = raw[k].z - zi;
+    min_image_ortho(box, dx, dy, dz);
+    return dx * dx + dy * dy + dz * dz <= rcsq;
+}
+
+// exact bond matrix + signatures for one atom (cold): cna.cpp:149-161 on the raw coordinates of the neighbours
+template <int STRIDE>
+__device__ __noinline__ int fused_exact_cna(const DBox &box, const SortedAtom *raw, const unsigned short *q, int nn,
+                                            double cutsq, unsigned short *nb)
+{
+    for (int a = 0; a < nn; ++a) nb[a * STRIDE] = 0;
+    for (int a = 0; a < nn; ++a) {
+        const SortedAtom &A_ = raw[q[a * STRIDE]];
+        for (int b = a + 1; b < nn; ++b) {
+            const SortedAtom &B_ = raw[q[b * STRIDE]];
+            double dx = B_.x - A_.x, dy = B_.y - A_.y, dz = B_.z - A_.z;
+            min_image_ortho(box, dx, dy, dz);
+            if (dx * dx + dy * dy + dz * dz <= cutsq) {
+                nb[a * STRIDE] |= (unsigned short)(1u << b);
+                nb[b * STRIDE] |= (unsigned short)(1u << a);
+            }
+        }
+    }
+    return cna_label(cna_signatures_smem<STRIDE>(nb, nn));
+}
+
+// Exact fallback for one atom through global memory (cold): atoms of overflow tiles and atoms far outside
+// the box (clamped into an edge cell of an open axis).  Neighbours by the list builder's exact test,
+// bonds by cna.cpp:149-161.
+template <int STRIDE>
+__device__ __noinline__ int fused_direct_atom(const TileArgs &A, int sg, unsigned short *nb)
+{
+    const CellGrid &g = A.g;
+    const DBox &box = A.box;
+    double xi, yi, zi;
+    int my_idx, my_cell;
+    load_rec(A.sorted + sg, xi, yi, zi, my_idx, my_cell);
+    wrap_ortho(box, xi, yi, zi);
+    int ic, jc, kc;
+    cell_decode(g, my_cell, ic, jc, kc);
+    int nbr[14];
+    int n = 0;
+#pragma unroll 1
+    for (int st = 0; st < 27; ++st) {
+        const int di = st / 9 - 1, dj = (st / 3) % 3 - 1, dk = st % 3 - 1;
+        const int c = cell_linear(g, wrap_cell(ic + di, g.n[0]), wrap_cell(jc + dj, g.n[1]), wrap_cell(kc + dk, g.n[2]));
+        if (c < 0) continue;
+        const int cb = __ldg(A.cell_start + c), ce = __ldg(A.cell_start + c + 1);
+        for (int q = ce - 1; q >= cb; --q) {
+            if (q == sg) continue;
+            double xj, yj, zj;
+            int jdx, jcell;
+            load_rec(A.sorted + q, xj, yj, zj, jdx, jcell);
+            double dx = xj - xi, dy = yj - yi, dz = zj - zi;
+            min_image_ortho(box, dx, dy, dz);
+            if (dx * dx + dy * dy + dz * dz <= A.rcsq) {
+                if (n < 14) nbr[n] = q;
+                ++n;
+            }
+        }
+    }
+    if (n != 12 && n != 14) return 0;
+    for (int a = 0; a < n; ++a) nb[a * STRIDE] = 0;
+    for (int a = 0; a < n; ++a) {
+        double xa, ya, za;
+        int t0, t1;
+        load_rec(A.sorted + nbr[a], xa, ya, za, t0, t1);
+        for (int b = a + 1; b < n; ++b) {
+            double xb, yb, zb;
+            load_rec(A.sorted + nbr[b], xb, yb, zb, t0, t1);
+            double dx = xb - xa, dy = yb - ya, dz = zb - za;
+            min_image_ortho(box, dx, dy, dz);
+            if (dx * dx + dy * dy + dz * dz <= A.rcsq) {
+                nb[a * STRIDE] |= (unsigned short)(1u << b);
+                nb[b * STRIDE] |= (unsigned short)(1u << a);
+            }
+        }
+    }
+    return cna_label(cna_signatures_smem<STRIDE>(nb, n));
+}
+
+template <int NN, int STRIDE>
+__device__ __forceinline__ int fused_cna_body(const DBox &box, const SortedAtom *raw, const float4 *f4,
+                                              const unsigned short *q, double cutsq, float cut_lo, float cut_hi,
+                                              unsigned short *nb)
+{
+    float rx[NN], ry[NN], rz[NN];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+        const float4 o = f4[q[a * STRIDE]];
+        rx[a] = o.x;
+        ry[a] = o.y;
+        rz[a] = o.z;
+    }
+    unsigned rows[NN];
+#pragma unroll
+    for (int a = 0; a < NN; ++a) rows[a] = 0;
+    bool ambiguous = false;
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+#pragma unroll
+        for (int b = a + 1; b < NN; ++b) {
+            const float dx = rx[b] - rx[a], dy = ry[b] - ry[a], dz = rz[b] - rz[a];
+            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+            if (d2 < cut_lo) {
+                rows[a] |= 1u << b;
+                rows[b] |= 1u << a;
+            } else if (d2 <= cut_hi)
+                ambiguous = true;
+        }
+    }
+    if (ambiguous) return fused_exact_cna<STRIDE>(box, raw, q, NN, cutsq, nb);
+    return cna_label(cna_signatures_regs<NN, STRIDE>(rows, nb));
+}
+
+template <int T, int TZ, int NT>
+__global__ void __launch_bounds__(NT, 3) k_fused_cna(const __grid_constant__ TileArgs A)
+{
+    constexpr int P = T + 2;
+    constexpr int PZ = TZ + 2;
+    constexpr int NPEN = P * P;
+    constexpr int NCELL = NPEN * PZ;
+    constexpr int CSW = PZ + 1;
+    constexpr int NW = NT / 32;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const unsigned o_f4 = (unsigned)A.cap * 32u;                       // [cap] 16 B
+    const unsigned o_queue = o_f4 + (unsigned)A.cap * 16u;             // [FUSED_QCAP][NT] u16, interleaved
+    const unsigned o_nb = o_queue + FUSED_QCAP * NT * 2u;              // [14][NT] u16 bond rows (flood / exact path)
+    const unsigned o_bar = o_nb + 14 * NT * 2u;                        // mbarrier (8 B, 16-byte slot)
+    const unsigned o_cs = o_bar + 16u;                                 // [NPEN][CSW] int
+    const unsigned o_gstart = o_cs + NPEN * CSW * 4u;                  // [NCELL]
+    const unsigned o_ptot = o_gstart + NCELL * 4u;                     // [NPEN + 1]
+    const unsigned o_opref = o_ptot + (NPEN + 1) * 4u;                 // [T*T + 1]
+    const unsigned o_flag = o_opref + (T * T + 1) * 4u;                // [4]
+    SortedAtom *raw = reinterpret_cast<SortedAtom *>(smem);
+    float4 *f4 = reinterpret_cast<float4 *>(smem + o_f4);
+    unsigned short *queue = reinterpret_cast<unsigned short *>(smem + o_queue);
+    unsigned short *nbs = reinterpret_cast<unsigned short *>(smem + o_nb);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + o_bar);
+    int *cs = reinterpret_cast<int *>(smem + o_cs);
+    int *gstart = reinterpret_cast<int *>(smem + o_gstart);
+    int *ptot = reinterpret_cast<int *>(smem + o_ptot);
+    int *opref = reinterpret_cast<int *>(smem + o_opref);
+
+    const int tid = threadIdx.x;
+    const CellGrid &g = A.g;
+    int tx, ty, tz;
+    if (A.tile_stride != 1) {   // grid too large for a 3-D launch: linear list of tiles
+        int tl = blockIdx.x * max(A.tile_stride, 1) + A.tile_offset;
+        if (tl >= A.n_tiles) return;
+        tz = tl % A.tiles_z;
+        tl /= A.tiles_z;
+        ty = tl % A.tiles_y;
+        tx = tl / A.tiles_y;
+    } else {   // strip order, see k_neighbor_coop
+        tz = blockIdx.x;
+        const int strip = blockIdx.z / A.tiles_x;
+        tx = blockIdx.z - strip * A.tiles_x;
+        ty = strip * 8 + blockIdx.y;
+        if (ty >= A.tiles_y) return;
+    }
+    const int u0x = A.p_lo + tx * T - 1, u0y = ty * T - 1, u0z = tz * TZ - 1;
+    const int amax = min(T, A.p_hi - (u0x + 1)), bmax = min(T, g.n[1] - (u0y + 1)), kmax = min(TZ, g.n[2] - (u0z + 1));
+
+    if (tid == 0) mbar_init(bar, 1);
+
+    // ---- A. population and global start of every cell of the block (z slots in memory order)
+    for (int c = tid; c < NCELL; c += NT) {
+        const int ks = c % PZ, b = (c / PZ) % P, a = c / (PZ * P);
+        const int kk = PZ - 1 - ks;
+        int px;
+        const int ux = u0x + a;
+        if (A.wrap_x) px = (ux >= A.p_lo - 1 && ux <= A.p_hi) ? map_axis(ux, g.n[0]) : -1;
+        else px = (ux >= A.p_lo - 1 && ux <= A.p_hi && ux >= 0 && ux < g.nxl) ? ux : -1;
+        const int py = map_axis(u0y + b, g.n[1]);
+        const int pz = map_axis(u0z + kk, g.n[2]);
+        int beg = -1, cnt = 0;
+        if (px >= 0 && py >= 0 && pz >= 0) {
+            const int cell = (px * g.n[1] + py) * g.n[2] + (g.n[2] - 1 - pz);
+            beg = __ldg(A.cell_start + cell);
+            cnt = __ldg(A.cell_start + cell + 1) - beg;
+        }
+        gstart[c] = beg;
+        cs[(a * P + b) * CSW + ks + 1] = cnt;
+    }
+    __syncthreads();
+    for (int p = tid; p < NPEN; p += NT) {
+        int s = 0;
+        for (int kk = 0; kk < PZ; ++kk) s += cs[p * CSW + kk + 1];
+        ptot[p] = s;
+    }
+    __syncthreads();
+    warp0_exclusive_scan(ptot, NPEN);
+    __syncthreads();
+    for (int p = tid; p < NPEN; p += NT) {
+        int off = ptot[p];
+        cs[p * CSW] = off;
+        for (int kk = 0; kk < PZ; ++kk) {
+            off += cs[p * CSW + kk + 1];
+            cs[p * CSW + kk + 1] = off;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < T * T; i += NT) {
+        const int a = i / T + 1, b = i % T + 1;
+        const int p = a * P + b;
+        opref[i] = (a <= amax && b <= bmax) ? cs[p * CSW + PZ - 1] - cs[p * CSW + PZ - 1 - kmax] : 0;
+    }
+    __syncthreads();
+    warp0_exclusive_scan(opref, T * T);
+    __syncthreads();
+    const int n_staged = ptot[NPEN];
+    const int n_owned = opref[T * T];
+    if (n_owned == 0) return;
+    const bool fits = n_staged <= A.cap;
+
+    const DBox &box = A.box;
+    const int warp = tid >> 5, lane = tid & 31;
+    auto pencil_of = [&](int t) {
+        int lo = 0, hi = T * T;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (opref[mid] <= t) lo = mid;
+            else hi = mid;
+        }
+        return lo;
+    };
+
+    if (fits) {
+        // ---- B. stage the records (TMA bulk copies, one per run of consecutive global cells of a pencil)
+        if (tid == 0) mbar_expect_tx(bar, (unsigned)n_staged * (unsigned)sizeof(SortedAtom));
+        __syncthreads();
+        for (int p = tid; p < NPEN; p += NT) {
+            int kk = 0;
+            while (kk < PZ) {
+                const int beg = gstart[p * PZ + kk];
+                const int dst0 = cs[p * CSW + kk];
+                int total = cs[p * CSW + kk + 1] - dst0;
+                int k2 = kk + 1;
+                if (beg >= 0) {
+                    while (k2 < PZ && gstart[p * PZ + k2] == beg + total) {
+                        total += cs[p * CSW + k2 + 1] - cs[p * CSW + k2];
+                        ++k2;
+                    }
+                    if (total > 0)
+                        bulk_g2s(raw + dst0, A.sorted + beg, (unsigned)total * (unsigned)sizeof(SortedAtom), bar);
+                }
+                kk = k2;
+            }
+        }
+        if (warp == 0) mbar_wait(bar, 0);   // one warp polls; the others sleep on the CTA barrier
+        __syncthreads();
+
+        // ---- C. fp32 positions relative to the tile centre (nearest periodic image), flat over the staged atoms
+        const double rcw = 1.0 / g.rc_inv;
+        const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0);
+        const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
+                     ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
+        for (int s = tid; s < n_staged; s += NT) {
+            const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
+            const double z = reinterpret_cast<const double *>(raw + s)[2];
+            double d0 = lo.x - ctr0, d1 = lo.y - ctr1, d2 = z - ctr2;
+            if (box.pbc[0]) d0 -= box.h[0] * rint(d0 * box.hinv[0]);
+            if (box.pbc[1]) d1 -= box.h[4] * rint(d1 * box.hinv[4]);
+            if (box.pbc[2]) d2 -= box.h[8] * rint(d2 * box.hinv[8]);
+            const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
+            const float w = __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0));
+            // An atom beyond the radius the fp32 bound covers (12.6 rc from the tile centre: an atom far outside
+            // the box clamped into an edge cell, the far side of an open axis, NaN) cannot be within rc of an
+            // owned atom that is inside it: as a CANDIDATE it never passes; as an OWNED atom it takes the exact
+            // fallback below.
+            f4[s] = (w <= A.w_limit) ? make_float4(f0, f1, f2, w) : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+        }
+        __syncthreads();
+    }
+    if (!fits) {
+        // overflow tile (more atoms than the shared buffers hold): exact walk through global memory
+        for (int t = tid; t < n_owned; t += NT) {
+            const int lo = pencil_of(t);
+            const int p = (lo / T + 1) * P + (lo % T + 1);
+            const int sg = gstart[p * PZ + PZ - 1 - kmax] + (t - opref[lo]);
+            const int idx = A.sorted[sg].idx;
+            if (idx < A.n_rows) A.pattern[idx] = fused_direct_atom<NT>(A, sg, nbs + tid);
+        }
+        return;
+    }
+
+    const unsigned f4_base = smem_u32(f4);
+    const unsigned q_base = smem_u32(queue) + 2u * tid;
+    constexpr unsigned QS = 2u * NT;
+    const unsigned q_full = q_base + QS * FUSED_QCAP;
+    const float rc2hi = A.rcsq_hi, rc2lo = A.rcsq_lo;
+#pragma unroll 1
+    for (int base = warp * 32; base < n_owned; base += NT) {
+        const int t = base + lane;
+        if (t >= n_owned) continue;
+        const int pi = pencil_of(t);
+        const int p = (pi / T + 1) * P + (pi % T + 1);
+        const int *prow = cs + p * CSW;
+        const int s_i = prow[PZ - 1 - kmax] + (t - opref[pi]);
+        int kk = PZ - 1 - kmax;   // my memory slot along z: owned slots are PZ-1-kmax .. PZ-2
+        while (kk < PZ - 2 && prow[kk + 1] <= s_i) ++kk;
+        const int idx = raw[s_i].idx;
+        if (idx >= A.n_rows) continue;   // ghost atom of a decomposed frame: neighbour only
+        const float4 me = f4[s_i];
+        if (!(me.w <= A.w_limit)) {   // far outside the box: exact fallback (see phase C)
+            A.pattern[idx] = fused_direct_atom<NT>(A, gstart[p * PZ + PZ - 1 - kmax] + (t - opref[pi]), nbs + tid);
+            continue;
+        }
+        const float fx = -2.0f * me.x, fy = -2.0f * me.y, fz = -2.0f * me.z;
+        const float thr_hi = rc2hi - me.w, thr_lo = rc2lo - me.w;
+        unsigned q_top = q_base;
+        int n = 0;
+        const unsigned self = f4_base + 16u * (unsigned)s_i;
+
+        // the 9 pencils of the stencil; the centre pencil in two pieces that leave the atom itself out
+        int pen_off = -P - 1, pen_y = 0;
+#pragma unroll 1
+        for (int pen = 0; pen < 9; ++pen) {
+            const int *row = cs + (p + pen_off) * CSW + kk;
+            const unsigned abeg = f4_base + 16u * (unsigned)row[-1];
+            const unsigned aend = f4_base + 16u * (unsigned)row[2];
+#pragma unroll 1
+            for (int piece = 0; piece < (pen == 4 ? 2 : 1); ++piece) {
+                unsigned lo_a = abeg, aq = aend;
+                if (pen == 4) {
+                    if (piece == 0) lo_a = self + 16u;
+                    else aq = self;
+                }
+                float4 o = lds_f4(aq - 16u);   // (a read below the run is harmless: it stays inside the staged arrays)
+#pragma unroll 2
+                while (aq > lo_a) {
+                    aq -= 16u;
+                    const float4 c = o;
+                    o = lds_f4(aq - 16u);
+                    const float t2 = __fmaf_rn(fx, c.x, __fmaf_rn(fy, c.y, __fmaf_rn(fz, c.z, c.w)));
+                    if (t2 <= thr_hi) {
+                        const int k = (int)((aq - f4_base) >> 4);
+                        bool in = t2 <= thr_lo;
+                        if (!in) in = fused_exact_neighbor(box, raw, s_i, k, A.rcsq);
+                        if (in) {
+                            if (q_top < q_full) {
+                                sts_u16(q_top, (unsigned)k);
+                                q_top += QS;
+                            }
+                            ++n;
+                        }
+                    }
+                }
+            }
+            if (++pen_y == 3) {
+                pen_y = 0;
+                pen_off += P - 2;
+            } else ++pen_off;
+        }
+        int label = 0;
+        const unsigned short *q = queue + tid;
+        unsigned short *nb = nbs + tid;
+        if (n == 12) label = fused_cna_body<12, NT>(box, raw, f4, q, A.rcsq, A.cut_lo, A.cut_hi, nb);
+        else if (n == 14) label = fused_cna_body<14, NT>(box, raw, f4, q, A.rcsq, A.cut_lo, A.cut_hi, nb);
+        A.pattern[idx] = label;
+    }
+}
+
+template <int T, int TZ, int NT> size_t fused_smem_bytes(int cap)
+{
+    constexpr int P = T + 2, PZ = TZ + 2, NPEN = P * P, NCELL = NPEN * PZ;
+    return (size_t)cap * (sizeof(SortedAtom) + sizeof(float4)) + sizeof(unsigned short) * (FUSED_QCAP + 14) * NT +
+           sizeof(int) * (NPEN * (PZ + 1) + NCELL + NPEN + 1 + T * T + 1 + 4) + 16 + 64;
+}
+
+template <int T, int TZ, int NT> void launch_fused_T(const TileArgs &A, int nblocks, cudaStream_t st)
+{
+    const size_t smem = fused_smem_bytes<T, TZ, NT>(A.cap);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(k_fused_cna<T, TZ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    dim3 grid(nblocks, 1, 1);
+    if (A.tile_stride == 1) {
+        const int strips = (A.tiles_y + 7) / 8;
+        grid = dim3(A.tiles_z, A.tiles_y < 8 ? A.tiles_y : 8, strips * A.tiles_x);
+    }
+    MDB_LAUNCH((k_fused_cna<T, TZ, NT>), grid, NT, smem, st, A);
+}
+
 }  // namespace
 
 // Returns false when the frame is not eligible (triclinic, or too few cells along a periodic axis for
@@ -1188,11 +1601,6 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
         int ocap = (int)(rho * TT * TT * TZ * 1.15) + 32;
         ocap = (ocap + 31) / 32 * 32;
         A.ocap = ocap > 1024 ? 1024 : ocap;
-        // pooled candidate-list space: 27 cells of mean population per owned cell, padded to whole rounds
-        // of 32 (+16 on average), + 25 %
-        const int ncell_own = TT * TT * TZ;
-        int ltot = (int)(ncell_own * (rho * 27 + 16) * 1.25) + 256;
-        A.ltot = (ltot + 31) / 32 * 32;
     }
     // Kernel choice (measured, profiles/r2_neighbor_kernel_study.md): the thread-per-atom kernel above is the
     // faster one while rows are short (FCC / BCC first shells: 20.5 vs 21.9 ms per 99.6 M atoms), the
@@ -1239,4 +1647,63 @@ int neighbor_tiled_max(MdbSystem &s, int *min_count)
     CUDA_TRY(cudaStreamSynchronize(s.stream));
     if (min_count) *min_count = v[1];
     return v[0];
+}
+
+// Fused neighbour search + fixed-cutoff CNA on the binned frame; labels into `pattern` (device).  Returns
+// false when the frame is not eligible for the tile kernels (the caller then takes the list path).
+// *n_fallback receives the number of atoms the kernel could not classify (label -1: overflow tiles).
+bool launch_fused_cna(MdbSystem &s, double rc, int *pattern, int *n_fallback)
+{
+    int T = 0;
+    if (!tiled_neighbor_plan(s, T)) return false;
+    TileArgs A{};
+    const CellGrid &g = s.grid;
+    A.sorted = s.sorted.as<SortedAtom>();
+    A.cell_start = s.cell_start.as<int>();
+    A.box = s.box;
+    A.g = g;
+    A.rcsq = rc * rc;
+    A.rcsq_hi = (float)(rc * rc * (1.0 + 4e-4)) * (1.0f + 1e-6f);
+    A.rcsq_lo = (float)(rc * rc * (1.0 - 4e-4)) * (1.0f - 1e-6f);
+    A.cut_lo = (float)(rc * rc * (1.0 - 1e-4));
+    A.cut_hi = (float)(rc * rc * (1.0 + 1e-4));
+    A.w_limit = (float)(160.0 * rc * rc);
+    A.n_rows = s.n_rows;
+    A.pattern = pattern;
+    int *counters = s.counters.ensure<int>(8);
+    A.max_count = counters + 6;
+    CUDA_TRY(cudaMemsetAsync(A.max_count, 0, sizeof(int), s.stream));
+    const bool slab = s.slab_nx > 0;
+    A.wrap_x = slab ? 0 : 1;
+    A.p_lo = slab ? 1 : 0;
+    A.p_hi = slab ? g.nxl - 1 : g.n[0];
+    const int TT = T >> 4, TZ = T & 15;
+    const int tiles_x = (A.p_hi - A.p_lo + TT - 1) / TT;
+    A.tiles_x = tiles_x;
+    A.tiles_y = (g.n[1] + TT - 1) / TT;
+    A.tiles_z = (g.n[2] + TZ - 1) / TZ;
+    A.n_tiles = tiles_x * A.tiles_y * A.tiles_z;
+    A.tile_stride = 1;
+    if ((long long)((A.tiles_y + 7) / 8) * tiles_x > 65535 || A.tiles_z > 65535) A.tile_stride = 0;
+    {
+        const double rho = (double)s.N / ((double)g.nxl * g.n[1] * g.n[2]);
+        int cap = (int)(rho * (TT + 2) * (TT + 2) * (TZ + 2) * 1.15) + 48;
+        cap = (cap + 15) / 16 * 16;
+        A.cap = cap < 256 ? 256 : (cap > 2048 ? 2048 : cap);
+    }
+    if (A.n_tiles <= 0) return true;
+    switch (T) {
+        case 8 * 16 + 8: launch_fused_T<8, 8, 256>(A, A.n_tiles, s.stream); break;
+        case 4 * 16 + 8: launch_fused_T<4, 8, 256>(A, A.n_tiles, s.stream); break;
+        case 4 * 16 + 6: launch_fused_T<4, 6, 256>(A, A.n_tiles, s.stream); break;
+        case 2 * 16 + 4: launch_fused_T<2, 4, 256>(A, A.n_tiles, s.stream); break;
+        case 2 * 16 + 2: launch_fused_T<2, 2, 256>(A, A.n_tiles, s.stream); break;
+        default: launch_fused_T<1, 1, 256>(A, A.n_tiles, s.stream); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (n_fallback) {
+        CUDA_TRY(cudaMemcpyAsync(n_fallback, A.max_count, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaStreamSynchronize(s.stream));
+    }
+    return true;
 }

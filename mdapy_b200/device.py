@@ -133,6 +133,14 @@ class DeviceSystem:
         L.check(self._lib.mdb_system_fcna(self._h, float(rc), L.iptr(out) if fetch else None))
         return out
 
+    def fused_cna(self, rc: float, fetch=True):
+        """Neighbour search + fixed-cutoff CNA without a list in HBM.  Returns (labels or None, used):
+        ``used`` is False when the frame is not eligible and nothing was computed."""
+        out = L.result_empty(self.n_rows, np.int32) if fetch else None
+        used = C.c_int(0)
+        L.check(self._lib.mdb_system_fused_cna(self._h, float(rc), L.iptr(out) if fetch else None, C.byref(used)))
+        return (out if used.value else None), bool(used.value)
+
     def acna(self, fetch=True):
         out = L.result_empty(self.n_rows, np.int32) if fetch else None
         L.check(self._lib.mdb_system_acna(self._h, L.iptr(out) if fetch else None))

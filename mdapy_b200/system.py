@@ -64,6 +64,9 @@ class System:
         self._host_list = {}                         # lazily fetched / user supplied NumPy arrays
         self._host_dirty = False                     # user assigned a list on the host side
         self._has_list = False
+        # cut-off of a list the reference would hold at this point but nobody has read yet: the fused
+        # neighbour + CNA kernel classified the frame without writing the list (see _materialize_pending)
+        self._pending_rc: Optional[float] = None
 
     def wrap_pos(self) -> None:
         """system.py:854-856: wrap positions into the box for periodic boundaries (resets the neighbour list)."""
@@ -114,7 +117,16 @@ class System:
         if reset_neighbor:
             self._reset_neighbor()
 
+    def _materialize_pending(self):
+        """Build the cut-off list a fused call left out (same rc, automatic width): from here on the state
+        is exactly the reference's after ``cal_common_neighbor_analysis(rc)``."""
+        rc = self.__dict__.get("_pending_rc")
+        if rc is not None:
+            self._pending_rc = None
+            self.build_neighbor(rc)
+
     def _reset_neighbor(self):
+        self._pending_rc = None
         self._has_list = False
         self._host_list = {}
         self._host_dirty = False
@@ -132,6 +144,10 @@ class System:
     # ------------------------------------------------------------------ lazy neighbour-list attributes
     def __getattr__(self, name):
         # only reached when normal lookup fails
+        if name in _LIST_ATTRS or name == "rc":
+            if self.__dict__.get("_pending_rc") is not None:
+                self._materialize_pending()       # the list is built on first access
+                return getattr(self, name)
         if name in _LIST_ATTRS:
             d = self.__dict__
             if not d.get("_has_list", False):
@@ -201,6 +217,7 @@ class System:
 
     # ------------------------------------------------------------------ list builders
     def build_neighbor(self, rc: float, max_neigh: Optional[int] = None) -> None:
+        self._pending_rc = None    # whatever was pending is replaced by this list
         neigh = Neighbor(rc, self.box, self.data, max_neigh, device=self._device)
         dev = None
         if "_enlarge_data" not in self.__dict__ and sum(self.box.check_small_box(float(rc))) == 3:
@@ -228,6 +245,10 @@ class System:
         self._has_list = True
 
     def build_nearest_neighbor(self, k: int) -> None:
+        if self._pending_rc is not None:
+            # the reference keeps self.rc of the earlier cut-off build (system.py:1262-1263) while the
+            # k-nearest list replaces the arrays: no need to build the list that is about to be replaced
+            self.rc, self._pending_rc = self._pending_rc, None
         kdt = NearestNeighbor(self.data, self.box, k, device=self._device)
         dev = None
         if "_enlarge_data" not in self.__dict__ and sum(kdt._check_repeat_nearest()) == 3:
@@ -257,6 +278,27 @@ class System:
     def cal_common_neighbor_analysis(self, rc: Optional[float] = None, max_neigh: Optional[int] = None):
         use_cached = False
         repeat = self._safe_repeat()
+        # Fused path: fixed cut-off, automatic width, no replication, and either no cached list or one with
+        # a smaller cut-off -- exactly the cases in which the reference builds a fresh list for rc and
+        # classifies from it.  The labels are the same (tests/test_gpu_fused.py); the list itself is built
+        # on first access (verlet_list / distance_list / neighbor_number / rc, or any cal_* that reuses it).
+        pend = self._pending_rc
+        if (rc is not None and max_neigh is None and sum(repeat) == 3 and "_enlarge_data" not in self.__dict__
+                and sum(self.box.check_small_box(float(rc))) == 3
+                and ((pend is None and "rc" not in self.__dict__) or (pend is not None and pend <= rc)
+                     or ("rc" in self.__dict__ and pend is None and self.rc < rc))):
+            dev = self._device_view()
+            labels, used = dev.fused_cna(float(rc))
+            if used:
+                self._pending_rc = float(rc) if (pend is None or pend < rc) else pend
+                if "rc" in self.__dict__:      # the smaller cached list is replaced (reference: build_neighbor(rc))
+                    del self.__dict__["rc"]
+                self._has_list = False
+                self._host_list = {}
+                self._host_dirty = False
+                self.update_data(self._data.with_columns(cna=labels[: self.N]))
+                return
+        self._materialize_pending()
         if sum(repeat) == 3:
             if "rc" in self.__dict__:
                 if rc is None:
@@ -541,3 +583,21 @@ class System:
                 cols.update(qx=output[:, 5].copy(), qy=output[:, 6].copy(), qz=output[:, 7].copy(), qw=output[:, 4].copy())
         self.update_data(self._data.with_columns(**cols))
         return ptm
+
+
+def _after_pending(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        self._materialize_pending()
+        return fn(self, *a, **k)
+
+    return wrapper
+
+
+for _name in list(vars(System)):
+    if (_name.startswith("cal_") and _name != "cal_common_neighbor_analysis") or _name in (
+            "average_by_neighbor", "_ensure_cutoff_list", "_min_neighbor_number", "_sort_neighbor", "_device_list"):
+        setattr(System, _name, _after_pending(getattr(System, _name)))
+del _name

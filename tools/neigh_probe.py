@@ -24,6 +24,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--max-neigh", type=int, default=0)
 ap.add_argument("--rc", type=float, default=RC_RATIO * A_AL)
 ap.add_argument("--cna", action="store_true")
+ap.add_argument("--fused", action="store_true", help="time the fused neighbour + CNA kernel instead")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 n, a = args.n, A_AL
@@ -38,7 +39,12 @@ ds.set_profiling(True)
 ts, tc = [], []
 for r in range(args.reps + 2):
     ds.set_atoms_device(x, y, z, box, np.zeros(3), np.array([1, 1, 1], np.int32), stream=torch.cuda.current_stream().cuda_stream)
-    M, mx = ds.build_neighbor(args.rc, args.max_neigh or None)
+    if args.fused:
+        lab, used = ds.fused_cna(args.rc, fetch=False)
+        assert used
+        M, mx = 0, 0
+    else:
+        M, mx = ds.build_neighbor(args.rc, args.max_neigh or None)
     t = ds.last_times()
     if args.cna:
         ds.fcna(args.rc, fetch=False)

@@ -96,6 +96,8 @@ def case_c2(tag, sigma, seed, with_csp):
     p = ds.fcna(rc)
     hist = np.bincount(p, minlength=5).tolist()
     check(f"{tag}.cna", np.array_equal(p, rp), f"labels other/fcc/hcp/bcc/ico = {hist}")
+    pf, used = ds.fused_cna(rc)
+    check(f"{tag}.fused neighbour+CNA (no list)", used and np.array_equal(pf, rp))
     if with_csp and int(rn.min()) >= 12:
         # system.py:1986-2003: the cached cut-off list is sorted (12 smallest first), then get_csp
         K.sort_verlet_by_distance(rv, rd, 12)
@@ -126,6 +128,8 @@ def case_c5(auto_too):
     check("c5.distance_list (bit pattern)", equal_chunked(d, rd))
     p = ds.fcna(rc)
     check("c5.cna", np.array_equal(p, rp), f"labels = {np.bincount(p, minlength=5).tolist()}")
+    pf, used = ds.fused_cna(rc)
+    check("c5.fused neighbour+CNA (no list)", used and np.array_equal(pf, rp))
     if auto_too:
         del v, d
         M2, mx2 = ds.build_neighbor(rc, None)
