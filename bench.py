@@ -190,8 +190,42 @@ def cpu_baseline_sample(n=100):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     N = x.shape[0]
-    return {"value": N / best, "unit": "atoms/s", "cores": cores, "kind": K.KIND,
-            "sample": f"{N}-atom FCC Al ({n}^3x4), neighbour(auto)+CNA, best of 2, all host threads"}
+    out = {"value": N / best, "unit": "atoms/s", "cores": cores, "kind": K.KIND,
+           "sample": f"{N}-atom FCC Al ({n}^3x4), neighbour(auto)+CNA, best of 2, all host threads"}
+    # The reference as CHECKER on a frame with non-trivial labels: the same sample at sigma = 0.2 A, labels of the
+    # list path and of the fused path against FixedCNA on the reference's own list (bit-exact bar).
+    try:
+        from mdapy_b200.device import DeviceSystem
+
+        rng = np.random.default_rng(1)
+        hx, hy, hz = (c + rng.normal(0.0, 0.2, c.shape) for c in (x, y, z))
+        rv, rd, rn = K.build_neighbor_auto(hx, hy, hz, box, o, bnd, rc, nt=cores)
+        ref = K.fcna(hx, hy, hz, box, o, bnd, rv, rn, rc, nt=cores)
+        ds = DeviceSystem(0)
+        ds.set_atoms(hx, hy, hz, box, o, bnd)
+        fused, used = ds.fused_cna(rc)
+        ds.build_neighbor(rc, None)
+        lst = ds.fcna(rc)
+        ok = bool(used and np.array_equal(fused, ref) and np.array_equal(lst, ref))
+        out["parity_probe"] = {"frame": f"{N} atoms, sigma 0.2", "labels other/fcc/hcp/bcc/ico": np.bincount(ref, minlength=5).tolist(),
+                               "list_path_equal": bool(np.array_equal(lst, ref)),
+                               "fused_path_equal": bool(used and np.array_equal(fused, ref))}
+        assert ok, out["parity_probe"]
+        ds.close()
+    except AssertionError:
+        raise
+    except Exception as exc:  # never fail the bench on the extra check's plumbing
+        out["parity_probe"] = {"unavailable": repr(exc)}
+    return out
+
+
+def traffic_of(kernel, n, source=False):
+    """DRAM bytes per launch from profiles/traffic.json ({kernel: {str(n): {"bytes":..., "capture":..., "date":...}}})."""
+    try:
+        rec = json.loads((ROOT / "profiles" / "traffic.json").read_text())[kernel][str(n)]
+        return f"{rec['capture']} ({rec['date']})" if source else float(rec["bytes"])
+    except Exception:
+        return None
 
 
 # --------------------------------------------------------------------------- this repo
@@ -293,6 +327,40 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
 
+    # ---- second mode (N = 1): fused neighbour search + CNA, no list in HBM (what System.cal_common_neighbor_analysis
+    # runs when nothing else reads the list; the list is then built lazily on first access)
+    fused = None
+    if world == 1:
+        t_f = []
+
+        def fused_step():
+            ds.set_atoms_device(x, y, z, box, origin, boundary)
+            lab, used = ds.fused_cna(rc, fetch=False)
+            assert used
+            t_f.append(ds.last_times())
+
+        for _ in range(args.warmup):
+            fused_step()
+        t_f.clear()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            fused_step()
+        f1.record()
+        barrier()
+        fms = f0.elapsed_time(f1) / max(args.steps, 1)
+        lab_host, used = ds.fused_cna(rc, fetch=True)   # untimed: the labels of one more pass, checked below
+        assert used
+        fused = {"value": N_total / (fms * 1e-3), "unit": "atoms/s", "ms_per_step": fms,
+                 "workload": "same frame, binning + fused neighbour search + CNA, NO neighbour list in HBM "
+                             "(28 B/atom algorithmic); the list is materialised lazily on first access",
+                 "kernel_ms": float(np.mean([t["neighbor_ms"] for t in t_f])),
+                 "binning_ms": float(np.mean([t["binning_ms"] for t in t_f])),
+                 "labels_fcc": int((lab_host == 1).sum()), "labels_total": int(N_total)}
+        assert fused["labels_fcc"] == N_total, "perfect FCC frame: every atom must be labelled fcc"
+        del lab_host
+
     # ---- e2e through the public API from pinned host arrays (rank-local slab for N > 1)
     e2e = None
     if world == 1:
@@ -392,9 +460,13 @@ def run_b200(args):
         "config": {"workload": f"BASELINE configs[4]: FCC Al a={a}, {n}^3x4 = {N_total} atoms, "
                                f"neighbor(rc={RC_RATIO}a, auto width M)+CNA, one frame per step",
                    "atoms": N_total, "rc": rc, "l2_policy": "inputs (2.4 GB) and lists (14 GB) exceed the 126 MB L2",
+                   "handle": "one device handle reused across frames: the sampled width estimate of the automatic list "
+                             "width runs on the first frame only (trajectory mode)",
                    "parallelism": "1 GPU" if world == 1 else f"{world} x-slabs of the cell grid, NCCL ghost planes"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
     }
+    if fused is not None:
+        line["fused"] = fused
     if world == 1:
         tn = float(np.mean(t_neigh))
         alg = (28 + 12 * M) * N_total
@@ -402,9 +474,10 @@ def run_b200(args):
             "kernel": "k_neighbor (cut-off neighbour build)", "bound": "hbm", "achieved": alg / (tn * 1e-3) / 1e9,
             "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if pk.exists() else "fallback",
             "unit": "GB/s", "frac": alg / (tn * 1e-3) / 1e9 / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default size, from the
-            # ncu --set full capture summarised in profiles/r1_s7_n292_ncu_full.txt (6.58 GB + 15.89 GB)
-            "traffic": 22.47e9 if n == 292 else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this size: read from
+            # the committed summary of the latest ncu --set full capture (profiles/traffic.json names the
+            # capture file and date); null when no capture exists for this size
+            "traffic": traffic_of("neighbor", n), "traffic_source": traffic_of("neighbor", n, True),
             "algorithmic_bytes_per_atom": 28 + 12 * M, "kernel_ms": tn,
             "step_breakdown_ms": {"binning": float(np.mean(t_bin)), "neighbor": tn, "cna": float(np.mean(t_cna))},
         }

@@ -1117,7 +1117,7 @@ template <int T, int TZ> void launch_T(const TileArgs &A, int nblocks, cudaStrea
 //      within 1e-4 rc^2 of the threshold sends the atom to the exact f64 bond matrix (cna.cpp:149-161 on
 //      raw coordinates); signatures from the bond rows in registers (cna_core.cuh).
 // Labels are identical to FixedCNA on the reference's list (tests/test_gpu_fused.py, at-scale parity tool).
-constexpr int FUSED_QCAP = 16;   // neighbour slots per thread (more than 14 neighbours -> label 0)
+constexpr int FUSED_QCAP = 24;   // candidate slots per thread (14 neighbours + guard-band candidates)
 
 // exact membership test of the list build for one pair (cold)
 __device__ __noinline__ bool fused_exact_neighbor(const DBox &box, const SortedAtom *raw, int s_i, int k, double rcsq)
@@ -1437,10 +1437,13 @@ __global__ void __launch_bounds__(NT, 3) k_fused_cna(const __grid_constant__ Til
         const float fx = -2.0f * me.x, fy = -2.0f * me.y, fz = -2.0f * me.z;
         const float thr_hi = rc2hi - me.w, thr_lo = rc2lo - me.w;
         unsigned q_top = q_base;
-        int n = 0;
         const unsigned self = f4_base + 16u * (unsigned)s_i;
 
-        // the 9 pencils of the stencil; the centre pencil in two pieces that leave the atom itself out
+        // the 9 pencils of the stencil; the centre pencil in two pieces that leave the atom itself out.
+        // The loop only collects the candidates whose fp32 d^2 is not clearly outside (<= rc^2 (1 + 4e-4));
+        // they are classified afterwards, so a candidate costs a load, three FMAs, a compare and a
+        // predicated store.  The queue pointer saturates at the last slot: a full queue means more than 14
+        // neighbours or a pathological frame, and sends the atom to the exact fallback.
         int pen_off = -P - 1, pen_y = 0;
 #pragma unroll 1
         for (int pen = 0; pen < 9; ++pen) {
@@ -1460,18 +1463,9 @@ __global__ void __launch_bounds__(NT, 3) k_fused_cna(const __grid_constant__ Til
                     aq -= 16u;
                     const float4 c = o;
                     o = lds_f4(aq - 16u);
-                    const float t2 = __fmaf_rn(fx, c.x, __fmaf_rn(fy, c.y, __fmaf_rn(fz, c.z, c.w)));
-                    if (t2 <= thr_hi) {
-                        const int k = (int)((aq - f4_base) >> 4);
-                        bool in = t2 <= thr_lo;
-                        if (!in) in = fused_exact_neighbor(box, raw, s_i, k, A.rcsq);
-                        if (in) {
-                            if (q_top < q_full) {
-                                sts_u16(q_top, (unsigned)k);
-                                q_top += QS;
-                            }
-                            ++n;
-                        }
+                    if (__fmaf_rn(fx, c.x, __fmaf_rn(fy, c.y, __fmaf_rn(fz, c.z, c.w))) <= thr_hi) {
+                        sts_u16(q_top, aq);
+                        q_top = min(q_top + QS, q_full);
                     }
                 }
             }
@@ -1479,6 +1473,24 @@ __global__ void __launch_bounds__(NT, 3) k_fused_cna(const __grid_constant__ Til
                 pen_y = 0;
                 pen_off += P - 2;
             } else ++pen_off;
+        }
+        // classify the collected candidates: well inside -> neighbour; inside the band -> exact f64 test
+        const int n_hi = (int)((q_top - q_base) / QS);
+        if (n_hi >= FUSED_QCAP) {   // queue saturated: exact fallback decides
+            A.pattern[idx] = fused_direct_atom<NT>(A, gstart[p * PZ + PZ - 1 - kmax] + (t - opref[pi]), nbs + tid);
+            continue;
+        }
+        int n = 0;
+        {
+            unsigned short *qw = queue + tid;
+            for (int a = 0; a < n_hi; ++a) {
+                const int k = (int)(((unsigned)qw[a * NT] - f4_base) & 0xffffu) >> 4;
+                const float4 c = f4[k];
+                const float t2 = __fmaf_rn(fx, c.x, __fmaf_rn(fy, c.y, __fmaf_rn(fz, c.z, c.w)));
+                bool in = t2 <= thr_lo;
+                if (!in) in = fused_exact_neighbor(box, raw, s_i, k, A.rcsq);
+                if (in) qw[(n++) * NT] = (unsigned short)k;   // compacted in place (n <= a)
+            }
         }
         int label = 0;
         const unsigned short *q = queue + tid;
