@@ -217,6 +217,16 @@ int mdb_cell_grid(const double *box9, const double *origin3, const int *boundary
 /* global x cell plane of each atom (device arrays), same arithmetic as src/neighbor.cpp:30-62 */
 int mdb_cell_planes_device(const double *dx, const double *dy, const double *dz, int N, const double *box9,
                            const double *origin3, const int *boundary3, double rc, int *dplane, void *cuda_stream);
+/* Device-side halo exchange of a decomposed frame (mdapy_b200/distributed.py; no host round trip per frame):
+ * pack appends the atoms of the first / last `halo` owned x cell planes [lo, hi) to two send buffers of `cap` rows
+ * of 4 doubles (x, y, z raw, global id); row 0 is a header holding the row count.  unpack appends the rows of one
+ * or two received buffers behind the n_owned owned atoms of dx/dy/dz/dgid (room = free rows there) and leaves the
+ * new atom count in *dtotal (-1: a buffer overflowed).  All pointers are device pointers. */
+int mdb_slab_pack_device(const double *dx, const double *dy, const double *dz, const int *dgid, int N,
+                         const double *box9, const double *origin3, const int *boundary3, double rc, int lo, int hi,
+                         int halo, double *send_left, double *send_right, int cap, int *dcounts, void *cuda_stream);
+int mdb_slab_unpack_device(const double *recv_a, const double *recv_b, int cap, double *dx, double *dy, double *dz,
+                           int *dgid, int n_owned, int room, int *dtotal, void *cuda_stream);
 
 /* cut-off list kept on the device.  max_neigh <= 0: size automatically
  * (neighbor.cpp:189 semantics, M = max(count,1)).  Returns row width and the

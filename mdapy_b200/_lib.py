@@ -79,6 +79,9 @@ PROTOTYPES = {
     "mdb_system_set_local_fraction": (C.c_int, [c_vp, C.c_double]),
     "mdb_cell_grid": (C.c_int, _BOX + [C.c_double, c_ip]),
     "mdb_cell_planes_device": (C.c_int, [c_vp, c_vp, c_vp, C.c_int] + _BOX + [C.c_double, c_vp, c_vp]),
+    "mdb_slab_pack_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int] + _BOX + [C.c_double, C.c_int, C.c_int, C.c_int,
+                                                                                 c_vp, c_vp, C.c_int, c_vp, c_vp]),
+    "mdb_slab_unpack_device": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
     "mdb_system_build_neighbor": (C.c_int, [c_vp, C.c_double, C.c_int, c_ip, c_ip]),
     "mdb_system_build_knn": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_sort_neighbor": (C.c_int, [c_vp, C.c_int]),

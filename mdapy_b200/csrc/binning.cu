@@ -222,6 +222,54 @@ __global__ void __launch_bounds__(256) k_cell_planes(const double *__restrict__ 
     plane[i] = ic;
 }
 
+// Halo exchange of a decomposed frame, device side (no host round trip): atoms of the first / last `halo` owned
+// planes are appended to two fixed-capacity send buffers of (x, y, z, global id) rows; row 0 of a buffer is its
+// header (row count).  The receiver appends both received buffers behind its owned atoms.
+__global__ void __launch_bounds__(256) k_slab_pack(const double *__restrict__ x, const double *__restrict__ y,
+                                                   const double *__restrict__ z, const int *__restrict__ gid, int N,
+                                                   DBox box, CellGrid g, int lo, int hi, int halo, double4 *__restrict__ left,
+                                                   double4 *__restrict__ right, int cap, int *__restrict__ counts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double xr = x[i], yr = y[i], zr = z[i];
+    double xi = xr, yi = yr, zi = zr;
+    if (box.any_pbc) wrap_into_box(box, xi, yi, zi);
+    int ic, jc, kc;
+    cell_of(box, g, xi, yi, zi, ic, jc, kc);
+    const double4 rec = make_double4(xr, yr, zr, (double)gid[i]);   // raw coordinates travel (neighbor.cpp uses x[j] raw)
+    if (ic >= lo && ic < lo + halo) {
+        const int slot = atomicAdd(counts, 1);
+        if (slot < cap - 1) left[slot + 1] = rec;
+    }
+    if (ic >= hi - halo && ic < hi) {
+        const int slot = atomicAdd(counts + 1, 1);
+        if (slot < cap - 1) right[slot + 1] = rec;
+    }
+}
+
+__global__ void k_slab_headers(double4 *left, double4 *right, const int *counts)
+{
+    if (threadIdx.x == 0) left[0] = make_double4((double)counts[0], 0.0, 0.0, 0.0);
+    if (threadIdx.x == 1) right[0] = make_double4((double)counts[1], 0.0, 0.0, 0.0);
+}
+
+__global__ void __launch_bounds__(256) k_slab_unpack(const double4 *__restrict__ a, const double4 *__restrict__ b, int cap,
+                                                     double *__restrict__ x, double *__restrict__ y, double *__restrict__ z,
+                                                     int *__restrict__ gid, int n_owned, int room, int *__restrict__ total)
+{
+    const int ca = (int)a[0].x, cb = b ? (int)b[0].x : 0;
+    const bool bad = ca > cap - 1 || cb > cap - 1 || ca + cb > room || ca < 0 || cb < 0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *total = bad ? -1 : n_owned + ca + cb;
+    if (bad || i >= ca + cb) return;
+    const double4 r = i < ca ? a[1 + i] : b[1 + i - ca];
+    x[n_owned + i] = r.x;
+    y[n_owned + i] = r.y;
+    z[n_owned + i] = r.z;
+    gid[n_owned + i] = (int)r.w;
+}
+
 __global__ void __launch_bounds__(256) k_translate_ids(const int *__restrict__ in, int *__restrict__ out, size_t n,
                                                        const int *__restrict__ gid)
 {
@@ -267,6 +315,27 @@ void launch_cell_planes(const double *x, const double *y, const double *z, int N
 {
     if (N <= 0) return;
     MDB_LAUNCH(k_cell_planes, (N + 255) / 256, 256, 0, st, x, y, z, N, b, g, plane);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_slab_pack(const double *x, const double *y, const double *z, const int *gid, int N, const DBox &b,
+                      const CellGrid &g, int lo, int hi, int halo, double *left, double *right, int cap, int *counts,
+                      cudaStream_t st)
+{
+    CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
+    if (N > 0)
+        MDB_LAUNCH(k_slab_pack, (N + 255) / 256, 256, 0, st, x, y, z, gid, N, b, g, lo, hi, halo,
+                   reinterpret_cast<double4 *>(left), reinterpret_cast<double4 *>(right), cap, counts);
+    MDB_LAUNCH(k_slab_headers, 1, 32, 0, st, reinterpret_cast<double4 *>(left), reinterpret_cast<double4 *>(right), counts);
+    CUDA_TRY(cudaGetLastError());
+}
+
+void launch_slab_unpack(const double *a, const double *b, int cap, double *x, double *y, double *z, int *gid, int n_owned,
+                        int room, int *total, cudaStream_t st)
+{
+    const int maxrows = 2 * cap;
+    MDB_LAUNCH(k_slab_unpack, (maxrows + 255) / 256, 256, 0, st, reinterpret_cast<const double4 *>(a),
+               reinterpret_cast<const double4 *>(b), cap, x, y, z, gid, n_owned, room, total);
     CUDA_TRY(cudaGetLastError());
 }
 

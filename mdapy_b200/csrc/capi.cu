@@ -529,6 +529,28 @@ int mdb_cell_planes_device(const double *dx, const double *dy, const double *dz,
     API_END
 }
 
+int mdb_slab_pack_device(const double *dx, const double *dy, const double *dz, const int *dgid, int N,
+                         const double *box9, const double *origin3, const int *boundary3, double rc, int lo, int hi,
+                         int halo, double *send_left, double *send_right, int cap, int *dcounts, void *cuda_stream)
+{
+    API_BEGIN
+    MDB_REQUIRE(rc > 0 && send_left && send_right && dcounts && cap > 1, MDB_ERR_VALUE, "bad slab pack arguments");
+    DBox b;
+    MDB_REQUIRE(dbox_make(b, box9, origin3, boundary3) == 0, MDB_ERR_BOX, "The volume of the box is zero.");
+    launch_slab_pack(dx, dy, dz, dgid, N, b, cellgrid_make(b, rc), lo, hi, halo, send_left, send_right, cap, dcounts,
+                     static_cast<cudaStream_t>(cuda_stream));
+    API_END
+}
+
+int mdb_slab_unpack_device(const double *recv_a, const double *recv_b, int cap, double *dx, double *dy, double *dz,
+                           int *dgid, int n_owned, int room, int *dtotal, void *cuda_stream)
+{
+    API_BEGIN
+    MDB_REQUIRE(recv_a && dtotal && cap > 1, MDB_ERR_VALUE, "bad slab unpack arguments");
+    launch_slab_unpack(recv_a, recv_b, cap, dx, dy, dz, dgid, n_owned, room, dtotal, static_cast<cudaStream_t>(cuda_stream));
+    API_END
+}
+
 int mdb_system_build_neighbor(mdb_system *s, double rc, int max_neigh, int *M, int *max_count)
 {
     API_BEGIN

@@ -169,6 +169,11 @@ void launch_knn(MdbSystem &s, int k);
 void launch_cell_planes(const double *x, const double *y, const double *z, int N, const DBox &b, const CellGrid &g,
                         int *plane, cudaStream_t st);
 void launch_translate_ids(MdbSystem &s, const int *local_ids, int *global_ids, size_t n);
+void launch_slab_pack(const double *x, const double *y, const double *z, const int *gid, int N, const DBox &b,
+                      const CellGrid &g, int lo, int hi, int halo, double *left, double *right, int cap, int *counts,
+                      cudaStream_t st);
+void launch_slab_unpack(const double *a, const double *b, int cap, double *x, double *y, double *z, int *gid, int n_owned,
+                        int room, int *total, cudaStream_t st);
 void launch_neighbor(MdbSystem &s, double rc, int M, bool count_only);
 void launch_compact_rows(MdbSystem &s, int M_from, int M_to);
 bool tiled_neighbor_plan(const MdbSystem &s, int &T);

@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
         // ---- C. fp32 positions relative to the tile centre (nearest periodic image) + cell tag.
         // One warp per pencil, lanes over the pencil's atoms.
         const double rcw = 1.0 / g.rc_inv;
-        const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0);  // global x cell of the first owned plane
+        const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0) % g.n[0];  // global x cell of the first owned plane
         const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
                      ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
         for (int p = warp; p < NPEN; p += TILE_THREADS / 32) {
@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_coop(const _
 
         // ---- C. fp32 positions relative to the tile centre (nearest periodic image), flat over the staged atoms
         const double rcw = 1.0 / g.rc_inv;
-        const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0);
+        const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0) % g.n[0];
         const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
                      ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
         for (int s = tid; s < n_staged; s += NT) {
@@ -1380,7 +1380,7 @@ __global__ void __launch_bounds__(NT, 3) k_fused_cna(const __grid_constant__ Til
 
         // ---- C. fp32 positions relative to the tile centre (nearest periodic image), flat over the staged atoms
         const double rcw = 1.0 / g.rc_inv;
-        const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0);
+        const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0) % g.n[0];
         const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
                      ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
         for (int s = tid; s < n_staged; s += NT) {

@@ -298,13 +298,120 @@ class SlabDecomposition:
                 ds.build_neighbor(self.rc, int(t.item()))   # binning is cached: only the fill pass reruns
         return ds
 
-    def make_step(self, x, y, z, gid):
-        """Benchmark step: one frame = planes + halo exchange + binning + neighbour build + CNA."""
+    # ------------------------------------------------------------------ resident frames (halo == 1)
+    # Trajectory / benchmark use: the slab lives in ONE preallocated buffer per coordinate, owned atoms at its
+    # head.  Per frame the device packs the boundary planes (one kernel), the two fixed-capacity buffers travel
+    # over NCCL (all_to_all_single with constant split sizes: no count exchange, no host round trip), and a
+    # second kernel appends the received ghosts behind the owned atoms.  The only host read per frame is the new
+    # atom count (one int).  PyTorch is the NCCL / memory plumbing; every byte of the data path is moved by the
+    # library's kernels.
+    def resident_buffers(self, n_owned: int, cap: Optional[int] = None):
+        """Allocate the frame buffers for ``n_owned`` owned atoms and return the (x, y, z, gid) views the
+        caller fills (device tensors; a host -> device copy can target them directly)."""
+        torch = self.torch
+        assert self.halo == 1, "the resident fast path covers halo == 1 (cut-off list, CNA, CSP, Steinhardt, RDF)"
+        if cap is None:   # rows per send buffer: one plane of the slab, + 50 %; the SAME on every rank
+            cap = int(1.5 * n_owned / max(self.hi - self.lo, 1)) + 4096
+            import torch.distributed as dist
+
+            if self.world > 1 and dist.is_available() and dist.is_initialized():
+                t = torch.tensor([cap], dtype=torch.int64, device=self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)   # set-up time, once per buffer set
+                cap = int(t.item())
+        total = n_owned + 2 * (cap - 1)
+        dev = self.device
+        self._res = {
+            "x": torch.empty(total, dtype=torch.float64, device=dev),
+            "y": torch.empty(total, dtype=torch.float64, device=dev),
+            "z": torch.empty(total, dtype=torch.float64, device=dev),
+            "g": torch.empty(total, dtype=torch.int32, device=dev),
+            "send": torch.zeros((2, cap, 4), dtype=torch.float64, device=dev),
+            "recv": torch.zeros((2, cap, 4), dtype=torch.float64, device=dev),
+            "counts": torch.zeros(2, dtype=torch.int32, device=dev),
+            "total": torch.zeros(1, dtype=torch.int32, device=dev),
+            "n_owned": int(n_owned), "cap": int(cap),
+        }
+        split = [0] * self.world
+        split[self.left] += cap
+        split[self.right] += cap
+        self._res["split"] = split
+        r = self._res
+        return r["x"][:n_owned], r["y"][:n_owned], r["z"][:n_owned], r["g"][:n_owned]
+
+    def resident_pack(self):
+        """Boundary planes of the resident frame -> the two send buffers (device kernel, no host sync)."""
+        torch = self.torch
+        r = self._res
+        n, cap = r["n_owned"], r["cap"]
+        stream = torch.cuda.current_stream().cuda_stream
+        b, o, p = L.box_args(self.box, self.origin, self.boundary)
+        # all_to_all_single wants the segments in rank order: [left, right] or [right, left]
+        li, ri = (0, 1) if self.left <= self.right else (1, 0)
+        L.check(L.lib().mdb_slab_pack_device(
+            C.c_void_p(r["x"].data_ptr()), C.c_void_p(r["y"].data_ptr()), C.c_void_p(r["z"].data_ptr()),
+            C.c_void_p(r["g"].data_ptr()), n, L.dptr(b), L.dptr(o), L.iptr(p), self.rc, int(self.lo), int(self.hi),
+            int(self.halo), C.c_void_p(r["send"][li].data_ptr()), C.c_void_p(r["send"][ri].data_ptr()), cap,
+            C.c_void_p(r["counts"].data_ptr()), C.c_void_p(int(stream))))
+
+    def resident_unpack(self, device_index: Optional[int] = None):
+        """Received buffers -> ghosts behind the owned atoms; returns the loaded DeviceSystem."""
+        torch = self.torch
+        r = self._res
+        n, cap = r["n_owned"], r["cap"]
+        stream = torch.cuda.current_stream().cuda_stream
+        L.check(L.lib().mdb_slab_unpack_device(
+            C.c_void_p(r["recv"][0].data_ptr()), C.c_void_p(r["recv"][1].data_ptr()), cap,
+            C.c_void_p(r["x"].data_ptr()), C.c_void_p(r["y"].data_ptr()), C.c_void_p(r["z"].data_ptr()),
+            C.c_void_p(r["g"].data_ptr()), n, 2 * (cap - 1), C.c_void_p(r["total"].data_ptr()), C.c_void_p(int(stream))))
+        total = int(r["total"].item())            # the one host read of the frame
+        if total < 0:
+            raise RuntimeError("halo buffers too small for this frame: call resident_buffers with a larger cap")
+        self.n_owned = self.n_rows = n
+        self.halo_atoms = total - n
+        ds = self.device_system(device_index)
+        ds.set_slab_device(r["x"][:total], r["y"][:total], r["z"][:total], r["g"][:total], n, self.plane0, self.nplanes,
+                           self.box, self.origin, self.boundary, stream=stream)
+        ds.set_local_fraction(min(1.0, self.nplanes / self.n0))
+        self.local = (r["x"][:total], r["y"][:total], r["z"][:total], r["g"][:total])
+        self.local_extra = None
+        return ds
+
+    def exchange_resident(self, device_index: Optional[int] = None):
+        """Halo exchange of the resident frame; returns the DeviceSystem loaded with owned + ghost atoms."""
+        import torch.distributed as dist
+
+        r = self._res
+        cap = r["cap"]
+        self.resident_pack()
+        dist.all_to_all_single(r["recv"].view(2 * cap, 4), r["send"].view(2 * cap, 4), output_split_sizes=r["split"],
+                               input_split_sizes=r["split"], group=self.group)
+        return self.resident_unpack(device_index)
+
+    def make_step(self, x, y, z, gid, fused: bool = False):
+        """Benchmark step: one frame = boundary pack + halo exchange + ghost append + binning + neighbour build
+        + CNA (``fused``: the fused neighbour + CNA kernel, no list)."""
+        if self.world == 1 or self.halo != 1:
+            def step():
+                ds = self.build(x, y, z, gid)
+                ds.fcna(self.rc, fetch=False)
+                return ds.M
+
+            return step
+        rx, ry, rz, rg = self.resident_buffers(int(x.shape[0]))
+        rx.copy_(x)
+        ry.copy_(y)
+        rz.copy_(z)
+        rg.copy_(gid.to(self.torch.int32))
 
         def step():
-            ds = self.build(x, y, z, gid)
+            ds = self.exchange_resident()
+            if fused:
+                lab, used = ds.fused_cna(self.rc, fetch=False)
+                assert used
+                return 0
+            M, mx = ds.build_neighbor(self.rc, None)
             ds.fcna(self.rc, fetch=False)
-            return ds.M
+            return M
 
         return step
 

@@ -99,6 +99,21 @@ def main():
             lt = dec.local_extra[0].cpu().numpy()
             counts = dec.all_reduce_sum(ds.rdf_counts(rc, 50, type_list=lt, ntype=2))
             check("rdf_allreduce", np.array_equal(counts, ref_rdf))
+            # resident fast path: device-side boundary pack, fixed-capacity exchange, ghost append (no host
+            # round trip besides the atom count), list + CNA and the fused kernel on the slab
+            if world > 1:
+                rdec = SlabDecomposition(box, o, bnd, rc, rank, world, dev, halo=1)
+                rx, ry, rz, rg = rdec.resident_buffers(int(mx.shape[0]))
+                rx.copy_(mx), ry.copy_(my), rz.copy_(mz), rg.copy_(mg)
+                for rep in range(2):   # the buffers are reused frame after frame
+                    rs = rdec.exchange_resident()
+                    rs.build_neighbor(rc, M_ref)
+                    v2, d2, n2 = rs.fetch_neighbor()
+                    check(f"resident_rows_{rep}", np.array_equal(v2[:n_own], fv[rows]) and np.array_equal(n2[:n_own], fn[rows])
+                          and np.array_equal(d2[:n_own].view(np.int64), fd[rows].view(np.int64)))
+                    check(f"resident_fcna_{rep}", np.array_equal(rs.fcna(rc)[:n_own], ref_cna[rows]))
+                    lab, used = rs.fused_cna(rc)
+                    check(f"resident_fused_cna_{rep}", used and np.array_equal(lab[:n_own], ref_cna[rows]))
         elif halo == 2:
             q, _, _ = ds.steinhardt([4, 6], rc=rc, average=True)
             check("steinhardt_average", np.array_equal(q[:n_own].view(np.int64), ref_qa[rows].view(np.int64)))
