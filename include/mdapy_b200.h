@@ -252,6 +252,32 @@ int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host);
  * list: what System.cal_common_neighbor_analysis(rc) needs when nothing else reads the list (it is built
  * lazily on first access).  *used = 0: frame not eligible (triclinic / tiny box), nothing was computed. */
 int mdb_system_fused_cna(mdb_system *s, double rc, int *pattern_host, int *used);
+
+/* ---- builders: benchmark-size inputs are generated in HBM ---------------------------------
+ * mdb_repeat_cell            <- _repeat_cell.repeat_cell(new_pos, old_box, old_pos, nx, ny, nz, num_t)
+ *                               (src/repeat_cell.cpp:19; new_pos: 3 * n_old * nx*ny*nz doubles, cell-major, iz fastest)
+ * mdb_transform_and_filter   <- _polycrystal.transform_and_filter(x, y, z, rotation, center, target, coeffs, num_t)
+ *                               (src/polycrystal.cpp:21; out_pos must hold 3 N doubles, *count rows are returned)
+ * mdb_filter_overlap_atom    <- _neighbor.filter_overlap_atom(x, y, z, box, origin, boundary, rc, num_t)
+ *                               (src/neighbor.cpp:390; keep: one byte per atom, 0 = the higher index of a close pair)
+ * mdb_system_set_atoms_lattice: the replicated crystal is generated straight into the handle (no host copy);
+ *                               box = cell rows scaled by (nx, ny, nz), like build_crystal. */
+int mdb_repeat_cell(double *new_pos, const double *old_box9, const double *old_pos, int n_old, int nx, int ny, int nz,
+                    int num_t);
+int mdb_transform_and_filter(const double *x, const double *y, const double *z, int N, const double *rotation9,
+                             const double *center3, const double *target3, const double *coeffs, int nfaces,
+                             double *out_pos, int *count, int num_t);
+int mdb_filter_overlap_atom(const double *x, const double *y, const double *z, int N, const double *box9,
+                            const double *origin3, const int *boundary3, double rc, unsigned char *keep, int num_t);
+int mdb_system_set_atoms_lattice(mdb_system *s, const double *cell9, const double *basis_pos, int n_basis, int nx, int ny,
+                                 int nz, const double *origin3, const int *boundary3);
+int mdb_system_positions_device(mdb_system *s, double **dx, double **dy, double **dz, int *N);
+int mdb_system_fetch_positions(mdb_system *s, double *x, double *y, double *z);
+int mdb_system_filter_overlap(mdb_system *s, double rc, unsigned char *keep_host);
+/* transform_and_filter on the atoms already held by the handle (the replicated lattice block of a polycrystal
+ * build is generated once on the device and reused for every grain) */
+int mdb_system_transform_and_filter(mdb_system *s, const double *rotation9, const double *center3,
+                                    const double *target3, const double *coeffs, int nfaces, double *out_pos, int *count);
 int mdb_system_acna(mdb_system *s, int *pattern_host);
 int mdb_system_ids(mdb_system *s, int *pattern_host);
 int mdb_system_csp(mdb_system *s, int nnei, double *csp_host);

@@ -27,6 +27,7 @@ def __getattr__(name):
         "BondAnalysis": ("bond_analysis", "BondAnalysis"),
         "AngularDistributionFunction": ("bond_analysis", "AngularDistributionFunction"),
         "build_crystal": ("lattice", "build_crystal"),
+        "CreatePolycrystal": ("create_polycrystal", "CreatePolycrystal"),
     }
     if name == "empty_cache":
         from ._lib import empty_cache

@@ -1104,6 +1104,141 @@ struct ScopedSystem {
     MdbSystem *operator->() { return s; }
 };
 
+// ---------------------------------------------------------------- builders
+int mdb_repeat_cell(double *new_pos, const double *old_box9, const double *old_pos, int n_old, int nx, int ny, int nz,
+                    int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(new_pos && old_box9 && old_pos && n_old > 0 && nx > 0 && ny > 0 && nz > 0, MDB_ERR_VALUE,
+                "repeat_cell: positions, box and positive replication counts are required");
+    ScopedSystem s;
+    DBox b{};
+    for (int i = 0; i < 9; ++i) b.h[i] = old_box9[i];
+    const size_t total = (size_t)n_old * nx * ny * nz;
+    double *dold = h2d(*s, s->scratch, old_pos, (size_t)n_old * 3);
+    double *dnew = s->out_f64.ensure<double>(total * 3);
+    launch_repeat_cell(*s, dold, n_old, b, nx, ny, nz, nullptr, nullptr, nullptr, dnew);
+    d2h(*s, new_pos, dnew, total * 3);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_system_set_atoms_lattice(mdb_system *s, const double *cell9, const double *basis_pos, int n_basis, int nx, int ny,
+                                 int nz, const double *origin3, const int *boundary3)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(cell9 && basis_pos && n_basis > 0 && nx > 0 && ny > 0 && nz > 0, MDB_ERR_VALUE,
+                "lattice: cell, basis and positive replication counts are required");
+    const size_t total = (size_t)n_basis * nx * ny * nz;
+    MDB_REQUIRE(total < ((size_t)1 << 31), MDB_ERR_VALUE, "lattice: more than 2^31 atoms");
+    DBox cell{};
+    double super9[9];
+    for (int i = 0; i < 9; ++i) cell.h[i] = cell9[i];
+    const int rep[3] = {nx, ny, nz};
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) super9[r * 3 + c] = cell9[r * 3 + c] * rep[r];   // build_crystal: rows scaled
+    set_box(*s, super9, origin3, boundary3);
+    double *dbasis = h2d(*s, s->scratch, basis_pos, (size_t)n_basis * 3);
+    double *dx = s->bx.ensure<double>(total), *dy = s->by.ensure<double>(total), *dz = s->bz.ensure<double>(total);
+    launch_repeat_cell(*s, dbasis, n_basis, cell, nx, ny, nz, dx, dy, dz, nullptr);
+    s->x = dx;
+    s->y = dy;
+    s->z = dz;
+    s->N = s->n_rows = (int)total;
+    s->gid = nullptr;
+    s->slab_x0 = s->slab_nx = 0;
+    s->local_frac = 1.0;
+    invalidate(*s);
+    API_END
+}
+
+int mdb_system_positions_device(mdb_system *s, double **dx, double **dy, double **dz, int *N)
+{
+    API_BEGIN
+    MDB_REQUIRE(s->N > 0, MDB_ERR_STATE, "no atoms uploaded");
+    if (dx) *dx = const_cast<double *>(s->x);
+    if (dy) *dy = const_cast<double *>(s->y);
+    if (dz) *dz = const_cast<double *>(s->z);
+    if (N) *N = s->N;
+    API_END
+}
+
+int mdb_system_fetch_positions(mdb_system *s, double *x, double *y, double *z)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->N > 0, MDB_ERR_STATE, "no atoms uploaded");
+    d2h(*s, x, s->x, (size_t)s->N);
+    d2h(*s, y, s->y, (size_t)s->N);
+    d2h(*s, z, s->z, (size_t)s->N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_transform_and_filter(const double *x, const double *y, const double *z, int N, const double *rotation9,
+                             const double *center3, const double *target3, const double *coeffs, int nfaces,
+                             double *out_pos, int *count, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(x && y && z && rotation9 && center3 && target3 && (coeffs || nfaces == 0) && out_pos && count,
+                MDB_ERR_VALUE, "transform_and_filter: missing argument");
+    *count = 0;
+    if (N <= 0) return MDB_OK;
+    ScopedSystem s;
+    double *dx = h2d(*s, s->bx, x, (size_t)N), *dy = h2d(*s, s->by, y, (size_t)N), *dz = h2d(*s, s->bz, z, (size_t)N);
+    double *dpl = h2d(*s, s->out_f64b, coeffs, (size_t)nfaces * 4);
+    double *dout = s->out_f64.ensure<double>((size_t)N * 3);
+    const int n = launch_transform_and_filter(*s, dx, dy, dz, N, rotation9, center3, target3, dpl, nfaces, dout);
+    d2h(*s, out_pos, dout, (size_t)n * 3);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *count = n;
+    API_END
+}
+
+int mdb_system_transform_and_filter(mdb_system *s, const double *rotation9, const double *center3,
+                                    const double *target3, const double *coeffs, int nfaces, double *out_pos, int *count)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->N > 0 && rotation9 && center3 && target3 && out_pos && count, MDB_ERR_VALUE,
+                "transform_and_filter: atoms on the device and all arguments are required");
+    double *dpl = h2d(*s, s->out_f64b, coeffs, (size_t)nfaces * 4);
+    double *dout = s->out_f64.ensure<double>((size_t)s->N * 3);
+    const int n = launch_transform_and_filter(*s, s->x, s->y, s->z, s->N, rotation9, center3, target3, dpl, nfaces, dout);
+    d2h(*s, out_pos, dout, (size_t)n * 3);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *count = n;
+    API_END
+}
+
+int mdb_filter_overlap_atom(const double *x, const double *y, const double *z, int N, const double *box9,
+                            const double *origin3, const int *boundary3, double rc, unsigned char *keep, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(rc > 0 && keep, MDB_ERR_VALUE, "filter_overlap_atom: rc must be positive");
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    unsigned char *dk = reinterpret_cast<unsigned char *>(s->out_i32.ensure<int>((size_t)N / 4 + 1));
+    launch_filter_overlap(*s, rc, dk);
+    d2h(*s, keep, dk, (size_t)N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_system_filter_overlap(mdb_system *s, double rc, unsigned char *keep_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->N > 0 && s->has_box && rc > 0, MDB_ERR_STATE, "no atoms uploaded / rc must be positive");
+    unsigned char *dk = reinterpret_cast<unsigned char *>(s->out_i32.ensure<int>((size_t)s->N / 4 + 1));
+    launch_filter_overlap(*s, rc, dk);
+    d2h(*s, keep_host, dk, (size_t)s->N);
+    if (keep_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 int mdb_build_neighbor(const double *x, const double *y, const double *z, int N, const double *box9,
                        const double *origin3, const int *boundary3, double rc, int *verlet, double *dist,
                        int *nn, int M, int /*num_t*/)

@@ -219,5 +219,11 @@ void launch_wrap_positions(MdbSystem &s, double *x, double *y, double *z, int N)
 int ptm_parse_flags(const char *structure);
 void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *types, double rmsd_threshold,
                 double *output, int ocols, int *indices, int icols);
+void launch_repeat_cell(MdbSystem &s, const double *old_pos_dev, int n_old, const DBox &b, int nx, int ny, int nz,
+                        double *ox, double *oy, double *oz, double *o3);
+int launch_transform_and_filter(MdbSystem &s, const double *x, const double *y, const double *z, int N, const double *R9,
+                                const double *center3, const double *target3, const double *planes_dev, int nfaces,
+                                double *out3);
+void launch_filter_overlap(MdbSystem &s, double rc, unsigned char *keep);
 int device_max_int(MdbSystem &s, const int *v, size_t n);
 int device_min_int(MdbSystem &s, const int *v, size_t n);

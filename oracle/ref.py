@@ -318,6 +318,28 @@ def repeat_cell(box, pos, nx, ny, nz, nt=None):
     return out.reshape(-1, 3)
 
 
+def filter_overlap_atom(x, y, z, box, origin, boundary, rc, nt=None):
+    """neighbor.cpp:390 -> keep flags (bool[N]); the higher index of every pair within rc is dropped."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    keep = np.zeros(x.shape[0], np.uint8)
+    _lib("neighbor").ref_filter_overlap_atom(_d(x), _d(y), _d(z), C.c_int(x.shape[0]), _d(b), _d(o), _i(p),
+                                             C.c_double(rc), keep.ctypes.data_as(C.c_void_p), C.c_int(nt or num_threads()))
+    return keep.astype(bool)
+
+
+def transform_and_filter(x, y, z, rotation, center, target, coeffs, nt=None):
+    """polycrystal.cpp:21 -> (count, 3) positions of the atoms inside the convex cell, input order."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    R, c, t, pl = _f64(rotation).reshape(3, 3), _f64(center).reshape(3), _f64(target).reshape(3), _f64(coeffs).reshape(-1, 4)
+    out = np.zeros((x.shape[0], 3))
+    lib = _lib("polycrystal")
+    lib.ref_transform_and_filter.restype = C.c_int
+    n = lib.ref_transform_and_filter(_d(x), _d(y), _d(z), C.c_int(x.shape[0]), _d(R), _d(c), _d(t), _d(pl),
+                                     C.c_int(pl.shape[0]), _d(out), C.c_int(nt or num_threads()))
+    return out[:n].copy()
+
+
 # --------------------------------------------------------------------------
 # further list consumers (SURVEY.md 8f.1): common neighbour parameter, Warren-Cowley, average_by_neighbor
 # --------------------------------------------------------------------------

@@ -39,4 +39,12 @@ void ref_average_by_neighbor(double rc, const int *verlet, int N, int M, const d
     average_by_neighbor(rc, A2I(verlet, N, M), A2D(dist, N, M), A1I(nn, N), A1D(value, N), W1D(value_ave, N),
                         include_self != 0, num_t);
 }
+// neighbor.cpp:390 filter_overlap_atom -> keep flags (1 byte per atom)
+void ref_filter_overlap_atom(const double *x, const double *y, const double *z, int N, BOXARGS, double rc,
+                             unsigned char *keep, int num_t)
+{
+    auto f = filter_overlap_atom(A1D(x, N), A1D(y, N), A1D(z, N), BOXPASS, rc, num_t);
+    for (int i = 0; i < N; ++i) keep[i] = f.data()[i] ? 1 : 0;
+    delete[] f.data();
+}
 }
