@@ -253,6 +253,23 @@ int mdb_system_fcna(mdb_system *s, double rc, int *pattern_host);
  * lazily on first access).  *used = 0: frame not eligible (triclinic / tiny box), nothing was computed. */
 int mdb_system_fused_cna(mdb_system *s, double rc, int *pattern_host, int *used);
 
+/* ---- CHILL+ and build_bond ---------------------------------------------------------------
+ * mdb_compute_chill_plus <- _chill_plus.compute_chill_plus(x, y, z, box, origin, boundary, verlet_list,
+ *                           distance_list, neighbor_number, rc, pattern, num_t)      (src/chill_plus.cpp:76)
+ * mdb_build_bond         <- _build_bond.build_bond(verlet_list, distance_list, neighbor_number, type_list,
+ *                           cutoff_matrix, num_t) -> (Nbond, 2)                       (src/build_bond.cpp:9)
+ *                           two calls: bonds == NULL returns *nbond, then a buffer of 2 * nbond ints is filled;
+ *                           rows come in (i, list slot) order (the reference's order depends on the OpenMP
+ *                           schedule; its caller sorts and de-duplicates, system.py:1405-1410). */
+int mdb_compute_chill_plus(const double *x, const double *y, const double *z, int N, const double *box9,
+                           const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                           const int *nn, double rc, int *pattern, int num_t);
+int mdb_build_bond(const int *verlet, int N, int M, const double *dist, const int *nn, const int *types,
+                   const double *cutoff_matrix, int ntype, int *bonds, int *nbond, int num_t);
+int mdb_system_chill_plus(mdb_system *s, double rc, int *pattern_host);
+int mdb_system_build_bond(mdb_system *s, const int *types, const double *cutoff_matrix, int ntype, int *bonds_host,
+                          int *nbond);
+
 /* ---- builders: benchmark-size inputs are generated in HBM ---------------------------------
  * mdb_repeat_cell            <- _repeat_cell.repeat_cell(new_pos, old_box, old_pos, nx, ny, nz, num_t)
  *                               (src/repeat_cell.cpp:19; new_pos: 3 * n_old * nx*ny*nz doubles, cell-major, iz fastest)

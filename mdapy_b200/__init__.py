@@ -26,6 +26,7 @@ def __getattr__(name):
         "AtomicTemperature": ("atomic_temperature", "AtomicTemperature"),
         "BondAnalysis": ("bond_analysis", "BondAnalysis"),
         "AngularDistributionFunction": ("bond_analysis", "AngularDistributionFunction"),
+        "ChillPlus": ("chill_plus", "ChillPlus"),
         "build_crystal": ("lattice", "build_crystal"),
         "CreatePolycrystal": ("create_polycrystal", "CreatePolycrystal"),
     }

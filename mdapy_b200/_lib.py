@@ -91,6 +91,10 @@ PROTOTYPES = {
     "mdb_system_neighbor_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), c_ip]),
     "mdb_system_fcna": (C.c_int, [c_vp, C.c_double, c_ip]),
     "mdb_system_fused_cna": (C.c_int, [c_vp, C.c_double, c_ip, c_ip]),
+    "mdb_compute_chill_plus": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, c_ip, C.c_double, c_ip, C.c_int]),
+    "mdb_build_bond": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, c_ip, c_dp, C.c_int, c_ip, c_ip, C.c_int]),
+    "mdb_system_chill_plus": (C.c_int, [c_vp, C.c_double, c_ip]),
+    "mdb_system_build_bond": (C.c_int, [c_vp, c_ip, c_dp, C.c_int, c_ip, c_ip]),
     "mdb_repeat_cell": (C.c_int, [c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mdb_transform_and_filter": (C.c_int, _XYZN + [c_dp, c_dp, c_dp, c_dp, C.c_int, c_dp, c_ip, C.c_int]),
     "mdb_filter_overlap_atom": (C.c_int, _XYZN + _BOX + [C.c_double, c_vp, C.c_int]),

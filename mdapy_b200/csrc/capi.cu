@@ -1104,6 +1104,74 @@ struct ScopedSystem {
     MdbSystem *operator->() { return s; }
 };
 
+// ---------------------------------------------------------------- CHILL+ and build_bond
+int mdb_system_chill_plus(mdb_system *s, double rc, int *pattern_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(rc > 0, MDB_ERR_VALUE, "cutoff must be positive, got %g.", rc);
+    int *pat = s->out_i32.ensure<int>(s->n_rows);
+    launch_chill_plus(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->M, rc, pat);
+    d2h(*s, pattern_host, pat, (size_t)s->n_rows);
+    if (pattern_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_compute_chill_plus(const double *x, const double *y, const double *z, int N, const double *box9,
+                           const double *origin3, const int *boundary3, const int *verlet, int M, const double *dist,
+                           const int *nn, double rc, int *pattern, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    set_box(*s, box9, origin3, boundary3);
+    upload_atoms(*s, x, y, z, N);
+    int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nn, M, rc, LIST_CUTOFF);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_chill_plus(s.s, rc, pattern);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+// bonds: *nbond rows of (i, j), i < j, in (i, list slot) order; two-call protocol: bonds_host == NULL returns the
+// count only, a second call with a buffer of 2 * count ints receives the rows.
+int mdb_system_build_bond(mdb_system *s, const int *types, const double *cutoff_matrix, int ntype, int *bonds_host,
+                          int *nbond)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    require_list(*s);
+    MDB_REQUIRE(types && cutoff_matrix && ntype > 0 && nbond, MDB_ERR_VALUE, "build_bond: types, cutoff matrix required");
+    int *dt = h2d(*s, s->types, types, (size_t)s->N);
+    double *dc = h2d(*s, s->out_f64b, cutoff_matrix, (size_t)ntype * ntype);
+    int *db = nullptr;
+    const int n = launch_build_bond(*s, s->verlet.as<int>(), list_dist(*s), s->nn.as<int>(), s->M, dt, dc, ntype, &db);
+    *nbond = n;
+    if (bonds_host && n > 0) {
+        d2h(*s, bonds_host, db, (size_t)n * 2);
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+    }
+    API_END
+}
+
+int mdb_build_bond(const int *verlet, int N, int M, const double *dist, const int *nn, const int *types,
+                   const double *cutoff_matrix, int ntype, int *bonds, int *nbond, int /*num_t*/)
+{
+    API_BEGIN
+    MDB_REQUIRE(verlet && dist && nn && N > 0 && M > 0, MDB_ERR_VALUE, "build_bond: lists are required");
+    ScopedSystem s;
+    s->N = s->n_rows = N;   // list-only consumer: no coordinates needed
+    h2d(*s, s->verlet, verlet, (size_t)N * M);
+    h2d(*s, s->dist, dist, (size_t)N * M);
+    h2d(*s, s->nn, nn, (size_t)N);
+    s->M = M;
+    s->list_kind = LIST_CUTOFF;
+    s->has_dist = true;
+    int rcode = mdb_system_build_bond(s.s, types, cutoff_matrix, ntype, bonds, nbond);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
 // ---------------------------------------------------------------- builders
 int mdb_repeat_cell(double *new_pos, const double *old_box9, const double *old_pos, int n_old, int nx, int ny, int nz,
                     int /*num_t*/)

@@ -225,5 +225,8 @@ int launch_transform_and_filter(MdbSystem &s, const double *x, const double *y, 
                                 const double *center3, const double *target3, const double *planes_dev, int nfaces,
                                 double *out3);
 void launch_filter_overlap(MdbSystem &s, double rc, unsigned char *keep);
+void launch_chill_plus(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc, int *pattern);
+int launch_build_bond(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, const int *types_dev,
+                      const double *cutoff_dev, int ntype, int **bonds_dev);
 int device_max_int(MdbSystem &s, const int *v, size_t n);
 int device_min_int(MdbSystem &s, const int *v, size_t n);

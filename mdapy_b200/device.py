@@ -204,6 +204,23 @@ class DeviceSystem:
                                          L.iptr(ind) if fetch else None))
         return out, ind
 
+    def chill_plus(self, rc: float, fetch=True):
+        """CHILL+ labels on the cached cut-off list (chill_plus.cpp:76)."""
+        out = L.result_empty(self.n_rows, np.int32) if fetch else None
+        L.check(self._lib.mdb_system_chill_plus(self._h, float(rc), L.iptr(out) if fetch else None))
+        return out
+
+    def build_bond(self, type_list, cutoff_matrix):
+        """(Nbond, 2) pairs i < j whose listed distance is within cutoff_matrix[type_i, type_j] (build_bond.cpp:9)."""
+        t, cm = L.i32(type_list), L.f64(np.asarray(cutoff_matrix, float))
+        assert t.shape[0] == self.N and cm.ndim == 2 and cm.shape[0] == cm.shape[1]
+        n = C.c_int(0)
+        L.check(self._lib.mdb_system_build_bond(self._h, L.iptr(t), L.dptr(cm), cm.shape[0], None, C.byref(n)))
+        out = np.empty((n.value, 2), np.int32)
+        if n.value:
+            L.check(self._lib.mdb_system_build_bond(self._h, L.iptr(t), L.dptr(cm), cm.shape[0], L.iptr(out), C.byref(n)))
+        return out
+
     def cnp(self, rc: float, fetch=True):
         """Common neighbour parameter on the cached cut-off list (common_neighbor_parameter.cpp:10)."""
         out = L.result_empty(self.n_rows, np.float64) if fetch else None

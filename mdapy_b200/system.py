@@ -22,6 +22,7 @@ from .atomic_temperature import AtomicTemperature
 from .bond_analysis import AngularDistributionFunction, BondAnalysis
 from .box import Box
 from .centro_symmetry_parameter import CentroSymmetryParameter
+from .chill_plus import ChillPlus
 from .cluster_analysis import ClusterAnalysis
 from .common_neighbor_analysis import CommonNeighborAnalysis
 from .common_neighbor_parameter import CommonNeighborParameter
@@ -319,6 +320,73 @@ class System:
         cna.compute()
         self.update_data(self._data.with_columns(cna=cna.pattern[: self.N]))
 
+    def cal_chill_plus(self, cutoff: float = 3.5) -> None:
+        """system.py:1531-1570 -> data['chill_plus'] (0 other, 1 hexagonal ice, 2 cubic ice, 3 interfacial ice,
+        4 gas hydrate, 5 interfacial gas hydrate); the frame must hold molecule centres only."""
+        has_neigh = "rc" in self.__dict__ and self.rc >= cutoff
+        if not has_neigh:
+            self.build_neighbor(cutoff)
+        box, data = self._get_compute_view()
+        cp = ChillPlus(data, box, cutoff, dev=self._device_list())
+        cp.compute()
+        self.update_data(self._data.with_columns(chill_plus=cp.pattern[: self.N]))
+
+    def build_bond(self, rc, max_neigh: Optional[int] = None) -> np.ndarray:
+        """system.py:1330-1411: bond pairs (Nbond, 2), 0-based, i < j, sorted and unique.  ``rc``: one cut-off,
+        a {(type_i, type_j): cut-off} / {(element_i, element_j): cut-off} dict, or a matrix over the sorted
+        unique types."""
+        if np.isscalar(rc):
+            max_rc = float(rc)
+        elif isinstance(rc, dict):
+            max_rc = float(np.max(np.asarray(list(rc.values()), float)))
+        else:
+            assert "type" in self.data.columns, "Data must contain type column for matrix bond cutoff."
+            max_rc = float(np.max(np.asarray(rc, float)))
+        assert max_rc > 0, "rc should be larger than 0."
+        if not ("rc" in self.__dict__ and self.rc >= max_rc):
+            self.build_neighbor(max_rc, max_neigh)
+        _, data = self._get_compute_view()
+        compact_type, cutoff_matrix = self._normalize_bond_cutoff(rc, data)
+        bond = self._device_list().build_bond(compact_type, cutoff_matrix)
+        if bond.size == 0:
+            self.bond = np.empty((0, 2), np.int32)
+            return self.bond
+        if "_enlarge_data" in self.__dict__:
+            bond %= self.N
+        bond.sort(axis=1)
+        bond = bond[bond[:, 0] != bond[:, 1]]
+        self.bond = np.unique(bond, axis=0) if bond.size else np.empty((0, 2), np.int32)
+        return self.bond
+
+    @staticmethod
+    def _normalize_bond_cutoff(rc, data):
+        """system.py:1266-1328: (compact type per atom, symmetric cut-off matrix)."""
+        n = data.shape[0]
+        if np.isscalar(rc):
+            return np.zeros(n, np.int32), np.array([[float(rc)]], float)
+        if isinstance(rc, dict):
+            assert len(rc) > 0, "pairwise rc should not be empty."
+            first = next(iter(rc))[0]
+            col = "element" if isinstance(first, str) else "type"
+            assert col in data.columns, f"Data must contain {col} column for pair bond cutoff."
+            labels = np.asarray(data[col])
+            uniq = np.unique(labels)
+            compact = np.searchsorted(uniq, labels).astype(np.int32)
+            index = {v: k for k, v in enumerate(uniq.tolist())}
+            cm = np.full((uniq.shape[0], uniq.shape[0]), -1.0, float)
+            for (a, b), c in rc.items():
+                assert a in index and b in index, f"type/element pair {(a, b)} is not in current system."
+                assert float(c) > 0, "pairwise rc should be larger than 0."
+                cm[index[a], index[b]] = cm[index[b], index[a]] = float(c)
+            assert not np.any(cm < 0), "every type pair needs a bond cutoff"
+            return compact, cm
+        labels = np.asarray(data["type"])
+        uniq = np.unique(labels)
+        cm = np.asarray(rc, float)
+        assert cm.shape == (uniq.shape[0], uniq.shape[0]), "cutoff matrix must be (ntype, ntype)"
+        assert np.allclose(cm, cm.T), "cutoff matrix must be symmetric"
+        return np.searchsorted(uniq, labels).astype(np.int32), cm
+
     def cal_identify_diamond_structure(self):
         """system.py:1493-1529 -> data['ids'] (0 other, 1-3 cubic diamond + shells, 4-6 hexagonal)."""
         dev = None
@@ -598,6 +666,7 @@ def _after_pending(fn):
 
 for _name in list(vars(System)):
     if (_name.startswith("cal_") and _name != "cal_common_neighbor_analysis") or _name in (
-            "average_by_neighbor", "_ensure_cutoff_list", "_min_neighbor_number", "_sort_neighbor", "_device_list"):
+            "average_by_neighbor", "build_bond", "_ensure_cutoff_list", "_min_neighbor_number", "_sort_neighbor",
+            "_device_list"):
         setattr(System, _name, _after_pending(getattr(System, _name)))
 del _name

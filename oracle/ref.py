@@ -318,6 +318,30 @@ def repeat_cell(box, pos, nx, ny, nz, nt=None):
     return out.reshape(-1, 3)
 
 
+def chill_plus(x, y, z, box, origin, boundary, verlet, dist, nn, rc, nt=None):
+    """chill_plus.cpp:76 compute_chill_plus -> pattern int32[N]."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    verlet, dist, nn = _i32(verlet), _f64(dist), _i32(nn)
+    pat = np.zeros(x.shape[0], np.int32)
+    _lib("chill").ref_compute_chill_plus(_d(x), _d(y), _d(z), C.c_int(x.shape[0]), _d(b), _d(o), _i(p), _i(verlet),
+                                         C.c_int(verlet.shape[1]), _d(dist), _i(nn), C.c_double(rc), _i(pat),
+                                         C.c_int(nt or num_threads()))
+    return pat
+
+
+def build_bond(verlet, dist, nn, type_list, cutoff_matrix, nt=None):
+    """build_bond.cpp:9 -> (Nbond, 2) int32 pairs i < j (row order depends on the OpenMP schedule)."""
+    verlet, dist, nn, t = _i32(verlet), _f64(dist), _i32(nn), _i32(type_list)
+    cm = _f64(cutoff_matrix)
+    out = np.zeros((verlet.size, 2), np.int32)
+    lib = _lib("buildbond")
+    lib.ref_build_bond.restype = C.c_int
+    n = lib.ref_build_bond(_i(verlet), C.c_int(verlet.shape[0]), C.c_int(verlet.shape[1]), _d(dist), _i(nn), _i(t), _d(cm),
+                           C.c_int(cm.shape[0]), _i(out), C.c_int(nt or num_threads()))
+    return out[:n].copy()
+
+
 def filter_overlap_atom(x, y, z, box, origin, boundary, rc, nt=None):
     """neighbor.cpp:390 -> keep flags (bool[N]); the higher index of every pair within rc is dropped."""
     x, y, z = _f64(x), _f64(y), _f64(z)
