@@ -270,6 +270,18 @@ int mdb_system_chill_plus(mdb_system *s, double rc, int *pattern_host);
 int mdb_system_build_bond(mdb_system *s, const int *types, const double *cutoff_matrix, int ntype, int *bonds_host,
                           int *nbond);
 
+/* ---- FCC planar faults on the PTM result -------------------------------------------------
+ * mdb_identify_sftb_fcc <- _fccpft.identify_sftb_fcc(hcp_indices, hcp_neighbors, ptm_indices[N,12], structure_types,
+ *                          fault_types, identify_esf, num_t)          (src/identify_fcc_planar_faults.cpp:43)
+ *   fault_types: 0 non-HCP, 1 other, 2 intrinsic SF, 3 coherent twin boundary, 4 multi-layer SF, 5 extrinsic SF.
+ *   hcp_indices / hcp_neighbors (the reference's scratch) are accepted and ignored.  index_order names the HCP
+ *   template point order of ptm_indices: 0 = this library's PTM, 1 = the reference's (extern/ptm).
+ * mdb_system_planar_faults: the same on the handle's last PTM result (device resident). */
+int mdb_identify_sftb_fcc(const int *hcp_indices, int n_hcp, int *hcp_neighbors, const int *ptm_indices,
+                          const int *structure_types, int N, int *fault_types, int identify_esf, int index_order,
+                          int num_t);
+int mdb_system_planar_faults(mdb_system *s, int identify_esf, int *fault_host);
+
 /* ---- builders: benchmark-size inputs are generated in HBM ---------------------------------
  * mdb_repeat_cell            <- _repeat_cell.repeat_cell(new_pos, old_box, old_pos, nx, ny, nz, num_t)
  *                               (src/repeat_cell.cpp:19; new_pos: 3 * n_old * nx*ny*nz doubles, cell-major, iz fastest)

@@ -27,6 +27,7 @@ def __getattr__(name):
         "BondAnalysis": ("bond_analysis", "BondAnalysis"),
         "AngularDistributionFunction": ("bond_analysis", "AngularDistributionFunction"),
         "ChillPlus": ("chill_plus", "ChillPlus"),
+        "IdentifyFccPlanarFaults": ("identify_fcc_planar_faults", "IdentifyFccPlanarFaults"),
         "build_crystal": ("lattice", "build_crystal"),
         "CreatePolycrystal": ("create_polycrystal", "CreatePolycrystal"),
     }

@@ -91,6 +91,8 @@ PROTOTYPES = {
     "mdb_system_neighbor_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp), C.POINTER(c_vp), c_ip]),
     "mdb_system_fcna": (C.c_int, [c_vp, C.c_double, c_ip]),
     "mdb_system_fused_cna": (C.c_int, [c_vp, C.c_double, c_ip, c_ip]),
+    "mdb_identify_sftb_fcc": (C.c_int, [c_ip, C.c_int, c_ip, c_ip, c_ip, C.c_int, c_ip, C.c_int, C.c_int, C.c_int]),
+    "mdb_system_planar_faults": (C.c_int, [c_vp, C.c_int, c_ip]),
     "mdb_compute_chill_plus": (C.c_int, _XYZN + _BOX + [c_ip, C.c_int, c_dp, c_ip, C.c_double, c_ip, C.c_int]),
     "mdb_build_bond": (C.c_int, [c_ip, C.c_int, C.c_int, c_dp, c_ip, c_ip, c_dp, C.c_int, c_ip, c_ip, C.c_int]),
     "mdb_system_chill_plus": (C.c_int, [c_vp, C.c_double, c_ip]),

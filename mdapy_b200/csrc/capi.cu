@@ -1172,6 +1172,45 @@ int mdb_build_bond(const int *verlet, int N, int M, const double *dist, const in
     API_END
 }
 
+// ---------------------------------------------------------------- FCC planar faults
+int mdb_system_planar_faults(mdb_system *s, int identify_esf, int *fault_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->ptm_out.p && s->ptm_idx.p, MDB_ERR_STATE, "run polyhedral template matching first");
+    MDB_REQUIRE(s->n_rows == s->N, MDB_ERR_STATE, "planar faults need the whole frame on one device");
+    const int N = s->N;
+    int *type = s->out_i32.ensure<int>((size_t)2 * N);
+    int *fault = type + N;
+    launch_types_from_ptm_output(*s, s->ptm_out.as<double>(), 8, N, type);
+    launch_planar_faults(*s, type, N, s->ptm_idx.as<int>(), 18, 1, /*order: this library's template*/ 0,
+                         identify_esf != 0, fault);
+    d2h(*s, fault_host, fault, (size_t)N);
+    if (fault_host) CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_identify_sftb_fcc(const int *hcp_indices, int n_hcp, int *hcp_neighbors, const int *ptm_indices,
+                          const int *structure_types, int N, int *fault_types, int identify_esf, int index_order,
+                          int /*num_t*/)
+{
+    API_BEGIN
+    (void)hcp_indices;
+    (void)n_hcp;
+    (void)hcp_neighbors;   // scratch of the reference; the device builds its own
+    MDB_REQUIRE(ptm_indices && structure_types && fault_types && N > 0, MDB_ERR_VALUE, "identify_sftb_fcc: arrays required");
+    MDB_REQUIRE(index_order == 0 || index_order == 1, MDB_ERR_VALUE, "index_order: 0 (mdapy_b200) or 1 (reference)");
+    ScopedSystem s;
+    s->N = s->n_rows = N;
+    int *type = h2d(*s, s->types, structure_types, (size_t)N);
+    int *idx = h2d(*s, s->ptm_idx, ptm_indices, (size_t)N * 12);
+    int *fault = s->out_i32.ensure<int>((size_t)N);
+    launch_planar_faults(*s, type, N, idx, 12, 0, index_order, identify_esf != 0, fault);
+    d2h(*s, fault_types, fault, (size_t)N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 // ---------------------------------------------------------------- builders
 int mdb_repeat_cell(double *new_pos, const double *old_box9, const double *old_pos, int n_old, int nx, int ny, int nz,
                     int /*num_t*/)

@@ -228,5 +228,8 @@ void launch_filter_overlap(MdbSystem &s, double rc, unsigned char *keep);
 void launch_chill_plus(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc, int *pattern);
 int launch_build_bond(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, const int *types_dev,
                       const double *cutoff_dev, int ntype, int **bonds_dev);
+void launch_planar_faults(MdbSystem &s, const int *type, int N, const int *ptm_idx, int stride, int col0, int order,
+                          bool identify_esf, int *fault);
+void launch_types_from_ptm_output(MdbSystem &s, const double *out, int ocols, int N, int *type);
 int device_max_int(MdbSystem &s, const int *v, size_t n);
 int device_min_int(MdbSystem &s, const int *v, size_t n);

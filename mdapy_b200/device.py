@@ -204,6 +204,12 @@ class DeviceSystem:
                                          L.iptr(ind) if fetch else None))
         return out, ind
 
+    def planar_faults(self, identify_esf: bool = True):
+        """FCC planar-fault labels from the last ``ptm`` call on this handle (identify_fcc_planar_faults.cpp:43)."""
+        out = L.result_empty(self.n_rows, np.int32)
+        L.check(self._lib.mdb_system_planar_faults(self._h, int(bool(identify_esf)), L.iptr(out)))
+        return out
+
     def chill_plus(self, rc: float, fetch=True):
         """CHILL+ labels on the cached cut-off list (chill_plus.cpp:76)."""
         out = L.result_empty(self.n_rows, np.int32) if fetch else None

@@ -627,8 +627,6 @@ class System:
     def cal_polyhedral_template_matching(self, structure="fcc-hcp-bcc", rmsd_threshold=0.1, return_ordering=False,
                                          return_rmsd=False, return_atomic_distance=False, return_orientation=False,
                                          identify_fcc_planar_faults=False, identify_esf=True):
-        if identify_fcc_planar_faults:
-            raise NotImplementedError("FCC planar-fault identification is outside the hot path (SURVEY.md 8f.1)")
         use_cached = False
         repeat = self._safe_repeat()
         if sum(repeat) == 3 and self._has_list and self._min_neighbor_number() >= 18:
@@ -649,6 +647,15 @@ class System:
                 cols["interatomic_distance"] = output[:, 3].copy()
             if return_orientation:
                 cols.update(qx=output[:, 5].copy(), qy=output[:, 6].copy(), qz=output[:, 7].copy(), qw=output[:, 4].copy())
+        if identify_fcc_planar_faults:
+            # system.py:1963-1968: planar faults from the structure types and the 12 matched neighbours of
+            # every atom (this library's template point order, see identify_fcc_planar_faults.py)
+            from .identify_fcc_planar_faults import IdentifyFccPlanarFaults
+
+            ifpt = IdentifyFccPlanarFaults(np.asarray(ptm.output[:, 0], np.int32),
+                                           np.ascontiguousarray(ptm.ptm_indices[:, 1:13]), identify_esf)
+            ifpt.compute()
+            cols["pft"] = ifpt.fault_types[: self.N].copy()
         self.update_data(self._data.with_columns(**cols))
         return ptm
 

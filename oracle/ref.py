@@ -318,6 +318,18 @@ def repeat_cell(box, pos, nx, ny, nz, nt=None):
     return out.reshape(-1, 3)
 
 
+def identify_sftb_fcc(structure_types, ptm_indices12, identify_esf=True, nt=None):
+    """identify_fcc_planar_faults.py:71-84 + identify_fcc_planar_faults.cpp:43 -> fault_types int32[N]."""
+    st = _i32(structure_types)
+    idx = _i32(np.ascontiguousarray(ptm_indices12))
+    hcp = np.where(st == 2)[0].astype(np.int32)
+    hn = np.zeros((hcp.shape[0], 12), np.int32)
+    fault = np.zeros_like(st)
+    _lib("fccpft").ref_identify_sftb_fcc(_i(hcp), C.c_int(hcp.shape[0]), _i(hn), _i(idx), _i(st), C.c_int(st.shape[0]),
+                                         _i(fault), C.c_int(int(bool(identify_esf))), C.c_int(nt or num_threads()))
+    return fault
+
+
 def chill_plus(x, y, z, box, origin, boundary, verlet, dist, nn, rc, nt=None):
     """chill_plus.cpp:76 compute_chill_plus -> pattern int32[N]."""
     x, y, z = _f64(x), _f64(y), _f64(z)

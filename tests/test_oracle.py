@@ -319,3 +319,29 @@ def test_port_wrap_positions_equals_reference():
         port.wrap_positions(*c, box, origin, bnd)
         for u, w in zip(a, c):
             assert np.array_equal(u.view(np.int64), w.view(np.int64))
+
+
+GOLD_DIR = Path(__file__).resolve().parent / "golden"
+
+
+# ---- further reference fixtures pinned on the compiled reference (round 2)
+def test_ref_chill_plus_reproduces_the_upstream_fixture():
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    d = np.load(GOLD_DIR / "chill_water.npz")
+    pos, box, bnd, rc = d["pos"], d["box"], d["boundary"], float(d["chill_plus_cutoff"])
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    v, dd, n = ref.build_neighbor_auto(x, y, z, box, np.zeros(3), bnd, rc)
+    assert np.array_equal(ref.chill_plus(x, y, z, box, np.zeros(3), bnd, v, dd, n, rc), d["chill_plus"])
+
+
+def test_ref_planar_faults_reproduce_the_upstream_fixture():
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    from oracle import pipeline as P
+
+    d = np.load(GOLD_DIR / "fcc_planar_faults.npz")
+    fr = P.Frame(d["pos"], d["box"], d["boundary"], d["origin"])
+    out, ind = P.cal_ptm(ref, fr, "all", 0.1)
+    got = ref.identify_sftb_fcc(out[:, 0].astype(np.int32), ind[:, 1:13], identify_esf=False)
+    assert np.array_equal(got, d["pft"])
