@@ -51,6 +51,7 @@ struct TileArgs {
     int use_tma;
     int tiles_x;     // tiles along x (warp-per-cell kernel: strip order of the tile list)
     int ocap;        // owned-atom capacity of the per-tile wrapped-position table
+    int strip;       // floor measurement: staging + row stores only (MDB_STRIP=1)
     int *pattern;    // fused neighbour + CNA kernel: labels out
     float rcsq_lo;   // fp32 bound below which a candidate is a neighbour without the exact test
     float cut_lo, cut_hi;   // fp32 band of the bond test among neighbours
@@ -382,6 +383,37 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
 
     // ---- D. one thread per owned atom
     int local_max = 0, local_min = INT_MAX;
+    if (A.strip) {
+        // FLOOR MEASUREMENT (MDB_STRIP=1, tools/neigh_probe.py --strip): tile tables + staging + fp32 copy as
+        // above, then every owned atom writes a full row of dummy entries with 16-byte stores and its count --
+        // everything the kernel does EXCEPT the search.  Not a product path (results are garbage).
+        for (int t = tid; t < n_owned; t += TILE_THREADS) {
+            int lo = 0, hi = T * T;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (opref[mid] <= t) lo = mid;
+                else hi = mid;
+            }
+            const int p = (lo / T + 1) * P + (lo % T + 1);
+            const int s_i = cs[p * CSW + PZ - 1 - kmax] + (t - opref[lo]);
+            const int idx = raw[s_i].idx;
+            if (idx >= A.n_rows) continue;
+            const float4 me = f4[s_i];
+            int *vrow = A.verlet + (size_t)idx * A.M;
+            double *drow = A.dist + (size_t)idx * A.M;
+            for (int u = 0; u + 3 < A.M; u += 4) {
+                *reinterpret_cast<int4 *>(vrow + u) = make_int4(s_i, u, t, idx);
+                *reinterpret_cast<double2 *>(drow + u) = make_double2(me.x, me.y);
+                *reinterpret_cast<double2 *>(drow + u + 2) = make_double2(me.z, me.w);
+            }
+            A.nn[idx] = A.M;
+        }
+        if (tid == 0) {
+            atomicMax(A.max_count, A.M);
+            atomicMin(A.min_count, A.M);
+        }
+        return;
+    }
     if (!staged_ok) {
 #pragma unroll 1
         for (int t = tid; t < n_owned; t += TILE_THREADS) {
@@ -850,7 +882,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_coop(const _
             if (!valid) e = 0xffffu << 12;   // owner no real atom has: a segment of its own
             const unsigned cand = e & 0xfffu, t = e >> 12;
             const unsigned tt = valid ? t : 0u;
-            const unsigned ra = raw_base + 32u * cand, oa = own_base + 32u * tt;
+            // (idle lanes read a staged record instead of own[0], which another warp may be writing)
+            const unsigned ra = raw_base + 32u * cand, oa = valid ? own_base + 32u * tt : raw_base;
             double xj, yj, zj, wj, xi, yi, zi, wi;
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xj), "=d"(yj) : "r"(ra));
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(zj), "=d"(wj) : "r"(ra + 16u));
@@ -1599,6 +1632,7 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     A.count_only = count_only ? 1 : 0;
     const char *env = getenv("MDB_STAGE");
     A.use_tma = !(env && !strcmp(env, "ldg"));
+    A.strip = getenv("MDB_STRIP") != nullptr && !count_only && (M & 3) == 0;
     {   // staged-atom capacity from the mean cell population (tiles above it take the in-kernel direct path)
         const double rho = (double)s.N / ((double)g.nxl * g.n[1] * g.n[2]);
         int cap = (int)(rho * (TT + 2) * (TT + 2) * (TZ + 2) * 1.12) + 32;
@@ -1619,7 +1653,7 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     // cooperative kernel wins as rows grow (M = 64: 20.9 vs 31.0 ms per 16.4 M atoms) -- dense frames use the
     // small tile shapes.  MDB_NEIGHBOR=tiled_v1 / coop forces one of them.
     const char *kenv = getenv("MDB_NEIGHBOR");
-    const bool v1 = kenv ? !strcmp(kenv, "tiled_v1") : TT >= 4;
+    const bool v1 = A.strip || (kenv ? !strcmp(kenv, "tiled_v1") : TT >= 4);
     if (!v1) {
         if (A.tile_stride == 1 && ((long long)((A.tiles_y + 7) / 8) * tiles_x > 65535 || A.tiles_z > 65535))
             A.tile_stride = 0;   // linear tile list

@@ -53,5 +53,7 @@ for r in range(args.reps + 2):
         ts.append(t["neighbor_ms"])
 N = x.numel()
 env = {k: v for k, v in os.environ.items() if k.startswith("MDB_")}
+if os.environ.get("MDB_STRIP"):
+    print("STRIPPED kernel (tile tables + staging + fp32 copy + row stores, no search): floor measurement")
 print(f"N={N} sigma={args.sigma} M={M} max={mx} env={env} neighbor_ms={np.mean(ts):.3f} (min {np.min(ts):.3f}) "
       f"GB/s={(28 + 12 * M) * N / np.mean(ts) / 1e6:.0f}" + (f" cna_ms={np.mean(tc[2:]):.3f}" if tc else ""), flush=True)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # tools/sanitize.sh -- compute-sanitizer over the small-configuration GPU parity tests.
-# memcheck on the neighbour / descriptor / kNN / cluster / PTM / distributed suites, racecheck on the kernels
-# with shared-memory queues, union-find and atomicMin claims.  Summaries -> gpurun_out/sanitizer_*.txt
+# memcheck on every suite, racecheck on the kernels with shared-memory queues / rings (both neighbour kernels, the
+# fused neighbour+CNA kernel), union-find and atomicMin claims.  Summaries -> gpurun_out/sanitizer_*.txt
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
@@ -14,12 +14,12 @@ run() {  # name tool tests...
     grep -E "ERROR SUMMARY|RACECHECK SUMMARY" $OUT/sanitizer_${name}_${tool}.log | tail -1 >> $OUT/sanitizer_summary.txt
 }
 : > $OUT/sanitizer_summary.txt
-run neighbor memcheck tests/test_gpu_neighbor.py tests/test_gpu_knn.py
-run descriptors memcheck tests/test_gpu_descriptors.py tests/test_gpu_list_consumers.py tests/test_gpu_ids.py
-run system memcheck tests/test_gpu_system.py tests/test_gpu_slab.py tests/test_gpu_distributed.py
-run ptm memcheck tests/test_gpu_ptm.py
-run neighbor racecheck tests/test_gpu_neighbor.py
+run neighbor memcheck tests/test_gpu_neighbor.py tests/test_gpu_knn.py tests/test_gpu_fused.py
+run descriptors memcheck tests/test_gpu_descriptors.py tests/test_gpu_list_consumers.py tests/test_gpu_ids.py tests/test_gpu_chill_bond.py
+run system memcheck tests/test_gpu_system.py tests/test_gpu_slab.py tests/test_gpu_distributed.py tests/test_gpu_builders.py
+run ptm memcheck tests/test_gpu_ptm.py tests/test_gpu_planar_faults.py
+run neighbor racecheck tests/test_gpu_neighbor.py tests/test_gpu_fused.py
+MDB_NEIGHBOR=tiled_v1 run neighbor_v1 racecheck tests/test_gpu_neighbor.py
 MDB_NEIGHBOR=coop run neighbor_coop racecheck tests/test_gpu_neighbor.py
-MDB_NEIGHBOR=coop run neighbor_coop memcheck tests/test_gpu_neighbor.py
-run cluster_ids racecheck tests/test_gpu_ids.py "tests/test_gpu_list_consumers.py" -k "cluster or ids or diamond"
+run cluster_ids racecheck tests/test_gpu_ids.py tests/test_gpu_list_consumers.py -k "cluster or ids or diamond"
 cat $OUT/sanitizer_summary.txt
