@@ -157,22 +157,35 @@ __global__ void __launch_bounds__(128) k_aja(const double *__restrict__ x, const
 // within rc, R_ij = sum over common neighbours k (within rc of both) of (r_ik + r_jk), each a
 // min-image vector; cnp_i = sum_j |R_ij|^2 / N_i, 1000 when no neighbour lies within rc.  Same loop
 // nesting and summation order as the reference.
+// CACHE: the row of atom i (indices + "within rc" flags) sits in shared memory, interleaved per thread, because the
+// innermost loop searches it for every neighbour of every neighbour (M^3 probes per atom); rows wider than the
+// cache (CNP_CACHE entries) read global memory as before.
+constexpr int CNP_CACHE = 48;
+template <bool CACHED>
 __global__ void __launch_bounds__(128) k_cnp(const double *__restrict__ x, const double *__restrict__ y,
                                              const double *__restrict__ z, int N, DBox box,
                                              const int *__restrict__ verlet, const double *__restrict__ dist,
                                              const int *__restrict__ nn, int M, double rc, double *__restrict__ cnp)
 {
+    __shared__ int sh_idx[CACHED ? CNP_CACHE * 128 : 1];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int ni = min(nn[i], M);
     const int *vi = verlet + (size_t)i * M;
     const double *di = dist + (size_t)i * M;
     const double xi = x[i], yi = y[i], zi = z[i];
+    int *row = sh_idx + threadIdx.x;
+    unsigned long long in_rc = 0ull;   // bit h: di[h] <= rc (CACHED: ni <= 48)
+    if (CACHED)
+        for (int h = 0; h < ni; ++h) {
+            row[h * 128] = vi[h];
+            if (di[h] <= rc) in_rc |= 1ull << h;
+        }
     int cnt = 0;
     double acc = 0.0;
     for (int m = 0; m < ni; ++m) {
-        if (!(di[m] <= rc)) continue;
-        const int j = vi[m];
+        if (CACHED ? !((in_rc >> m) & 1ull) : !(di[m] <= rc)) continue;
+        const int j = CACHED ? row[m * 128] : vi[m];
         ++cnt;
         double rx = 0.0, ry = 0.0, rz = 0.0;
         const int nj = min(nn[j], M);
@@ -182,8 +195,8 @@ __global__ void __launch_bounds__(128) k_cnp(const double *__restrict__ x, const
         for (int s = 0; s < nj; ++s) {
             const int k = vj[s];
             for (int h = 0; h < ni; ++h) {
-                if (vi[h] != k) continue;
-                if (dj[s] <= rc && di[h] <= rc) {
+                if ((CACHED ? row[h * 128] : vi[h]) != k) continue;
+                if (dj[s] <= rc && (CACHED ? ((in_rc >> h) & 1ull) != 0ull : di[h] <= rc)) {
                     const double xk = x[k], yk = y[k], zk = z[k];
                     double ax = xi - xk, ay = yi - yk, az = zi - zk;
                     double bx = xj - xk, by = yj - yk, bz = zj - zk;
@@ -511,7 +524,8 @@ void launch_aja(MdbSystem &s, const int *verlet, int M, const double *dist, int 
 void launch_cnp(MdbSystem &s, const int *verlet, const double *dist, const int *nn, int M, double rc, double *cnp)
 {
     const int N = s.n_rows;
-    MDB_LAUNCH(k_cnp, (N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, dist, nn, M, rc, cnp);
+    if (M <= CNP_CACHE) MDB_LAUNCH(k_cnp<true>, (N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, dist, nn, M, rc, cnp);
+    else MDB_LAUNCH(k_cnp<false>, (N + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, N, s.box, verlet, dist, nn, M, rc, cnp);
     CUDA_TRY(cudaGetLastError());
 }
 

@@ -124,6 +124,63 @@ __device__ __forceinline__ double near_image(double x, double L, double invL)
     return x - L * n;
 }
 
+// Tile centre and centre-relative nearest-image position of a staged atom, orthogonal and triclinic boxes.
+// Cells are (cx, cy, cz) in CELL units along the three lattice directions; a cell is rc / thickness wide in
+// fractional coordinates (cell_of, src/neighbor.cpp:30-62).  Only the fp32 pre-filter uses these positions: two
+// atoms reduced around the same centre differ by the reference's minimum-image vector whenever that vector is
+// short (the block spans well under half a box length), and everything that decides an output is re-evaluated
+// with the reference's exact expression.
+struct TileCentre {
+    double c[3];
+};
+__device__ __forceinline__ TileCentre tile_centre(const DBox &box, const CellGrid &g, double cx, double cy, double cz)
+{
+    const double rcw = 1.0 / g.rc_inv;
+    TileCentre t;
+    if (!box.triclinic) {
+        t.c[0] = box.origin[0] + cx * rcw;
+        t.c[1] = box.origin[1] + cy * rcw;
+        t.c[2] = box.origin[2] + cz * rcw;
+    } else {
+        const double f0 = cx * rcw / box.thick[0], f1 = cy * rcw / box.thick[1], f2 = cz * rcw / box.thick[2];
+        t.c[0] = box.origin[0] + f0 * box.h[0] + f1 * box.h[3] + f2 * box.h[6];
+        t.c[1] = box.origin[1] + f0 * box.h[1] + f1 * box.h[4] + f2 * box.h[7];
+        t.c[2] = box.origin[2] + f0 * box.h[2] + f1 * box.h[5] + f2 * box.h[8];
+    }
+    return t;
+}
+// returns true when a periodic shift was applied
+__device__ __forceinline__ bool rel_image(const DBox &box, const TileCentre &t, double x, double y, double z, double &d0,
+                                          double &d1, double &d2)
+{
+    d0 = x - t.c[0];
+    d1 = y - t.c[1];
+    d2 = z - t.c[2];
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+    if (!box.triclinic) {
+        if (box.pbc[0]) n0 = rint(d0 * box.hinv[0]);
+        if (box.pbc[1]) n1 = rint(d1 * box.hinv[4]);
+        if (box.pbc[2]) n2 = rint(d2 * box.hinv[8]);
+        d0 -= box.h[0] * n0;
+        d1 -= box.h[4] * n1;
+        d2 -= box.h[8] * n2;
+    } else {
+        double f0 = d0 * box.hinv[0] + d1 * box.hinv[3] + d2 * box.hinv[6];
+        double f1 = d0 * box.hinv[1] + d1 * box.hinv[4] + d2 * box.hinv[7];
+        double f2 = d0 * box.hinv[2] + d1 * box.hinv[5] + d2 * box.hinv[8];
+        if (box.pbc[0]) n0 = rint(f0);
+        if (box.pbc[1]) n1 = rint(f1);
+        if (box.pbc[2]) n2 = rint(f2);
+        f0 -= n0;
+        f1 -= n1;
+        f2 -= n2;
+        d0 = f0 * box.h[0] + f1 * box.h[3] + f2 * box.h[6];
+        d1 = f0 * box.h[1] + f1 * box.h[4] + f2 * box.h[7];
+        d2 = f0 * box.h[2] + f1 * box.h[5] + f2 * box.h[8];
+    }
+    return (n0 != 0.0) | (n1 != 0.0) | (n2 != 0.0);
+}
+
 __device__ __forceinline__ void load_rec(const SortedAtom *p, double &x, double &y, double &z, int &idx, int &cell)
 {
     const double2 *q = reinterpret_cast<const double2 *>(p);
@@ -177,7 +234,7 @@ __device__ __noinline__ int direct_atom(const TileArgs &A, int sg)
     int my_idx, my_cell, cnt = 0;
     load_rec(A.sorted + sg, xi, yi, zi, my_idx, my_cell);
     if (my_idx >= A.n_rows) return -1;
-    wrap_ortho(box, xi, yi, zi);
+    wrap_into_box(box, xi, yi, zi);
     int *vrow = A.verlet + (size_t)my_idx * A.M;
     double *drow = A.dist + (size_t)my_idx * A.M;
     int ic, jc, kc;
@@ -194,7 +251,7 @@ __device__ __noinline__ int direct_atom(const TileArgs &A, int sg)
             int jdx, jcell;
             load_rec(A.sorted + q, xj, yj, zj, jdx, jcell);
             double dx = xj - xi, dy = yj - yi, dz = zj - zi;
-            min_image_ortho(box, dx, dy, dz);
+            min_image(box, dx, dy, dz);
             const double d2 = dx * dx + dy * dy + dz * dz;
             if (d2 <= A.rcsq) {
                 if (!COUNT_ONLY && cnt < A.M) {
@@ -351,25 +408,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
 
         // ---- C. fp32 positions relative to the tile centre (nearest periodic image) + cell tag.
         // One warp per pencil, lanes over the pencil's atoms.
-        const double rcw = 1.0 / g.rc_inv;
         const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0) % g.n[0];  // global x cell of the first owned plane
-        const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
-                     ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
+        const TileCentre ctr = tile_centre(box, g, gx0 + 0.5 * T, u0y + 1 + 0.5 * T, u0z + 1 + 0.5 * TZ);
         for (int p = warp; p < NPEN; p += TILE_THREADS / 32) {
             const int *row = cs + p * CSW;
             const int beg = row[0], end = row[PZ];
             for (int s = beg + lane; s < end; s += 32) {
                 const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
                 const double zr = reinterpret_cast<const double *>(raw + s)[2];
-                double d0 = lo.x - ctr0, d1 = lo.y - ctr1, d2 = zr - ctr2;
-                double n0 = 0.0, n1 = 0.0, n2 = 0.0;
-                if (box.pbc[0]) n0 = rint(d0 * box.hinv[0]);
-                if (box.pbc[1]) n1 = rint(d1 * box.hinv[4]);
-                if (box.pbc[2]) n2 = rint(d2 * box.hinv[8]);
-                d0 -= box.h[0] * n0;
-                d1 -= box.h[4] * n1;
-                d2 -= box.h[8] * n2;
-                if ((n0 != 0.0) | (n1 != 0.0) | (n2 != 0.0)) far_flag[1] = 1;  // some staged atom is a periodic image
+                double d0, d1, d2;
+                if (rel_image(box, ctr, lo.x, lo.y, zr, d0, d1, d2)) far_flag[1] = 1;  // some staged atom is a periodic image
                 const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
                 const float w = __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0));
                 if (!(w <= A.w_limit)) far_flag[0] = 1;  // outside the radius the fp32 bound covers (or NaN)
@@ -466,17 +514,19 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
             // img: the exact test needs the minimum-image step.  When no staged atom of the tile is a
             // periodic image and this atom lies inside the box, every pre-filter survivor has
             // |dx| <= ~rc << L/2, so n = floor(dx/L + 0.5) = 0 and dx - L*0 == dx: the step is skipped.
-            bool img = tile_shifted;
+            bool img = tile_shifted || box.triclinic;   // triclinic: the fractional round trip of box.h:98-114 always runs
             int i0 = 0, i1 = 0, i2 = 0, i3 = 0;  // last four accepted indices (shift register)
             double e0 = 0.0, e1 = 0.0;            // last two accepted distances
             if (active) {
                 s_i = cs[p * CSW + PZ - 1 - kmax] + (t - opref[pi]);
                 load_rec(raw + s_i, xi, yi, zi, my_idx, my_cell);
                 live = my_idx < A.n_rows;
-                if (px) { const double d = xi - box.origin[0]; img |= !(d >= box.wrap_t[0][1] && d < box.wrap_t[0][2]); }
-                if (py) { const double d = yi - box.origin[1]; img |= !(d >= box.wrap_t[1][1] && d < box.wrap_t[1][2]); }
-                if (pz) { const double d = zi - box.origin[2]; img |= !(d >= box.wrap_t[2][1] && d < box.wrap_t[2][2]); }
-                wrap_ortho(box, xi, yi, zi);
+                if (!box.triclinic) {
+                    if (px) { const double d = xi - box.origin[0]; img |= !(d >= box.wrap_t[0][1] && d < box.wrap_t[0][2]); }
+                    if (py) { const double d = yi - box.origin[1]; img |= !(d >= box.wrap_t[1][1] && d < box.wrap_t[1][2]); }
+                    if (pz) { const double d = zi - box.origin[2]; img |= !(d >= box.wrap_t[2][1] && d < box.wrap_t[2][2]); }
+                }
+                wrap_into_box(box, xi, yi, zi);
                 const float4 me = f4[s_i];
                 fx = -2.0f * me.x;
                 fy = -2.0f * me.y;
@@ -508,9 +558,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
                     const int jdx = __double2loint(sw ? a1 : b1);
                     double dx = xj - xi, dy = yj - yi, dz = zj - zi;
                     if (decltype(IMG)::value) {
-                        if (px) dx = near_image(dx, Lx, iLx);
-                        if (py) dy = near_image(dy, Ly, iLy);
-                        if (pz) dz = near_image(dz, Lz, iLz);
+                        if (box.triclinic) min_image(box, dx, dy, dz);
+                        else {
+                            if (px) dx = near_image(dx, Lx, iLx);
+                            if (py) dy = near_image(dy, Ly, iLy);
+                            if (pz) dz = near_image(dz, Lz, iLz);
+                        }
                     }
                     const double d2 = dx * dx + dy * dy + dz * dz;
                     if (d2 <= rcsq) {
@@ -822,22 +875,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_coop(const _
         }
 
         // ---- C. fp32 positions relative to the tile centre (nearest periodic image), flat over the staged atoms
-        const double rcw = 1.0 / g.rc_inv;
         const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0) % g.n[0];
-        const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
-                     ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
+        const TileCentre ctr = tile_centre(box, g, gx0 + 0.5 * T, u0y + 1 + 0.5 * T, u0z + 1 + 0.5 * TZ);
         for (int s = tid; s < n_staged; s += NT) {
             const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
             const double z = reinterpret_cast<const double *>(raw + s)[2];
-            double d0 = lo.x - ctr0, d1 = lo.y - ctr1, d2 = z - ctr2;
-            double n0 = 0.0, n1 = 0.0, n2 = 0.0;
-            if (box.pbc[0]) n0 = rint(d0 * box.hinv[0]);
-            if (box.pbc[1]) n1 = rint(d1 * box.hinv[4]);
-            if (box.pbc[2]) n2 = rint(d2 * box.hinv[8]);
-            d0 -= box.h[0] * n0;
-            d1 -= box.h[4] * n1;
-            d2 -= box.h[8] * n2;
-            if ((n0 != 0.0) | (n1 != 0.0) | (n2 != 0.0)) far_flag[1] = 1;   // some staged atom is a periodic image
+            double d0, d1, d2;
+            if (rel_image(box, ctr, lo.x, lo.y, z, d0, d1, d2)) far_flag[1] = 1;   // some staged atom is a periodic image
             const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
             const float w = __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0));
             if (!(w <= A.w_limit)) far_flag[0] = 1;   // outside the radius the fp32 bound covers (or NaN)
@@ -893,7 +937,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_coop(const _
             const int jdx = __double2loint(wj);
             const int idx = __double2loint(wi), fl = __double2hiint(wi);
             double dx = xj - xi, dy = yj - yi, dz = zj - zi;
-            if (tile_shifted || __any_sync(0xffffffffu, valid && (fl & 1))) {
+            if (box.triclinic) min_image(box, dx, dy, dz);   // the fractional round trip of box.h:98-114 always runs
+            else if (tile_shifted || __any_sync(0xffffffffu, valid && (fl & 1))) {
                 if (px) dx = near_image(dx, Lx, iLx);
                 if (py) dy = near_image(dy, Ly, iLy);
                 if (pz) dz = near_image(dz, Lz, iLz);
@@ -938,10 +983,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2) k_neighbor_coop(const _
                 live = idx < A.n_rows;
                 double xi = lo.x, yi = lo.y, zi = hi.x;
                 int fl = 0;
-                if (box.pbc[0]) { const double d = xi - box.origin[0]; fl |= !(d >= box.wrap_t[0][1] && d < box.wrap_t[0][2]); }
-                if (box.pbc[1]) { const double d = yi - box.origin[1]; fl |= !(d >= box.wrap_t[1][1] && d < box.wrap_t[1][2]); }
-                if (box.pbc[2]) { const double d = zi - box.origin[2]; fl |= !(d >= box.wrap_t[2][1] && d < box.wrap_t[2][2]); }
-                wrap_ortho(box, xi, yi, zi);
+                if (!box.triclinic) {
+                    if (box.pbc[0]) { const double d = xi - box.origin[0]; fl |= !(d >= box.wrap_t[0][1] && d < box.wrap_t[0][2]); }
+                    if (box.pbc[1]) { const double d = yi - box.origin[1]; fl |= !(d >= box.wrap_t[1][1] && d < box.wrap_t[1][2]); }
+                    if (box.pbc[2]) { const double d = zi - box.origin[2]; fl |= !(d >= box.wrap_t[2][1] && d < box.wrap_t[2][2]); }
+                }
+                wrap_into_box(box, xi, yi, zi);
                 OwnAtom o;
                 o.x = xi;
                 o.y = yi;
@@ -1156,9 +1203,9 @@ constexpr int FUSED_QCAP = 24;   // candidate slots per thread (14 neighbours + 
 __device__ __noinline__ bool fused_exact_neighbor(const DBox &box, const SortedAtom *raw, int s_i, int k, double rcsq)
 {
     double xi = raw[s_i].x, yi = raw[s_i].y, zi = raw[s_i].z;
-    wrap_ortho(box, xi, yi, zi);
+    wrap_into_box(box, xi, yi, zi);
     double dx = raw[k].x - xi, dy = raw[k].y - yi, dz = raw[k].z - zi;
-    min_image_ortho(box, dx, dy, dz);
+    min_image(box, dx, dy, dz);
     return dx * dx + dy * dy + dz * dz <= rcsq;
 }
 
@@ -1173,7 +1220,7 @@ __device__ __noinline__ int fused_exact_cna(const DBox &box, const SortedAtom *r
         for (int b = a + 1; b < nn; ++b) {
             const SortedAtom &B_ = raw[q[b * STRIDE]];
             double dx = B_.x - A_.x, dy = B_.y - A_.y, dz = B_.z - A_.z;
-            min_image_ortho(box, dx, dy, dz);
+            min_image(box, dx, dy, dz);
             if (dx * dx + dy * dy + dz * dz <= cutsq) {
                 nb[a * STRIDE] |= (unsigned short)(1u << b);
                 nb[b * STRIDE] |= (unsigned short)(1u << a);
@@ -1194,7 +1241,7 @@ __device__ __noinline__ int fused_direct_atom(const TileArgs &A, int sg, unsigne
     double xi, yi, zi;
     int my_idx, my_cell;
     load_rec(A.sorted + sg, xi, yi, zi, my_idx, my_cell);
-    wrap_ortho(box, xi, yi, zi);
+    wrap_into_box(box, xi, yi, zi);
     int ic, jc, kc;
     cell_decode(g, my_cell, ic, jc, kc);
     int nbr[14];
@@ -1211,7 +1258,7 @@ __device__ __noinline__ int fused_direct_atom(const TileArgs &A, int sg, unsigne
             int jdx, jcell;
             load_rec(A.sorted + q, xj, yj, zj, jdx, jcell);
             double dx = xj - xi, dy = yj - yi, dz = zj - zi;
-            min_image_ortho(box, dx, dy, dz);
+            min_image(box, dx, dy, dz);
             if (dx * dx + dy * dy + dz * dz <= A.rcsq) {
                 if (n < 14) nbr[n] = q;
                 ++n;
@@ -1228,7 +1275,7 @@ __device__ __noinline__ int fused_direct_atom(const TileArgs &A, int sg, unsigne
             double xb, yb, zb;
             load_rec(A.sorted + nbr[b], xb, yb, zb, t0, t1);
             double dx = xb - xa, dy = yb - ya, dz = zb - za;
-            min_image_ortho(box, dx, dy, dz);
+            min_image(box, dx, dy, dz);
             if (dx * dx + dy * dy + dz * dz <= A.rcsq) {
                 nb[a * STRIDE] |= (unsigned short)(1u << b);
                 nb[b * STRIDE] |= (unsigned short)(1u << a);
@@ -1412,17 +1459,13 @@ __global__ void __launch_bounds__(NT, 3) k_fused_cna(const __grid_constant__ Til
         __syncthreads();
 
         // ---- C. fp32 positions relative to the tile centre (nearest periodic image), flat over the staged atoms
-        const double rcw = 1.0 / g.rc_inv;
         const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0) % g.n[0];
-        const double ctr0 = box.origin[0] + (gx0 + 0.5 * T) * rcw, ctr1 = box.origin[1] + (u0y + 1 + 0.5 * T) * rcw,
-                     ctr2 = box.origin[2] + (u0z + 1 + 0.5 * TZ) * rcw;
+        const TileCentre ctr = tile_centre(box, g, gx0 + 0.5 * T, u0y + 1 + 0.5 * T, u0z + 1 + 0.5 * TZ);
         for (int s = tid; s < n_staged; s += NT) {
             const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
             const double z = reinterpret_cast<const double *>(raw + s)[2];
-            double d0 = lo.x - ctr0, d1 = lo.y - ctr1, d2 = z - ctr2;
-            if (box.pbc[0]) d0 -= box.h[0] * rint(d0 * box.hinv[0]);
-            if (box.pbc[1]) d1 -= box.h[4] * rint(d1 * box.hinv[4]);
-            if (box.pbc[2]) d2 -= box.h[8] * rint(d2 * box.hinv[8]);
+            double d0, d1, d2;
+            rel_image(box, ctr, lo.x, lo.y, z, d0, d1, d2);
             const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
             const float w = __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0));
             // An atom beyond the radius the fp32 bound covers (12.6 rc from the tile centre: an atom far outside
@@ -1563,8 +1606,11 @@ template <int T, int TZ, int NT> void launch_fused_T(const TileArgs &A, int nblo
 // an unambiguous nearest image); the caller then uses the direct kernel.
 bool tiled_neighbor_plan(const MdbSystem &s, int &T)
 {
-    if (s.box.triclinic) return false;
     const CellGrid &g = s.grid;
+    {   // triclinic boxes take the tile kernels as well; MDB_TRICLINIC=direct restores the old path
+        const char *tenv = getenv("MDB_TRICLINIC");
+        if (s.box.triclinic && tenv && !strcmp(tenv, "direct")) return false;
+    }
     const double rho = (double)s.N / ((double)g.nxl * g.n[1] * g.n[2]);  // atoms per cell
     // tile shape code: T*16 + TZ.  ~240 owned atoms per 256-thread CTA, <= ~900 staged atoms
     int code = rho <= 0.45 ? (8 * 16 + 8) : (rho <= 1.6 ? (4 * 16 + 8) : (rho <= 3.6 ? (4 * 16 + 6) : (rho <= 8.0 ? (2 * 16 + 4)

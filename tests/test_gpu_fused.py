@@ -50,6 +50,10 @@ def _cases():
     out.append(("fcc_vacancies", pv, b, [1, 1, 1], rc))
     g, bg = H.random_gas(6000, 40.0, 7)
     out.append(("gas", g, bg, [1, 1, 1], 3.2))
+    ps, bs = H.shear(H.rattle(p, 0.08, 11), b, xy=0.2, xz=0.1, yz=-0.15)
+    out.append(("fcc_triclinic", ps, bs, [1, 1, 1], rc))
+    ps, bs = H.shear(H.rattle(p2, 0.05, 12), b2, xy=0.5, xz=-0.2, yz=0.3)
+    out.append(("bcc_tilted_open_y", ps, bs, [1, 0, 1], 2.8665 * 1.207))
     # exact ties: rc exactly at a shell (every neighbour test and bond test lands in the guard band)
     out.append(("fcc_rc_on_second_shell", p, b, [1, 1, 1], 3.615))
     return out
@@ -75,6 +79,7 @@ def test_fused_labels_equal_fixed_cna_on_the_reference_list(case):
 
 
 def test_not_eligible_frames_report_unused():
+    """Fewer than 7 cells along a periodic axis: no unambiguous nearest image inside a tile -> the list path."""
     from mdapy_b200.device import DeviceSystem
 
     p, b = H.fcc(3.615, 6)

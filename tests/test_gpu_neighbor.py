@@ -39,6 +39,15 @@ def _cases():
     out.append(("gas", g, bg, [1, 1, 1], 4.0))
     g2, bg2 = H.random_gas(200, 60.0, 8)
     out.append(("sparse_zero_neigh", g2, bg2, [1, 1, 1], 0.5))
+    # triclinic frames large enough for the cell-tile kernels (>= 7 cells per periodic axis): sheared, strongly
+    # tilted with an open axis, and an origin off zero
+    p12, b12 = H.fcc(3.615, 12)
+    ps, bs = H.shear(H.rattle(p12, 0.06, 21), b12, xy=0.2, xz=0.1, yz=-0.15)
+    out.append(("fcc12_triclinic", ps, bs, [1, 1, 1], 3.615 * 0.8536))
+    ps, bs = H.shear(H.rattle(p12, 0.25, 22), b12, xy=0.55, xz=-0.3, yz=0.4)
+    out.append(("fcc12_tilted_hot_mixed", ps, bs, [1, 0, 1], 3.3))
+    ps, bs = H.shear(H.rattle(p12, 0.06, 23), b12, xy=-0.25, xz=0.0, yz=0.2)
+    out.append(("fcc12_triclinic_rc5", ps, bs, [1, 1, 1], 5.0))
     # far outside the box on every axis (unwrapped trajectory)
     out.append(("fcc6_far_images", H.rattle(p, 0.05, 9) + np.array([3, -2, 5]) * np.diag(b), b, [1, 1, 1], 3.2))
     return out
