@@ -7,6 +7,8 @@
 #include "ptm_tables.h"
 #include <mutex>
 
+constexpr int PTM_RESIDENT_DEFAULT = 512;   // threads per SM for k_ptm_match (see launch_ptm)
+
 namespace {
 
 struct DeviceTables {
@@ -184,7 +186,22 @@ void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *ty
     const int R = s.n_rows;
     unsigned char *order = s.scratch.ensure<unsigned char>((size_t)R * ptm::MAX_IN);
     MDB_LAUNCH(k_ptm_order, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order);
-    MDB_LAUNCH(k_ptm_match, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
+    // The matching kernel keeps ~5 KB of per-thread scratch in local memory.  With all 512 resident threads per SM
+    // that is 390 MB chip-wide -- three times the L2 -- and every scratch line is written back to DRAM (7 KB of
+    // traffic per atom).  Reserving shared memory caps the residency so that the scratch of all resident threads
+    // stays inside the L2 (MDB_PTM_RESIDENT threads per SM; measured optimum in profiles/r2_ptm_residency.txt).
+    static const int resident = getenv("MDB_PTM_RESIDENT") ? atoi(getenv("MDB_PTM_RESIDENT")) : PTM_RESIDENT_DEFAULT;
+    size_t pad = 0;
+    if (resident > 0 && resident < 512) {
+        const int blocks = resident / 64 > 0 ? resident / 64 : 1;
+        pad = (size_t)(220 * 1024) / blocks - 1024;
+        static bool configured = false;
+        if (!configured) {
+            CUDA_TRY(cudaFuncSetAttribute(k_ptm_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+            configured = true;
+        }
+    }
+    MDB_LAUNCH(k_ptm_match, (R + 63) / 64, 64, pad, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
                flags & 255, rmsd_threshold, T, output, ocols, indices, icols);
     CUDA_TRY(cudaGetLastError());
 }

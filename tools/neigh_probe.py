@@ -24,6 +24,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--max-neigh", type=int, default=0)
 ap.add_argument("--rc", type=float, default=RC_RATIO * A_AL)
 ap.add_argument("--cna", action="store_true")
+ap.add_argument("--shear", type=float, default=0.0, help="triclinic frame: xy tilt factor (xz = xy/2, yz = -xy)")
 ap.add_argument("--fused", action="store_true", help="time the fused neighbour + CNA kernel instead")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -34,6 +35,10 @@ if args.sigma > 0:
     for t in (x, y, z):
         t += torch.randn(t.shape, generator=g, device=dev, dtype=torch.float64) * args.sigma
 box = np.diag([n * a] * 3).astype(float)
+if args.shear:
+    F = np.array([[1.0, 0.0, 0.0], [args.shear, 1.0, 0.0], [args.shear / 2, -args.shear, 1.0]])
+    x, y, z = (x + F[1, 0] * y + F[2, 0] * z).contiguous(), (y + F[2, 1] * z).contiguous(), z
+    box = box @ F
 ds = DeviceSystem(0)
 ds.set_profiling(True)
 ts, tc = [], []
