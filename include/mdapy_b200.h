@@ -97,9 +97,10 @@ int mdb_compute_aja(const double *x, const double *y, const double *z, int N, co
 
 /* _ptm.get_ptm, src/polyhedral_template_matching.cpp:135.  verlet rows: nearest neighbours in ascending
  * distance (18 wanted).  output (N, ocols): type, ordering, rmsd, interatomic distance, qw, qx, qy, qz;
- * ptm_indices (N, icols): the atom, then its matched neighbours, -1 padded.  Structures sc / fcc / hcp /
- * ico / bcc; dcub / dhex / graphene are ignored when combined with those and rejected on their own.
- * ptm_indices follow THIS library's template point order. */
+ * ptm_indices (N, icols): the atom, then its matched neighbours, -1 padded.  All eight structures of the
+ * reference: sc / fcc / hcp / ico / bcc and the two-shell dcub / dhex / graphene (neighbours of neighbours).
+ * ptm_indices follow THIS library's template point order (mdb_identify_sftb_fcc
+ * carries the matching layer table). */
 int mdb_get_ptm(const char *structure, const double *x, const double *y, const double *z, int N, const double *box9,
                 const double *origin3, const int *boundary3, const int *verlet, int M, const int *atom_types,
                 int ntypes, double rmsd_threshold, double *output, int ocols, int *ptm_indices, int icols,

@@ -7,8 +7,8 @@
 // __host__ __device__ so the same arithmetic can be exercised on the CPU by the tests; the product
 // only ever runs it inside the CUDA kernel of ptm.cu.
 //
-// Pipeline for one atom (SC / FCC / HCP / ICO / BCC; the diamond and graphene structures need
-// neighbours-of-neighbours and are not built yet):
+// Pipeline for one atom (SC / FCC / HCP / ICO / BCC; the two-shell structures DCUB / DHEX / graphene go through
+// the same steps on the neighbours of the four / three first neighbours, see match_two_shell below):
 //   1. neighbour vectors r_k = min_image(x_k - x_i) of the <= 18 listed nearest neighbours;
 //   2. pre-ordering: Voronoi cell of the atom against those points, faces ranked by solid angle
 //      (descending), ties by distance, then input order -- ptm_neighbour_ordering.cpp:28-201.
