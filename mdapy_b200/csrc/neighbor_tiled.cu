@@ -294,12 +294,23 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
 
     const int tid = threadIdx.x;
     const CellGrid &g = A.g;
-    int tl = blockIdx.x * A.tile_stride + A.tile_offset;
-    if (tl >= A.n_tiles) return;
-    const int tz = tl % A.tiles_z;
-    tl /= A.tiles_z;
-    const int ty = tl % A.tiles_y;
-    const int tx = tl / A.tiles_y;
+    int tx, ty, tz;
+    if (A.tile_stride != 1) {   // sampled estimate pass (stride > 1) or a grid too large for a 3-D launch (stride 0)
+        int tl = blockIdx.x * max(A.tile_stride, 1) + A.tile_offset;
+        if (tl >= A.n_tiles) return;
+        tz = tl % A.tiles_z;
+        tl /= A.tiles_z;
+        ty = tl % A.tiles_y;
+        tx = tl / A.tiles_y;
+    } else {
+        // strip order (round 2): grid = (tiles_z, 8 rows of tiles in y, strips * tiles_x) -- x- and y-neighbouring
+        // tiles run within a few hundred CTAs of each other, so shared halo planes are re-staged from L2
+        tz = blockIdx.x;
+        const int strip = blockIdx.z / A.tiles_x;
+        tx = blockIdx.z - strip * A.tiles_x;
+        ty = strip * 8 + blockIdx.y;
+        if (ty >= A.tiles_y) return;
+    }
     const int u0x = A.p_lo + tx * T - 1, u0y = ty * T - 1, u0z = tz * TZ - 1;  // unwrapped coords of position 0
     // owned positions inside the block: 1..amax x 1..bmax x 1..kmax (edge tiles are cut at the grid end;
     // positions beyond it only serve as wrapped candidates)
@@ -391,7 +402,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
                     kk = k2;
                 }
             }
-            mbar_wait(bar, 0);
+            if (warp == 0) mbar_wait(bar, 0);   // one warp polls; the others sleep on the CTA barrier
+            __syncthreads();
         } else {
             for (int c = warp; c < NCELL; c += TILE_THREADS / 32) {
                 const int beg = gstart[c];
@@ -410,19 +422,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_neighbor_tiled(const __grid
         // One warp per pencil, lanes over the pencil's atoms.
         const int gx0 = A.wrap_x ? (u0x + 1) : (u0x + 1 + g.x0) % g.n[0];  // global x cell of the first owned plane
         const TileCentre ctr = tile_centre(box, g, gx0 + 0.5 * T, u0y + 1 + 0.5 * T, u0z + 1 + 0.5 * TZ);
-        for (int p = warp; p < NPEN; p += TILE_THREADS / 32) {
-            const int *row = cs + p * CSW;
-            const int beg = row[0], end = row[PZ];
-            for (int s = beg + lane; s < end; s += 32) {
-                const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
-                const double zr = reinterpret_cast<const double *>(raw + s)[2];
-                double d0, d1, d2;
-                if (rel_image(box, ctr, lo.x, lo.y, zr, d0, d1, d2)) far_flag[1] = 1;  // some staged atom is a periodic image
-                const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
-                const float w = __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0));
-                if (!(w <= A.w_limit)) far_flag[0] = 1;  // outside the radius the fp32 bound covers (or NaN)
-                f4[s] = make_float4(f0, f1, f2, w);
-            }
+        for (int s = tid; s < n_staged; s += TILE_THREADS) {   // flat over the staged atoms (all lanes busy)
+            const double2 lo = reinterpret_cast<const double2 *>(raw + s)[0];
+            const double zr = reinterpret_cast<const double *>(raw + s)[2];
+            double d0, d1, d2;
+            if (rel_image(box, ctr, lo.x, lo.y, zr, d0, d1, d2)) far_flag[1] = 1;  // some staged atom is a periodic image
+            const float f0 = (float)d0, f1 = (float)d1, f2 = (float)d2;
+            const float w = __fmaf_rn(f2, f2, __fmaf_rn(f1, f1, f0 * f0));
+            if (!(w <= A.w_limit)) far_flag[0] = 1;  // outside the radius the fp32 bound covers (or NaN)
+            f4[s] = make_float4(f0, f1, f2, w);
         }
         __syncthreads();
     }
@@ -1178,8 +1186,13 @@ template <int T, int TZ> void launch_T(const TileArgs &A, int nblocks, cudaStrea
                                       200 * 1024));
         configured = true;
     }
-    if (A.count_only) MDB_LAUNCH((k_neighbor_tiled<T, TZ, true>), nblocks, TILE_THREADS, smem, st, A);
-    else MDB_LAUNCH((k_neighbor_tiled<T, TZ, false>), nblocks, TILE_THREADS, smem, st, A);
+    dim3 grid(nblocks, 1, 1);
+    if (A.tile_stride == 1) {   // strip order (see the kernel)
+        const int strips = (A.tiles_y + 7) / 8;
+        grid = dim3(A.tiles_z, A.tiles_y < 8 ? A.tiles_y : 8, strips * A.tiles_x);
+    }
+    if (A.count_only) MDB_LAUNCH((k_neighbor_tiled<T, TZ, true>), grid, TILE_THREADS, smem, st, A);
+    else MDB_LAUNCH((k_neighbor_tiled<T, TZ, false>), grid, TILE_THREADS, smem, st, A);
 }
 
 // =====================================================================================================
@@ -1700,9 +1713,9 @@ void launch_neighbor_tiled(MdbSystem &s, double rc, int M, int T, bool count_onl
     // small tile shapes.  MDB_NEIGHBOR=tiled_v1 / coop forces one of them.
     const char *kenv = getenv("MDB_NEIGHBOR");
     const bool v1 = A.strip || (kenv ? !strcmp(kenv, "tiled_v1") : TT >= 4);
+    if (A.tile_stride == 1 && ((long long)((A.tiles_y + 7) / 8) * tiles_x > 65535 || A.tiles_z > 65535))
+        A.tile_stride = 0;   // grid too large for the 3-D strip launch: linear tile list
     if (!v1) {
-        if (A.tile_stride == 1 && ((long long)((A.tiles_y + 7) / 8) * tiles_x > 65535 || A.tiles_z > 65535))
-            A.tile_stride = 0;   // linear tile list
         static const int nt = getenv("MDB_CELLS_NT") ? atoi(getenv("MDB_CELLS_NT")) : 256;
         switch (T) {
             case 8 * 16 + 8: launch_cells_T<8, 8, 256>(A, nblocks, s.stream); break;
