@@ -359,6 +359,33 @@ int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 int mdb_system_set_profiling(mdb_system *s, int on);
 int mdb_system_last_times(mdb_system *s, float *t_binning_ms, float *t_neighbor_ms, float *t_cna_ms);
 
+/* ================================================================================================
+ * Section C: device group -- one process, several GPUs (mdapy_b200/csrc/group.cu)
+ * ================================================================================================
+ * The reference runs src/neighbor.cpp + src/cna.cpp as OpenMP loops over one address space; the group is the
+ * multi-GPU form of that call for System(..., devices=[...]): ONE unpartitioned host frame in, labels in the
+ * original atom order out.  Member d uploads the d-th contiguous chunk of x, y, z over its own PCIe link; a
+ * routing kernel pushes every atom (and the boundary-plane ghosts) into the slab of the member that owns its x
+ * cell plane with peer stores over NVLink; each member runs the fused neighbour + CNA kernel on its slab; the
+ * labels travel back the same way.  No host-side partitioning, no NCCL, no PyTorch.  A device may be listed
+ * more than once (several slabs on one GPU; used by the single-GPU tests). */
+typedef struct mdb_group mdb_group;
+int mdb_group_create(const int *devices, int ndev, mdb_group **out);
+void mdb_group_destroy(mdb_group *g);
+int mdb_group_size(mdb_group *g);
+/* start uploading one host frame (pageable or page-locked); the arrays must stay valid until the next group
+ * call returns */
+int mdb_group_set_atoms(mdb_group *g, const double *x, const double *y, const double *z, int N, const double *box9,
+                        const double *origin3, const int *boundary3);
+/* FixedCNA labels of the uploaded frame (same values as mdb_compute_fcna on the list of mdb_build_neighbor_*),
+ * original atom order, N ints.  *members = devices the frame ran on (1: too few x cell planes to decompose, or
+ * the fused kernel declined the frame -- the chunks were gathered on the first member with peer copies). */
+int mdb_group_fused_cna(mdb_group *g, double rc, int *pattern_host, int *members);
+/* host-clock phase times of the last frame, ms: upload issue, route, slab compute, label push, label download,
+ * set_atoms-to-labels total */
+int mdb_group_last_times(mdb_group *g, float *ms6);
+int mdb_group_member_atoms(mdb_group *g, int member, int *n_owned, int *n_local);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -128,6 +128,14 @@ PROTOTYPES = {
     "mdb_system_result_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "mdb_system_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_last_times": (C.c_int, [c_vp, c_fp, c_fp, c_fp]),
+    # section C: device group (one process, several GPUs)
+    "mdb_group_create": (C.c_int, [c_ip, C.c_int, C.POINTER(c_vp)]),
+    "mdb_group_destroy": (None, [c_vp]),
+    "mdb_group_size": (C.c_int, [c_vp]),
+    "mdb_group_set_atoms": (C.c_int, [c_vp, c_dp, c_dp, c_dp, C.c_int] + _BOX),
+    "mdb_group_fused_cna": (C.c_int, [c_vp, C.c_double, c_ip, c_ip]),
+    "mdb_group_last_times": (C.c_int, [c_vp, c_fp]),
+    "mdb_group_member_atoms": (C.c_int, [c_vp, C.c_int, c_ip, c_ip]),
 }
 
 

@@ -8,7 +8,7 @@
 #include <unordered_map>
 #include <vector>
 
-long long g_mdb_launches = 0;
+std::atomic<long long> g_mdb_launches{0};
 static thread_local char g_err[1024] = "";
 
 void mdb_set_error(const char *fmt, ...)
@@ -375,7 +375,7 @@ extern "C" {
 
 const char *mdb_last_error(void) { return g_err; }
 const char *mdb_version(void) { return "mdapy_b200 0.1 (sm_100a)"; }
-long long mdb_launch_count(void) { return g_mdb_launches; }
+long long mdb_launch_count(void) { return g_mdb_launches.load(); }
 
 int mdb_device_count(int *count)
 {

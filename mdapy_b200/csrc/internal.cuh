@@ -1,5 +1,6 @@
 // mdapy_b200/csrc/internal.cuh -- device-side state behind the C ABI (include/mdapy_b200.h).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +24,7 @@ void mdb_set_error(const char *fmt, ...);
 
 // every kernel launch goes through here so the library can report how many of
 // its own kernels ran (bench.py "gpu_launches")
-extern long long g_mdb_launches;
+extern std::atomic<long long> g_mdb_launches;
 #define MDB_LAUNCH(kern, grid, block, smem, st, ...)              \
     do {                                                          \
         kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);     \

@@ -312,3 +312,64 @@ class DeviceSystem:
         a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
         L.check(self._lib.mdb_system_last_times(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"binning_ms": a.value, "neighbor_ms": b.value, "cna_ms": c.value}
+
+
+class DeviceGroup:
+    """Several GPUs driven by ONE process (section C of include/mdapy_b200.h, csrc/group.cu): the neighbour
+    search + CNA path of one unpartitioned host frame, sharded into x slabs with peer stores over NVLink.
+    ``devices`` may name a GPU more than once (several slabs on one GPU)."""
+
+    def __init__(self, devices):
+        self._lib = L.lib()
+        devs = np.ascontiguousarray(np.asarray(list(devices), np.int32).reshape(-1))
+        if devs.size < 1:
+            raise ValueError("devices must name at least one GPU")
+        h = L.c_vp()
+        L.check(self._lib.mdb_group_create(L.iptr(devs), int(devs.size), C.byref(h)))
+        self._h = h
+        self.devices = [int(d) for d in devs]
+        self.N = 0
+        self.members_used = 0
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mdb_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_atoms(self, x, y, z, box, origin, boundary):
+        """Start the upload of a host frame (pageable or page-locked float64 arrays, original atom order)."""
+        x, y, z = L.f64(x), L.f64(y), L.f64(z)
+        b, o, p = L.box_args(box, origin, boundary)
+        L.check(self._lib.mdb_group_set_atoms(self._h, L.dptr(x), L.dptr(y), L.dptr(z), x.shape[0],
+                                              L.dptr(b), L.dptr(o), L.iptr(p)))
+        self.N = x.shape[0]
+        self._keep = (x, y, z)
+
+    def fused_cna(self, rc: float):
+        """FixedCNA labels (cna.cpp:429-506) of the uploaded frame in the original atom order."""
+        out = L.result_empty(self.N, np.int32)
+        used = C.c_int(0)
+        L.check(self._lib.mdb_group_fused_cna(self._h, float(rc), L.iptr(out), C.byref(used)))
+        self.members_used = int(used.value)
+        return out
+
+    def last_times(self):
+        t = (C.c_float * 6)()
+        L.check(self._lib.mdb_group_last_times(self._h, t))
+        keys = ("upload_issue", "route", "compute", "label_push", "download", "total")
+        return {k: float(v) for k, v in zip(keys, t)}
+
+    def member_atoms(self):
+        out = []
+        for d in range(len(self.devices)):
+            a, b = C.c_int(0), C.c_int(0)
+            L.check(self._lib.mdb_group_member_atoms(self._h, d, C.byref(a), C.byref(b)))
+            out.append((int(a.value), int(b.value)))
+        return out

@@ -41,7 +41,11 @@ _LIST_ATTRS = ("verlet_list", "distance_list", "neighbor_number")
 
 
 class System:
-    def __init__(self, filename=None, data=None, pos=None, box=None, device: int = 0, **_unused):
+    def __init__(self, filename=None, data=None, pos=None, box=None, device: int = 0, devices=None, **_unused):
+        """``device``: the GPU every call runs on.  ``devices=[...]`` (two or more GPUs, one process):
+        ``cal_common_neighbor_analysis(rc)`` shards the frame into x slabs over those GPUs (csrc/group.cu: chunked
+        upload, peer-store routing over NVLink, fused neighbour + CNA per slab); every other call, and the
+        neighbour list a later call may read, uses ``devices[0]``."""
         self.global_info = {}
         if filename is not None:
             # text readers of SURVEY.md 8f.3 (LAMMPS dump, XYZ, optionally .gz); system.py:186-198
@@ -59,7 +63,11 @@ class System:
                 "One must at least provide filename or [data, box] or [pos, box] or ase_atom or ovito_atom."
             )
         self._box = box if isinstance(box, Box) else Box(box)
-        self._device = int(device)
+        self._devices = None if devices is None else [int(d) for d in devices]
+        if self._devices is not None and len(self._devices) == 0:
+            raise ValueError("devices must name at least one GPU")
+        self._device = int(device) if self._devices is None else self._devices[0]
+        self._group = None                           # DeviceGroup over `devices` (created on first use)
         self._dev: Optional[DeviceSystem] = None     # device copy of the compute view
         self._dev_enlarged = False
         self._host_list = {}                         # lazily fetched / user supplied NumPy arrays
@@ -188,6 +196,16 @@ class System:
             self._dev, self._dev_enlarged = dev, enlarged
         return self._dev
 
+    def _group_cna(self, rc: float):
+        """FixedCNA labels through the device group (one unpartitioned host frame in, original order out)."""
+        from .device import DeviceGroup
+
+        if self._group is None:
+            self._group = DeviceGroup(self._devices)
+        box, data = self.box, self.data
+        self._group.set_atoms(data["x"], data["y"], data["z"], box.box, box.origin, box.boundary)
+        return self._group.fused_cna(rc)
+
     def _device_list(self) -> DeviceSystem:
         """Device view with the cached list in place (pushes a host-assigned list first)."""
         dev = self._device_view()
@@ -288,8 +306,10 @@ class System:
                 and sum(self.box.check_small_box(float(rc))) == 3
                 and ((pend is None and "rc" not in self.__dict__) or (pend is not None and pend <= rc)
                      or ("rc" in self.__dict__ and pend is None and self.rc < rc))):
-            dev = self._device_view()
-            labels, used = dev.fused_cna(float(rc))
+            if self._devices is not None and len(self._devices) > 1:
+                labels, used = self._group_cna(float(rc)), True
+            else:
+                labels, used = self._device_view().fused_cna(float(rc))
             if used:
                 self._pending_rc = float(rc) if (pend is None or pend < rc) else pend
                 if "rc" in self.__dict__:      # the smaller cached list is replaced (reference: build_neighbor(rc))
