@@ -52,9 +52,10 @@ static void upload_atoms(MdbSystem &s, const double *x, const double *y, const d
     MDB_REQUIRE(N > 0, MDB_ERR_VALUE, "data must contain at least one atom.");
     MDB_REQUIRE(x && y && z, MDB_ERR_VALUE, "x, y, z are required");
     double *dx = s.bx.ensure<double>(N), *dy = s.by.ensure<double>(N), *dz = s.bz.ensure<double>(N);
-    CUDA_TRY(cudaMemcpyAsync(dx, x, sizeof(double) * N, cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(dy, y, sizeof(double) * N, cudaMemcpyHostToDevice, s.stream));
-    CUDA_TRY(cudaMemcpyAsync(dz, z, sizeof(double) * N, cudaMemcpyHostToDevice, s.stream));
+    void *dst[3] = {dx, dy, dz};
+    const void *src[3] = {x, y, z};
+    const size_t bytes[3] = {sizeof(double) * N, sizeof(double) * N, sizeof(double) * N};
+    mdb_h2d(3, dst, src, bytes, s.stream, mdb_upload_threads());
     s.x = dx;
     s.y = dy;
     s.z = dz;

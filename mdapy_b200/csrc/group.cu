@@ -338,14 +338,17 @@ int mdb_group_set_atoms(mdb_group *g, const double *x, const double *y, const do
             CUDA_TRY(cudaEventRecord(W.ready, W.sys->stream));
             for (int k = 0; k < 3; ++k) CUDA_TRY(cudaStreamWaitEvent(W.up[k], W.ready, 0));
         }
-        const double *src[3] = {x, y, z};
-        for_members(*g, 3 * g->D, [&](int task) {
-            Member &W = g->m[task % g->D];
-            const int k = task / g->D;
-            double *dst = (k == 0 ? W.cx : k == 1 ? W.cy : W.cz).as<double>();
-            if (W.count)
-                CUDA_TRY(cudaMemcpyAsync(dst, src[k] + W.start, sizeof(double) * W.count, cudaMemcpyHostToDevice, W.up[k]));
-            CUDA_TRY(cudaEventRecord(W.up_ev[k], W.up[k]));
+        // one host thread per member; pageable input is staged by a share of the host cores each (staging.cu)
+        const int threads = std::max(2, 2 * mdb_upload_threads() / g->D);
+        for_members(*g, g->D, [&](int d) {
+            Member &W = g->m[d];
+            if (W.count) {
+                void *dst[3] = {W.cx.as<double>(), W.cy.as<double>(), W.cz.as<double>()};
+                const void *src[3] = {x + W.start, y + W.start, z + W.start};
+                const size_t bytes[3] = {sizeof(double) * W.count, sizeof(double) * W.count, sizeof(double) * W.count};
+                mdb_h2d(3, dst, src, bytes, W.up[0], threads);
+            }
+            for (int k = 0; k < 3; ++k) CUDA_TRY(cudaEventRecord(W.up_ev[k], W.up[0]));
         });
         g->has_atoms = true;
         g->times[0] = (float)(now_ms() - g->t_upload0);

@@ -163,6 +163,11 @@ struct MdbSystem {
     }
 };
 
+// ---- host -> device upload of caller columns (staging.cu): pageable sources are staged through page-locked ring
+// buffers by `threads` host threads, page-locked sources go down as one asynchronous copy
+void mdb_h2d(int n, void *const *dst, const void *const *src, const size_t *bytes, cudaStream_t consumer, int threads);
+int mdb_upload_threads();
+
 // ---- kernels launchers (one per .cu) ---------------------------------------
 void launch_binning(MdbSystem &s, double rc);
 void finish_binning(MdbSystem &s, int nc, const double *X, const double *Y, const double *Z);

@@ -1151,14 +1151,11 @@ template <int T, int TZ, int NT> size_t coop_smem_bytes(int cap, int ocap)
 template <int T, int TZ, int NT> void launch_cells_T(const TileArgs &A, int nblocks, cudaStream_t st)
 {
     const size_t smem = coop_smem_bytes<T, TZ, NT>(A.cap, A.ocap);
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_coop<T, TZ, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      200 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_coop<T, TZ, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      200 * 1024));
-        configured = true;
-    }
+    // per launch: the attribute belongs to the current device (several devices per process: group.cu)
+    CUDA_TRY(cudaFuncSetAttribute(k_neighbor_coop<T, TZ, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_neighbor_coop<T, TZ, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  200 * 1024));
     dim3 grid(nblocks, 1, 1);
     if (A.tile_stride == 1) {   // strip order (see the kernel)
         const int strips = (A.tiles_y + 7) / 8;
@@ -1178,14 +1175,11 @@ template <int T, int TZ> size_t tile_smem_bytes(int cap)
 template <int T, int TZ> void launch_T(const TileArgs &A, int nblocks, cudaStream_t st)
 {
     const size_t smem = tile_smem_bytes<T, TZ>(A.cap);
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_tiled<T, TZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      200 * 1024));
-        CUDA_TRY(cudaFuncSetAttribute(k_neighbor_tiled<T, TZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      200 * 1024));
-        configured = true;
-    }
+    // per launch: the attribute belongs to the current device (several devices per process: group.cu)
+    CUDA_TRY(cudaFuncSetAttribute(k_neighbor_tiled<T, TZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(k_neighbor_tiled<T, TZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  200 * 1024));
     dim3 grid(nblocks, 1, 1);
     if (A.tile_stride == 1) {   // strip order (see the kernel)
         const int strips = (A.tiles_y + 7) / 8;
@@ -1600,11 +1594,8 @@ template <int T, int TZ, int NT> size_t fused_smem_bytes(int cap)
 template <int T, int TZ, int NT> void launch_fused_T(const TileArgs &A, int nblocks, cudaStream_t st)
 {
     const size_t smem = fused_smem_bytes<T, TZ, NT>(A.cap);
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(k_fused_cna<T, TZ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    // per launch: the attribute belongs to the current device (several devices per process: group.cu)
+    CUDA_TRY(cudaFuncSetAttribute(k_fused_cna<T, TZ, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dim3 grid(nblocks, 1, 1);
     if (A.tile_stride == 1) {
         const int strips = (A.tiles_y + 7) / 8;

@@ -195,11 +195,8 @@ void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *ty
     if (resident > 0 && resident < 512) {
         const int blocks = resident / 64 > 0 ? resident / 64 : 1;
         pad = (size_t)(220 * 1024) / blocks - 1024;
-        static bool configured = false;
-        if (!configured) {
-            CUDA_TRY(cudaFuncSetAttribute(k_ptm_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-            configured = true;
-        }
+        // per launch: the attribute belongs to the current device (several devices per process: group.cu)
+        CUDA_TRY(cudaFuncSetAttribute(k_ptm_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     }
     MDB_LAUNCH(k_ptm_match, (R + 63) / 64, 64, pad, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
                flags & 255, rmsd_threshold, T, output, ocols, indices, icols);

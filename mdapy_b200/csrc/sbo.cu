@@ -10,6 +10,7 @@
 // the reference to the last bit for a given list.  Everything that depends only on (l, m) --
 // sqrt((2l+1)/(4 pi prod)), sqrt(4 pi/(2l+1)), the Clebsch-Gordan coefficients -- is evaluated
 // on the host with the reference's expressions and passed in.
+#include <mutex>
 #include "internal.cuh"
 #include <vector>
 
@@ -424,14 +425,19 @@ __global__ void k_div_small_check(const double *__restrict__ a, int n, int d, un
 
 void upload_rcp_table(cudaStream_t st)
 {
-    static bool done = false;
-    if (done) return;
+    // constant memory is per device: once per device of this process (several devices: group.cu)
+    static std::mutex mu;
+    static unsigned long long done = 0;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (done >> (dev & 63) & 1ull) return;
     double h[SBO_MAX_L + 2];
     h[0] = 0.0;
     for (int d = 1; d < SBO_MAX_L + 2; ++d) h[d] = 1.0 / d;
     CUDA_TRY(cudaMemcpyToSymbolAsync(c_rcp, h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    done = true;
+    done |= 1ull << (dev & 63);
 }
 
 }  // namespace
@@ -488,11 +494,8 @@ void launch_steinhardt(MdbSystem &s, const int *verlet, const double *dist, cons
     {
         // accumulators in shared memory when the compact slots of a 128-thread block fit (l = {4, 6}: 45 KB)
         const size_t smem = (size_t)2 * P.off[ndeg] * 128 * sizeof(double);
-        static bool configured = false;
-        if (!configured) {
-            CUDA_TRY(cudaFuncSetAttribute(k_qlm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            configured = true;
-        }
+        // per launch: the attribute belongs to the current device (several devices per process: group.cu)
+        CUDA_TRY(cudaFuncSetAttribute(k_qlm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         const char *env = getenv("MDB_SBO");
         if (smem <= 100 * 1024 && !(env && !strcmp(env, "local")))
             MDB_LAUNCH(k_qlm<2>, nb, 128, smem, st, s.x, s.y, s.z, N, s.box, verlet, dist, nn, weight, M, P, qr, qi);

@@ -7,6 +7,7 @@ not round-trip over PCIe.  NumPy views are materialised only when asked for.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -331,6 +332,7 @@ class DeviceGroup:
         self.N = 0
         self.members_used = 0
         self._keep = None
+        self.lock = threading.Lock()     # one frame at a time (System objects of several host threads share a group)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -373,3 +375,18 @@ class DeviceGroup:
             L.check(self._lib.mdb_group_member_atoms(self._h, d, C.byref(a), C.byref(b)))
             out.append((int(a.value), int(b.value)))
         return out
+
+
+_GROUPS = {}
+_GROUPS_LOCK = threading.Lock()
+
+
+def shared_group(devices) -> DeviceGroup:
+    """The process-wide DeviceGroup of a device list (System creates one System per frame; the group's
+    streams, peer mappings and slab buffers are reused from frame to frame)."""
+    key = tuple(int(d) for d in devices)
+    with _GROUPS_LOCK:
+        g = _GROUPS.get(key)
+        if g is None or not getattr(g, "_h", None):
+            g = _GROUPS[key] = DeviceGroup(key)
+        return g

@@ -198,13 +198,14 @@ class System:
 
     def _group_cna(self, rc: float):
         """FixedCNA labels through the device group (one unpartitioned host frame in, original order out)."""
-        from .device import DeviceGroup
+        from .device import shared_group
 
         if self._group is None:
-            self._group = DeviceGroup(self._devices)
+            self._group = shared_group(self._devices)   # streams, peer mappings and buffers outlive the frame
         box, data = self.box, self.data
-        self._group.set_atoms(data["x"], data["y"], data["z"], box.box, box.origin, box.boundary)
-        return self._group.fused_cna(rc)
+        with self._group.lock:
+            self._group.set_atoms(data["x"], data["y"], data["z"], box.box, box.origin, box.boundary)
+            return self._group.fused_cna(rc)
 
     def _device_list(self) -> DeviceSystem:
         """Device view with the cached list in place (pushes a host-assigned list first)."""

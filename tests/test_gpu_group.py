@@ -197,3 +197,28 @@ def test_group_real_devices():
         shuffled = pos[rng.permutation(pos.shape[0])]
         lab, (used, _, _) = _group_labels(devs, shuffled, b, [1, 1, 1], rc)
         assert used == len(devs) and np.array_equal(lab, _ref_labels(shuffled, b, [1, 1, 1], rc))
+
+
+def test_second_device_runs_every_kernel_family():
+    """Per-device state (dynamic shared memory attributes, constant tables) must follow the device of the
+    handle, not the first device the process touched."""
+    if _n_gpus() < 2:
+        pytest.skip("needs at least two GPUs")
+    import mdapy_b200 as mp
+
+    p, b = H.fcc(3.615, 10)
+    pos = H.rattle(p, 0.1, 3)
+    cols = {}
+    for dev in (0, 1):
+        s = mp.System(pos=pos, box=mp.Box(b), device=dev)
+        s.cal_common_neighbor_analysis(3.615 * 0.8536)
+        s.cal_steinhardt_bond_orientation([4, 6], rc=3.615 * 0.8536, average=True)
+        s.cal_polyhedral_template_matching(return_rmsd=True)
+        s.cal_centro_symmetry_parameter(12)
+        s.cal_ackland_jones_analysis()
+        cols[dev] = {k: np.asarray(s.data[k]) for k in s.data.columns if k not in ("x", "y", "z")}
+        v = s.verlet_list
+        cols[dev]["verlet"] = np.asarray(v)
+    assert cols[0].keys() == cols[1].keys() and len(cols[0]) >= 6
+    for k in cols[0]:
+        assert np.array_equal(cols[0][k], cols[1][k]), k
