@@ -413,6 +413,24 @@ def run_b200(args):
         e2e = {"value": N_total / dt, "unit": "atoms/s", "h2d_bytes_per_step": 24 * N_total,
                "d2h_bytes_per_step": 4 * N_total, "ms_per_step": dt * 1e3, "ms_each": [round(v, 2) for v in per_rep],
                "api": "System(data, box).cal_common_neighbor_analysis(rc) -> data['cna'] (host)"}
+        # the same call from ordinary (pageable) NumPy arrays: the library stages them through page-locked ring
+        # buffers with several host threads (csrc/staging.cu)
+        px, py, pz = np.array(hxn), np.array(hyn), np.array(hzn)
+
+        def pageable_step():
+            system = mp.System(data={"x": px, "y": py, "z": pz}, box=mp.Box(box), device=local)
+            system.cal_common_neighbor_analysis(rc)
+            return system.data["cna"]
+
+        keep = [pageable_step(), pageable_step()]
+        del keep
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cna = pageable_step()
+        dtp = (time.perf_counter() - t0) / reps
+        assert int(np.asarray(cna).min()) == 1 and int(np.asarray(cna).max()) == 1
+        e2e["pageable_input"] = {"value": N_total / dtp, "ms_per_step": dtp * 1e3}
+        del px, py, pz, cna
         # Extra information (NOT the headline `value`): the same public call issued from two host threads, as
         # a trajectory analysis would do -- every frame still uploads its positions and reads its labels back,
         # but frame k+1's upload overlaps frame k's kernels (each System owns a non-blocking stream).
@@ -469,10 +487,57 @@ def run_b200(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
         assert int(lab.min()) == 1 and int(lab.max()) == 1
-        e2e = {"value": N_total / dt, "unit": "atoms/s", "h2d_bytes_per_step": 28 * N_total,
-               "d2h_bytes_per_step": 4 * N_total, "ms_per_step": dt * 1e3,
-               "api": "per rank: pinned slab (x, y, z, ids) -> SlabDecomposition.exchange_resident() -> fused_cna "
-                      "labels (host)"}
+        per_rank = {"value": N_total / dt, "unit": "atoms/s", "h2d_bytes_per_step": 28 * N_total,
+                    "d2h_bytes_per_step": 4 * N_total, "ms_per_step": dt * 1e3,
+                    "api": "per rank: pinned slab (x, y, z, ids) -> SlabDecomposition.exchange_resident() -> "
+                           "fused_cna labels (host); one process per GPU, NCCL ghost planes"}
+        # ---- the public API at N GPUs: ONE process (rank 0) hands ONE unpartitioned host frame to
+        # System(devices=[0..N-1]); the other ranks wait on a CPU (gloo) barrier so no NCCL kernel spins on their
+        # GPUs meanwhile.  Headline e2e = page-locked input; the pageable figure sits beside it.
+        del rx, ry, rz, rg, hx, hy, hz, hid, lab
+        cpu_group = dist.new_group(backend="gloo")
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        e2e = per_rank
+        if rank == 0:
+            import mdapy_b200 as mp
+            from mdapy_b200 import _lib as L_
+
+            fx, fy, fz = fcc_host(n, a)
+            pin = [L_.result_empty(N_total, np.float64) for _ in range(3)]
+            for dst, src in zip(pin, (fx, fy, fz)):
+                dst[:] = src
+            devs = list(range(world))
+
+            def api_step(cols):
+                system = mp.System(data={"x": cols[0], "y": cols[1], "z": cols[2]}, box=mp.Box(box), devices=devs)
+                system.cal_common_neighbor_analysis(rc)
+                return system.data["cna"], system._group
+
+            out = {}
+            for kind, cols in (("pinned", pin), ("pageable", (fx, fy, fz))):
+                keep = [api_step(cols), api_step(cols)]   # two result columns alive, like the timed loop
+                del keep
+                per = []
+                for _ in range(reps):
+                    t1 = time.perf_counter()
+                    cna, grp = api_step(cols)
+                    per.append((time.perf_counter() - t1) * 1e3)
+                assert int(np.asarray(cna).min()) == 1 and int(np.asarray(cna).max()) == 1
+                assert grp.members_used == world, grp.members_used
+                out[kind] = {"ms_per_step": float(np.mean(per)), "ms_each": [round(v, 2) for v in per],
+                             "phases_ms": {k: round(v, 2) for k, v in grp.last_times().items()}}
+            dt_api = out["pinned"]["ms_per_step"] * 1e-3
+            e2e = {"value": N_total / dt_api, "unit": "atoms/s", "h2d_bytes_per_step": 24 * N_total,
+                   "d2h_bytes_per_step": 4 * N_total, "ms_per_step": dt_api * 1e3,
+                   "ms_each": out["pinned"]["ms_each"], "phases_ms": out["pinned"]["phases_ms"],
+                   "api": f"System(data, box, devices=[0..{world - 1}]).cal_common_neighbor_analysis(rc) -> "
+                          "data['cna'] (host): one process, one unpartitioned page-locked host frame, chunked upload "
+                          "over every GPU's PCIe link, peer-store routing over NVLink, fused kernel per slab",
+                   "pageable_input": {"value": N_total / (out["pageable"]["ms_per_step"] * 1e-3), **out["pageable"]},
+                   "per_rank_slabs": per_rank}
+            del fx, fy, fz, pin
+        dist.barrier(group=cpu_group)
 
     if rank != 0:
         return
@@ -531,6 +596,18 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def fcc_host(n, a):
+    """The whole n^3 FCC frame as host columns, cell-major like build_crystal (repeat_cell.cpp:41-59)."""
+    basis = np.array([[0, 0, 0], [0.5, 0.5, 0], [0.5, 0, 0.5], [0, 0.5, 0.5]]) * a
+    g = np.arange(n, dtype=np.float64) * a
+    cols = [np.empty((n, n, n, 4)) for _ in range(3)]
+    for k in range(4):
+        cols[0][..., k] = g[:, None, None] + basis[k, 0]
+        cols[1][..., k] = g[None, :, None] + basis[k, 1]
+        cols[2][..., k] = g[None, None, :] + basis[k, 2]
+    return tuple(c.reshape(-1) for c in cols)
 
 
 def main():
