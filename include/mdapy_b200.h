@@ -359,6 +359,24 @@ int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 int mdb_system_set_profiling(mdb_system *s, int on);
 int mdb_system_last_times(mdb_system *s, float *t_binning_ms, float *t_neighbor_ms, float *t_cna_ms);
 
+/* ---- Voronoi cells (orthogonal boxes) ------------------------------------------------------
+ * mdb_get_voronoi_volume_number_radius <- _voronoi.get_voronoi_volume_number_radius(x, y, z, box, origin, boundary,
+ *                                          volume, neighbor_number, cavity_radius, num_t)   (src/voronoi.cpp:16)
+ * mdb_system_voronoi_neighbor + mdb_system_voronoi_fetch <- _voronoi.get_voronoi_neighbor(x, y, z, box, origin,
+ *   boundary, a_face_area_threshold, r_face_area_threshold, num_t) -> (verlet_list, distance_list, face_area,
+ *   neighbor_number)                                                                        (src/voronoi.cpp:307)
+ *   The reference allocates (N, max faces) arrays itself; here the first call computes and reports that width M, the
+ *   caller allocates, the second call copies.  Values as the reference's: wall faces and faces at or below the area
+ *   threshold hold -1 / 10000.0 / 0.0 in place, neighbor_number counts every face, distances are minimum-image.
+ *   Rows list the faces in this library's insertion order, not voro++'s vertex-table order (same set per row). */
+int mdb_get_voronoi_volume_number_radius(const double *x, const double *y, const double *z, int N, const double *box9,
+                                         const double *origin3, const int *boundary3, double *volume,
+                                         int *neighbor_number, double *cavity_radius, int num_t);
+int mdb_system_voronoi_volume(mdb_system *s, double *volume_host, int *neighbor_number_host, double *cavity_radius_host);
+int mdb_system_voronoi_neighbor(mdb_system *s, double a_face_area_threshold, double r_face_area_threshold, int *M);
+int mdb_system_voronoi_fetch(mdb_system *s, int *verlet_host, double *distance_host, double *face_area_host,
+                             int *neighbor_number_host);
+
 /* ================================================================================================
  * Section C: device group -- one process, several GPUs (mdapy_b200/csrc/group.cu)
  * ================================================================================================

@@ -28,6 +28,8 @@ def __getattr__(name):
         "AngularDistributionFunction": ("bond_analysis", "AngularDistributionFunction"),
         "ChillPlus": ("chill_plus", "ChillPlus"),
         "IdentifyFccPlanarFaults": ("identify_fcc_planar_faults", "IdentifyFccPlanarFaults"),
+        "Voronoi": ("voronoi", "Voronoi"),
+        "DeviceGroup": ("device", "DeviceGroup"),
         "build_crystal": ("lattice", "build_crystal"),
         "CreatePolycrystal": ("create_polycrystal", "CreatePolycrystal"),
     }

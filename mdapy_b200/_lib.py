@@ -128,6 +128,10 @@ PROTOTYPES = {
     "mdb_system_result_device": (C.c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "mdb_system_set_profiling": (C.c_int, [c_vp, C.c_int]),
     "mdb_system_last_times": (C.c_int, [c_vp, c_fp, c_fp, c_fp]),
+    "mdb_get_voronoi_volume_number_radius": (C.c_int, _XYZN + _BOX + [c_dp, c_ip, c_dp, C.c_int]),
+    "mdb_system_voronoi_volume": (C.c_int, [c_vp, c_dp, c_ip, c_dp]),
+    "mdb_system_voronoi_neighbor": (C.c_int, [c_vp, C.c_double, C.c_double, c_ip]),
+    "mdb_system_voronoi_fetch": (C.c_int, [c_vp, c_ip, c_dp, c_dp, c_ip]),
     # section C: device group (one process, several GPUs)
     "mdb_group_create": (C.c_int, [c_ip, C.c_int, C.POINTER(c_vp)]),
     "mdb_group_destroy": (None, [c_vp]),

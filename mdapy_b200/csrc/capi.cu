@@ -1066,6 +1066,54 @@ int mdb_system_ptm(mdb_system *s, const char *structure, const int *types_host, 
     API_END
 }
 
+// ---- Voronoi cells (voronoi.cu; src/voronoi.cpp:16-71, 307-447) ----------------------------------------------
+int mdb_system_voronoi_volume(mdb_system *s, double *volume_host, int *neighbor_number_host, double *cavity_radius_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->N > 0 && s->has_box, MDB_ERR_STATE, "no atoms uploaded");
+    double *vol = s->out_f64.ensure<double>(s->N), *rad = s->out_f64b.ensure<double>(s->N);
+    int *nf = s->out_i32.ensure<int>(s->N);
+    launch_voronoi(*s, false, vol, nf, rad);
+    d2h(*s, volume_host, vol, (size_t)s->N);
+    d2h(*s, neighbor_number_host, nf, (size_t)s->N);
+    d2h(*s, cavity_radius_host, rad, (size_t)s->N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
+int mdb_system_voronoi_neighbor(mdb_system *s, double a_face_area_threshold, double r_face_area_threshold, int *M)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->N > 0 && s->has_box, MDB_ERR_STATE, "no atoms uploaded");
+    MDB_REQUIRE(M, MDB_ERR_VALUE, "M is required");
+    double *vol = s->out_f64.ensure<double>(s->N), *rad = s->out_f64b.ensure<double>(s->N);
+    int *nf = s->vor_nn.ensure<int>(s->N);
+    const int width = launch_voronoi(*s, true, vol, nf, rad);
+    s->vor_M = width;   // voronoi.cpp:368-376: the row width is the largest face count (walls included)
+    const size_t n = (size_t)s->N * (width ? width : 1);
+    launch_voronoi_rows(*s, nf, width, a_face_area_threshold, r_face_area_threshold, s->vor_verlet.ensure<int>(n),
+                        s->vor_dist.ensure<double>(n), s->vor_farea.ensure<double>(n));
+    *M = width;
+    API_END
+}
+
+int mdb_system_voronoi_fetch(mdb_system *s, int *verlet_host, double *distance_host, double *face_area_host,
+                             int *neighbor_number_host)
+{
+    API_BEGIN
+    CUDA_TRY(cudaSetDevice(s->device));
+    MDB_REQUIRE(s->vor_M > 0 && s->vor_verlet.p, MDB_ERR_STATE, "no Voronoi neighbours on the device; build them first");
+    const size_t n = (size_t)s->N * s->vor_M;
+    d2h(*s, verlet_host, s->vor_verlet.as<int>(), n);
+    d2h(*s, distance_host, s->vor_dist.as<double>(), n);
+    d2h(*s, face_area_host, s->vor_farea.as<double>(), n);
+    d2h(*s, neighbor_number_host, s->vor_nn.as<int>(), (size_t)s->N);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    API_END
+}
+
 int mdb_system_result_device(mdb_system *s, int **i32, double **f64)
 {
     API_BEGIN
@@ -1501,6 +1549,19 @@ int mdb_compute_cnp(const double *x, const double *y, const double *z, int N, co
     int rcode = mdb_system_put_neighbor(s.s, verlet, dist, nn, M, rc, LIST_CUTOFF);
     if (rcode != MDB_OK) return rcode;
     rcode = mdb_system_cnp(s.s, rc, cnp);
+    if (rcode != MDB_OK) return rcode;
+    API_END
+}
+
+int mdb_get_voronoi_volume_number_radius(const double *x, const double *y, const double *z, int N, const double *box9,
+                                         const double *origin3, const int *boundary3, double *volume,
+                                         int *neighbor_number, double *cavity_radius, int /*num_t*/)
+{
+    API_BEGIN
+    ScopedSystem s;
+    int rcode = mdb_system_set_atoms(s.s, x, y, z, N, box9, origin3, boundary3);
+    if (rcode != MDB_OK) return rcode;
+    rcode = mdb_system_voronoi_volume(s.s, volume, neighbor_number, cavity_radius);
     if (rcode != MDB_OK) return rcode;
     API_END
 }

@@ -139,6 +139,10 @@ struct MdbSystem {
     // per-atom outputs kept on device until fetched
     DevBuf out_i32, out_f64, out_f64b, out_f64c, scratch, scratch2;
     DevBuf wx, wy, wz;  // kNN: wrapped coordinates (fast_knn.cpp wrap arithmetic)
+    // Voronoi cells (voronoi.cu): raw (neighbour id, face area) rows of width vor_W, face counts, and the
+    // reference-shaped arrays of width vor_M built from them
+    DevBuf vor_id, vor_area, vor_nn, vor_verlet, vor_dist, vor_farea;
+    int vor_W{0}, vor_M{0};
     // Steinhardt state kept for identifySolidLiquid / repeated reads
     DevBuf qlm_r, qlm_i, qn, types, weight, ptm_out, ptm_idx;
     int sbo_ndeg{0}, sbo_nz{0}, sbo_ncol{0};
@@ -154,7 +158,7 @@ struct MdbSystem {
         DevBuf *all[] = {&bx, &by, &bz, &cell_count, &cell_start, &perm, &perm_tmp, &sorted, &scan_tmp, &big_cells,
                          &counters, &verlet, &dist, &nn, &verlet_tmp, &dist_tmp, &out_i32, &out_f64, &out_f64b,
                          &out_f64c, &scratch, &scratch2, &wx, &wy, &wz, &qlm_r, &qlm_i, &qn, &types, &weight,
-                         &ptm_out, &ptm_idx};
+                         &ptm_out, &ptm_idx, &vor_id, &vor_area, &vor_nn, &vor_verlet, &vor_dist, &vor_farea};
         for (DevBuf *b : all) f(*b);
     }
     void bind_buffers()
@@ -172,6 +176,9 @@ int mdb_upload_threads();
 void launch_binning(MdbSystem &s, double rc);
 void finish_binning(MdbSystem &s, int nc, const double *X, const double *Y, const double *Z);
 void launch_knn(MdbSystem &s, int k);
+int launch_voronoi(MdbSystem &s, bool want_rows, double *volume, int *nfaces, double *radius);
+void launch_voronoi_rows(MdbSystem &s, const int *nfaces, int M, double a_thr, double r_thr, int *verlet, double *dist,
+                         double *area);
 void launch_cell_planes(const double *x, const double *y, const double *z, int N, const DBox &b, const CellGrid &g,
                         int *plane, cudaStream_t st);
 void launch_translate_ids(MdbSystem &s, const int *local_ids, int *global_ids, size_t n);

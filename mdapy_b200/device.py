@@ -228,6 +228,27 @@ class DeviceSystem:
             L.check(self._lib.mdb_system_build_bond(self._h, L.iptr(t), L.dptr(cm), cm.shape[0], L.iptr(out), C.byref(n)))
         return out
 
+    def voronoi_volume(self):
+        """(volume, face count, cavity radius) of every atom's Voronoi cell (voronoi.cpp:16-71)."""
+        vol = L.result_empty(self.N, np.float64)
+        nn = L.result_empty(self.N, np.int32)
+        rad = L.result_empty(self.N, np.float64)
+        L.check(self._lib.mdb_system_voronoi_volume(self._h, L.dptr(vol), L.iptr(nn), L.dptr(rad)))
+        return vol, nn, rad
+
+    def voronoi_neighbor(self, a_face_area_threshold: float = -1.0, r_face_area_threshold: float = -1.0):
+        """(verlet_list, distance_list, face_area, neighbor_number) of voronoi.cpp:307-447."""
+        M = C.c_int(0)
+        L.check(self._lib.mdb_system_voronoi_neighbor(self._h, float(a_face_area_threshold),
+                                                      float(r_face_area_threshold), C.byref(M)))
+        m = int(M.value)
+        verlet = L.result_empty((self.N, m), np.int32)
+        dist = L.result_empty((self.N, m), np.float64)
+        area = L.result_empty((self.N, m), np.float64)
+        nn = L.result_empty(self.N, np.int32)
+        L.check(self._lib.mdb_system_voronoi_fetch(self._h, L.iptr(verlet), L.dptr(dist), L.dptr(area), L.iptr(nn)))
+        return verlet, dist, area, nn
+
     def cnp(self, rc: float, fetch=True):
         """Common neighbour parameter on the cached cut-off list (common_neighbor_parameter.cpp:10)."""
         out = L.result_empty(self.n_rows, np.float64) if fetch else None

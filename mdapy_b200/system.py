@@ -33,6 +33,7 @@ from .knn import NearestNeighbor
 from .neighbor import Neighbor
 from .polyhedral_template_matching import PolyhedralTemplateMatching
 from .radial_distribution_function import RadialDistributionFunction
+from .voronoi import Voronoi
 from .steinhardt_bond_orientation import SteinhardtBondOrientation
 from .structure_entropy import StructureEntropy
 from .warren_cowley_parameter import WarrenCowleyParameter
@@ -569,8 +570,18 @@ class System:
                                         r_face_area_threshold: float = -1, identify_liquid: bool = False,
                                         threshold: float = 0.7, n_bond: int = 7, max_neigh: Optional[int] = None):
         if use_voronoi:
-            raise NotImplementedError("Voronoi neighbours are outside the hot path (SURVEY.md 2.2 / 8f.4); "
-                                      "pass nnn or rc")
+            # system.py:1781-1789: the Voronoi rows replace the cut-off / k-nearest list for this call only
+            self.build_voronoi_neighbor(a_face_area_threshold, r_face_area_threshold)
+            if use_weight and weight is None:
+                weight = self.voro_face_area
+            box, data = self._get_compute_view()
+            SBO = SteinhardtBondOrientation(box, data, np.asarray(llist, int), nnn, rc, average, True, use_weight,
+                                            weight, self.voro_verlet_list, self.voro_distance_list,
+                                            self.voro_neighbor_number, wl=wl, wlhat=wlhat,
+                                            identify_liquid=identify_liquid, threshold=threshold, n_bond=n_bond,
+                                            device=self._device)
+            SBO.compute()
+            return self._store_steinhardt(SBO, llist, wl, wlhat, identify_liquid)
         if nnn > 0:
             has_sort_neigh = False
             if self._has_list and self._min_neighbor_number() >= nnn:
@@ -590,6 +601,9 @@ class System:
                                         weight, wl=wl, wlhat=wlhat, identify_liquid=identify_liquid,
                                         threshold=threshold, n_bond=n_bond, dev=self._device_list())
         SBO.compute()
+        return self._store_steinhardt(SBO, llist, wl, wlhat, identify_liquid)
+
+    def _store_steinhardt(self, SBO, llist, wl, wlhat, identify_liquid):
         cols = {}
         if SBO.qnarray.shape[1] > 1:
             names = [f"ql{i}" for i in llist]
@@ -606,6 +620,27 @@ class System:
             cols["nbond"] = SBO.nbond[: self.N]
         self.update_data(self.data.with_columns(**cols))
         return SBO
+
+    def build_voronoi_neighbor(self, a_face_area_threshold: float = -1.0, r_face_area_threshold: float = -1.0) -> None:
+        """system.py:1168-1224 -> voro_verlet_list / voro_distance_list / voro_face_area / voro_neighbor_number
+        (rows list each cell's faces; walls and faces under the area threshold hold -1)."""
+        vor = Voronoi(self.box, self.data, dev=self._device_view() if "_enlarge_data" not in self.__dict__ else None,
+                      device=self._device)
+        (self.voro_verlet_list, self.voro_distance_list, self.voro_face_area,
+         self.voro_neighbor_number) = vor.get_neighbor(a_face_area_threshold, r_face_area_threshold)
+        if hasattr(vor, "_enlarge_box"):
+            self._enlarge_box = vor._enlarge_box
+            self._enlarge_data = vor._enlarge_data
+            self._dev = None            # the device copy described the original frame
+            self._dev_enlarged = False
+
+    def cal_voronoi_volume(self) -> None:
+        """system.py:2544-2573 -> data['volume'], data['neighbor_number'], data['cavity_radius']."""
+        vor = Voronoi(self.box, self.data, dev=self._device_view() if "_enlarge_data" not in self.__dict__ else None,
+                      device=self._device)
+        volume, neighbor_number, cavity_radius = vor.get_volume()
+        self.update_data(self._data.with_columns(volume=volume, neighbor_number=neighbor_number,
+                                                 cavity_radius=cavity_radius))
 
     def cal_radial_distribution_function(self, rc: float, nbin: int = 200, max_neigh: Optional[int] = None,
                                          streaming: Optional[bool] = None) -> RadialDistributionFunction:

@@ -483,3 +483,37 @@ def compute_adf(x, y, z, box, origin, boundary, verlet, dist, nn, rc_list, pair_
                             C.c_double(180.0 / nbin), _d(rcl), _i(pl), C.c_int(pl.shape[0]), _i(t), C.c_int(nbin), _i(out),
                             C.c_int(nt or num_threads()))
     return out
+
+
+def voronoi_volume(x, y, z, box, origin, boundary, nt=None):
+    """voronoi.cpp:16 get_voronoi_volume_number_radius -> (volume f64[N], faces int32[N], cavity_radius f64[N])."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    N = x.shape[0]
+    vol, nn, rad = np.zeros(N), np.zeros(N, np.int32), np.zeros(N)
+    _lib("voronoi").ref_voronoi_volume_number_radius(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _d(vol),
+                                                     _i(nn), _d(rad), C.c_int(nt or num_threads()))
+    return vol, nn, rad
+
+
+def voronoi_neighbor(x, y, z, box, origin, boundary, a_face_area_threshold=-1.0, r_face_area_threshold=-1.0, nt=None):
+    """voronoi.cpp:307 get_voronoi_neighbor -> (verlet int32[N,M], dist f64[N,M], face_area f64[N,M], nn int32[N]);
+    rows in voro++'s face order, filtered entries are -1 / 10000 / 0 in place."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    b, o, p = _boxargs(box, origin, boundary)
+    N = x.shape[0]
+    lib = _lib("voronoi")
+    lib.ref_voronoi_neighbor.restype = C.c_int
+    pv, pd, pa, pn = c_ip(), c_dp(), c_dp(), c_ip()
+    M = lib.ref_voronoi_neighbor(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), C.c_double(a_face_area_threshold),
+                                 C.c_double(r_face_area_threshold), C.byref(pv), C.byref(pd), C.byref(pa), C.byref(pn),
+                                 C.c_int(nt or num_threads()))
+    verlet = np.ctypeslib.as_array(pv, shape=(N, M)).copy()
+    dist = np.ctypeslib.as_array(pd, shape=(N, M)).copy()
+    area = np.ctypeslib.as_array(pa, shape=(N, M)).copy()
+    nn = np.ctypeslib.as_array(pn, shape=(N,)).copy()
+    lib.ref_voro_free_int(pv)
+    lib.ref_voro_free_double(pd)
+    lib.ref_voro_free_double(pa)
+    lib.ref_voro_free_int(pn)
+    return verlet, dist, area, nn

@@ -1,0 +1,69 @@
+"""CPU test of the Voronoi cell core: tests/host/voronoi_host_harness.cpp builds the __host__ __device__ core of
+mdapy_b200/csrc/voronoi_core.cuh for the CPU (test-only) and the result is compared with the golden vectors
+(tests/golden/voronoi.npz: the reference's OVITO fixtures and outputs of its own voro++ build).  The GPU runs the
+same functions inside k_voronoi (tests/test_gpu_voronoi.py)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD_DIR = ROOT / "tests" / "golden"
+GOLD = np.load(GOLD_DIR / "voronoi.npz")
+dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    out = tmp_path_factory.mktemp("voro") / "libvoro_host.so"
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", str(out),
+                    str(ROOT / "tests" / "host" / "voronoi_host_harness.cpp")], check=True)
+    return C.CDLL(str(out))
+
+
+def cells(lib, pos, box, origin, boundary, W=40, scale=1.0):
+    x, y, z = (np.ascontiguousarray(pos[:, k], np.float64) for k in range(3))
+    N = x.shape[0]
+    b = np.ascontiguousarray(np.asarray(box, float)[:3].reshape(9))
+    o, p = np.ascontiguousarray(origin, np.float64), np.ascontiguousarray(boundary, np.int32)
+    vol, nn, rad = np.zeros(N), np.zeros(N, np.int32), np.zeros(N)
+    ids, area = np.full((N, W), -1, np.int32), np.zeros((N, W))
+    rc = lib.voronoi_host(x.ctypes.data_as(dp), y.ctypes.data_as(dp), z.ctypes.data_as(dp), N, b.ctypes.data_as(dp),
+                          o.ctypes.data_as(dp), p.ctypes.data_as(ip), C.c_double(scale), vol.ctypes.data_as(dp),
+                          nn.ctypes.data_as(ip), rad.ctypes.data_as(dp), ids.ctypes.data_as(ip), area.ctypes.data_as(dp), W)
+    assert rc >= 0, rc
+    return vol, nn, rad, ids, area
+
+
+@pytest.mark.parametrize("name", [str(n) for n in GOLD["fixture_names"]])
+def test_upstream_fixture(harness, name):
+    d = np.load(GOLD_DIR / f"sa_{name}.npz")
+    box = np.asarray(d["box"], float)
+    origin = box[3] if box.shape[0] == 4 else np.zeros(3)
+    vol, nn, rad, _, _ = cells(harness, d["pos"], box, origin, d["boundary"])
+    assert np.array_equal(nn, GOLD[f"{name}__voronoi_coord"])          # perfect lattices included: 12 / 14 / 16 faces
+    assert np.allclose(vol, GOLD[f"{name}__voronoi_volume"], atol=1e-6)
+    assert np.allclose(rad * 0.5, GOLD[f"{name}__voronoi_cavity_radius"], atol=1e-6)
+
+
+@pytest.mark.parametrize("scale", [1.0, 0.6, 1.7])
+@pytest.mark.parametrize("name", [str(n) for n in GOLD["run_names"]])
+def test_reference_run_vectors(harness, name, scale):
+    """The cells do not depend on the candidate grid (cell width scaled by 0.6 / 1.7: more shells / bigger shells)."""
+    pos, box, bd = GOLD[f"run_{name}__pos"], GOLD[f"run_{name}__box"], GOLD[f"run_{name}__boundary"]
+    vol, nn, rad, ids, area = cells(harness, pos, box, np.zeros(3), bd, scale=scale)
+    assert np.array_equal(nn, GOLD[f"run_{name}__faces"])
+    assert np.allclose(vol, GOLD[f"run_{name}__volume"], rtol=1e-9, atol=0)
+    assert np.allclose(rad, GOLD[f"run_{name}__radius"], rtol=1e-9, atol=0)
+    # rows as sets: neighbour ids (walls = -1) and face areas against the unfiltered reference rows
+    rv, ra = GOLD[f"run_{name}__none_verlet"], GOLD[f"run_{name}__none_area"]
+    M = rv.shape[1]
+    ids = np.where(ids < 0, -1, ids)[:, :M]
+    area = np.where(ids < 0, 0.0, area[:, :M])          # the reference zeroes wall faces (voronoi.cpp:421-426)
+    key = np.where(ids < 0, np.iinfo(np.int32).max, ids)
+    order = np.lexsort((area, key), axis=1)
+    assert np.array_equal(np.take_along_axis(ids, order, axis=1), rv)
+    assert np.allclose(np.take_along_axis(area, order, axis=1), ra, rtol=1e-7, atol=1e-9)
