@@ -33,6 +33,7 @@ struct Cell {
     int pid[VP];
     unsigned char ta[VT], tb[VT], tc[VT];
     double vx[VT], vy[VT], vz[VT];
+    unsigned long long em[VP];   // scratch of clip(): edge matrix of the removed triangles
     int np, nt, fail;
     double rmax2;
 
@@ -79,6 +80,7 @@ struct Cell {
         }
         nt = 8;
         fail = 0;
+        for (int q = 0; q < VP; ++q) em[q] = 0;
         update_rmax();
     }
     // drop planes no vertex refers to (they were cut away), keeping the insertion order
@@ -100,16 +102,15 @@ struct Cell {
     // cut with n.x <= d; returns true when the plane removed something
     MDB_HD bool clip(double nx, double ny, double nz, double d, int id, double tolh)
     {
-        unsigned long long out0 = 0, out1 = 0;
+        unsigned char rem[VE];   // vertices beyond the plane, ascending
         int nout = 0;
         for (int t = 0; t < nt; ++t)
             if (nx * vx[t] + ny * vy[t] + nz * vz[t] - d > tolh) {
-                if (t < 64) out0 |= 1ull << t;
-                else out1 |= 1ull << (t - 64);
+                if (nout < VE) rem[nout] = (unsigned char)t;
                 ++nout;
             }
         if (nout == 0) return false;
-        if (nout == nt) {   // nothing would be left: cannot happen for a bisector of a distinct point
+        if (nout == nt || nout > VE) {   // nothing left (cannot happen for a bisector of a distinct point) / too many
             fail = 1;
             return false;
         }
@@ -120,45 +121,74 @@ struct Cell {
         }
         const int p = np++;
         plane(p, nx, ny, nz, d, id);
-        // oriented edges of the removed triangles; an interior edge appears twice with opposite orientation
+        // em[u] bit v: the removed set holds the oriented edge (u, v).  An edge of the set lies on its boundary when
+        // the opposite edge is not in the set (the triangle across it stays).  em is all zero between calls.
+        unsigned long long dup = 0;
+        for (int k = 0; k < nout; ++k) {
+            const int t = rem[k];
+            const int a = ta[t], b = tb[t], c = tc[t];
+            dup |= (em[a] >> b) & 1ull;
+            em[a] |= 1ull << b;
+            dup |= (em[b] >> c) & 1ull;
+            em[b] |= 1ull << c;
+            dup |= (em[c] >> a) & 1ull;
+            em[c] |= 1ull << a;
+        }
         unsigned char ea[VE], eb[VE];
         int ne = 0;
-        for (int t = 0; t < nt; ++t) {
-            if (!((t < 64 ? out0 >> t : out1 >> (t - 64)) & 1ull)) continue;
-            const unsigned char tri[4] = {ta[t], tb[t], tc[t], ta[t]};
-            for (int k = 0; k < 3; ++k) {
-                const unsigned char u = tri[k], v = tri[k + 1];
-                int hit = -1;
-                for (int e = 0; e < ne; ++e)
-                    if (ea[e] == v && eb[e] == u) {
-                        hit = e;
-                        break;
-                    }
-                if (hit >= 0) {
-                    --ne;
-                    ea[hit] = ea[ne], eb[hit] = eb[ne];
-                } else if (ne < VE) {
-                    ea[ne] = u, eb[ne] = v;
-                    ++ne;
-                } else fail = 1;
+        if (!dup) {
+            for (int k = 0; k < nout; ++k) {
+                const int t = rem[k];
+                const unsigned char tri[4] = {ta[t], tb[t], tc[t], ta[t]};
+                for (int e = 0; e < 3; ++e) {
+                    const unsigned char u = tri[e], v = tri[e + 1];
+                    if (em[v] >> u & 1ull) continue;
+                    if (ne < VE) {
+                        ea[ne] = u, eb[ne] = v;
+                        ++ne;
+                    } else fail = 1;
+                }
+            }
+        } else {
+            // a tolerance decision left the same oriented edge in two triangles (near-degenerate input): pair the
+            // edges one by one instead, an edge cancels exactly one opposite edge
+            for (int k = 0; k < nout; ++k) {
+                const int t = rem[k];
+                const unsigned char tri[4] = {ta[t], tb[t], tc[t], ta[t]};
+                for (int q = 0; q < 3; ++q) {
+                    const unsigned char u = tri[q], v = tri[q + 1];
+                    int hit = -1;
+                    for (int e = 0; e < ne && hit < 0; ++e)
+                        if (ea[e] == v && eb[e] == u) hit = e;
+                    if (hit >= 0) {
+                        --ne;
+                        ea[hit] = ea[ne], eb[hit] = eb[ne];
+                    } else if (ne < VE) {
+                        ea[ne] = u, eb[ne] = v;
+                        ++ne;
+                    } else fail = 1;
+                }
             }
         }
-        if (fail) return false;
-        int w = 0;
-        for (int t = 0; t < nt; ++t) {
-            if ((t < 64 ? out0 >> t : out1 >> (t - 64)) & 1ull) continue;
-            if (w != t) ta[w] = ta[t], tb[w] = tb[t], tc[w] = tc[t], vx[w] = vx[t], vy[w] = vy[t], vz[w] = vz[t];
-            ++w;
+        for (int k = 0; k < nout; ++k) {
+            const int t = rem[k];
+            em[ta[t]] = 0, em[tb[t]] = 0, em[tc[t]] = 0;
         }
-        nt = w;
-        if (nt + ne > VT) {
+        if (fail || nt - nout + ne > VT) {
             fail = 1;
             return false;
         }
+        // the new vertices (boundary edge + new plane) take the freed slots; a cut that removes whole planes frees
+        // more slots than it fills, and the tail of the array moves into those
         for (int e = 0; e < ne; ++e) {
-            ta[nt] = ea[e], tb[nt] = eb[e], tc[nt] = (unsigned char)p;
-            vertex(nt);
-            ++nt;
+            const int slot = e < nout ? rem[e] : nt++;
+            ta[slot] = ea[e], tb[slot] = eb[e], tc[slot] = (unsigned char)p;
+            vertex(slot);
+        }
+        for (int k = nout - 1; k >= ne; --k) {
+            const int h = rem[k], last = nt - 1;
+            if (h != last) ta[h] = ta[last], tb[h] = tb[last], tc[h] = tc[last], vx[h] = vx[last], vy[h] = vy[last], vz[h] = vz[last];
+            --nt;
         }
         update_rmax();
         return true;

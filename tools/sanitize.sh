@@ -18,8 +18,10 @@ run neighbor memcheck tests/test_gpu_neighbor.py tests/test_gpu_knn.py tests/tes
 run descriptors memcheck tests/test_gpu_descriptors.py tests/test_gpu_list_consumers.py tests/test_gpu_ids.py tests/test_gpu_chill_bond.py
 run system memcheck tests/test_gpu_system.py tests/test_gpu_slab.py tests/test_gpu_distributed.py tests/test_gpu_builders.py
 run ptm memcheck tests/test_gpu_ptm.py tests/test_gpu_planar_faults.py
+run group_voronoi memcheck tests/test_gpu_group.py tests/test_gpu_voronoi.py
 run neighbor racecheck tests/test_gpu_neighbor.py tests/test_gpu_fused.py
 MDB_NEIGHBOR=tiled_v1 run neighbor_v1 racecheck tests/test_gpu_neighbor.py
 MDB_NEIGHBOR=coop run neighbor_coop racecheck tests/test_gpu_neighbor.py
+run group racecheck tests/test_gpu_group.py -k "labels_equal_reference and (fcc_hot or shuffled or gas)"
 run cluster_ids racecheck tests/test_gpu_ids.py tests/test_gpu_list_consumers.py -k "cluster or ids or diamond"
 cat $OUT/sanitizer_summary.txt
