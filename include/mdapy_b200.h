@@ -359,7 +359,10 @@ int mdb_system_result_device(mdb_system *s, int **i32, double **f64);
 int mdb_system_set_profiling(mdb_system *s, int on);
 int mdb_system_last_times(mdb_system *s, float *t_binning_ms, float *t_neighbor_ms, float *t_cna_ms);
 
-/* ---- Voronoi cells (orthogonal boxes) ------------------------------------------------------
+/* ---- Voronoi cells --------------------------------------------------------------------------
+ * Orthogonal boxes with any mix of periodic / open axes (open axes end at the box faces, like voro++'s container_3d);
+ * triclinic boxes with all three axes periodic (voro++'s container_triclinic is periodic: the reference's Python
+ * side triples the open axes first, src/mdapy/voronoi.py:148-152, and so does mdapy_b200/voronoi.py).
  * mdb_get_voronoi_volume_number_radius <- _voronoi.get_voronoi_volume_number_radius(x, y, z, box, origin, boundary,
  *                                          volume, neighbor_number, cavity_radius, num_t)   (src/voronoi.cpp:16)
  * mdb_system_voronoi_neighbor + mdb_system_voronoi_fetch <- _voronoi.get_voronoi_neighbor(x, y, z, box, origin,

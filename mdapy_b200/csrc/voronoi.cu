@@ -84,11 +84,14 @@ __global__ void __launch_bounds__(128) k_voronoi_rows(const double *__restrict__
 // (width s.vor_W >= the largest face count, which is returned).
 int launch_voronoi(MdbSystem &s, bool want_rows, double *volume, int *nfaces, double *radius)
 {
-    MDB_REQUIRE(!s.box.triclinic, MDB_ERR_VALUE, "Voronoi cells are built for orthogonal boxes only");
+    MDB_REQUIRE(!s.box.triclinic || (s.box.pbc[0] && s.box.pbc[1] && s.box.pbc[2]), MDB_ERR_VALUE,
+                "Voronoi cells of a triclinic box need periodic boundaries on all three axes (the reference's "
+                "container_triclinic is periodic; its Python side triples the open axes first)");
     MDB_REQUIRE(s.n_rows == s.N, MDB_ERR_STATE, "Voronoi cells need the whole frame on one device");
     const int N = s.N;
     const DBox &b = s.box;
-    const double L[3] = {b.h[0], b.h[4], b.h[8]};
+    const double L[3] = {b.triclinic ? b.thick[0] : b.h[0], b.triclinic ? b.thick[1] : b.h[4],
+                         b.triclinic ? b.thick[2] : b.h[8]};
     // cell width: ~2 R_max of a close-packed crystal at this density, so the first shell usually ends the walk
     const double vol = fabs(dbox_volume(b));
     double w = 1.75 * cbrt(vol / N);
@@ -102,9 +105,12 @@ int launch_voronoi(MdbSystem &s, bool want_rows, double *volume, int *nfaces, do
     A.g = s.grid;
     A.w = w;
     double len2 = 0.0;
+    A.R0 = 0.0;
     for (int d = 0; d < 3; ++d) {
         A.L[d] = L[d];
-        len2 += L[d] * L[d] * (b.pbc[d] ? 0.25 : 1.0);   // container_3d: max_len_sq of the initial cell
+        const double edge = sqrt(b.h[3 * d] * b.h[3 * d] + b.h[3 * d + 1] * b.h[3 * d + 1] + b.h[3 * d + 2] * b.h[3 * d + 2]);
+        A.R0 += edge;
+        len2 += edge * edge * (b.pbc[d] ? 0.25 : 1.0);   // container_3d: max_len_sq of the initial cell
     }
     A.tolh = 0.5 * 10.0 * 2.220446049250313e-16 * len2;
     A.volume = volume;

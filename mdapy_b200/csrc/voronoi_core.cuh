@@ -17,7 +17,8 @@ template <class Rec> struct VoroArgs {
     DBox box;
     CellGrid g;
     double w;       // cell width of the grid (the last cell of an axis takes the remainder)
-    double L[3];
+    double L[3];    // extent of the grid axes: box lengths (orthogonal) / perpendicular thicknesses (triclinic)
+    double R0;      // triclinic: half-width of the initial cube (the atom's own images bound the cell inside it)
     double tolh;    // half of voro++'s tolerance on (2 n.v - |r|^2)
     double *volume;
     int *nfaces;
@@ -249,9 +250,14 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
 {
     const Rec me = A.sorted[s];
     const DBox &box = A.box;
-    double p[3] = {me.x, me.y, me.z};
-    if (box.any_pbc) wrap_into_box(box, p[0], p[1], p[2]);
-    for (int d = 0; d < 3; ++d) p[d] -= box.origin[d];
+    double pc[3] = {me.x, me.y, me.z};   // Cartesian, relative to the box origin
+    if (box.any_pbc) wrap_into_box(box, pc[0], pc[1], pc[2]);
+    for (int d = 0; d < 3; ++d) pc[d] -= box.origin[d];
+    // p: the coordinate the grid slabs are measured in -- Cartesian for an orthogonal box, fractional coordinate x
+    // perpendicular thickness for a triclinic one (cell_of(); a slab of cells is A.w thick along its own normal)
+    double p[3] = {pc[0], pc[1], pc[2]};
+    if (box.triclinic)
+        for (int d = 0; d < 3; ++d) p[d] = (pc[0] * box.hinv[d] + pc[1] * box.hinv[3 + d] + pc[2] * box.hinv[6 + d]) * A.L[d];
     const int i = me.idx;
     bool inside = true;
     for (int d = 0; d < 3; ++d) inside = inside && (box.pbc[d] || (p[d] >= 0.0 && p[d] <= A.L[d]));
@@ -267,8 +273,8 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
     {
         double lo[3], hi[3];
         for (int d = 0; d < 3; ++d) {
-            lo[d] = box.pbc[d] ? -0.5 * A.L[d] : -p[d];
-            hi[d] = box.pbc[d] ? 0.5 * A.L[d] : A.L[d] - p[d];
+            lo[d] = box.triclinic ? -A.R0 : (box.pbc[d] ? -0.5 * A.L[d] : -p[d]);
+            hi[d] = box.triclinic ? A.R0 : (box.pbc[d] ? 0.5 * A.L[d] : A.L[d] - p[d]);
         }
         C.init(lo, hi);
     }
@@ -308,7 +314,7 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
                         }
                         const int off[3] = {di, dj, dk};
                         int kk[3];
-                        double shift[3], gap2 = 0.0;
+                        double shift[3] = {0.0, 0.0, 0.0}, gap2 = 0.0;
                         bool valid = true;
                         for (int d = 0; d < 3; ++d) {
                             const int k = c[d] + off[d];
@@ -318,11 +324,15 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
                             }
                             const int m = floor_div(k, n[d]);
                             kk[d] = k - m * n[d];
-                            shift[d] = m * A.L[d];
+                            if (box.triclinic) {   // image shift m x (box vector d)
+                                shift[0] += m * box.h[3 * d], shift[1] += m * box.h[3 * d + 1], shift[2] += m * box.h[3 * d + 2];
+                            } else shift[d] = m * A.L[d];
                             double lo, hi;
                             cell_span(k, n[d], A.w, A.L[d], lo, hi);
                             const double gap = fmax(0.0, fmax(lo - p[d], p[d] - hi));
-                            gap2 += gap * gap;
+                            // orthogonal: the gaps are the components of the distance; triclinic: each is a distance
+                            // along a slab normal, the largest one bounds the distance from below
+                            gap2 = box.triclinic ? fmax(gap2, gap * gap) : gap2 + gap * gap;
                         }
                         if (!valid || gap2 >= 4.0 * C.rmax2) continue;
                         const int cell = cell_linear(A.g, kk[0], kk[1], kk[2]);
@@ -335,8 +345,8 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
                             bool ok = true;
                             for (int d = 0; d < 3; ++d) {
                                 r[d] -= box.origin[d];
-                                ok = ok && (box.pbc[d] || (r[d] >= 0.0 && r[d] <= A.L[d]));
-                                r[d] = r[d] + shift[d] - p[d];
+                                ok = ok && (box.pbc[d] || (r[d] >= 0.0 && r[d] <= A.L[d]));   // open axes: orthogonal only
+                                r[d] = r[d] + shift[d] - pc[d];
                             }
                             const double d2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
                             if (!ok || !(d2 > 0.0) || d2 >= 4.0 * C.rmax2) continue;

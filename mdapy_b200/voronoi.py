@@ -1,6 +1,8 @@
 """Voronoi tessellation, mirroring ``mdapy.voronoi.Voronoi`` (src/mdapy/voronoi.py:32-400): cell volume, face
 count and cavity radius per atom, and Voronoi neighbours with face areas.  The cells are built on the GPU
-(csrc/voronoi.cu) instead of by voro++; orthogonal boxes with any mix of periodic and open boundaries."""
+(csrc/voronoi.cu) instead of by voro++: orthogonal boxes with any mix of periodic and open boundaries (open axes end
+at the box faces), and triclinic boxes the way the reference treats them -- every axis periodic, open axes tripled
+first (voronoi.py:148-152; voro++'s container_triclinic is periodic)."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -20,14 +22,21 @@ class Voronoi:
         self._dev = dev
         self._device = device
 
-    def _device_for(self, box: Box, data: Frame, reuse: bool) -> DeviceSystem:
-        if box.triclinic:
-            raise NotImplementedError("Voronoi cells are built for orthogonal boxes only (the reference rotates a "
-                                      "triclinic cell into voro++'s container_triclinic: src/mdapy/voronoi.py:140-166)")
+    def _device_for(self, box: Box, data: Frame, reuse: bool, nopbc: bool = False) -> DeviceSystem:
+        cell, boundary = box.box, box.boundary
+        if box.triclinic and not nopbc and sum(box.boundary) < 3:
+            # voronoi.py:148-152: the open axes of a triclinic cell are tripled and the container is periodic.  (The
+            # reference also rotates the cell into LAMMPS form first; the cells do not depend on the orientation.)
+            cell = np.array(box.box, float)
+            for i in range(3):
+                if box.boundary[i] == 0:
+                    cell[i] *= 3
+            boundary = np.ones(3, np.int32)
+            reuse = False
         if reuse and self._dev is not None:
             return self._dev
         dev = DeviceSystem(self._device)
-        dev.set_atoms(data["x"], data["y"], data["z"], box.box, box.origin, box.boundary)
+        dev.set_atoms(data["x"], data["y"], data["z"], cell, box.origin, boundary)
         return dev
 
     def get_neighbor(self, a_face_area_threshold: float = -1.0,

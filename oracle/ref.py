@@ -517,3 +517,60 @@ def voronoi_neighbor(x, y, z, box, origin, boundary, a_face_area_threshold=-1.0,
     lib.ref_voro_free_double(pa)
     lib.ref_voro_free_int(pn)
     return verlet, dist, area, nn
+
+
+def _voronoi_tri_setup(box, boundary):
+    """src/mdapy/voronoi.py:140-152 + box.py:425-443: rotate the cell into LAMMPS form, triple the open axes."""
+    box = np.asarray(box, float)[:3]
+    need_rotation = bool(abs(box[0, 1]) > 1e-10 or abs(box[0, 2]) > 1e-10 or abs(box[1, 2]) > 1e-10
+                         or box[0, 0] < 0 or box[1, 1] < 0 or box[2, 2] < 0)
+    ax = np.linalg.norm(box[0])
+    bx = box[1] @ (box[0] / ax)
+    by = np.sqrt(np.linalg.norm(box[1]) ** 2 - bx ** 2)
+    cx = box[2] @ (box[0] / ax)
+    cy = (box[1] @ box[2] - bx * cx) / by
+    cz = np.sqrt(np.linalg.norm(box[2]) ** 2 - cx ** 2 - cy ** 2)
+    aligned = np.array([[ax, bx, cx], [0, by, cy], [0, 0, cz]], dtype=np.float64).T
+    rotation = np.linalg.solve(box, aligned)
+    for i in range(3):
+        if boundary[i] == 0:
+            aligned[i] *= 3
+    return np.ascontiguousarray(aligned), np.ascontiguousarray(rotation), need_rotation
+
+
+def voronoi_volume_tri(x, y, z, box, origin, boundary, nt=None):
+    """voronoi.py:303-322 -> voronoi.cpp:73 get_voronoi_volume_number_radius_tri (triclinic cells)."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    aligned, rotation, need = _voronoi_tri_setup(box, boundary)
+    b, o, p = _boxargs(aligned, origin, boundary)
+    N = x.shape[0]
+    vol, nn, rad = np.zeros(N), np.zeros(N, np.int32), np.zeros(N)
+    _lib("voronoi").ref_voronoi_volume_number_radius_tri(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p),
+                                                         _d(rotation), _d(vol), _i(nn), _d(rad), C.c_int(int(need)),
+                                                         C.c_int(nt or num_threads()))
+    return vol, nn, rad
+
+
+def voronoi_neighbor_tri(x, y, z, box, origin, boundary, a_face_area_threshold=-1.0, r_face_area_threshold=-1.0, nt=None):
+    """voronoi.py:140-166 -> voronoi.cpp:149 get_voronoi_neighbor_tri.  NOTE the reference takes minimum images of the
+    UNROTATED coordinate differences in the ROTATED cell: distances are only meaningful when no rotation is needed."""
+    x, y, z = _f64(x), _f64(y), _f64(z)
+    aligned, rotation, need = _voronoi_tri_setup(box, boundary)
+    b, o, p = _boxargs(aligned, origin, boundary)
+    N = x.shape[0]
+    lib = _lib("voronoi")
+    lib.ref_voronoi_neighbor_tri.restype = C.c_int
+    pv, pd, pa, pn = c_ip(), c_dp(), c_dp(), c_ip()
+    M = lib.ref_voronoi_neighbor_tri(_d(x), _d(y), _d(z), C.c_int(N), _d(b), _d(o), _i(p), _d(rotation),
+                                     C.c_int(int(need)), C.c_double(a_face_area_threshold),
+                                     C.c_double(r_face_area_threshold), C.byref(pv), C.byref(pd), C.byref(pa),
+                                     C.byref(pn), C.c_int(nt or num_threads()))
+    verlet = np.ctypeslib.as_array(pv, shape=(N, M)).copy()
+    dist = np.ctypeslib.as_array(pd, shape=(N, M)).copy()
+    area = np.ctypeslib.as_array(pa, shape=(N, M)).copy()
+    nn = np.ctypeslib.as_array(pn, shape=(N,)).copy()
+    lib.ref_voro_free_int(pv)
+    lib.ref_voro_free_double(pd)
+    lib.ref_voro_free_double(pa)
+    lib.ref_voro_free_int(pn)
+    return verlet, dist, area, nn

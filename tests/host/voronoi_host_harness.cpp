@@ -17,7 +17,7 @@ extern "C" int voronoi_host(const double *x, const double *y, const double *z, i
 {
     DBox b;
     if (dbox_make(b, box9, origin3, boundary3)) return -1;
-    if (b.triclinic) return -2;
+    if (b.triclinic && !(b.pbc[0] && b.pbc[1] && b.pbc[2])) return -2;
     const double vol = std::fabs(dbox_volume(b));
     const double w = 1.75 * std::cbrt(vol / N) * cell_scale;
     CellGrid g = cellgrid_make(b, w);
@@ -42,9 +42,12 @@ extern "C" int voronoi_host(const double *x, const double *y, const double *z, i
     A.g = g;
     A.w = w;
     double len2 = 0.0;
+    A.R0 = 0.0;
     for (int d = 0; d < 3; ++d) {
-        A.L[d] = b.h[d * 4];
-        len2 += A.L[d] * A.L[d] * (b.pbc[d] ? 0.25 : 1.0);
+        A.L[d] = b.triclinic ? b.thick[d] : b.h[d * 4];
+        const double edge = std::sqrt(b.h[3 * d] * b.h[3 * d] + b.h[3 * d + 1] * b.h[3 * d + 1] + b.h[3 * d + 2] * b.h[3 * d + 2]);
+        A.R0 += edge;
+        len2 += edge * edge * (b.pbc[d] ? 0.25 : 1.0);
     }
     A.tolh = 0.5 * 10.0 * 2.220446049250313e-16 * len2;
     A.volume = volume;

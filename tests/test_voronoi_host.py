@@ -43,7 +43,7 @@ def test_upstream_fixture(harness, name):
     d = np.load(GOLD_DIR / f"sa_{name}.npz")
     box = np.asarray(d["box"], float)
     origin = box[3] if box.shape[0] == 4 else np.zeros(3)
-    vol, nn, rad, _, _ = cells(harness, d["pos"], box, origin, d["boundary"])
+    vol, nn, rad, _, _ = cells(harness, d["pos"], box, origin, d["boundary"])       # 3 of the 15 are triclinic
     assert np.array_equal(nn, GOLD[f"{name}__voronoi_coord"])          # perfect lattices included: 12 / 14 / 16 faces
     assert np.allclose(vol, GOLD[f"{name}__voronoi_volume"], atol=1e-6)
     assert np.allclose(rad * 0.5, GOLD[f"{name}__voronoi_cavity_radius"], atol=1e-6)
@@ -54,6 +54,11 @@ def test_upstream_fixture(harness, name):
 def test_reference_run_vectors(harness, name, scale):
     """The cells do not depend on the candidate grid (cell width scaled by 0.6 / 1.7: more shells / bigger shells)."""
     pos, box, bd = GOLD[f"run_{name}__pos"], GOLD[f"run_{name}__box"], GOLD[f"run_{name}__boundary"]
+    if np.abs(box - np.diag(np.diag(box))).max() > 1e-10 and not all(bd):
+        box, bd = box.copy(), np.ones(3, np.int32)      # mdapy_b200/voronoi.py: open triclinic axes are tripled
+        for k in range(3):
+            if GOLD[f"run_{name}__boundary"][k] == 0:
+                box[k] *= 3
     vol, nn, rad, ids, area = cells(harness, pos, box, np.zeros(3), bd, scale=scale)
     assert np.array_equal(nn, GOLD[f"run_{name}__faces"])
     assert np.allclose(vol, GOLD[f"run_{name}__volume"], rtol=1e-9, atol=0)

@@ -40,11 +40,26 @@ def host_cells(lib, pos, box, origin, boundary, W=48, scale=1.0):
     return rc, vol, nn, rad, ids, area
 
 
+def is_triclinic(box):
+    b = np.asarray(box, float)[:3]
+    return np.abs(b - np.diag(np.diag(b))).max() > 1e-10
+
+
 def compare(lib, name, pos, box, origin, boundary, verbose=True):
     x, y, z = (np.ascontiguousarray(pos[:, k], np.float64) for k in range(3))
     bd = np.asarray(boundary, np.int32)
-    rvol, rnn, rrad = ref.voronoi_volume(x, y, z, np.asarray(box, float)[:3], origin, bd)
-    rc, vol, nn, rad, ids, area = host_cells(lib, pos, box, origin, bd)
+    if is_triclinic(box):
+        rvol, rnn, rrad = ref.voronoi_volume_tri(x, y, z, np.asarray(box, float)[:3], origin, bd)
+        # mdapy_b200/voronoi.py: open axes of a triclinic cell are tripled and everything is periodic, as the
+        # reference's Python side does before container_triclinic (voronoi.py:148-152)
+        cell = np.asarray(box, float)[:3].copy()
+        for k in range(3):
+            if bd[k] == 0:
+                cell[k] *= 3
+        rc, vol, nn, rad, ids, area = host_cells(lib, pos, cell, origin, [1, 1, 1])
+    else:
+        rvol, rnn, rrad = ref.voronoi_volume(x, y, z, np.asarray(box, float)[:3], origin, bd)
+        rc, vol, nn, rad, ids, area = host_cells(lib, pos, box, origin, bd)
     bad = np.nonzero(nn != rnn)[0]
     ev = np.abs(vol - rvol).max() / np.abs(rvol).max()
     er = np.abs(rad - rrad).max() / np.abs(rrad).max()
@@ -61,8 +76,6 @@ if __name__ == "__main__":
     for p in sorted((ROOT / "tests" / "golden").glob("sa_*.npz")):
         d = np.load(p)
         box = np.asarray(d["box"], float)
-        if np.abs(box[:3] - np.diag(np.diag(box[:3]))).max() > 1e-10:
-            continue
         origin = box[3] if box.shape[0] == 4 else np.zeros(3)
         ok &= compare(lib, p.stem, d["pos"], box, origin, d["boundary"])
     rng = np.random.default_rng(4)
@@ -87,4 +100,11 @@ if __name__ == "__main__":
     ok &= compare(lib, "fcc_tiny_noise_1e-6", H.rattle(pf, 1e-6, 3), bf, np.zeros(3), [1, 1, 1])
     b2, bb2 = H.bcc(2.8665, 6)
     ok &= compare(lib, "bcc_2x_small_images", b2[:16] * 1.0, np.diag([2.8665 * 2] * 3), np.zeros(3), [1, 1, 1], verbose=True) if False else True
+    ps, bs = H.shear(H.rattle(pf, 0.1, 7), bf, xy=0.2, xz=0.1, yz=-0.15)
+    ok &= compare(lib, "fcc_rattled_triclinic", ps, bs, np.zeros(3), [1, 1, 1])
+    ps, bs = H.shear(H.rattle(b2, 0.05, 8), bb2, xy=0.5, xz=-0.2, yz=0.3)
+    ok &= compare(lib, "bcc_tilted_open_y", ps, bs, np.zeros(3), [1, 0, 1])
+    gg, bgg = H.random_gas(600, 12.0, 9)
+    gs, bgs = H.shear(gg, bgg, xy=0.4, xz=0.3, yz=0.35)
+    ok &= compare(lib, "gas_small_triclinic", gs, bgs, np.zeros(3), [1, 1, 1])
     sys.exit(0 if ok else 1)
