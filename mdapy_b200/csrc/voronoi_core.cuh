@@ -105,6 +105,9 @@ struct Cell {
     {
         unsigned char rem[VE];   // vertices beyond the plane, ascending
         int nout = 0;
+#ifdef VORO_COUNT
+        ++g_clips, g_scan += nt;
+#endif
         for (int t = 0; t < nt; ++t)
             if (nx * vx[t] + ny * vy[t] + nz * vz[t] - d > tolh) {
                 if (nout < VE) rem[nout] = (unsigned char)t;
@@ -192,6 +195,9 @@ struct Cell {
             --nt;
         }
         update_rmax();
+#ifdef VORO_COUNT
+        ++g_accept;
+#endif
         return true;
     }
     // area of the face of plane p (vertices visited around the plane node), 0 for a plane without vertices;
@@ -281,7 +287,13 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
     int c[3];
     cell_decode(A.g, me.cell, c[0], c[1], c[2]);
     const int *n = A.g.n;
-    for (int sh = 0;; ++sh) {
+    // Schedule: the atom's own cell and the first shell are walked twice, first for the candidates closer than
+    // 0.8 cell widths (about the first neighbour shell of a crystal at this density), then for the rest -- planes of
+    // near atoms shrink the cell before the far ones are tested, so fewer planes are inserted only to be cut away.
+    const double near2 = 0.64 * A.w * A.w;
+    for (int it = 0;; ++it) {
+        const int sh = it < 4 ? (it & 1) : it - 2;
+        const int part = it < 2 ? 1 : (it < 4 ? 2 : 0);   // 1: near candidates only, 2: far only, 0: all
         if (sh > 0) {
             // distance from the atom to the boundary of the block of shells < sh: nothing beyond it can cut
             double dmin = 1.0e300;
@@ -348,8 +360,12 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
                                 ok = ok && (box.pbc[d] || (r[d] >= 0.0 && r[d] <= A.L[d]));   // open axes: orthogonal only
                                 r[d] = r[d] + shift[d] - pc[d];
                             }
+#ifdef VORO_COUNT
+                            ++g_cand;
+#endif
                             const double d2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
                             if (!ok || !(d2 > 0.0) || d2 >= 4.0 * C.rmax2) continue;
+                            if ((part == 1 && d2 >= near2) || (part == 2 && d2 < near2)) continue;
                             C.clip(r[0], r[1], r[2], 0.5 * d2, o.idx, A.tolh);
                         }
                     }
