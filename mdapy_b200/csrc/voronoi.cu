@@ -31,7 +31,7 @@ using voro::VP;
 using voro::VT;
 typedef voro::VoroArgs<SortedAtom> VoroArgs;
 
-__global__ void __launch_bounds__(voro::VB) k_voronoi(const VoroArgs A)
+__global__ void __launch_bounds__(voro::VB, 16) k_voronoi(const VoroArgs A)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.N) return;
@@ -96,7 +96,24 @@ int launch_voronoi(MdbSystem &s, bool want_rows, double *volume, int *nfaces, do
     const double vol = fabs(dbox_volume(b));
     double w = 1.75 * cbrt(vol / N);
     if (const char *e = getenv("MDB_VORONOI_CELL")) w *= atof(e);
-    if (s.bin_rc != w) launch_binning(s, w);
+    // the records carry WRAPPED coordinates (one wrap per atom here instead of one per candidate in the kernel)
+    {
+        double *wx = s.wx.ensure<double>(N), *wy = s.wy.ensure<double>(N), *wz = s.wz.ensure<double>(N);
+        const size_t bytes = sizeof(double) * N;
+        CUDA_TRY(cudaMemcpyAsync(wx, s.x, bytes, cudaMemcpyDeviceToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(wy, s.y, bytes, cudaMemcpyDeviceToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(wz, s.z, bytes, cudaMemcpyDeviceToDevice, s.stream));
+        if (b.any_pbc) launch_wrap_positions(s, wx, wy, wz, N);
+        const double *rx = s.x, *ry = s.y, *rz = s.z;
+        s.x = wx, s.y = wy, s.z = wz;
+        try {
+            launch_binning(s, w);
+        } catch (...) {
+            s.x = rx, s.y = ry, s.z = rz;
+            throw;
+        }
+        s.x = rx, s.y = ry, s.z = rz;
+    }
     VoroArgs A{};
     A.sorted = s.sorted.as<SortedAtom>();
     A.cell_start = s.cell_start.as<int>();
@@ -104,6 +121,8 @@ int launch_voronoi(MdbSystem &s, bool want_rows, double *volume, int *nfaces, do
     A.box = b;
     A.g = s.grid;
     A.w = w;
+    A.wrapped = 1;
+    A.has_open = !(b.pbc[0] && b.pbc[1] && b.pbc[2]);
     double len2 = 0.0;
     A.R0 = 0.0;
     for (int d = 0; d < 3; ++d) {
@@ -127,7 +146,17 @@ int launch_voronoi(MdbSystem &s, bool want_rows, double *volume, int *nfaces, do
             A.row_area = s.vor_area.ensure<double>((size_t)N * W);
         }
         CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int) * 2, s.stream));
-        MDB_LAUNCH(k_voronoi, (N + VB - 1) / VB, VB, 0, s.stream, A);
+        // MDB_VORONOI_RESIDENT caps the resident threads per SM with dynamic shared memory padding (experiment knob:
+        // throughput grows with residency up to the register limit -- the kernel is latency bound, not capacity bound)
+        int resident = 0;
+        if (const char *e = getenv("MDB_VORONOI_RESIDENT")) resident = atoi(e);
+        size_t pad = 0;
+        if (resident > 0 && resident < 896) {
+            const int blocks = resident / VB > 0 ? resident / VB : 1;
+            pad = (size_t)(220 * 1024) / blocks - 1024;
+            CUDA_TRY(cudaFuncSetAttribute(k_voronoi, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        }
+        MDB_LAUNCH(k_voronoi, (N + VB - 1) / VB, VB, pad, s.stream, A);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(h, status, sizeof(h), cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaStreamSynchronize(s.stream));

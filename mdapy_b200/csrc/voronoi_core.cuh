@@ -19,6 +19,8 @@ template <class Rec> struct VoroArgs {
     double w;       // cell width of the grid (the last cell of an axis takes the remainder)
     double L[3];    // extent of the grid axes: box lengths (orthogonal) / perpendicular thicknesses (triclinic)
     double R0;      // triclinic: half-width of the initial cube (the atom's own images bound the cell inside it)
+    int wrapped;    // the records hold coordinates already wrapped into the box
+    int has_open;   // some axis is not periodic
     double tolh;    // half of voro++'s tolerance on (2 n.v - |r|^2)
     double *volume;
     int *nfaces;
@@ -250,6 +252,28 @@ MDB_HD void cell_span(int k, int n, double w, double L, double &lo, double &hi)
     hi = kk == n - 1 ? m * L + L : m * L + fmin((kk + 1) * w, L);
 }
 
+// One axis of a grid cell seen from the atom: k may lie outside [0, n) (a periodic image).
+struct AxisCell {
+    bool valid;
+    int kk;         // cell index inside the grid
+    double gap2;    // squared distance from the atom's slab coordinate to the cell's slab
+    double s[3];    // image shift (Cartesian)
+};
+template <class Rec> MDB_HD AxisCell axis_cell(const VoroArgs<Rec> &A, int d, int k, double pd)
+{
+    AxisCell a;
+    const int n = A.g.n[d];
+    a.valid = A.box.pbc[d] || (k >= 0 && k < n);
+    const int m = floor_div(k, n);
+    a.kk = k - m * n;
+    double lo, hi;
+    cell_span(k, n, A.w, A.L[d], lo, hi);
+    const double gap = fmax(0.0, fmax(lo - pd, pd - hi));
+    a.gap2 = gap * gap;
+    a.s[0] = m * A.box.h[3 * d], a.s[1] = m * A.box.h[3 * d + 1], a.s[2] = m * A.box.h[3 * d + 2];
+    return a;
+}
+
 // Cell of the atom at position s of the cell-sorted order.  Returns its face count, -1 when the cell outgrew the
 // buffers, 0 for an atom outside an open container.
 template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
@@ -257,7 +281,7 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
     const Rec me = A.sorted[s];
     const DBox &box = A.box;
     double pc[3] = {me.x, me.y, me.z};   // Cartesian, relative to the box origin
-    if (box.any_pbc) wrap_into_box(box, pc[0], pc[1], pc[2]);
+    if (!A.wrapped && box.any_pbc) wrap_into_box(box, pc[0], pc[1], pc[2]);
     for (int d = 0; d < 3; ++d) pc[d] -= box.origin[d];
     // p: the coordinate the grid slabs are measured in -- Cartesian for an orthogonal box, fractional coordinate x
     // perpendicular thickness for a triclinic one (cell_of(); a slab of cells is A.w thick along its own normal)
@@ -316,59 +340,52 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
         }
         // shell cells in three passes: face-, edge-, corner-adjacent offsets (nearest cells cut first)
         for (int pass = (sh == 0 ? 0 : 1); pass <= (sh == 0 ? 0 : 3); ++pass)
-            for (int di = -sh; di <= sh; ++di)
-                for (int dj = -sh; dj <= sh; ++dj)
+            for (int di = -sh; di <= sh; ++di) {
+                const AxisCell a0 = axis_cell(A, 0, c[0] + di, p[0]);
+                if (!a0.valid) continue;
+                for (int dj = -sh; dj <= sh; ++dj) {
+                    const AxisCell a1 = axis_cell(A, 1, c[1] + dj, p[1]);
+                    if (!a1.valid) continue;
                     for (int dk = -sh; dk <= sh; ++dk) {
                         const int ai = di < 0 ? -di : di, aj = dj < 0 ? -dj : dj, ak = dk < 0 ? -dk : dk;
                         if (sh > 0) {
                             if (ai != sh && aj != sh && ak != sh) continue;
                             if ((ai == sh) + (aj == sh) + (ak == sh) != pass) continue;
                         }
-                        const int off[3] = {di, dj, dk};
-                        int kk[3];
-                        double shift[3] = {0.0, 0.0, 0.0}, gap2 = 0.0;
-                        bool valid = true;
-                        for (int d = 0; d < 3; ++d) {
-                            const int k = c[d] + off[d];
-                            if (!box.pbc[d] && (k < 0 || k >= n[d])) {
-                                valid = false;
-                                break;
-                            }
-                            const int m = floor_div(k, n[d]);
-                            kk[d] = k - m * n[d];
-                            if (box.triclinic) {   // image shift m x (box vector d)
-                                shift[0] += m * box.h[3 * d], shift[1] += m * box.h[3 * d + 1], shift[2] += m * box.h[3 * d + 2];
-                            } else shift[d] = m * A.L[d];
-                            double lo, hi;
-                            cell_span(k, n[d], A.w, A.L[d], lo, hi);
-                            const double gap = fmax(0.0, fmax(lo - p[d], p[d] - hi));
-                            // orthogonal: the gaps are the components of the distance; triclinic: each is a distance
-                            // along a slab normal, the largest one bounds the distance from below
-                            gap2 = box.triclinic ? fmax(gap2, gap * gap) : gap2 + gap * gap;
-                        }
-                        if (!valid || gap2 >= 4.0 * C.rmax2) continue;
-                        const int cell = cell_linear(A.g, kk[0], kk[1], kk[2]);
+                        const AxisCell a2 = axis_cell(A, 2, c[2] + dk, p[2]);
+                        if (!a2.valid) continue;
+                        // orthogonal: the gaps are the components of the distance; triclinic: each is a distance
+                        // along a slab normal, the largest one bounds the distance from below
+                        const double gap2 = box.triclinic ? fmax(a0.gap2, fmax(a1.gap2, a2.gap2)) : a0.gap2 + a1.gap2 + a2.gap2;
+                        if (gap2 >= 4.0 * C.rmax2) continue;
+                        // candidate - atom = record + image shift - pc
+                        const double ox = a0.s[0] + a1.s[0] + a2.s[0] - pc[0], oy = a0.s[1] + a1.s[1] + a2.s[1] - pc[1],
+                                     oz = a0.s[2] + a1.s[2] + a2.s[2] - pc[2];
+                        const int cell = cell_linear(A.g, a0.kk, a1.kk, a2.kk);
                         const int b0 = A.cell_start[cell], b1 = A.cell_start[cell + 1];
                         for (int q = b0; q < b1; ++q) {
                             if (q == s && di == 0 && dj == 0 && dk == 0) continue;
                             const Rec o = A.sorted[q];
                             double r[3] = {o.x, o.y, o.z};
-                            if (box.any_pbc) wrap_into_box(box, r[0], r[1], r[2]);
-                            bool ok = true;
-                            for (int d = 0; d < 3; ++d) {
-                                r[d] -= box.origin[d];
-                                ok = ok && (box.pbc[d] || (r[d] >= 0.0 && r[d] <= A.L[d]));   // open axes: orthogonal only
-                                r[d] = r[d] + shift[d] - pc[d];
+                            if (!A.wrapped && box.any_pbc) wrap_into_box(box, r[0], r[1], r[2]);
+                            for (int d = 0; d < 3; ++d) r[d] -= box.origin[d];
+                            if (A.has_open) {   // an atom outside an open container is not stored by voro++
+                                bool ok = true;
+                                for (int d = 0; d < 3; ++d) ok = ok && (box.pbc[d] || (r[d] >= 0.0 && r[d] <= A.L[d]));
+                                if (!ok) continue;
                             }
+                            r[0] += ox, r[1] += oy, r[2] += oz;
 #ifdef VORO_COUNT
                             ++g_cand;
 #endif
                             const double d2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-                            if (!ok || !(d2 > 0.0) || d2 >= 4.0 * C.rmax2) continue;
+                            if (!(d2 > 0.0) || d2 >= 4.0 * C.rmax2) continue;
                             if ((part == 1 && d2 >= near2) || (part == 2 && d2 < near2)) continue;
                             C.clip(r[0], r[1], r[2], 0.5 * d2, o.idx, A.tolh);
                         }
                     }
+                }
+            }
         if (C.fail) break;
     }
     if (C.fail) {

@@ -49,6 +49,8 @@ extern "C" int voronoi_host(const double *x, const double *y, const double *z, i
         A.R0 += edge;
         len2 += edge * edge * (b.pbc[d] ? 0.25 : 1.0);
     }
+    A.wrapped = 0;
+    A.has_open = !(b.pbc[0] && b.pbc[1] && b.pbc[2]);
     A.tolh = 0.5 * 10.0 * 2.220446049250313e-16 * len2;
     A.volume = volume;
     A.nfaces = nfaces;
