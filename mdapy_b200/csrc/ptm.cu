@@ -107,7 +107,8 @@ struct DeviceSrc {
 };
 
 // Pass 2 (polyhedral_template_matching.cpp:255-316): template matching on the ranked neighbours.
-__global__ void __launch_bounds__(64) k_ptm_match(const double *__restrict__ x, const double *__restrict__ y,
+template <int MINB>
+__global__ void __launch_bounds__(64, MINB) k_ptm_match(const double *__restrict__ x, const double *__restrict__ y,
                                                   const double *__restrict__ z, int N, int n_rows,
                                                   const __grid_constant__ DBox box, const int *__restrict__ verlet, int M,
                                                   const unsigned char *__restrict__ order_in,
@@ -196,9 +197,19 @@ void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *ty
         const int blocks = resident / 64 > 0 ? resident / 64 : 1;
         pad = (size_t)(220 * 1024) / blocks - 1024;
         // per launch: the attribute belongs to the current device (several devices per process: group.cu)
-        CUDA_TRY(cudaFuncSetAttribute(k_ptm_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(k_ptm_match<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     }
-    MDB_LAUNCH(k_ptm_match, (R + 63) / 64, 64, pad, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
-               flags & 255, rmsd_threshold, T, output, ocols, indices, icols);
+    // experiment knob: register budget of the matching kernel (8 blocks/SM = 128 registers, 12 = 80, 16 = 64)
+    int minb = 8;
+    if (const char *e = getenv("MDB_PTM_MINB")) minb = atoi(e);
+    if (minb == 12)
+        MDB_LAUNCH(k_ptm_match<12>, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
+                   flags & 255, rmsd_threshold, T, output, ocols, indices, icols);
+    else if (minb == 16)
+        MDB_LAUNCH(k_ptm_match<16>, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
+                   flags & 255, rmsd_threshold, T, output, ocols, indices, icols);
+    else
+        MDB_LAUNCH(k_ptm_match<8>, (R + 63) / 64, 64, pad, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
+                   flags & 255, rmsd_threshold, T, output, ocols, indices, icols);
     CUDA_TRY(cudaGetLastError());
 }
