@@ -199,17 +199,16 @@ void launch_ptm(MdbSystem &s, int flags, const int *verlet, int M, const int *ty
         // per launch: the attribute belongs to the current device (several devices per process: group.cu)
         CUDA_TRY(cudaFuncSetAttribute(k_ptm_match<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     }
-    // experiment knob: register budget of the matching kernel (8 blocks/SM = 128 registers, 12 = 80, 16 = 64)
-    int minb = 8;
+    // Register budget: 16 CTAs/SM (64 registers, 1024 resident threads) beats 8 CTAs/SM (128 registers, 512 threads)
+    // by 8 % (4.19 M rattled BCC: 166 vs 179 ms) -- the kernel is latency bound, residency wins over spills.  The
+    // 128-register build is kept for the MDB_PTM_RESIDENT / MDB_PTM_MINB=8 experiments.
+    int minb = 16;
     if (const char *e = getenv("MDB_PTM_MINB")) minb = atoi(e);
-    if (minb == 12)
-        MDB_LAUNCH(k_ptm_match<12>, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
-                   flags & 255, rmsd_threshold, T, output, ocols, indices, icols);
-    else if (minb == 16)
-        MDB_LAUNCH(k_ptm_match<16>, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
+    if (minb == 8 || pad)
+        MDB_LAUNCH(k_ptm_match<8>, (R + 63) / 64, 64, pad, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
                    flags & 255, rmsd_threshold, T, output, ocols, indices, icols);
     else
-        MDB_LAUNCH(k_ptm_match<8>, (R + 63) / 64, 64, pad, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
+        MDB_LAUNCH(k_ptm_match<16>, (R + 63) / 64, 64, 0, s.stream, s.x, s.y, s.z, s.N, R, s.box, verlet, M, order, types,
                    flags & 255, rmsd_threshold, T, output, ocols, indices, icols);
     CUDA_TRY(cudaGetLastError());
 }

@@ -14,8 +14,8 @@ ROOT = Path(__file__).resolve().parent.parent
 pytestmark = pytest.mark.gpu
 
 
-def _run(cases):
-    out = subprocess.run([sys.executable, str(ROOT / "tools" / "parity_at_scale.py"), *cases], capture_output=True,
+def _run(cases, tool="parity_at_scale.py"):
+    out = subprocess.run([sys.executable, str(ROOT / "tools" / tool), *cases], capture_output=True,
                          text=True, timeout=3000)
     tail = out.stdout[-3000:] + out.stderr[-2000:]
     assert out.returncode == 0, tail
@@ -29,3 +29,14 @@ def test_config2_10M_rattled_and_hot():
 @pytest.mark.skipif(os.environ.get("MDB_SCALE_FULL") != "1", reason="99.6 M atoms: set MDB_SCALE_FULL=1")
 def test_config5_100M_rattled_fixed_and_auto_width():
     _run(["c5", "c5auto"])
+
+
+def test_configs_3_and_4_code_path_on_small_frames():
+    """tools/parity_at_scale_more.py (kNN + Ackland-Jones + PTM on BCC, polycrystal neighbour + Steinhardt + RDF) on
+    frames of 10^5 atoms; the 49.8 M / 19.7 M-atom runs are committed in profiles/r2_parity_at_scale_configs23.log."""
+    _run(["c3small", "c4small"], tool="parity_at_scale_more.py")
+
+
+@pytest.mark.skipif(os.environ.get("MDB_SCALE_FULL") != "1", reason="49.8 M + 19.7 M atoms: set MDB_SCALE_FULL=1")
+def test_configs_3_and_4_full_size():
+    _run(["c3", "c4"], tool="parity_at_scale_more.py")
