@@ -40,7 +40,9 @@ struct Cell {
     int np, nt, fail;
     double rmax2;
 
-    MDB_HD void vertex(int t)
+    // Position of vertex t from its three planes (Cramer).  Returns the squared normalised determinant of the three
+    // normals: near zero the planes almost share a line and the solve loses accuracy (see refine()).
+    MDB_HD double vertex(int t)
     {
         const int a = ta[t], b = tb[t], c = tc[t];
         const double ax = px[a], ay = py[a], az = pz[a];
@@ -49,11 +51,30 @@ struct Cell {
         const double bcx = by * cz - bz * cy, bcy = bz * cx - bx * cz, bcz = bx * cy - by * cx;
         const double cax = cy * az - cz * ay, cay = cz * ax - cx * az, caz = cx * ay - cy * ax;
         const double abx = ay * bz - az * by, aby = az * bx - ax * bz, abz = ax * by - ay * bx;
-        const double inv = 1.0 / (ax * bcx + ay * bcy + az * bcz);
+        const double det = ax * bcx + ay * bcy + az * bcz;
+        const double inv = 1.0 / det;
         const double da = pd[a], db = pd[b], dc = pd[c];
         vx[t] = (da * bcx + db * cax + dc * abx) * inv;
         vy[t] = (da * bcy + db * cay + dc * aby) * inv;
         vz[t] = (da * bcz + db * caz + dc * abz) * inv;
+        return det * det / ((ax * ax + ay * ay + az * az) * (bx * bx + by * by + bz * bz) * (cx * cx + cy * cy + cz * cz));
+    }
+    // An ill-conditioned new vertex (a, b, p): it lies on the cell edge shared by planes a and b, between the removed
+    // vertex tu and the kept vertex across the edge (the one holding the opposite dual edge (b, a)); interpolate along
+    // that edge to the cutting plane instead, as voro++ places its new vertices.
+    MDB_HD void refine(int t, int tu, int limit, double nx, double ny, double nz, double d)
+    {
+        const int a = ta[t], b = tb[t];
+        int tv = -1;
+        for (int u = 0; u < limit && tv < 0; ++u)
+            if ((ta[u] == b && tb[u] == a) || (tb[u] == b && tc[u] == a) || (tc[u] == b && ta[u] == a)) tv = u;
+        if (tv < 0) return;
+        const double su = nx * vx[tu] + ny * vy[tu] + nz * vz[tu] - d, sv = nx * vx[tv] + ny * vy[tv] + nz * vz[tv] - d;
+        if (!(su > 0.0) || !(sv < 0.0)) return;   // the edge does not cross the plane cleanly: keep the solve
+        const double w = sv / (sv - su);          // V + w (U - V) lies on the plane
+        vx[t] = vx[tv] + w * (vx[tu] - vx[tv]);
+        vy[t] = vy[tv] + w * (vy[tu] - vy[tv]);
+        vz[t] = vz[tv] + w * (vz[tu] - vz[tv]);
     }
     MDB_HD void plane(int p, double nx, double ny, double nz, double d, int id)
     {
@@ -140,7 +161,7 @@ struct Cell {
             dup |= (em[c] >> a) & 1ull;
             em[c] |= 1ull << a;
         }
-        unsigned char ea[VE], eb[VE];
+        unsigned char ea[VE], eb[VE], et[VE];   // boundary edges and the removed vertex each one belongs to
         int ne = 0;
         if (!dup) {
             for (int k = 0; k < nout; ++k) {
@@ -150,7 +171,7 @@ struct Cell {
                     const unsigned char u = tri[e], v = tri[e + 1];
                     if (em[v] >> u & 1ull) continue;
                     if (ne < VE) {
-                        ea[ne] = u, eb[ne] = v;
+                        ea[ne] = u, eb[ne] = v, et[ne] = (unsigned char)t;
                         ++ne;
                     } else fail = 1;
                 }
@@ -168,9 +189,9 @@ struct Cell {
                         if (ea[e] == v && eb[e] == u) hit = e;
                     if (hit >= 0) {
                         --ne;
-                        ea[hit] = ea[ne], eb[hit] = eb[ne];
+                        ea[hit] = ea[ne], eb[hit] = eb[ne], et[hit] = et[ne];
                     } else if (ne < VE) {
-                        ea[ne] = u, eb[ne] = v;
+                        ea[ne] = u, eb[ne] = v, et[ne] = (unsigned char)t;
                         ++ne;
                     } else fail = 1;
                 }
@@ -180,18 +201,20 @@ struct Cell {
             const int t = rem[k];
             em[ta[t]] = 0, em[tb[t]] = 0, em[tc[t]] = 0;
         }
-        if (fail || nt - nout + ne > VT) {
+        if (fail || nt + ne > VT) {
             fail = 1;
             return false;
         }
-        // the new vertices (boundary edge + new plane) take the freed slots; a cut that removes whole planes frees
-        // more slots than it fills, and the tail of the array moves into those
+        // the new vertices (boundary edge + new plane) go behind the array while the removed ones are still in place
+        // (refine() reads them), then the tail moves into the freed slots
+        const int base = nt;
         for (int e = 0; e < ne; ++e) {
-            const int slot = e < nout ? rem[e] : nt++;
+            const int slot = base + e;
             ta[slot] = ea[e], tb[slot] = eb[e], tc[slot] = (unsigned char)p;
-            vertex(slot);
+            if (vertex(slot) < 1.0e-8) refine(slot, et[e], base, nx, ny, nz, d);
         }
-        for (int k = nout - 1; k >= ne; --k) {
+        nt = base + ne;
+        for (int k = nout - 1; k >= 0; --k) {
             const int h = rem[k], last = nt - 1;
             if (h != last) ta[h] = ta[last], tb[h] = tb[last], tc[h] = tc[last], vx[h] = vx[last], vy[h] = vy[last], vz[h] = vz[last];
             --nt;

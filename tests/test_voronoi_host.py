@@ -72,3 +72,40 @@ def test_reference_run_vectors(harness, name, scale):
     order = np.lexsort((area, key), axis=1)
     assert np.array_equal(np.take_along_axis(ids, order, axis=1), rv)
     assert np.allclose(np.take_along_axis(area, order, axis=1), ra, rtol=1e-7, atol=1e-9)
+
+
+def test_fuzz_against_compiled_reference(harness):
+    """Random boxes (3..30 per axis, any boundary mix), 2..400 atoms: uniform, clustered, lattice + noise of
+    1e-8..1e-1, far periodic images -- face counts equal, volume and radius to 1e-9 against the reference's voro++."""
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("needs oracle/_ref (the reference compiled in the dev container)")
+    rng = np.random.default_rng(2024)
+    for trial in range(80):
+        N = int(rng.integers(2, 400))
+        L = rng.uniform(3, 30, 3)
+        bd = rng.integers(0, 2, 3).astype(np.int32)
+        mode = trial % 4
+        if mode == 0:
+            pos = rng.random((N, 3)) * L
+        elif mode == 1:
+            c = rng.random((max(1, N // 20), 3)) * L
+            pos = c[rng.integers(0, len(c), N)] + rng.normal(0, 0.4, (N, 3))
+            pos = np.where(bd == 1, pos % L, np.clip(pos, 1e-6, L - 1e-6))
+        elif mode == 2:
+            n = int(round(N ** (1 / 3))) + 1
+            g = np.stack(np.meshgrid(*[np.arange(n)] * 3, indexing="ij"), -1).reshape(-1, 3)[:N]
+            pos = (g + 0.5) * (L / n) + rng.normal(0, 10 ** rng.uniform(-8, -1), (len(g), 3))
+            pos = np.where(bd == 1, pos % L, np.clip(pos, 1e-6, L - 1e-6))
+        else:
+            pos = rng.random((N, 3)) * L
+            pos = np.where(bd == 1, pos + rng.integers(-2, 3, (N, 3)) * L, pos)
+        box = np.diag(L)
+        x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+        rvol, rnn, rrad = ref.voronoi_volume(x, y, z, box, np.zeros(3), bd)
+        vol, nn, rad, _, _ = cells(harness, pos, box, np.zeros(3), bd, W=64)
+        m = rvol > 0
+        assert np.array_equal(nn, rnn), (trial, mode)
+        assert np.allclose(vol[m], rvol[m], rtol=1e-9, atol=0), (trial, mode)
+        assert np.allclose(rad[m], rrad[m], rtol=1e-9, atol=0), (trial, mode)
