@@ -38,6 +38,8 @@ struct Cell {
     double vx[VT], vy[VT], vz[VT];
     unsigned long long em[VP];   // scratch of clip(): edge matrix of the removed triangles
     int np, nt, fail;
+    int careful;   // 0: new vertices solved in place; 1: appended and refined (after an ill-conditioned solve was seen)
+    int ill;       // fast mode met a vertex whose three planes almost share a line
     double rmax2;
 
     // Position of vertex t from its three planes (Cramer).  Returns the squared normalised determinant of the three
@@ -104,6 +106,7 @@ struct Cell {
         }
         nt = 8;
         fail = 0;
+        ill = 0;
         for (int q = 0; q < VP; ++q) em[q] = 0;
         update_rmax();
     }
@@ -201,23 +204,38 @@ struct Cell {
             const int t = rem[k];
             em[ta[t]] = 0, em[tb[t]] = 0, em[tc[t]] = 0;
         }
-        if (fail || nt + ne > VT) {
+        if (fail || (careful ? nt + ne : nt - nout + ne) > VT) {
             fail = 1;
             return false;
         }
-        // the new vertices (boundary edge + new plane) go behind the array while the removed ones are still in place
-        // (refine() reads them), then the tail moves into the freed slots
-        const int base = nt;
-        for (int e = 0; e < ne; ++e) {
-            const int slot = base + e;
-            ta[slot] = ea[e], tb[slot] = eb[e], tc[slot] = (unsigned char)p;
-            if (vertex(slot) < 1.0e-8) refine(slot, et[e], base, nx, ny, nz, d);
-        }
-        nt = base + ne;
-        for (int k = nout - 1; k >= 0; --k) {
-            const int h = rem[k], last = nt - 1;
-            if (h != last) ta[h] = ta[last], tb[h] = tb[last], tc[h] = tc[last], vx[h] = vx[last], vy[h] = vy[last], vz[h] = vz[last];
-            --nt;
+        if (!careful) {
+            // the new vertices (boundary edge + new plane) take the freed slots; a cut that removes whole planes
+            // frees more slots than it fills, and the tail of the array moves into those
+            for (int e = 0; e < ne; ++e) {
+                const int slot = e < nout ? rem[e] : nt++;
+                ta[slot] = ea[e], tb[slot] = eb[e], tc[slot] = (unsigned char)p;
+                if (vertex(slot) < 1.0e-8) ill = 1;   // the caller rebuilds this cell in careful mode
+            }
+            for (int k = nout - 1; k >= ne; --k) {
+                const int h = rem[k], last = nt - 1;
+                if (h != last) ta[h] = ta[last], tb[h] = tb[last], tc[h] = tc[last], vx[h] = vx[last], vy[h] = vy[last], vz[h] = vz[last];
+                --nt;
+            }
+        } else {
+            // the new vertices go behind the array while the removed ones are still in place (refine() reads them),
+            // then the tail moves into the freed slots
+            const int base = nt;
+            for (int e = 0; e < ne; ++e) {
+                const int slot = base + e;
+                ta[slot] = ea[e], tb[slot] = eb[e], tc[slot] = (unsigned char)p;
+                if (vertex(slot) < 1.0e-8) refine(slot, et[e], base, nx, ny, nz, d);
+            }
+            nt = base + ne;
+            for (int k = nout - 1; k >= 0; --k) {
+                const int h = rem[k], last = nt - 1;
+                if (h != last) ta[h] = ta[last], tb[h] = tb[last], tc[h] = tc[last], vx[h] = vx[last], vy[h] = vy[last], vz[h] = vz[last];
+                --nt;
+            }
         }
         update_rmax();
 #ifdef VORO_COUNT
@@ -323,17 +341,21 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
         return 0;
     }
     Cell C;
+    int c[3];
+    cell_decode(A.g, me.cell, c[0], c[1], c[2]);
+    const int *n = A.g.n;
+    // Fast mode first; a cell that met an ill-conditioned vertex solve (three planes almost sharing a line: lattices
+    // with ~1e-8 noise) is rebuilt once in careful mode, where such vertices are interpolated along the cut edge.
+    for (int careful = 0; careful < 2; ++careful) {
     {
         double lo[3], hi[3];
         for (int d = 0; d < 3; ++d) {
             lo[d] = box.triclinic ? -A.R0 : (box.pbc[d] ? -0.5 * A.L[d] : -p[d]);
             hi[d] = box.triclinic ? A.R0 : (box.pbc[d] ? 0.5 * A.L[d] : A.L[d] - p[d]);
         }
+        C.careful = careful;
         C.init(lo, hi);
     }
-    int c[3];
-    cell_decode(A.g, me.cell, c[0], c[1], c[2]);
-    const int *n = A.g.n;
     // Schedule: the atom's own cell and the first shell are walked twice, first for the candidates closer than
     // 0.8 cell widths (about the first neighbour shell of a crystal at this density), then for the rest -- planes of
     // near atoms shrink the cell before the far ones are tested, so fewer planes are inserted only to be cut away.
@@ -410,6 +432,8 @@ template <class Rec> MDB_HD int voronoi_atom(const VoroArgs<Rec> &A, int s)
                 }
             }
         if (C.fail) break;
+    }
+    if (C.fail || !C.ill) break;
     }
     if (C.fail) {
         A.volume[i] = 0.0;
