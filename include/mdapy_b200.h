@@ -389,7 +389,8 @@ int mdb_system_voronoi_fetch(mdb_system *s, int *verlet_host, double *distance_h
  * routing kernel pushes every atom (and the boundary-plane ghosts) into the slab of the member that owns its x
  * cell plane with peer stores over NVLink; each member runs the fused neighbour + CNA kernel on its slab; the
  * labels travel back the same way.  No host-side partitioning, no NCCL, no PyTorch.  A device may be listed
- * more than once (several slabs on one GPU; used by the single-GPU tests). */
+ * more than once (several slabs on one GPU; used by the single-GPU tests).  A group works on one frame at a time:
+ * calls on the same group must not overlap (different groups, and groups next to mdb_system handles, may). */
 typedef struct mdb_group mdb_group;
 int mdb_group_create(const int *devices, int ndev, mdb_group **out);
 void mdb_group_destroy(mdb_group *g);
