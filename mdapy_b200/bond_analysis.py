@@ -9,7 +9,6 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-from . import _lib as L
 from .box import Box
 from .device import LIST_CUTOFF, DeviceSystem
 from .frame import Frame

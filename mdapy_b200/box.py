@@ -7,8 +7,6 @@ replication decisions agree with the reference.
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional, Union
-
 import numpy as np
 
 

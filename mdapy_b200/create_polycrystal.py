@@ -23,7 +23,6 @@ import numpy as np
 from . import _lib as L
 from . import builders as B
 from .box import Box
-from .device import DeviceSystem
 from .lattice import _BASES
 
 

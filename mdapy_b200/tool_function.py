@@ -3,7 +3,6 @@ sort_neighbor 75-119).  Replication only ever touches tiny boxes, so it is plain
 reference's operation order (repeat_cell.cpp:41-59: shift = ix*a1 + iy*a2 + iz*a3, new = old + shift)."""
 from __future__ import annotations
 
-import ctypes as C
 from typing import Tuple
 
 import numpy as np

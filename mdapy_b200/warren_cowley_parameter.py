@@ -7,7 +7,7 @@ from typing import Optional
 
 import numpy as np
 
-from .device import LIST_CUTOFF, DeviceSystem
+from .device import DeviceSystem
 from .frame import Frame
 
 
