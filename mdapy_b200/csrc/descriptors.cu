@@ -42,7 +42,103 @@ __global__ void __launch_bounds__(128) k_sort_rows(int *__restrict__ verlet, dou
     }
 }
 
+// The same swap sequence with the block's 128 rows staged in shared memory: the rows are read and written once,
+// coalesced (they are contiguous in HBM), and the k scans of a row run on shared memory.  Element q of thread t
+// lives at [q * 129 + t]: the padding keeps both the cooperative copy (consecutive q) and the per-thread scans
+// (consecutive t) on distinct banks.
+constexpr int SORT_LD = 129;
+__global__ void __launch_bounds__(128) k_sort_rows_staged(int *__restrict__ verlet, double *__restrict__ dist, int N, int M,
+                                                          int k)
+{
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    double *d = reinterpret_cast<double *>(sort_smem);
+    int *v = reinterpret_cast<int *>(d + (size_t)M * SORT_LD);
+    const int tid = threadIdx.x;
+    const size_t row0 = (size_t)blockIdx.x * 128;
+    const int rows = (int)((size_t)N - row0 < 128 ? (size_t)N - row0 : 128);
+    const int total = rows * M;
+    const size_t base = row0 * M;
+    for (int e = tid; e < total; e += 128) {
+        const int r = e / M, q = e - r * M;
+        d[q * SORT_LD + r] = dist[base + e];
+        v[q * SORT_LD + r] = verlet[base + e];
+    }
+    __syncthreads();
+    if (tid < rows) {
+        const int eff = k < M ? k : M;
+        for (int j = 0; j < eff; ++j) {
+            int mi = j;
+            double md = d[j * SORT_LD + tid];
+            for (int q = j + 1; q < M; ++q) {
+                const double dq = d[q * SORT_LD + tid];
+                if (dq < md) {
+                    md = dq;
+                    mi = q;
+                }
+            }
+            if (mi != j) {
+                const double td = d[j * SORT_LD + tid];
+                d[j * SORT_LD + tid] = md;
+                d[mi * SORT_LD + tid] = td;
+                const int tv = v[j * SORT_LD + tid];
+                v[j * SORT_LD + tid] = v[mi * SORT_LD + tid];
+                v[mi * SORT_LD + tid] = tv;
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < total; e += 128) {
+        const int r = e / M, q = e - r * M;
+        dist[base + e] = d[q * SORT_LD + r];
+        verlet[base + e] = v[q * SORT_LD + r];
+    }
+}
+
 constexpr int CSP_MAX_N = 64;
+
+// csp for a compile-time neighbour count: vectors and the running N/2 smallest pair values stay in registers
+// (every loop unrolls).  Same arithmetic and the same order of additions as k_csp below.
+template <int NN>
+__global__ void __launch_bounds__(128) k_csp_fixed(const double *__restrict__ x, const double *__restrict__ y,
+                                                   const double *__restrict__ z, int N, DBox box,
+                                                   const int *__restrict__ verlet, int M, double *__restrict__ csp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double xi = x[i], yi = y[i], zi = z[i];
+    double rx[NN], ry[NN], rz[NN];
+    const int *row = verlet + (size_t)i * M;
+#pragma unroll
+    for (int a = 0; a < NN; ++a) {
+        const int j = row[a];
+        double dx = x[j] - xi, dy = y[j] - yi, dz = z[j] - zi;
+        min_image(box, dx, dy, dz);
+        rx[a] = dx, ry[a] = dy, rz[a] = dz;
+    }
+    constexpr int HALF = NN / 2;
+    double best[HALF];   // ascending; +inf until filled (a value equal to best[HALF-1] is not inserted, as in k_csp)
+#pragma unroll
+    for (int q = 0; q < HALF; ++q) best[q] = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+    for (int a = 0; a < NN; ++a)
+#pragma unroll
+        for (int b = a + 1; b < NN; ++b) {
+            const double sx = rx[a] + rx[b], sy = ry[a] + ry[b], sz = rz[a] + rz[b];
+            const double v = sx * sx + sy * sy + sz * sz;
+            // Insertion into the ascending list, branch free.  With c = number of entries <= v (ties stay in front
+            // of the newcomer, like the strict comparison of k_csp's shifting loop): entries above c move up one
+            // slot, slot c takes v, the largest entry falls out; v >= every entry changes nothing.
+#pragma unroll
+            for (int q = HALF - 1; q >= 0; --q) {
+                const double below = q > 0 ? best[q - 1] : 0.0;
+                best[q] = (q > 0 && below > v) ? below : (best[q] > v ? v : best[q]);
+            }
+        }
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < HALF; ++q) sum += best[q];
+    csp[i] = sum;
+}
 
 // csp = sum of the N/2 smallest |r_j + r_k|^2 over all neighbour pairs, added in ascending order
 // (std::partial_sort then a forward sum, centro_symmetry_parameter.cpp:82-90).
@@ -501,7 +597,14 @@ __global__ void __launch_bounds__(128) k_adf_hist(const double *__restrict__ x, 
 void launch_sort_rows(MdbSystem &s, int *verlet, double *dist, int N, int M, int k)
 {
     if (N <= 0 || M <= 0 || k <= 0) return;
-    MDB_LAUNCH(k_sort_rows, (N + 127) / 128, 128, 0, s.stream, verlet, dist, N, M, k);
+    const size_t smem = (size_t)M * SORT_LD * (sizeof(double) + sizeof(int));
+    const char *mode = getenv("MDB_SORT");
+    if (smem <= 200 * 1024 && !(mode && !strcmp(mode, "global"))) {
+        CUDA_TRY(cudaFuncSetAttribute(k_sort_rows_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MDB_LAUNCH(k_sort_rows_staged, (N + 127) / 128, 128, smem, s.stream, verlet, dist, N, M, k);
+    } else {
+        MDB_LAUNCH(k_sort_rows, (N + 127) / 128, 128, 0, s.stream, verlet, dist, N, M, k);
+    }
     CUDA_TRY(cudaGetLastError());
 }
 
@@ -510,7 +613,13 @@ void launch_csp(MdbSystem &s, const int *verlet, int M, int nnei, double *csp)
     MDB_REQUIRE(nnei > 0 && nnei % 2 == 0, MDB_ERR_VALUE, "N must be a positive even number: %d.", nnei);
     MDB_REQUIRE(nnei <= CSP_MAX_N, MDB_ERR_VALUE, "N=%d exceeds the device limit %d", nnei, CSP_MAX_N);
     MDB_REQUIRE(nnei <= M, MDB_ERR_VALUE, "N=%d exceeds neighbour row width %d", nnei, M);
-    MDB_LAUNCH(k_csp, (s.n_rows + 127) / 128, 128, 0, s.stream, s.x, s.y, s.z, s.n_rows, s.box, verlet, M, nnei, csp);
+    const int R = s.n_rows, nb = (R + 127) / 128;
+    const char *mode = getenv("MDB_CSP");
+    const bool generic = mode && !strcmp(mode, "generic");
+    if (nnei == 12 && !generic) MDB_LAUNCH(k_csp_fixed<12>, nb, 128, 0, s.stream, s.x, s.y, s.z, R, s.box, verlet, M, csp);
+    else if (nnei == 8 && !generic) MDB_LAUNCH(k_csp_fixed<8>, nb, 128, 0, s.stream, s.x, s.y, s.z, R, s.box, verlet, M, csp);
+    else if (nnei == 14 && !generic) MDB_LAUNCH(k_csp_fixed<14>, nb, 128, 0, s.stream, s.x, s.y, s.z, R, s.box, verlet, M, csp);
+    else MDB_LAUNCH(k_csp, nb, 128, 0, s.stream, s.x, s.y, s.z, R, s.box, verlet, M, nnei, csp);
     CUDA_TRY(cudaGetLastError());
 }
 
