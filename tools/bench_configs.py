@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel throughput of the other BASELINE configs on one GPU (device-resident, CUDA-synchronised
 wall clock around each library call, best of 3), next to the reference C++ on the host cores on a
-bounded sample.  Writes profiles/r1_config_throughput.json.  Not the headline bench (that is bench.py)."""
+bounded sample.  Writes gpurun_out/r2_config_throughput_1gpu.json (copied to profiles/).  Not the headline bench (that is bench.py)."""
 import json
 import os
 import sys
@@ -148,7 +148,7 @@ def main():
     row("C4* 20M thermal FCC Al", "RDF streaming rc=6 500 bins", N, t_rs, (ns / c_rs, ns))
     row("C4* 20M thermal FCC Al", "neighbour list rc=6 (auto M)", N, t_l6)
     row("C4* 20M thermal FCC Al", "RDF from list rc=6 500 bins", N, t_rl)
-    out = ROOT / "gpurun_out" / "r1_config_throughput.json"
+    out = ROOT / "gpurun_out" / "r2_config_throughput_1gpu.json"
     out.parent.mkdir(exist_ok=True)
     out.write_text(json.dumps(report, indent=1))
 
