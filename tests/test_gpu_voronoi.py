@@ -172,3 +172,32 @@ def test_triclinic_with_open_axes_needs_the_python_side():
     ds.set_atoms(*(np.ascontiguousarray(ps[:, k]) for k in range(3)), bs, O3, np.array([1, 0, 1], np.int32))
     with pytest.raises(ValueError):
         ds.voronoi_volume()
+
+
+def test_steinhardt_on_voronoi_rows_end_to_end():
+    """q_l / w_l-hat with Voronoi neighbours, face-area weights, an absolute area threshold and neighbour averaging:
+    bit-identical to the reference kernel on the same rows, and equal to rounding (row order only permutes the sums)
+    to the reference end to end (voro++ rows -> get_sq)."""
+    import mdapy_b200 as mp
+
+    if K.KIND != "reference":
+        pytest.skip("needs oracle/_ref")
+    p, b = H.bcc(2.8665, 8)
+    pos = H.rattle(p, 0.08, 7)
+    PB = np.array([1, 1, 1], np.int32)
+    s = mp.System(pos=pos, box=mp.Box(b))
+    sbo = s.cal_steinhardt_bond_orientation([4, 6, 8], use_voronoi=True, use_weight=True, average=True, wlhat=True,
+                                            a_face_area_threshold=0.3)
+    x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+    qn, _, _ = K.get_sq(x, y, z, b, O3, PB, np.array(s.voro_verlet_list), np.array(s.voro_distance_list),
+                        np.array(s.voro_neighbor_number), [4, 6, 8], average=True, wlhat=True, use_voronoi=True,
+                        weight=np.array(s.voro_face_area))
+    assert np.array_equal(sbo.qnarray, qn)
+    rv, rd, ra, rn = K.voronoi_neighbor(x, y, z, b, O3, PB, 0.3, -1.0)
+    qr, _, _ = K.get_sq(x, y, z, b, O3, PB, rv, rd, rn, [4, 6, 8], average=True, wlhat=True, use_voronoi=True, weight=ra)
+    assert np.allclose(sbo.qnarray, qr, rtol=0, atol=1e-13)
+    # fewer than 50 atoms: replicated like the reference, columns come back for the original atoms
+    p2, b2 = H.fcc(3.615, 2)
+    t = mp.System(pos=H.rattle(p2, 0.05, 6), box=mp.Box(b2))
+    t.cal_steinhardt_bond_orientation([4, 6], use_voronoi=True, average=True, identify_liquid=True, wl=True)
+    assert np.asarray(t.data["ql6"]).shape == (32,) and np.asarray(t.data["solidliquid"]).shape == (32,)
