@@ -177,3 +177,35 @@ def test_system_cache_semantics():
     s3.rc = 3.0
     s3.cal_centro_symmetry_parameter(12)
     assert np.allclose(np.asarray(s3.data["csp"]), 0.0, atol=1e-10)
+
+
+def test_staged_upload_of_pageable_columns_round_trips():
+    """csrc/staging.cu: pageable NumPy columns go up through page-locked ring buffers in 4 MiB slices from several
+    host threads; page-locked columns go up directly.  Both must leave the same bytes on the device (odd sizes, a
+    last partial slice, non-contiguous views made contiguous by the binding)."""
+    import os
+
+    from mdapy_b200 import _lib as L
+    from mdapy_b200.builders import fetch_positions
+    from mdapy_b200.device import DeviceSystem
+
+    rng = np.random.default_rng(5)
+    N = 3_000_001                                     # 24 MB per column: 5 full slices + a partial one
+    pos = rng.random((N, 3)) * 50.0
+    box, o, b = np.diag([50.0] * 3), np.zeros(3), np.array([1, 1, 1], np.int32)
+    cols = [np.ascontiguousarray(pos[:, k]) for k in range(3)]
+    for threads in ("1", "3", "8"):
+        os.environ["MDB_UPLOAD_THREADS"] = threads
+        ds = DeviceSystem(0)
+        ds.set_atoms(*cols, box, o, b)
+        back = fetch_positions(ds)
+        assert all(np.array_equal(np.asarray(g), c) for g, c in zip(back, cols)), threads
+        ds.close()
+    os.environ.pop("MDB_UPLOAD_THREADS")
+    pinned = [L.result_empty(N, np.float64) for _ in range(3)]
+    for dst, src in zip(pinned, cols):
+        dst[:] = src
+    ds = DeviceSystem(0)
+    ds.set_atoms(*pinned, box, o, b)
+    assert all(np.array_equal(np.asarray(g), c) for g, c in zip(fetch_positions(ds), cols))
+    ds.close()
