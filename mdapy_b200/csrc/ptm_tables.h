@@ -361,6 +361,40 @@ inline void build_tables(HostTables &H)
                         if (std::find(labs.begin(), labs.end(), la) == labs.end()) labs.push_back(la);
                     }
                 }
+            // Two labellings that differ by a rigid rotation of the ideal template (t_sigma(u) = R t_u) give
+            // correlation matrices R A and A: the same optimal-rotation eigenvalue, hence the same RMSD up to
+            // rounding, whatever the environment.  The reference evaluates all of them (ptm_structure_matcher.cpp:
+            // 57-105) and rounding noise picks the winner; here one labelling per class of rotation-equivalent
+            // labellings is kept.  (All 24 labellings of the BCC hull are rotations of one another.)
+            if (!getenv("MDB_PTM_ALL_AUTOMORPHISMS")) {
+                std::vector<std::array<signed char, MAX_NB>> kept;
+                for (const auto &la : labs) {
+                    bool equivalent = false;
+                    for (const auto &lb : kept) {
+                        int sigma[MAX_NB];   // template neighbour u of `la` plays the role of sigma[u] in `lb`
+                        for (int u = 0; u < n; ++u)
+                            for (int v = 0; v < n; ++v)
+                                if (lb[v] == la[u]) sigma[u] = v;
+                        bool iso = true;
+                        for (int u = 0; u < n && iso; ++u) {
+                            const double *tu = T.tpl[s][1 + u], *su = T.tpl[s][1 + sigma[u]];
+                            if (std::fabs(dot3(tu, tu) - dot3(su, su)) > 1e-9) iso = false;
+                            for (int v = u + 1; v < n && iso; ++v) {
+                                const double *tv = T.tpl[s][1 + v], *sv = T.tpl[s][1 + sigma[v]];
+                                const double a[3] = {tu[0] - tv[0], tu[1] - tv[1], tu[2] - tv[2]};
+                                const double b[3] = {su[0] - sv[0], su[1] - sv[1], su[2] - sv[2]};
+                                if (std::fabs(dot3(a, a) - dot3(b, b)) > 1e-9) iso = false;
+                            }
+                        }
+                        if (iso) {
+                            equivalent = true;
+                            break;
+                        }
+                    }
+                    if (!equivalent) kept.push_back(la);
+                }
+                labs.swap(kept);
+            }
             classes[rep] = Entry{code_hash(best.data(), (int)best.size()), labs};
         }
         std::vector<Entry> sorted;
