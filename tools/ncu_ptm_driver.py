@@ -1,7 +1,9 @@
 """Driver for an ncu capture of the PTM kernels: 1.02 M rattled BCC atoms, kNN(18) + PTM fcc-hcp-bcc."""
 import sys
 import numpy as np
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / 'tests'))
 import helpers as H
 from mdapy_b200.device import DeviceSystem
 p, b = H.bcc(2.8665, 80)

@@ -1,5 +1,7 @@
 import sys, numpy as np
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / 'tests'))
 import helpers as H
 from mdapy_b200.device import DeviceSystem
 p,b=H.fcc(3.615,60); pos=H.rattle(p,0.05,0)
