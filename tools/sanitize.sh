@@ -23,5 +23,6 @@ run neighbor racecheck tests/test_gpu_neighbor.py tests/test_gpu_fused.py
 MDB_NEIGHBOR=tiled_v1 run neighbor_v1 racecheck tests/test_gpu_neighbor.py
 MDB_NEIGHBOR=coop run neighbor_coop racecheck tests/test_gpu_neighbor.py
 run group racecheck tests/test_gpu_group.py -k "labels_equal_reference and (fcc_hot or shuffled or gas)"
+run sort_staged racecheck tests/test_gpu_neighbor.py tests/test_gpu_descriptors.py -k "sort_and_descriptors or host_pointer_dropins"
 run cluster_ids racecheck tests/test_gpu_ids.py tests/test_gpu_list_consumers.py -k "cluster or ids or diamond"
 cat $OUT/sanitizer_summary.txt
