@@ -27,6 +27,17 @@ __device__ __forceinline__ void hist_add(unsigned *sh, unsigned long long *gl, b
         atomicAdd(&gl[slot], (unsigned long long)v);
 }
 
+// floor(d / dr) as the reference computes it (the IEEE quotient, truncated), without the division sequence for
+// almost every entry: k0 = trunc(d * (1/dr)) can only differ from it when d / dr lies within a few ulps of an
+// integer; those entries (fractional part of the product within 1e-9 of 0 or 1) take the real division.
+__device__ __forceinline__ int rdf_bin(double d, double dr, double inv_dr)
+{
+    const double t = d * inv_dr;
+    const double f = t - floor(t);
+    if (f < 1e-9 || f > 1.0 - 1e-9) return (int)(d / dr);
+    return (int)t;
+}
+
 __device__ __forceinline__ void hist_flush(unsigned *sh, unsigned long long *gl, int nslot)
 {
     __syncthreads();
@@ -34,6 +45,40 @@ __device__ __forceinline__ void hist_flush(unsigned *sh, unsigned long long *gl,
         const unsigned v = sh[t];
         if (v) atomicAdd(&gl[t], (unsigned long long)v);
     }
+}
+
+// The same counts with one thread per LIST ENTRY (flat index over the N x M arrays): the distance and index
+// rows are read once, fully coalesced, and the 32 entries of a warp belong to one or two atoms, so their bins
+// differ (thread-per-row put the j-th neighbours of 32 atoms -- in a crystal: the same shell, the same bin -- into
+// one atomic instruction).
+__global__ void __launch_bounds__(256) k_rdf_list_flat(const int *__restrict__ verlet, const double *__restrict__ dist,
+                                                       const int *__restrict__ nn, int N, int M,
+                                                       const int *__restrict__ types, int ntype, double rc, int nbin,
+                                                       const int *__restrict__ gid, unsigned long long *__restrict__ hist)
+{
+    extern __shared__ unsigned sh[];
+    const int nslot = (types ? ntype * ntype : 1) * nbin;
+    const bool use_sh = nslot <= RDF_SMEM_BINS;
+    if (use_sh) {
+        for (int t = threadIdx.x; t < nslot; t += blockDim.x) sh[t] = 0;
+        __syncthreads();
+    }
+    const double dr = rc / nbin, inv_dr = 1.0 / dr;
+    const size_t total = (size_t)N * M, step = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+        const double d = dist[e];
+        if (!(d < rc)) continue;
+        const int i = (int)(e / M), q = (int)(e - (size_t)i * M);
+        if (q >= nn[i]) continue;
+        const int k = rdf_bin(d, dr, inv_dr);
+        if (k >= nbin || k < 0) continue;
+        const int j = verlet[e];
+        if (types)
+            hist_add(sh, hist, use_sh, (types[i] * ntype + types[j]) * nbin + k, 1u);
+        else if (gid ? gid[j] > gid[i] : j > i)
+            hist_add(sh, hist, use_sh, k, 2u);
+    }
+    if (use_sh) hist_flush(sh, hist, nslot);
 }
 
 // _rdf (typed) and _rdf_single_species (types == nullptr)
@@ -149,7 +194,15 @@ void launch_rdf_list(MdbSystem &s, const int *verlet, const double *dist, const 
     const size_t smem = nslot <= RDF_SMEM_BINS ? sizeof(unsigned) * nslot : 0;
     int nb = (N + 255) / 256;
     if (nb > 1184) nb = 1184;
-    MDB_LAUNCH(k_rdf_list, nb, 256, smem, st, verlet, dist, nn, N, M, types, ntype, rc, nbin, s.gid, hist);
+    const char *mode = getenv("MDB_RDF");
+    if (mode && !strcmp(mode, "rows")) {
+        MDB_LAUNCH(k_rdf_list, nb, 256, smem, st, verlet, dist, nn, N, M, types, ntype, rc, nbin, s.gid, hist);
+    } else {
+        const size_t total = (size_t)N * M;
+        size_t nbf = (total + 255) / 256;
+        if (nbf > 148 * 16) nbf = 148 * 16;
+        MDB_LAUNCH(k_rdf_list_flat, (int)nbf, 256, smem, st, verlet, dist, nn, N, M, types, ntype, rc, nbin, s.gid, hist);
+    }
     MDB_LAUNCH(k_hist_accumulate, (nslot + 255) / 256, 256, 0, st, hist, nslot, g);
     CUDA_TRY(cudaGetLastError());
 }
