@@ -63,21 +63,35 @@ __global__ void __launch_bounds__(256) k_rdf_list_flat(const int *__restrict__ v
         for (int t = threadIdx.x; t < nslot; t += blockDim.x) sh[t] = 0;
         __syncthreads();
     }
-    const double dr = rc / nbin, inv_dr = 1.0 / dr;
+    const double dr = rc / nbin, inv_dr = 1.0 / dr, inv_M = 1.0 / M;
     const size_t total = (size_t)N * M, step = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
-        const double d = dist[e];
-        if (!(d < rc)) continue;
-        const int i = (int)(e / M), q = (int)(e - (size_t)i * M);
-        if (q >= nn[i]) continue;
+    auto one = [&](size_t e, double d, int j) {
+        if (!(d < rc)) return;
+        // row of entry e without a 64-bit integer division: the double quotient is off by at most one
+        int i = (int)((double)e * inv_M);
+        if ((size_t)(i + 1) * M <= e) ++i;
+        else if ((size_t)i * M > e) --i;
+        const int q = (int)(e - (size_t)i * M);
+        if (q >= nn[i]) return;
         const int k = rdf_bin(d, dr, inv_dr);
-        if (k >= nbin || k < 0) continue;
-        const int j = verlet[e];
+        if (k >= nbin || k < 0) return;
         if (types)
             hist_add(sh, hist, use_sh, (types[i] * ntype + types[j]) * nbin + k, 1u);
         else if (gid ? gid[j] > gid[i] : j > i)
             hist_add(sh, hist, use_sh, k, 2u);
+    };
+    // four entries per thread and trip, all eight loads issued before the first is used (eight per trip is slower:
+    // the registers cost more residency than the extra loads in flight gain)
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; e + 3 * step < total; e += 4 * step) {
+        const double d0 = dist[e], d1 = dist[e + step], d2 = dist[e + 2 * step], d3 = dist[e + 3 * step];
+        const int j0 = verlet[e], j1 = verlet[e + step], j2 = verlet[e + 2 * step], j3 = verlet[e + 3 * step];
+        one(e, d0, j0);
+        one(e + step, d1, j1);
+        one(e + 2 * step, d2, j2);
+        one(e + 3 * step, d3, j3);
     }
+    for (; e < total; e += step) one(e, dist[e], verlet[e]);
     if (use_sh) hist_flush(sh, hist, nslot);
 }
 
