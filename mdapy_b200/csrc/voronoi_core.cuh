@@ -7,7 +7,7 @@
 namespace voro {
 constexpr int VT = 128;   // vertices (dual triangles) per cell
 constexpr int VP = 64;    // planes per cell, walls included
-constexpr int VE = 64;    // boundary edges of one cut
+constexpr int VE = 128;   // boundary edges / removed vertices of one cut (a cut can remove most of a large cell)
 constexpr int VB = 64;    // threads per block
 
 template <class Rec> struct VoroArgs {

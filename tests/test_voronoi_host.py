@@ -109,3 +109,34 @@ def test_fuzz_against_compiled_reference(harness):
         assert np.array_equal(nn, rnn), (trial, mode)
         assert np.allclose(vol[m], rvol[m], rtol=1e-9, atol=0), (trial, mode)
         assert np.allclose(rad[m], rrad[m], rtol=1e-9, atol=0), (trial, mode)
+
+
+def test_fuzz_triclinic_against_compiled_reference(harness):
+    """Sheared boxes (tilt factors up to +-0.5), periodic and open axes (open axes tripled like the reference's
+    Python side): uniform points and full lattices with 1e-8..1e-2 noise against get_voronoi_volume_number_radius_tri."""
+    from oracle import ref
+
+    if not ref.available():
+        pytest.skip("needs oracle/_ref (the reference compiled in the dev container)")
+    rng = np.random.default_rng(77)
+    for trial in range(60):
+        L = rng.uniform(6, 25, 3)
+        F = np.array([[1, 0, 0], [rng.uniform(-0.5, 0.5), 1, 0], [rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), 1]])
+        box = np.diag(L) @ F
+        bd = np.array([1, 1, 1], np.int32) if trial % 3 else rng.integers(0, 2, 3).astype(np.int32)
+        if trial % 2:
+            n = int(rng.integers(3, 7))
+            g = np.stack(np.meshgrid(*[np.arange(n)] * 3, indexing="ij"), -1).reshape(-1, 3)
+            frac = ((g + 0.5) / n + rng.normal(0, 10 ** rng.uniform(-8, -2), g.shape)) % 1.0
+        else:
+            frac = rng.random((int(rng.integers(20, 400)), 3))
+        pos = frac @ box
+        x, y, z = (np.ascontiguousarray(pos[:, k]) for k in range(3))
+        rvol, rnn, rrad = ref.voronoi_volume_tri(x, y, z, box, np.zeros(3), bd)
+        cell = box.copy()
+        for k in range(3):
+            if bd[k] == 0:
+                cell[k] *= 3
+        vol, nn, rad, _, _ = cells(harness, pos, cell, np.zeros(3), [1, 1, 1], W=64)
+        assert np.array_equal(nn, rnn), trial
+        assert np.allclose(vol, rvol, rtol=1e-9, atol=0) and np.allclose(rad, rrad, rtol=1e-9, atol=0), trial
