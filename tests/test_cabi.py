@@ -102,3 +102,28 @@ def test_host_mirror_classes():
         old = np.stack([np.asarray(fr[c]) for c in "xyz"], 1)
         assert np.array_equal(tool.repeat_cell(np.eye(3) * 5.0, old, 2, 1, 3),
                               port.repeat_cell(np.eye(3) * 5.0, old, 2, 1, 3))
+
+
+def test_devices_keyword_and_group_without_gpu():
+    """System(devices=[...]) is host-side bookkeeping until a cal_* call runs; the device group fails loudly (no
+    CPU path) when there is no GPU, and rejects an empty device list."""
+    import torch
+
+    import mdapy_b200 as mp
+
+    pos = np.random.default_rng(0).random((60, 3)) * 12.0
+    with pytest.raises(ValueError):
+        mp.System(pos=pos, box=12.0, devices=[])
+    s = mp.System(pos=pos, box=12.0, devices=[2, 0, 1])
+    assert s._devices == [2, 0, 1] and s._device == 2 and s._group is None      # every other call uses devices[0]
+    assert mp.System(pos=pos, box=12.0, device=3)._devices is None
+    if torch.cuda.is_available():
+        return
+    from mdapy_b200.device import DeviceGroup
+
+    with pytest.raises((RuntimeError, ValueError)):
+        DeviceGroup([0, 1])
+    with pytest.raises(ValueError):
+        DeviceGroup([])
+    with pytest.raises((RuntimeError, ValueError)):
+        s.cal_common_neighbor_analysis(3.0)
